@@ -1,0 +1,29 @@
+"""pytest configuration: the `gpu` marker, import paths, shared fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "python-sph_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """Outputs of the reference itself (tests/golden/make_golden.py)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "pyfluid_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.build()
+    return oracle
