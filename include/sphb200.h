@@ -1,0 +1,202 @@
+/*
+ * sphb200.h -- C-ABI of libsphb200.so: the B200 (sm_100a) implementation of python-sph's
+ * per-step particle loop (TRU-astrophysics/python-sph, pyfluid.py).
+ *
+ * The reference is pure Python; its "FFI" for this path is the set of module-level functions of
+ * pyfluid.py.  Each entry point below names the reference function(s) it replaces (file:line).  The
+ * Python drop-in module (python-sph_b200/pyfluid.py) binds these with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all sizes are int64_t; all entry points are stream-ordered on `stream` (a cudaStream_t passed
+ *     as void*), never synchronise, and return 0 on success or a negative SPHB_E_* code;
+ *   - workspace is caller-owned (sphb_*_workspace_bytes);
+ *   - particles are handled in "grid order": sphb_grid_build() sorts them by cell and every later
+ *     call takes and returns arrays in that order; `perm[s]` is the caller index of sorted slot s;
+ *   - soft failures and the reference's RuntimeError conditions are reported through a device
+ *     status block (sphb_status), read by the host once per stage.
+ */
+#ifndef SPHB200_H
+#define SPHB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB_ABI_VERSION 1
+
+/* error codes */
+#define SPHB_OK 0
+#define SPHB_E_ARG (-1)      /* bad argument (null pointer, n < 0, grid too large ...) */
+#define SPHB_E_CUDA (-2)     /* a CUDA runtime call failed; sphb_last_cuda_error() has the text */
+#define SPHB_E_NODEVICE (-3) /* no sm_100 device / kernel image not loadable */
+
+/* status bits (pyfluid.py RuntimeError sites); identical to oracle/sph_oracle.c ORC_* */
+#define SPHB_ST_NEG_H 1        /* "Obtained negative smoothing length."             pyfluid.py:209-210 */
+#define SPHB_ST_NEG_P 2        /* "Obtained negative pressure."                     pyfluid.py:257-258 */
+#define SPHB_ST_NEG_PI 4       /* "Obtained negative value for Pi"                  pyfluid.py:281-282 */
+#define SPHB_ST_NEG_VISC 8     /* "Obtained negative energy rate due to viscosity." pyfluid.py:349-350 */
+#define SPHB_ST_NEG_E 16       /* "Obtained negative energy."                       pyfluid.py:514-515,527-528 */
+#define SPHB_ST_BISECT_NONE 32 /* bisection_h fell through and returned None        pyfluid.py:153 */
+
+/* pyfluid.py:5-41 -- module constants, passed per call (the reference reads them at call time) */
+typedef struct sphb_consts {
+    double particle_mass;  /* PARTICLE_MASS                     :5  */
+    double coupling_const; /* COUPLING_CONST (eta)              :9  */
+    double h_tol;          /* SMOOTHLENGTH_VARIATION_TOLERANCE  :13 */
+    int32_t newton_limit;  /* NEWTON_ITERATION_LIMIT            :14 */
+    int32_t bisect_limit;  /* BISECTION_ITERATION_LIMIT         :23 */
+    double alpha;          /* ALPHA_SPH                         :18 */
+    double beta;           /* BETA_SPH                          :19 */
+    double epsilon;        /* EPSILON                           :20 */
+    double bisect_tol;     /* BISECTION_TOLERANCE               :24 */
+    double bisect_a;       /* INITIAL_BISECTION_SMOOTHLENGTH_A  :25 */
+    double bisect_b;       /* INITIAL_BISECTION_SMOOTHLENGTH_B  :26 */
+    double G;              /* G (gravity is outside this path; must be 0 for sphb_force) :35 */
+    double gamma;          /* ADIABATIC_INDEX                   :41 */
+} sphb_consts;
+
+/* Uniform cell grid.  Cell of a point: c = clamp(floor((x - origin)/cell), 0, dim-1) per axis,
+ * linear id = (cz*ny + cy)*nx + cx.  (The reference has no cell list; SURVEY.md 8(c) "self-oracle".) */
+typedef struct sphb_grid {
+    double ox, oy, oz; /* origin */
+    double cell;       /* cell edge */
+    int32_t nx, ny, nz;
+    int32_t pad_;
+} sphb_grid;
+
+/* device status block, zeroed by sphb_status_reset */
+typedef struct sphb_status {
+    int32_t flags;          /* OR of SPHB_ST_* */
+    int32_t newton_warn;    /* # "WARNING: Failure to converge in newton_new_h."   pyfluid.py:178 */
+    int32_t bisect_oob;     /* # "ERROR: Root out of bisection bounds."            pyfluid.py:136 */
+    int32_t bisect_none;    /* # "ERROR: Failure to converge in Bisection_new_h."  pyfluid.py:153 */
+    int32_t nfail;          /* entries in the Newton-failure list (internal)        */
+    int32_t reserved[3];
+} sphb_status;
+
+/* sorted-order particle views built by sphb_grid_build and consumed by every gather kernel */
+typedef struct sphb_cells {
+    sphb_grid grid;
+    int64_t n;                  /* particles in the grid (targets + ghosts) */
+    const uint32_t *cell_start; /* [ncell+1] first sorted slot of each cell */
+    const float *cell_hmax;     /* [ncell]   max h in the cell, rounded up to float */
+    const uint32_t *cell_id;    /* [n]       linear cell id of each sorted slot */
+    const double *posh;         /* [n][4]    x, y, z, h   (fp64, exact) */
+    const float *frec;          /* [n][4]    x-ox, y-oy, z-oz, (2h+delta)^2 upper bound (fp32 prefilter record) */
+    float delta;                /* absolute error bound of the fp32 positions */
+    float pad_;
+} sphb_cells;
+
+const char *sphb_last_cuda_error(void);
+int sphb_abi_version(void);
+/* number of CUDA devices with compute capability 10.x visible to the library (0 = none) */
+int sphb_device_ok(void);
+
+int sphb_status_reset(sphb_status *status, void *stream);
+
+/* ---- K1: cell-list build (no reference counterpart; enables O(N n_ngb) sums) ------------------ */
+int64_t sphb_grid_ncell(const sphb_grid *g);
+int64_t sphb_grid_workspace_bytes(int64_t n, const sphb_grid *g);
+/* pack caller-order AoS (pos (n,3), h (n)) into posh (n,4) */
+int sphb_pack_posh(const double *pos, const double *h, int64_t n, double *posh, void *stream);
+/* Sort `posh_in` (any order) into grid order.  Outputs: perm[s] = index into posh_in of sorted
+ * slot s (stable: ties in cell id keep ascending input index), cell_start, cell_hmax, cell_id,
+ * posh_sorted, frec_sorted.  delta = fp32 position error bound to bake into frec.w. */
+int sphb_grid_build(const double *posh_in, int64_t n, const sphb_grid *g, float delta, uint32_t *perm,
+                    uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id, double *posh_sorted,
+                    float *frec_sorted, void *workspace, int64_t workspace_bytes, void *stream);
+/* refresh h in posh/frec/cell_hmax of an existing grid (positions unchanged) */
+int sphb_grid_set_h(const double *h_sorted, int64_t n, const sphb_grid *g, float delta, const uint32_t *cell_start,
+                    float *cell_hmax, double *posh_sorted, float *frec_sorted, void *stream);
+/* dst[s*ncomp + k] = src[perm[s]*ncomp + k]  (apply a build's permutation to any fp64 array) */
+int sphb_gather_f64(const double *src, const uint32_t *perm, int64_t n, int32_t ncomp, double *dst, void *stream);
+/* dst[perm[s]*ncomp + k] = src[s*ncomp + k]  (undo it) */
+int sphb_scatter_f64(const double *src, const uint32_t *perm, int64_t n, int32_t ncomp, double *dst, void *stream);
+int sphb_gather_u32(const uint32_t *src, const uint32_t *perm, int64_t n, uint32_t *dst, void *stream);
+
+/* ---- K2: M4 density summation + grad-h sums ----------------------------------------------------
+ * replaces density/density_arr (pyfluid.py:218-232) and omega_j/omega_arr (pyfluid.py:91-105).
+ * For every slot j whose `target` flag is set (NULL = all slots):
+ *   rho_sum[j]  = sum_i m W(|r_j - r_i|, h_j)                      (incl. i = j)
+ *   dwdh_sum[j] = sum_i m dW/dh(|r_j - r_i|, h_j)
+ *   omega[j]    = 1 + h_j/(3 rho_j) dwdh_sum[j]                    (if omega non-NULL; rho_j = rho_in[j], or
+ *                                                                   var_density(h_j) = m (eta/h_j)^3 when rho_in is NULL,
+ *                                                                   which is what the step uses, pyfluid.py:502-503)
+ * h_j is cells->posh[j][3] unless h_target != NULL.  ngb_count (optional) = #{i : q < 2}. */
+int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *h_target,
+                       const double *rho_in, double *rho_sum, double *dwdh_sum, double *omega, int32_t *ngb_count,
+                       void *stream);
+
+/* ---- K3: Newton-Raphson smoothing-length solve ---------------------------------------------------
+ * replaces newton_smoothlength_iteration/_while/_arr (pyfluid.py:155-179, 203-211) and
+ * bisection_h (pyfluid.py:123-153).  h_out[j]: converged h, or the bisection result, or NaN when
+ * bisection returned None.  iters[j]: Newton iterations performed.  code[j]: 0 Newton converged,
+ * 1 bisection converged, 2 bisection returned None.  Counters/flags land in *status. */
+int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *h_guess,
+                  double *h_out, int32_t *iters, int32_t *code, uint32_t *fail_list, sphb_status *status,
+                  void *stream);
+/* bisection for an explicit list of target slots (also used for bisection_h(j, pos) itself);
+ * n_list < 0: take the list length from status->nfail (device side).  oob (optional, per list entry) */
+int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, const uint32_t *list, int64_t n_list,
+                  double *h_out, int32_t *code, int32_t *oob, int32_t indexed_by_slot, sphb_status *status,
+                  void *stream);
+
+/* ---- neighbour sets (SURVEY.md 8(c) oracle: NB(j) = {i : distance(r_j, r_i)/h_j < 2}) -------------
+ * exact reference arithmetic (fma-ordered dot, IEEE sqrt and divide).  Writes, for each of the
+ * n_query slots in `query`, up to `cap` neighbour slots (ascending slot order) and the true count.
+ * symmetric != 0: the force support {i : q_j < 2 or q_i < 2}; needs hmax_global (sphb_hmax). */
+int sphb_neighbours(const sphb_cells *cells, const uint32_t *query, int64_t n_query, int32_t symmetric,
+                    const float *hmax_global, uint32_t *out, int64_t cap, int32_t *count, void *stream);
+
+/* ---- K4: EOS prologue + momentum/energy sums ------------------------------------------------------
+ * sphb_eos: replaces var_density_arr (:240), pressure_arr (:251) and builds the per-particle force
+ * records: rho = m (eta/h)^3, P = (gamma-1) u rho, A = P/(omega rho^2), cs = sqrt(gamma P/rho).
+ * recB[j] = {vx, vy, vz, A}; recC[j] = {rho, cs, 1/h, 1/(pi h^4)}.
+ * rho_in / P_in (optional): take density / pressure from the caller instead (energy_rate_arr and
+ * acceleration_arr receive them as arguments, pyfluid.py:355,487); u may then be NULL.
+ * recB/recC may be NULL (var_density_arr / pressure_arr only). */
+int sphb_eos(const double *posh, const double *vel, const double *u, const double *omega, const double *rho_in,
+             const double *P_in, int64_t n, const sphb_consts *k, double *rho, double *P, double *recB, double *recC,
+             sphb_status *status, void *stream);
+/* sphb_force: replaces energy_rate/_arr (pyfluid.py:316-361), Pi (:261-285),
+ * fluid_accel_viscosity_comp (:459-474) and acceleration/_arr (:477-493) with G = 0.
+ * acc (n,3) and dudt (n) for target slots. */
+int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *recB,
+               const double *recC, const float *hmax_global, double *acc, double *dudt, sphb_status *status,
+               void *stream);
+
+/* ---- K5: integrator updates (pyfluid.py:511-515 predictor, :524-528 corrector) ------------------- */
+int sphb_predict(const double *posh0, const double *vel0, const double *u0, const double *acc0, const double *dudt0,
+                 double dt, int64_t n, double *posh_mid, double *vel_mid, double *u_mid, sphb_status *status,
+                 void *stream);
+int sphb_correct(const double *posh0, const double *vel0, const double *u0, const double *acc_mid,
+                 const double *dudt_mid, double dt, int64_t n, double *posh1, double *vel1, double *u1,
+                 sphb_status *status, void *stream);
+
+/* ---- helpers ------------------------------------------------------------------------------------ */
+/* out[0..5] = min x,y,z, max x,y,z ; out[6] = max h ; out[7] = sum h   over posh (n,4) */
+int sphb_bounds(const double *posh, int64_t n, double *out8, void *workspace, int64_t workspace_bytes, void *stream);
+int64_t sphb_bounds_workspace_bytes(int64_t n);
+/* hmax_out[0] = (float, rounded up) max h over posh */
+int sphb_hmax(const double *posh, int64_t n, float *hmax_out, void *stream);
+/* distance(rj, ri) = sqrt((rj-ri).dot(rj-ri)) for n pairs of 3-vectors (pyfluid.py:43-47) */
+int sphb_distance(const double *rj, const double *ri, int64_t n, double *out, void *stream);
+/* M4(dist,h), M4_d1(dist,h), M4_smoothlength_derivative(dist,h) elementwise (pyfluid.py:56-70,85-87);
+ * any output may be NULL */
+int sphb_m4_eval(const double *dist, const double *h, int64_t n, double *W, double *dW, double *dWdh, void *stream);
+/* OR `flag` into status if any h_out < 0 (newton_smoothlength_arr's final check, pyfluid.py:209) */
+int sphb_check_neg_h(const double *h, int64_t n, sphb_status *status, void *stream);
+/* DFMA-throughput microbenchmark: runs `iters` dependent-chain rounds on blocks x 256 threads and
+ * writes elapsed ms (CUDA events, synchronises) and flops done */
+int sphb_fp64_peak(int32_t blocks, int32_t iters, double *ms_host, double *flops_host);
+/* launch counter: number of kernels this library has launched since load (for bench.py gpu_launches) */
+int64_t sphb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB200_H */

@@ -1,0 +1,151 @@
+// sphb_common.cuh -- shared device helpers for libsphb200 (sm_100a only).
+//
+// Pair math follows pyfluid.py of TRU-astrophysics/python-sph; each helper cites the lines it
+// restates.  Prefactors 1/(pi h^3), 1/(pi h^4) are hoisted out of the sums (SURVEY.md 8(a) note).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/sphb200.h"
+
+#define SPHB_FULL 0xffffffffu
+#define SPHB_PI 3.141592653589793
+
+extern thread_local char g_sphb_err[256];
+extern long long g_sphb_launches;
+
+#define SPHB_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            snprintf(g_sphb_err, sizeof(g_sphb_err), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return SPHB_E_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define SPHB_LAUNCHED()                                                                              \
+    do {                                                                                             \
+        ++g_sphb_launches;                                                                           \
+        SPHB_CUDA(cudaGetLastError());                                                               \
+    } while (0)
+
+static inline cudaStream_t sphb_stream(void *s) { return (cudaStream_t)s; }
+
+// ---------------------------------------------------------------------------------------------
+// exact reference geometry (membership tests, pyfluid.py:43-47): d.dot(d) is
+// fma(dz,dz,fma(dy,dy,dx*dx)) on the reference's numpy (tests/golden/make_golden.py self-test)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sphb_d2(double dx, double dy, double dz)
+{
+    return __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ double sphb_dot3(double ax, double ay, double az, double bx, double by, double bz)
+{
+    return __fma_rn(az, bz, __fma_rn(ay, by, __dmul_rn(ax, bx)));
+}
+
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed (~2^-20) + one third-order step -> ~1e-17 rel.
+__device__ __forceinline__ double sphb_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = x * y;
+    double e = fma(-t, y, 1.0);          // 1 - x y^2
+    double p = fma(0.375, e, 0.5);       // 1/2 + 3/8 e
+    double ye = y * e;
+    return fma(ye, p, y);                // y (1 + e/2 + 3/8 e^2)
+}
+
+// 1/x for normal x: MUFU.RCP64H seed + one third-order step
+__device__ __forceinline__ double sphb_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// M4 cubic spline, dimensionless parts (pyfluid.py:56-70): W = f(q)/(pi h^3), W' = fp(q)/(pi h^4)
+// np.piecewise semantics: q >= 2 -> 0, 1 <= q < 2 -> middle, q < 1 -> inner (also negative q), NaN -> 0
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sphb_m4(double q, double &f, double &fp)
+{
+    double q2 = q * q;
+    double fin = fma(q2, fma(0.75, q, -1.5), 1.0);   // 1 - 3/2 q^2 + 3/4 q^3
+    double fpin = q * fma(2.25, q, -3.0);            // 9/4 q^2 - 3 q
+    double t = 2.0 - q;
+    double t2 = t * t;
+    double fmid = (0.25 * t) * t2;                   // 1/4 (2-q)^3
+    double fpmid = -0.75 * t2;                       // -3/4 (2-q)^2
+    bool inner = q < 1.0;
+    bool mid = (q >= 1.0) && (q < 2.0);
+    f = inner ? fin : (mid ? fmid : 0.0);
+    fp = inner ? fpin : (mid ? fpmid : 0.0);
+}
+
+__device__ __forceinline__ double sphb_m4_fp(double q)
+{
+    double fpin = q * fma(2.25, q, -3.0);
+    double t = 2.0 - q;
+    double fpmid = -0.75 * (t * t);
+    bool inner = q < 1.0;
+    bool mid = (q >= 1.0) && (q < 2.0);
+    return inner ? fpin : (mid ? fpmid : 0.0);
+}
+
+// pyfluid.py:237-238 var_density(): m (eta/h)^3
+__device__ __forceinline__ double sphb_var_density(const sphb_consts &k, double h)
+{
+    double t = k.coupling_const / h;
+    return k.particle_mass * (t * t * t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions (all 32 lanes participate)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sphb_f2ord(float f)
+{
+    int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float sphb_ord2f(int i)
+{
+    return __int_as_float(i ^ ((i >> 31) & 0x7fffffff));
+}
+__device__ __forceinline__ float sphb_warp_min(float v)
+{
+    return sphb_ord2f(__reduce_min_sync(SPHB_FULL, sphb_f2ord(v)));
+}
+__device__ __forceinline__ float sphb_warp_max(float v)
+{
+    return sphb_ord2f(__reduce_max_sync(SPHB_FULL, sphb_f2ord(v)));
+}
+__device__ __forceinline__ double sphb_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SPHB_FULL, v, o);
+    return v;
+}
+
+// float upper bounds
+__device__ __forceinline__ float sphb_f_up(double x) { return __double2float_ru(x); }
+
+// fp32 prefilter threshold for a support radius 2h: ((2h)(1+2^-20) + delta)^2 (1 + 1e-5), rounded up.
+// !(h > 0) (negative, zero, NaN) means "unbounded support" in the reference's formulas (q < 1 for
+// every distance when h < 0, pyfluid.py:57-60): +inf.
+__device__ __forceinline__ float sphb_thr_of_h(double h, float delta)
+{
+    if (!(h > 0.0)) return CUDART_INF_F;
+    float R = __fadd_ru(__fmul_ru(sphb_f_up(2.0 * h), 1.000001f), delta);
+    float t = __fmul_ru(__fmul_ru(R, R), 1.00001f);
+    return t;
+}
+__device__ __forceinline__ float sphb_radius_of_h(double h, float delta)
+{
+    if (!(h > 0.0)) return CUDART_INF_F;
+    return __fmul_ru(__fadd_ru(__fmul_ru(sphb_f_up(2.0 * h), 1.000001f), delta), 1.00001f);
+}

@@ -1,0 +1,482 @@
+// sphb_force.cu -- K4: EOS prologue and the fused momentum + energy sums (pressure gradient with
+// grad-h terms + Monaghan artificial viscosity), and K5: the predictor / corrector updates.
+#include <stdio.h>
+
+#include "sphb_scan.cuh"
+
+#define SPHB_WARPS 4
+#define SPHB_THREADS (SPHB_WARPS * 32)
+
+__device__ __forceinline__ void sphb_load4(const double *rec, size_t i, double &a, double &b, double &c, double &d)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(rec) + 2 * i;
+    const double2 u = __ldg(p), v = __ldg(p + 1);
+    a = u.x;
+    b = u.y;
+    c = v.x;
+    d = v.y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EOS prologue: var_density (pyfluid.py:237-245), pressure (:248-259), plus the per-particle factors
+// every pair term needs: A = P/(omega rho^2) (:466-467,:352), cs = (gamma P/rho)^0.5 (:274-275),
+// 1/h and 1/(pi h^4) (:66)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_eos(const double *__restrict__ posh, const double *__restrict__ vel, const double *__restrict__ u,
+                      const double *__restrict__ omega, const double *__restrict__ rho_in,
+                      const double *__restrict__ P_in, long long n, sphb_consts k, double *__restrict__ rho_out,
+                      double *__restrict__ P_out, double *__restrict__ recB, double *__restrict__ recC,
+                      sphb_status *__restrict__ status)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double h = posh[4 * i + 3];
+    const double rho = rho_in ? rho_in[i] : sphb_var_density(k, h);
+    // (ADIABATIC_INDEX - 1) * energy * density
+    const double P = P_in ? P_in[i] : __dmul_rn(__dmul_rn(k.gamma - 1.0, u[i]), rho);
+    if (P < 0.0) atomicOr(&status->flags, SPHB_ST_NEG_P);
+    if (rho_out) rho_out[i] = rho;
+    if (P_out) P_out[i] = P;
+    if (!recB || !recC) return;
+    const double om = omega[i];
+    const double A = P / (om * (rho * rho));
+    const double cs = sqrt(k.gamma * P / rho);
+    double2 *b = reinterpret_cast<double2 *>(recB) + 2 * i;
+    b[0] = make_double2(vel[3 * i], vel[3 * i + 1]);
+    b[1] = make_double2(vel[3 * i + 2], A);
+    const double h2 = h * h;
+    double2 *c = reinterpret_cast<double2 *>(recC) + 2 * i;
+    c[0] = make_double2(rho, cs);
+    c[1] = make_double2(1.0 / h, 1.0 / (SPHB_PI * (h2 * h2)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 pair sums.  For target j over i with q_j < 2 or q_i < 2 (pair terms vanish otherwise) and
+// r_ji != 0 (coincident particles contribute exactly 0: pyfluid.py:51-52,461):
+//   gradW(h) = W'(r,h) (r_j - r_i)/r = s (r_j - r_i),  s = fp(q)/(pi h^4)/r
+//   dens  += s_j (v_ji . r_ji)                                        :327-331
+//   Pi_ji  per :261-285 (convergent pairs only)
+//   acc   -= (A_j s_j + A_i s_i + Pi/2 (s_j + s_i)) r_ji              :464-474
+//   visc  += Pi (1/2 (s_j + s_i)) (v_ji . r_ji)                       :333-343
+// m, and the final 1/2 of :346, are applied once per target.
+// ------------------------------------------------------------------------------------------------
+struct SphbForceAcc {
+    double xj, yj, zj, hj;
+    double vxj, vyj, vzj, Aj;
+    double rhoj, csj, hinvj, gj;
+    double ax, ay, az, dens, visc;
+    int negpi;
+};
+
+__device__ __forceinline__ void sphb_force_flush(const double *posh, const double *recB, const double *recC,
+                                                 const uint32_t *list, int lane, int cnt, const sphb_consts &k,
+                                                 SphbForceAcc &a)
+{
+    for (int n_ = 0; n_ < cnt; ++n_) {
+        const uint32_t i = list[n_ * 32 + lane];
+        double x, y, z, hi;
+        sphb_load4(posh, i, x, y, z, hi);
+        const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
+        const double d2 = sphb_d2(dx, dy, dz);
+        if (!(d2 > 0.0)) continue;
+        double rhoi, csi, hinvi, gi;
+        sphb_load4(recC, i, rhoi, csi, hinvi, gi);
+        const double rinv = sphb_rsqrt(d2);
+        const double r = d2 * rinv;
+        const double qj = r * a.hinvj, qi = r * hinvi;
+        if (!(qj < 2.0) && !(qi < 2.0)) continue;   // prefilter false positive
+        double vxi, vyi, vzi, Ai;
+        sphb_load4(recB, i, vxi, vyi, vzi, Ai);
+        const double sj = sphb_m4_fp(qj) * a.gj * rinv;
+        const double si = sphb_m4_fp(qi) * gi * rinv;
+        const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
+        const double vdr = sphb_dot3(dx, dy, dz, dvx, dvy, dvz);
+        a.dens = fma(sj, vdr, a.dens);
+        const double sm = sj + si;
+        double pi_half = 0.0;
+        if (vdr < 0.0) {
+            const double mean_h = 0.5 * (a.hj + hi);
+            const double den = fma(k.epsilon * mean_h, mean_h, d2);
+            const double mean_rho = 0.5 * (a.rhoj + rhoi);
+            const double inv = sphb_rcp(den * mean_rho);
+            const double mu = (mean_h * vdr) * (inv * mean_rho);
+            const double cs = 0.5 * (csi + a.csj);
+            const double pi = (mu * fma(k.beta, mu, -k.alpha * cs)) * (inv * den);
+            if (pi < 0.0) a.negpi = 1;
+            pi_half = 0.5 * pi;
+        }
+        const double coef = fma(a.Aj, sj, fma(Ai, si, pi_half * sm));
+        a.ax = fma(-coef, dx, a.ax);
+        a.ay = fma(-coef, dy, a.ay);
+        a.az = fma(-coef, dz, a.az);
+        a.visc = fma(pi_half * sm, vdr, a.visc);
+    }
+}
+
+__global__ void __launch_bounds__(SPHB_THREADS)
+    k_force(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ recB,
+            const double *__restrict__ recC, const float *__restrict__ hmax_global, double *__restrict__ acc,
+            double *__restrict__ dudt, sphb_status *__restrict__ status)
+{
+    __shared__ SphbWarpShared sh[SPHB_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long base = ((long long)blockIdx.x * SPHB_WARPS + warp) * 32;
+    if (base >= c.n) return;
+    const long long j = base + lane;
+    const bool valid = j < c.n;
+    const bool tgt = valid && (target == nullptr || target[j] != 0);
+    const SphbScanCtx g = sphb_make_ctx(c);
+    SphbWarpShared &ws = sh[warp];
+
+    SphbForceAcc a;
+    a.xj = a.yj = a.zj = 0.0;
+    a.hj = 1.0;
+    a.vxj = a.vyj = a.vzj = a.Aj = 0.0;
+    a.rhoj = a.csj = a.hinvj = a.gj = 0.0;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t row = 0xffffffffu;
+    if (valid) {
+        sphb_load4(c.posh, (size_t)j, a.xj, a.yj, a.zj, a.hj);
+        sphb_load4(recB, (size_t)j, a.vxj, a.vyj, a.vzj, a.Aj);
+        sphb_load4(recC, (size_t)j, a.rhoj, a.csj, a.hinvj, a.gj);
+        f = __ldg(g.frec + j);
+        row = c.cell_id[j] / (uint32_t)g.nx;
+    }
+    a.ax = a.ay = a.az = a.dens = a.visc = 0.0;
+    a.negpi = 0;
+    const float Rj = sphb_radius_of_h(a.hj, g.delta), thr = f.w;
+    const float RH = sphb_radius_of_h((double)hmax_global[0], g.delta);
+    int cnt = 0;
+    auto flush = [&](int n_) { sphb_force_flush(c.posh, recB, recC, ws.list, lane, n_, k, a); };
+    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, RH, cnt, flush);
+    flush(cnt);
+    if (tgt) {
+        const double m = k.particle_mass;
+        acc[3 * j] = m * a.ax;
+        acc[3 * j + 1] = m * a.ay;
+        acc[3 * j + 2] = m * a.az;
+        const double visc = 0.5 * (m * a.visc);                 // viscosity_sum *= 0.5, pyfluid.py:346
+        dudt[j] = fma(a.Aj, m * a.dens, visc);                  // P_j/(rho_j^2 omega_j) * density_change + viscosity_sum
+        int fl = 0;
+        if (a.negpi) fl |= SPHB_ST_NEG_PI;
+        if (visc < 0.0) fl |= SPHB_ST_NEG_VISC;
+        if (fl) atomicOr(&status->flags, fl);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: predictor (pyfluid.py:511-515) and corrector (:524-528); arithmetic in the reference's order
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sphb_axpy_half(double a, double b, double dt)
+{
+    return __dadd_rn(a, __dmul_rn(__dmul_rn(b, 0.5), dt));   // a + b * 0.5 * dt
+}
+
+__global__ void k_predict(const double *__restrict__ posh0, const double *__restrict__ vel0, const double *__restrict__ u0,
+                          const double *__restrict__ acc0, const double *__restrict__ dudt0, double dt, long long n,
+                          double *__restrict__ posh_mid, double *__restrict__ vel_mid, double *__restrict__ u_mid,
+                          sphb_status *__restrict__ status)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v[3], p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        v[k] = vel0[3 * i + k];
+        p[k] = sphb_axpy_half(posh0[4 * i + k], v[k], dt);                 // pos0 + vel0 * 0.5 * dt
+        vel_mid[3 * i + k] = sphb_axpy_half(v[k], acc0[3 * i + k], dt);    // vel0 + acc0 * 0.5 * dt
+    }
+    const double e = sphb_axpy_half(u0[i], dudt0[i], dt);                  // energy0 + energy_rate0 * 0.5 * dt
+    if (e < 0.0) atomicOr(&status->flags, SPHB_ST_NEG_E);
+    u_mid[i] = e;
+    double2 *o = reinterpret_cast<double2 *>(posh_mid) + 2 * i;
+    o[0] = make_double2(p[0], p[1]);
+    o[1] = make_double2(p[2], posh0[4 * i + 3]);
+}
+
+__global__ void k_correct(const double *__restrict__ posh0, const double *__restrict__ vel0, const double *__restrict__ u0,
+                          const double *__restrict__ acc_mid, const double *__restrict__ dudt_mid, double dt, long long n,
+                          double *__restrict__ posh1, double *__restrict__ vel1, double *__restrict__ u1,
+                          sphb_status *__restrict__ status)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double v0 = vel0[3 * i + k];
+        const double v1 = __dadd_rn(v0, __dmul_rn(acc_mid[3 * i + k], dt));                       // vel0 + acc_mid * dt
+        p[k] = __dadd_rn(posh0[4 * i + k], __dmul_rn(__dmul_rn(0.5, __dadd_rn(v0, v1)), dt));     // pos0 + 0.5*(vel0+vel1)*dt
+        vel1[3 * i + k] = v1;
+    }
+    const double e = __dadd_rn(u0[i], __dmul_rn(dudt_mid[i], dt));                                // energy0 + rate_mid * dt
+    if (e < 0.0) atomicOr(&status->flags, SPHB_ST_NEG_E);
+    u1[i] = e;
+    double2 *o = reinterpret_cast<double2 *>(posh1) + 2 * i;
+    o[0] = make_double2(p[0], p[1]);
+    o[1] = make_double2(p[2], posh0[4 * i + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers: bounds / h_max reductions, negative-h check, DFMA peak probe
+// ------------------------------------------------------------------------------------------------
+#define RED_THREADS 256
+
+__global__ void __launch_bounds__(RED_THREADS)
+    k_bounds_partial(const double *__restrict__ posh, long long n, double *__restrict__ part /*[grid][8]*/)
+{
+    __shared__ double sh[RED_THREADS / 32][8];
+    double mn[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, mx[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+    double hm = -CUDART_INF, hs = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 a = reinterpret_cast<const double2 *>(posh)[2 * i];
+        const double2 b = reinterpret_cast<const double2 *>(posh)[2 * i + 1];
+        mn[0] = fmin(mn[0], a.x); mx[0] = fmax(mx[0], a.x);
+        mn[1] = fmin(mn[1], a.y); mx[1] = fmax(mx[1], a.y);
+        mn[2] = fmin(mn[2], b.x); mx[2] = fmax(mx[2], b.x);
+        hm = fmax(hm, b.y);
+        hs += b.y;
+    }
+    double v[8] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], hm, hs};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = fmin(v[k], __shfl_xor_sync(SPHB_FULL, v[k], o));
+#pragma unroll
+        for (int k = 3; k < 7; ++k) v[k] = fmax(v[k], __shfl_xor_sync(SPHB_FULL, v[k], o));
+        v[7] += __shfl_xor_sync(SPHB_FULL, v[7], o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int k = 0; k < 8; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < RED_THREADS / 32; ++w) {
+            for (int k = 0; k < 3; ++k) v[k] = fmin(v[k], sh[w][k]);
+            for (int k = 3; k < 7; ++k) v[k] = fmax(v[k], sh[w][k]);
+            v[7] += sh[w][7];
+        }
+        for (int k = 0; k < 8; ++k) part[(size_t)blockIdx.x * 8 + k] = v[k];
+    }
+}
+
+__global__ void k_bounds_final(const double *__restrict__ part, int nb, double *__restrict__ out8, float *__restrict__ hmax_f)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double v[8];
+    for (int k = 0; k < 8; ++k) v[k] = part[k];
+    for (int b = 1; b < nb; ++b) {
+        for (int k = 0; k < 3; ++k) v[k] = fmin(v[k], part[(size_t)b * 8 + k]);
+        for (int k = 3; k < 7; ++k) v[k] = fmax(v[k], part[(size_t)b * 8 + k]);
+        v[7] += part[(size_t)b * 8 + 7];
+    }
+    if (out8)
+        for (int k = 0; k < 8; ++k) out8[k] = v[k];
+    if (hmax_f) hmax_f[0] = sphb_f_up(v[6]);
+}
+
+#define BOUNDS_BLOCKS 592
+
+extern "C" int64_t sphb_bounds_workspace_bytes(int64_t n)
+{
+    (void)n;
+    return (int64_t)BOUNDS_BLOCKS * 8 * sizeof(double);
+}
+
+extern "C" int sphb_bounds(const double *posh, int64_t n, double *out8, void *workspace, int64_t workspace_bytes,
+                           void *stream)
+{
+    if (n <= 0 || !posh || !out8 || !workspace || workspace_bytes < sphb_bounds_workspace_bytes(n)) return SPHB_E_ARG;
+    int nb = (int)((n + RED_THREADS - 1) / RED_THREADS);
+    if (nb > BOUNDS_BLOCKS) nb = BOUNDS_BLOCKS;
+    k_bounds_partial<<<nb, RED_THREADS, 0, sphb_stream(stream)>>>(posh, n, (double *)workspace);
+    SPHB_LAUNCHED();
+    k_bounds_final<<<1, 32, 0, sphb_stream(stream)>>>((const double *)workspace, nb, out8, nullptr);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+// atomicMax on a non-negative float through its int pattern
+__global__ void k_hmax(const double *__restrict__ posh, long long n, int *__restrict__ hmax_bits)
+{
+    float hm = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double h = posh[4 * i + 3];
+        hm = (h > 0.0) ? fmaxf(hm, sphb_f_up(h)) : CUDART_INF_F;
+    }
+    hm = sphb_warp_max(hm);
+    if ((threadIdx.x & 31) == 0) atomicMax(hmax_bits, __float_as_int(hm));
+}
+
+extern "C" int sphb_hmax(const double *posh, int64_t n, float *hmax_out, void *stream)
+{
+    if (n < 0 || !hmax_out || (n > 0 && !posh)) return SPHB_E_ARG;
+    SPHB_CUDA(cudaMemsetAsync(hmax_out, 0, sizeof(float), sphb_stream(stream)));
+    if (n == 0) return SPHB_OK;
+    int nb = (int)((n + RED_THREADS - 1) / RED_THREADS);
+    if (nb > BOUNDS_BLOCKS) nb = BOUNDS_BLOCKS;
+    k_hmax<<<nb, RED_THREADS, 0, sphb_stream(stream)>>>(posh, n, (int *)hmax_out);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+__global__ void k_check_neg_h(const double *__restrict__ h, long long n, sphb_status *__restrict__ status)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && h[i] < 0.0) atomicOr(&status->flags, SPHB_ST_NEG_H);
+}
+
+extern "C" int sphb_check_neg_h(const double *h, int64_t n, sphb_status *status, void *stream)
+{
+    if (n < 0 || !status || (n > 0 && !h)) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_check_neg_h<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(h, n, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+// M4 / M4_d1 / M4_smoothlength_derivative, pyfluid.py:56-70,85-87 (true division for q, like the reference)
+__global__ void k_m4_eval(const double *__restrict__ dist, const double *__restrict__ h, long long n,
+                          double *__restrict__ W, double *__restrict__ dW, double *__restrict__ dWdh)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double hh = h[i], q = dist[i] / hh;
+    double f, fp;
+    sphb_m4(q, f, fp);
+    const double h3 = hh * hh * hh;
+    const double w = 1.0 / (SPHB_PI * h3) * f;
+    const double wp = 1.0 / (SPHB_PI * (h3 * hh)) * fp;
+    if (W) W[i] = w;
+    if (dW) dW[i] = wp;
+    if (dWdh) dWdh[i] = -q * wp - 3.0 / hh * w;
+}
+
+extern "C" int sphb_m4_eval(const double *dist, const double *h, int64_t n, double *W, double *dW, double *dWdh,
+                            void *stream)
+{
+    if (n < 0 || (n > 0 && (!dist || !h))) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_m4_eval<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(dist, h, n, W, dW, dWdh);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+// distance(), pyfluid.py:43-47
+__global__ void k_distance(const double *__restrict__ rj, const double *__restrict__ ri, long long n,
+                           double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __dsqrt_rn(sphb_d2(rj[3 * i] - ri[3 * i], rj[3 * i + 1] - ri[3 * i + 1], rj[3 * i + 2] - ri[3 * i + 2]));
+}
+
+extern "C" int sphb_distance(const double *rj, const double *ri, int64_t n, double *out, void *stream)
+{
+    if (n < 0 || (n > 0 && (!rj || !ri || !out))) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_distance<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(rj, ri, n, out);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+// 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double *__restrict__ sink)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int sphb_fp64_peak(int32_t blocks, int32_t iters, double *ms_host, double *flops_host)
+{
+    if (blocks <= 0 || iters <= 0 || !ms_host || !flops_host) return SPHB_E_ARG;
+    double *sink = nullptr;
+    SPHB_CUDA(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    SPHB_CUDA(cudaEventCreate(&e0));
+    SPHB_CUDA(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, 256>>>(iters / 8 + 1, sink);   // warm-up
+    SPHB_CUDA(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, 256>>>(iters, sink);
+    SPHB_CUDA(cudaEventRecord(e1));
+    SPHB_CUDA(cudaEventSynchronize(e1));
+    g_sphb_launches += 2;
+    float ms = 0.f;
+    SPHB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_host = (double)ms;
+    *flops_host = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return SPHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int sphb_eos(const double *posh, const double *vel, const double *u, const double *omega,
+                        const double *rho_in, const double *P_in, int64_t n, const sphb_consts *k, double *rho, double *P,
+                        double *recB, double *recC, sphb_status *status, void *stream)
+{
+    if (n < 0 || !k || !status) return SPHB_E_ARG;
+    if (n > 0 && (!posh || (!u && !P_in))) return SPHB_E_ARG;
+    if ((recB != nullptr) != (recC != nullptr)) return SPHB_E_ARG;
+    if (n > 0 && recB && (!vel || !omega)) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_eos<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh, vel, u, omega, rho_in, P_in, n, *k, rho, P,
+                                                                        recB, recC, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *recB,
+                          const double *recC, const float *hmax_global, double *acc, double *dudt, sphb_status *status,
+                          void *stream)
+{
+    if (!cells || !k || !recB || !recC || !hmax_global || !acc || !dudt || !status) return SPHB_E_ARG;
+    if (cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh || !cells->frec)
+        return SPHB_E_ARG;
+    if (k->G != 0.0) return SPHB_E_ARG;   // self-gravity is outside this path
+    if (cells->n == 0) return SPHB_OK;
+    const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
+    k_force<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, hmax_global, acc,
+                                                                        dudt, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_predict(const double *posh0, const double *vel0, const double *u0, const double *acc0,
+                            const double *dudt0, double dt, int64_t n, double *posh_mid, double *vel_mid, double *u_mid,
+                            sphb_status *status, void *stream)
+{
+    if (n < 0 || !status || (n > 0 && (!posh0 || !vel0 || !u0 || !acc0 || !dudt0 || !posh_mid || !vel_mid || !u_mid)))
+        return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_predict<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh0, vel0, u0, acc0, dudt0, dt, n,
+                                                                            posh_mid, vel_mid, u_mid, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_correct(const double *posh0, const double *vel0, const double *u0, const double *acc_mid,
+                            const double *dudt_mid, double dt, int64_t n, double *posh1, double *vel1, double *u1,
+                            sphb_status *status, void *stream)
+{
+    if (n < 0 || !status || (n > 0 && (!posh0 || !vel0 || !u0 || !acc_mid || !dudt_mid || !posh1 || !vel1 || !u1)))
+        return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_correct<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh0, vel0, u0, acc_mid, dudt_mid, dt, n,
+                                                                            posh1, vel1, u1, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}

@@ -1,0 +1,389 @@
+// sphb_gather.cu -- K2 (M4 density + grad-h sums), K3 (Newton-Raphson h solve + bisection fallback)
+// and the exact neighbour-set kernel.  See include/sphb200.h for the reference lines each replaces.
+#include <stdio.h>
+
+#include "sphb_scan.cuh"
+
+#define SPHB_WARPS 4
+#define SPHB_THREADS (SPHB_WARPS * 32)
+
+__device__ __forceinline__ void sphb_load_posh(const double *posh, size_t i, double &x, double &y, double &z, double &h)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(posh) + 2 * i;
+    const double2 a = __ldg(p), b = __ldg(p + 1);
+    x = a.x;
+    y = a.y;
+    z = b.x;
+    h = b.y;
+}
+
+// One evaluation of sumF = sum f(q), sumG = sum (q f'(q) + 3 f(q)) over the lane's list.
+// rho_sum = m sumF/(pi h^3) (pyfluid.py:218-224), sum m dW/dh = -m sumG/(pi h^4) (pyfluid.py:85-87,91-97).
+struct SphbOwnAcc {
+    double xj, yj, zj, hinv;
+    double sumF, sumG;
+    int nn;
+};
+
+__device__ __forceinline__ void sphb_own_flush(const double *posh, const uint32_t *list, int lane, int cnt, SphbOwnAcc &a)
+{
+#pragma unroll 2
+    for (int k = 0; k < cnt; ++k) {
+        const uint32_t i = list[k * 32 + lane];
+        double x, y, z, h;
+        sphb_load_posh(posh, i, x, y, z, h);
+        const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
+        const double d2 = sphb_d2(dx, dy, dz);
+        const double r = d2 > 0.0 ? d2 * sphb_rsqrt(d2) : 0.0;
+        const double q = r * a.hinv;
+        double f, fp;
+        sphb_m4(q, f, fp);
+        a.sumF += f;
+        a.sumG += fma(q, fp, 3.0 * f);
+        a.nn += (q < 2.0) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPHB_THREADS)
+    k_density_omega(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_target,
+                    const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
+                    double *__restrict__ omega, int32_t *__restrict__ ngb_count)
+{
+    __shared__ SphbWarpShared sh[SPHB_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long base = ((long long)blockIdx.x * SPHB_WARPS + warp) * 32;
+    if (base >= c.n) return;
+    const long long j = base + lane;
+    const bool valid = j < c.n;
+    const bool tgt = valid && (target == nullptr || target[j] != 0);
+    const SphbScanCtx g = sphb_make_ctx(c);
+
+    SphbOwnAcc a;
+    double h = 1.0;
+    a.xj = a.yj = a.zj = 0.0;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t row = 0xffffffffu;
+    if (valid) {
+        sphb_load_posh(c.posh, (size_t)j, a.xj, a.yj, a.zj, h);
+        if (h_target) h = h_target[j];
+        f = __ldg(g.frec + j);
+        row = c.cell_id[j] / (uint32_t)g.nx;
+    }
+    a.hinv = 1.0 / h;
+    a.sumF = a.sumG = 0.0;
+    a.nn = 0;
+    const float Rj = sphb_radius_of_h(h, g.delta), thr = sphb_thr_of_h(h, g.delta);
+    int cnt = 0;
+    SphbWarpShared &ws = sh[warp];
+    auto flush = [&](int n_) { sphb_own_flush(c.posh, ws.list, lane, n_, a); };
+    sphb_warp_scan<false>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, 0.f, cnt, flush);
+    flush(cnt);
+    if (tgt) {
+        const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
+        const double rs = pref * a.sumF;
+        const double ds = -(pref / h) * a.sumG;
+        if (rho_sum) rho_sum[j] = rs;
+        if (dwdh_sum) dwdh_sum[j] = ds;
+        if (omega) {
+            const double rho = rho_in ? rho_in[j] : sphb_var_density(k, h);
+            omega[j] = 1.0 + h / (3.0 * rho) * ds;   // pyfluid.py:97
+        }
+        if (ngb_count) ngb_count[j] = a.nn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: per-lane Newton loop with warp-vote convergence mask (pyfluid.py:155-179)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPHB_THREADS)
+    k_newton_h(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_guess,
+               double *__restrict__ h_out, int32_t *__restrict__ iters, int32_t *__restrict__ code,
+               uint32_t *__restrict__ fail_list, sphb_status *__restrict__ status)
+{
+    __shared__ SphbWarpShared sh[SPHB_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long base = ((long long)blockIdx.x * SPHB_WARPS + warp) * 32;
+    if (base >= c.n) return;
+    const long long j = base + lane;
+    const bool valid = j < c.n;
+    const bool tgt = valid && (target == nullptr || target[j] != 0);
+    const SphbScanCtx g = sphb_make_ctx(c);
+    SphbWarpShared &ws = sh[warp];
+
+    SphbOwnAcc a;
+    a.xj = a.yj = a.zj = 0.0;
+    double h_old = 1.0, hdummy;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t row = 0xffffffffu;
+    if (valid) {
+        sphb_load_posh(c.posh, (size_t)j, a.xj, a.yj, a.zj, hdummy);
+        f = __ldg(g.frec + j);
+        row = c.cell_id[j] / (uint32_t)g.nx;
+    }
+    if (tgt) h_old = h_guess[j];
+    bool active = tgt;
+    int it = 0;
+    while (__any_sync(SPHB_FULL, active)) {
+        a.hinv = 1.0 / h_old;
+        a.sumF = a.sumG = 0.0;
+        a.nn = 0;
+        const float Rj = sphb_radius_of_h(h_old, g.delta), thr = sphb_thr_of_h(h_old, g.delta);
+        int cnt = 0;
+        auto flush = [&](int n_) { sphb_own_flush(c.posh, ws.list, lane, n_, a); };
+        sphb_warp_scan<false>(g, ws, lane, active, f.x, f.y, f.z, Rj, thr, row, 0.f, cnt, flush);
+        flush(cnt);
+        if (active) {
+            // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
+            const double pref = k.particle_mass / (SPHB_PI * (h_old * h_old * h_old));
+            const double rho = pref * a.sumF;
+            const double sdh = -(pref / h_old) * a.sumG;
+            const double vd = sphb_var_density(k, h_old);
+            const double zeta = vd - rho;
+            const double zetap = -sdh - 3.0 * vd / h_old;
+            const double h_new = h_old - zeta / zetap;
+            ++it;
+            // smoothlength_variation(old, new) = |old - new| / |new|, pyfluid.py:119-120,172
+            if (fabs(h_old - h_new) / fabs(h_new) < k.h_tol && h_new > 0.0) {
+                h_out[j] = h_new;
+                if (iters) iters[j] = it;
+                if (code) code[j] = 0;
+                active = false;
+            } else {
+                h_old = h_new;
+                if (it >= k.newton_limit) {
+                    // "WARNING: Failure to converge in newton_new_h." -> bisection_h(j, pos), pyfluid.py:178-179
+                    atomicAdd(&status->newton_warn, 1);
+                    const int slot = atomicAdd(&status->nfail, 1);
+                    fail_list[slot] = (uint32_t)j;
+                    h_out[j] = CUDART_NAN;
+                    if (iters) iters[j] = it;
+                    if (code) code[j] = 1;
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide brute-force density at an arbitrary h for ONE particle (bisection path).  All threads
+// of the block call it; returns the same value in every thread.
+// ------------------------------------------------------------------------------------------------
+__device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, double xj, double yj, double zj,
+                                     double fxj, double fyj, double fzj, double h, double *red /*[SPHB_WARPS]*/)
+{
+    const SphbScanCtx g = sphb_make_ctx(c);
+    const double R = (h > 0.0) ? (2.0 * h * 1.000001 + (double)g.delta) * 1.00001 : (double)CUDART_INF_F;
+    const int cxl = sphb_cell_lo(fxj - R, g.inv_cell, g.nx), cxh = sphb_cell_hi(fxj + R, g.inv_cell, g.nx);
+    const int cyl = sphb_cell_lo(fyj - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fyj + R, g.inv_cell, g.ny);
+    const int czl = sphb_cell_lo(fzj - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fzj + R, g.inv_cell, g.nz);
+    const bool fullx = (cxl == 0 && cxh == g.nx - 1);
+    const bool fully = fullx && (cyl == 0 && cyh == g.ny - 1);
+    const double hinv = 1.0 / h;
+    double sum = 0.0;
+    // spans: merge rows when the x range (and the y range) cover the whole axis
+    const int nzs = fully ? 1 : (czh - czl + 1);
+    const int nys = fullx ? 1 : (cyh - cyl + 1);
+    for (int iz = 0; iz < nzs; ++iz) {
+        for (int iy = 0; iy < nys; ++iy) {
+            size_t c0, c1;
+            if (fully) {
+                c0 = ((size_t)czl * g.ny) * g.nx;
+                c1 = ((size_t)(czh + 1) * g.ny) * g.nx;
+            } else if (fullx) {
+                c0 = ((size_t)(czl + iz) * g.ny + cyl) * g.nx;
+                c1 = ((size_t)(czl + iz) * g.ny + cyh + 1) * g.nx;
+            } else {
+                const size_t rowbase = ((size_t)(czl + iz) * g.ny + (cyl + iy)) * g.nx;
+                c0 = rowbase + cxl;
+                c1 = rowbase + cxh + 1;
+            }
+            const uint32_t s = g.cell_start[c0], e = g.cell_start[c1];
+            for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x) {
+                double x, y, z, hh;
+                sphb_load_posh(c.posh, i, x, y, z, hh);
+                const double dx = xj - x, dy = yj - y, dz = zj - z;
+                const double d2 = sphb_d2(dx, dy, dz);
+                const double q = sqrt(d2) * hinv;
+                double f, fp;
+                sphb_m4(q, f, fp);
+                sum += f;
+            }
+        }
+    }
+    sum = sphb_warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    return k.particle_mass / (SPHB_PI * (h * h * h)) * tot;
+}
+
+// bisection_h, pyfluid.py:123-153 (density at h_a / h_b is re-used instead of recomputed: same value)
+__global__ void __launch_bounds__(SPHB_THREADS)
+    k_bisect_h(sphb_cells c, sphb_consts k, const uint32_t *__restrict__ list, long long n_list_arg,
+               double *__restrict__ h_out, int32_t *__restrict__ code, int32_t *__restrict__ oob_out,
+               int indexed_by_slot, sphb_status *__restrict__ status)
+{
+    __shared__ double red[SPHB_WARPS];
+    const long long n_list = n_list_arg >= 0 ? n_list_arg : (long long)status->nfail;
+    for (long long e = blockIdx.x; e < n_list; e += gridDim.x) {
+        const uint32_t j = list[e];
+        double xj, yj, zj, hj;
+        sphb_load_posh(c.posh, j, xj, yj, zj, hj);
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(c.frec) + j);
+        double h_a = k.bisect_a, h_b = k.bisect_b;
+        double zeta_a = sphb_var_density(k, h_a) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, h_a, red);
+        double zeta_b = sphb_var_density(k, h_b) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, h_b, red);
+        int i = 0, oob = 0, res = 2;
+        double root = CUDART_NAN;
+        while (i < k.bisect_limit) {
+            if (zeta_a * zeta_b > 0.0) ++oob;   // "ERROR: Root out of bisection bounds."
+            const double cand = (h_a + h_b) / 2.0;
+            const double zeta_root =
+                sphb_var_density(k, cand) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, cand, red);
+            if (fabs(zeta_root) < k.bisect_tol) {
+                root = cand;
+                res = 1;
+                break;
+            }
+            if (zeta_a * zeta_root < 0.0) {
+                h_b = cand;
+                zeta_b = zeta_root;
+            } else if (zeta_b * zeta_root < 0.0) {
+                h_a = cand;
+                zeta_a = zeta_root;
+            }
+            ++i;
+        }
+        if (threadIdx.x == 0) {
+            const long long o = indexed_by_slot ? (long long)j : e;
+            h_out[o] = root;
+            if (code) code[o] = res;
+            if (oob_out) oob_out[o] = oob;
+            if (oob) atomicAdd(&status->bisect_oob, oob);
+            if (res == 2) {
+                atomicAdd(&status->bisect_none, 1);   // "ERROR: Failure to converge in Bisection_new_h."
+                atomicOr(&status->flags, SPHB_ST_BISECT_NONE);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact neighbour sets: one warp per query slot, reference arithmetic
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPHB_THREADS)
+    k_neighbours(sphb_cells c, const uint32_t *__restrict__ query, long long n_query, int symmetric,
+                 const float *__restrict__ hmax_global, uint32_t *__restrict__ out, long long cap,
+                 int32_t *__restrict__ count)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long qi = (long long)blockIdx.x * SPHB_WARPS + warp;
+    if (qi >= n_query) return;
+    const SphbScanCtx g = sphb_make_ctx(c);
+    const uint32_t j = query[qi];
+    double xj, yj, zj, hj;
+    sphb_load_posh(c.posh, j, xj, yj, zj, hj);
+    const float4 fj = __ldg(g.frec + j);
+    double hr = hj;
+    if (symmetric && hmax_global && !((double)hmax_global[0] <= hr)) hr = (double)hmax_global[0];
+    const double R = (hr > 0.0) ? (2.0 * hr * 1.000001 + (double)g.delta) * 1.00001 : (double)CUDART_INF_F;
+    const int cxl = sphb_cell_lo(fj.x - R, g.inv_cell, g.nx), cxh = sphb_cell_hi(fj.x + R, g.inv_cell, g.nx);
+    const int cyl = sphb_cell_lo(fj.y - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fj.y + R, g.inv_cell, g.ny);
+    const int czl = sphb_cell_lo(fj.z - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fj.z + R, g.inv_cell, g.nz);
+    long long total = 0;
+    for (int rz = czl; rz <= czh; ++rz)
+        for (int ry = cyl; ry <= cyh; ++ry) {
+            const size_t rowbase = ((size_t)rz * g.ny + ry) * g.nx;
+            const uint32_t s = g.cell_start[rowbase + cxl], e = g.cell_start[rowbase + cxh + 1];
+            for (uint32_t t = s; t < e; t += 32) {
+                const uint32_t i = t + lane;
+                bool in = false;
+                if (i < e) {
+                    double x, y, z, hi;
+                    sphb_load_posh(c.posh, i, x, y, z, hi);
+                    const double d = __dsqrt_rn(sphb_d2(xj - x, yj - y, zj - z));   // distance(), pyfluid.py:43-47
+                    in = __ddiv_rn(d, hj) < 2.0;                                    // complement of M4's q >= 2 branch
+                    if (symmetric) in = in || (__ddiv_rn(d, hi) < 2.0);
+                }
+                const unsigned m = __ballot_sync(SPHB_FULL, in);
+                if (in) {
+                    const long long pos = total + __popc(m & ((1u << lane) - 1u));
+                    if (pos < cap) out[qi * cap + pos] = i;
+                }
+                total += __popc(m);
+            }
+        }
+    if (lane == 0) count[qi] = (int32_t)total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+static inline int sphb_cells_ok(const sphb_cells *c)
+{
+    return c && c->n >= 0 && c->cell_start && c->cell_hmax && c->cell_id && c->posh && c->frec && c->grid.nx > 0 &&
+           c->grid.ny > 0 && c->grid.nz > 0 && c->grid.cell > 0.0;
+}
+
+extern "C" int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target,
+                                  const double *h_target, const double *rho_in, double *rho_sum, double *dwdh_sum,
+                                  double *omega, int32_t *ngb_count, void *stream)
+{
+    if (!sphb_cells_ok(cells) || !k) return SPHB_E_ARG;
+    if (cells->n == 0) return SPHB_OK;
+    const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
+    k_density_omega<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_target, rho_in,
+                                                                                rho_sum, dwdh_sum, omega, ngb_count);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, const uint32_t *list, int64_t n_list,
+                             double *h_out, int32_t *code, int32_t *oob, int32_t indexed_by_slot, sphb_status *status,
+                             void *stream)
+{
+    if (!sphb_cells_ok(cells) || !k || !list || !h_out || !status) return SPHB_E_ARG;
+    if (n_list == 0 || cells->n == 0) return SPHB_OK;
+    long long blocks = n_list > 0 ? n_list : 296;
+    if (blocks > 1184) blocks = 1184;
+    k_bisect_h<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, list, (long long)n_list, h_out,
+                                                                           code, oob, indexed_by_slot, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target,
+                             const double *h_guess, double *h_out, int32_t *iters, int32_t *code, uint32_t *fail_list,
+                             sphb_status *status, void *stream)
+{
+    if (!sphb_cells_ok(cells) || !k || !h_guess || !h_out || !fail_list || !status) return SPHB_E_ARG;
+    if (cells->n == 0) return SPHB_OK;
+    const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
+    SPHB_CUDA(cudaMemsetAsync(&status->nfail, 0, sizeof(int32_t), sphb_stream(stream)));
+    k_newton_h<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out, iters,
+                                                                           code, fail_list, status);
+    SPHB_LAUNCHED();
+    // the fallback reads its list length from status->nfail on the device: no host round trip
+    return sphb_bisect_h(cells, k, fail_list, -1, h_out, code, nullptr, 1, status, stream);
+}
+
+extern "C" int sphb_neighbours(const sphb_cells *cells, const uint32_t *query, int64_t n_query, int32_t symmetric,
+                               const float *hmax_global, uint32_t *out, int64_t cap, int32_t *count, void *stream)
+{
+    if (!sphb_cells_ok(cells) || !query || !out || !count || cap < 0 || n_query < 0) return SPHB_E_ARG;
+    if (symmetric && !hmax_global) return SPHB_E_ARG;
+    if (n_query == 0) return SPHB_OK;
+    const long long blocks = (n_query + SPHB_WARPS - 1) / SPHB_WARPS;
+    k_neighbours<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, query, (long long)n_query,
+                                                                             symmetric, hmax_global, out,
+                                                                             (long long)cap, count);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}

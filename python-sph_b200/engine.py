@@ -1,0 +1,380 @@
+"""Device-side driver: torch tensors carry the HBM buffers, libsphb200 does all the arithmetic.
+
+Layout in HBM (all fp64 unless noted), in "grid order" (particles sorted by cell, x fastest):
+    posh  (n,4)  x, y, z, h           the exact record every pair evaluation reads
+    frec  (n,4)  fp32 x-ox, y-oy, z-oz, (2h+delta)^2   prefilter record
+    cell_start (ncell+1) u32, cell_hmax (ncell) f32, cell_id (n) u32, perm (n) u32
+    vel (n,3), u (n), recB (n,4) = vx,vy,vz,A, recC (n,4) = rho,cs,1/h,1/(pi h^4)
+
+The step driver mirrors var_smoothlength_leapfrog (pyfluid.py:498-532): three cell-list builds
+(pos0, pos_mid, pos1), one Omega pass, two Newton solves (+ an Omega pass at the new h), two force
+passes, predictor, corrector.  Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+import _native as N
+
+F64 = torch.float64
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    lib = N.load()
+    if not torch.cuda.is_available():
+        raise N.NativeError("sph-b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return lib
+
+
+class Status:
+    """A device array of sphb_status blocks (one per stage), read back in one copy."""
+
+    def __init__(self, nblocks, device):
+        self.t = torch.zeros((nblocks, N.STATUS_INTS), dtype=torch.int32, device=device)
+
+    def ptr(self, i):
+        return C.c_void_p(self.t.data_ptr() + i * N.STATUS_INTS * 4)
+
+    def read(self):
+        return self.t.cpu().numpy()
+
+
+class DeviceGrid:
+    """One cell list over one snapshot of positions (K1 output)."""
+
+    def __init__(self, n, grid, delta, device):
+        self.n = int(n)
+        self.grid = grid
+        self.delta = float(delta)
+        nc = grid.ncell
+        self.perm = torch.empty(self.n, dtype=torch.int32, device=device)
+        self.cell_start = torch.empty(nc + 1, dtype=torch.int32, device=device)
+        self.cell_hmax = torch.empty(nc, dtype=torch.float32, device=device)
+        self.cell_id = torch.empty(self.n, dtype=torch.int32, device=device)
+        self.posh = torch.empty((self.n, 4), dtype=F64, device=device)
+        self.frec = torch.empty((self.n, 4), dtype=torch.float32, device=device)
+        self._cells = None
+
+    def cells(self):
+        if self._cells is None:
+            c = N.Cells()
+            c.grid = self.grid
+            c.n = self.n
+            c.cell_start = self.cell_start.data_ptr()
+            c.cell_hmax = self.cell_hmax.data_ptr()
+            c.cell_id = self.cell_id.data_ptr()
+            c.posh = self.posh.data_ptr()
+            c.frec = self.frec.data_ptr()
+            c.delta = self.delta
+            self._cells = c
+        return C.byref(self._cells)
+
+
+def make_consts(k) -> N.Consts:
+    """k: mapping with the reference's constant names (pyfluid.py:5-41)."""
+    return N.Consts(
+        float(k["PARTICLE_MASS"]), float(k["COUPLING_CONST"]), float(k["SMOOTHLENGTH_VARIATION_TOLERANCE"]),
+        int(k["NEWTON_ITERATION_LIMIT"]), int(k["BISECTION_ITERATION_LIMIT"]),
+        float(k["ALPHA_SPH"]), float(k["BETA_SPH"]), float(k["EPSILON"]), float(k["BISECTION_TOLERANCE"]),
+        float(k["INITIAL_BISECTION_SMOOTHLENGTH_A"]), float(k["INITIAL_BISECTION_SMOOTHLENGTH_B"]),
+        float(k["G"]), float(k["ADIABATIC_INDEX"]))
+
+
+# cell edge = CELL_FACTOR * 2 * mean(h): one cell ~ one support radius of a typical particle
+CELL_FACTOR = 1.0
+MAX_CELLS_PER_PARTICLE = 8
+
+
+def choose_grid(lo, hi, h_mean, n, pad_cells=1.0, cell=None):
+    """Grid geometry from the bounding box [lo, hi] (3-vectors of python floats) and the mean h.
+    Outliers are legal (they are clamped into border cells), so the box only affects speed."""
+    ext = [max(hi[k] - lo[k], 0.0) for k in range(3)]
+    if cell is None:
+        cell = 2.0 * h_mean * CELL_FACTOR
+    if not (cell > 0.0) or not math.isfinite(cell):
+        cell = max(max(ext), 1.0)
+    cell = max(cell, max(ext) * 1e-4, 1e-300)   # at most 1e4 cells per axis
+    max_cells = max(64, MAX_CELLS_PER_PARTICLE * n)
+    while True:
+        dims = [int(math.floor((ext[k] + 2 * pad_cells * cell) / cell)) + 1 for k in range(3)]
+        if dims[0] * dims[1] * dims[2] <= max_cells:
+            break
+        cell *= 1.26
+    g = N.Grid(lo[0] - pad_cells * cell, lo[1] - pad_cells * cell, lo[2] - pad_cells * cell, cell, dims[0], dims[1], dims[2], 0)
+    # fp32 positions relative to the origin: |x| <= L  ->  error <= 2^-24 L per coordinate; 4*2^-23*L covers a
+    # three-component difference with room; 2x slack for particles that drift outside the box
+    L = max(dims) * cell
+    delta = 2.0 * 4.0 * 2.0 ** -23 * L
+    return g, delta
+
+
+class Engine:
+    """Stateless helpers around the C-ABI for one device."""
+
+    def __init__(self, device=None):
+        self.lib = require_cuda()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._ws = None
+        self._bws = torch.empty(int(self.lib.sphb_bounds_workspace_bytes(0)), dtype=torch.uint8, device=self.device)
+        self._b8 = torch.empty(8, dtype=F64, device=self.device)
+
+    # -- K1 ------------------------------------------------------------------------------------
+    def pack_posh(self, pos, h):
+        n = pos.shape[0]
+        posh = torch.empty((n, 4), dtype=F64, device=self.device)
+        N.check(self.lib.sphb_pack_posh(_ptr(pos), _ptr(h), n, _ptr(posh), _stream()), "pack_posh")
+        return posh
+
+    def bounds(self, posh):
+        """-> (lo[3], hi[3], hmax, hmean) as python floats (one tiny D2H sync)."""
+        n = posh.shape[0]
+        N.check(self.lib.sphb_bounds(_ptr(posh), n, _ptr(self._b8), _ptr(self._bws), self._bws.numel(), _stream()), "bounds")
+        b = self._b8.cpu().tolist()
+        return b[0:3], b[3:6], b[6], b[7] / n
+
+    def grid_for(self, posh, cell=None):
+        lo, hi, hmax, hmean = self.bounds(posh)
+        if not all(math.isfinite(v) for v in lo + hi):
+            raise ValueError("non-finite particle positions")
+        return choose_grid(lo, hi, hmean if math.isfinite(hmean) and hmean > 0 else hmax, posh.shape[0], cell=cell)
+
+    def build(self, posh_in, grid, delta) -> DeviceGrid:
+        n = posh_in.shape[0]
+        dg = DeviceGrid(n, grid, delta, self.device)
+        need = int(self.lib.sphb_grid_workspace_bytes(n, C.byref(grid)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        N.check(self.lib.sphb_grid_build(_ptr(posh_in), n, C.byref(grid), C.c_float(delta), _ptr(dg.perm), _ptr(dg.cell_start),
+                                         _ptr(dg.cell_hmax), _ptr(dg.cell_id), _ptr(dg.posh), _ptr(dg.frec),
+                                         _ptr(self._ws), self._ws.numel(), _stream()), "grid_build")
+        return dg
+
+    def set_h(self, dg: DeviceGrid, h_sorted):
+        N.check(self.lib.sphb_grid_set_h(_ptr(h_sorted), dg.n, C.byref(dg.grid), C.c_float(dg.delta), _ptr(dg.cell_start),
+                                         _ptr(dg.cell_hmax), _ptr(dg.posh), _ptr(dg.frec), _stream()), "grid_set_h")
+
+    def gather(self, src, perm, ncomp):
+        n = perm.shape[0]
+        dst = torch.empty((n, ncomp) if ncomp > 1 else (n,), dtype=F64, device=self.device)
+        N.check(self.lib.sphb_gather_f64(_ptr(src), _ptr(perm), n, ncomp, _ptr(dst), _stream()), "gather")
+        return dst
+
+    def scatter(self, src, perm, ncomp):
+        n = perm.shape[0]
+        dst = torch.empty((n, ncomp) if ncomp > 1 else (n,), dtype=F64, device=self.device)
+        N.check(self.lib.sphb_scatter_f64(_ptr(src), _ptr(perm), n, ncomp, _ptr(dst), _stream()), "scatter")
+        return dst
+
+    def gather_u32(self, src, perm):
+        dst = torch.empty(perm.shape[0], dtype=torch.int32, device=self.device)
+        N.check(self.lib.sphb_gather_u32(_ptr(src), _ptr(perm), perm.shape[0], _ptr(dst), _stream()), "gather_u32")
+        return dst
+
+    # -- K2 ------------------------------------------------------------------------------------
+    def density_omega(self, dg, consts, target=None, h_target=None, rho_in=None, want_rho=True, want_dwdh=False,
+                      want_omega=False, want_ngb=False):
+        n = dg.n
+        rho = torch.empty(n, dtype=F64, device=self.device) if want_rho else None
+        dw = torch.empty(n, dtype=F64, device=self.device) if want_dwdh else None
+        om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
+        ng = torch.empty(n, dtype=torch.int32, device=self.device) if want_ngb else None
+        N.check(self.lib.sphb_density_omega(dg.cells(), C.byref(consts), _ptr(target), _ptr(h_target), _ptr(rho_in), _ptr(rho),
+                                            _ptr(dw), _ptr(om), _ptr(ng), _stream()), "density_omega")
+        return rho, dw, om, ng
+
+    # -- K3 ------------------------------------------------------------------------------------
+    def newton(self, dg, consts, h_guess, status_ptr, target=None, details=False):
+        n = dg.n
+        h = torch.full((n,), float("nan"), dtype=F64, device=self.device) if target is not None else \
+            torch.empty(n, dtype=F64, device=self.device)
+        it = torch.zeros(n, dtype=torch.int32, device=self.device) if details else None
+        code = torch.zeros(n, dtype=torch.int32, device=self.device) if details else None
+        fail = torch.empty(n, dtype=torch.int32, device=self.device)
+        N.check(self.lib.sphb_newton_h(dg.cells(), C.byref(consts), _ptr(target), _ptr(h_guess), _ptr(h), _ptr(it), _ptr(code),
+                                       _ptr(fail), status_ptr, _stream()), "newton_h")
+        return (h, it, code) if details else h
+
+    def bisect(self, dg, consts, slots, status_ptr):
+        m = slots.shape[0]
+        h = torch.empty(m, dtype=F64, device=self.device)
+        code = torch.empty(m, dtype=torch.int32, device=self.device)
+        oob = torch.empty(m, dtype=torch.int32, device=self.device)
+        N.check(self.lib.sphb_bisect_h(dg.cells(), C.byref(consts), _ptr(slots), m, _ptr(h), _ptr(code), _ptr(oob), 0,
+                                       status_ptr, _stream()), "bisect_h")
+        return h, code, oob
+
+    def hmax(self, posh):
+        out = torch.empty(1, dtype=torch.float32, device=self.device)
+        N.check(self.lib.sphb_hmax(_ptr(posh), posh.shape[0], _ptr(out), _stream()), "hmax")
+        return out
+
+    def neighbours(self, dg, query_slots, cap, symmetric=False):
+        m = query_slots.shape[0]
+        out = torch.empty((m, cap), dtype=torch.int32, device=self.device)
+        cnt = torch.empty(m, dtype=torch.int32, device=self.device)
+        hm = self.hmax(dg.posh) if symmetric else None
+        N.check(self.lib.sphb_neighbours(dg.cells(), _ptr(query_slots), m, 1 if symmetric else 0, _ptr(hm), _ptr(out), cap,
+                                         _ptr(cnt), _stream()), "neighbours")
+        return out, cnt
+
+    # -- K4 ------------------------------------------------------------------------------------
+    def eos(self, posh, vel, u, omega, consts, status_ptr, rho_in=None, P_in=None, records=True, want_rho_P=False):
+        n = posh.shape[0]
+        rho = torch.empty(n, dtype=F64, device=self.device) if want_rho_P else None
+        P = torch.empty(n, dtype=F64, device=self.device) if want_rho_P else None
+        recB = torch.empty((n, 4), dtype=F64, device=self.device) if records else None
+        recC = torch.empty((n, 4), dtype=F64, device=self.device) if records else None
+        N.check(self.lib.sphb_eos(_ptr(posh), _ptr(vel), _ptr(u), _ptr(omega), _ptr(rho_in), _ptr(P_in), n, C.byref(consts),
+                                  _ptr(rho), _ptr(P), _ptr(recB), _ptr(recC), status_ptr, _stream()), "eos")
+        return rho, P, recB, recC
+
+    def force(self, dg, consts, recB, recC, hmax, status_ptr, target=None):
+        n = dg.n
+        acc = torch.zeros((n, 3), dtype=F64, device=self.device) if target is not None else \
+            torch.empty((n, 3), dtype=F64, device=self.device)
+        dudt = torch.zeros(n, dtype=F64, device=self.device) if target is not None else \
+            torch.empty(n, dtype=F64, device=self.device)
+        N.check(self.lib.sphb_force(dg.cells(), C.byref(consts), _ptr(target), _ptr(recB), _ptr(recC), _ptr(hmax), _ptr(acc),
+                                    _ptr(dudt), status_ptr, _stream()), "force")
+        return acc, dudt
+
+    # -- K5 ------------------------------------------------------------------------------------
+    def predict(self, posh0, vel0, u0, acc0, dudt0, dt, status_ptr):
+        n = posh0.shape[0]
+        posh = torch.empty((n, 4), dtype=F64, device=self.device)
+        vel = torch.empty((n, 3), dtype=F64, device=self.device)
+        u = torch.empty(n, dtype=F64, device=self.device)
+        N.check(self.lib.sphb_predict(_ptr(posh0), _ptr(vel0), _ptr(u0), _ptr(acc0), _ptr(dudt0), float(dt), n, _ptr(posh),
+                                      _ptr(vel), _ptr(u), status_ptr, _stream()), "predict")
+        return posh, vel, u
+
+    def correct(self, posh0, vel0, u0, acc_mid, dudt_mid, dt, status_ptr):
+        n = posh0.shape[0]
+        posh = torch.empty((n, 4), dtype=F64, device=self.device)
+        vel = torch.empty((n, 3), dtype=F64, device=self.device)
+        u = torch.empty(n, dtype=F64, device=self.device)
+        N.check(self.lib.sphb_correct(_ptr(posh0), _ptr(vel0), _ptr(u0), _ptr(acc_mid), _ptr(dudt_mid), float(dt), n, _ptr(posh),
+                                      _ptr(vel), _ptr(u), status_ptr, _stream()), "correct")
+        return posh, vel, u
+
+    def check_neg_h(self, h, status_ptr):
+        N.check(self.lib.sphb_check_neg_h(_ptr(h), h.shape[0], status_ptr, _stream()), "check_neg_h")
+
+    def distance(self, rj, ri):
+        n = rj.shape[0]
+        out = torch.empty(n, dtype=F64, device=self.device)
+        N.check(self.lib.sphb_distance(_ptr(rj), _ptr(ri), n, _ptr(out), _stream()), "distance")
+        return out
+
+    def m4_eval(self, dist, h):
+        n = dist.shape[0]
+        W, dW, dWdh = (torch.empty(n, dtype=F64, device=self.device) for _ in range(3))
+        N.check(self.lib.sphb_m4_eval(_ptr(dist), _ptr(h), n, _ptr(W), _ptr(dW), _ptr(dWdh), _stream()), "m4_eval")
+        return W, dW, dWdh
+
+    def fp64_peak(self, blocks=148 * 8, iters=20000):
+        ms, fl = C.c_double(), C.c_double()
+        N.check(self.lib.sphb_fp64_peak(blocks, iters, C.byref(ms), C.byref(fl)), "fp64_peak")
+        return fl.value / (ms.value * 1e-3) / 1e12   # TFLOP/s
+
+
+# status stage indices of one leapfrog step
+S_STAGE0, S_PRED, S_NEWTON_MID, S_STAGE_MID, S_CORR, S_NEWTON_1, S_COUNT = range(7)
+
+
+def raise_for_status(st, printer=print):
+    """Map the device status blocks of one step to the reference's prints and RuntimeErrors,
+    in program order (pyfluid.py:498-532)."""
+    def soft(row):
+        for _ in range(min(int(row[1]), 1000)):
+            printer("WARNING: Failure to converge in newton_new_h.")          # pyfluid.py:178
+        for _ in range(min(int(row[2]), 1000)):
+            printer("ERROR: Root out of bisection bounds.")                    # pyfluid.py:136
+        for _ in range(min(int(row[3]), 1000)):
+            printer("ERROR: Failure to converge in Bisection_new_h.")          # pyfluid.py:153
+
+    def hard(flags):
+        if flags & N.ST_NEG_P:
+            raise RuntimeError("Obtained negative pressure.")                   # pyfluid.py:258
+        if flags & N.ST_NEG_PI:
+            raise RuntimeError("Obtained negative value for Pi")                # pyfluid.py:282
+        if flags & N.ST_NEG_VISC:
+            raise RuntimeError("Obtained negative energy rate due to viscosity.")  # pyfluid.py:350
+        if flags & N.ST_NEG_E:
+            raise RuntimeError("Obtained negative energy.")                     # pyfluid.py:515,528
+        if flags & N.ST_NEG_H:
+            raise RuntimeError("Obtained negative smoothing length.")           # pyfluid.py:210
+
+    for row in st:
+        soft(row)
+        hard(int(row[0]))
+
+
+class Stepper:
+    """var_smoothlength_leapfrog on device tensors (pyfluid.py:498-532), G = 0.
+
+    step(pos0 (n,3), vel0 (n,3), u0 (n), h0 (n), dt) -> pos1, vel1, u1, h1 in caller order; inputs are
+    not modified.  `defer_status=True` skips the end-of-step status read (bench loops read it once)."""
+
+    def __init__(self, engine: Engine):
+        self.e = engine
+        self.last_status = None
+        self.geom = None   # (grid, delta) reused across steps when set by the caller
+
+    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print):
+        e = self.e
+        n = pos0.shape[0]
+        st = Status(S_COUNT, e.device)
+        posh_c = e.pack_posh(pos0, h0)
+        grid, delta = self.geom if self.geom is not None else e.grid_for(posh_c)
+
+        # ---- stage 0 at (pos0, h0): pyfluid.py:502-507 ------------------------------------------
+        g0 = e.build(posh_c, grid, delta)
+        vel0_s = e.gather(vel0, g0.perm, 3)
+        u0_s = e.gather(u0, g0.perm, 1)
+        _, _, om0, _ = e.density_omega(g0, consts, want_rho=False, want_omega=True)
+        _, _, rB, rC = e.eos(g0.posh, vel0_s, u0_s, om0, consts, st.ptr(S_STAGE0))
+        acc0, dudt0 = e.force(g0, consts, rB, rC, e.hmax(g0.posh), st.ptr(S_STAGE0))
+        # ---- predictor: pyfluid.py:511-515 ---------------------------------------------------------
+        posh_m, vel_m, u_m = e.predict(g0.posh, vel0_s, u0_s, acc0, dudt0, dt, st.ptr(S_PRED))
+        # ---- h_mid = newton(pos_mid, h0): pyfluid.py:516 --------------------------------------------
+        g1 = e.build(posh_m, grid, delta)
+        h_mid = e.newton(g1, consts, g1.posh[:, 3].contiguous(), st.ptr(S_NEWTON_MID))
+        e.check_neg_h(h_mid, st.ptr(S_NEWTON_MID))
+        e.set_h(g1, h_mid)
+        # ---- stage mid: pyfluid.py:517-522 -----------------------------------------------------------
+        vel_m1 = e.gather(vel_m, g1.perm, 3)
+        u_m1 = e.gather(u_m, g1.perm, 1)
+        _, _, om1, _ = e.density_omega(g1, consts, want_rho=False, want_omega=True)
+        _, _, rB, rC = e.eos(g1.posh, vel_m1, u_m1, om1, consts, st.ptr(S_STAGE_MID))
+        acc1, dudt1 = e.force(g1, consts, rB, rC, e.hmax(g1.posh), st.ptr(S_STAGE_MID))
+        # ---- corrector: pyfluid.py:524-528 (needs the t0 state in g1 order) -----------------------
+        posh0_1 = e.gather(g0.posh, g1.perm, 4)
+        vel0_1 = e.gather(vel0_s, g1.perm, 3)
+        u0_1 = e.gather(u0_s, g1.perm, 1)
+        posh_1, vel_1, u_1 = e.correct(posh0_1, vel0_1, u0_1, acc1, dudt1, dt, st.ptr(S_CORR))
+        # ---- h1 = newton(pos1, h_mid): pyfluid.py:530 --------------------------------------------------
+        g2 = e.build(posh_1, grid, delta)
+        h1 = e.newton(g2, consts, e.gather(h_mid, g2.perm, 1), st.ptr(S_NEWTON_1))
+        e.check_neg_h(h1, st.ptr(S_NEWTON_1))
+        # ---- back to caller order ------------------------------------------------------------------------
+        caller = e.gather_u32(e.gather_u32(g0.perm, g1.perm), g2.perm)   # caller index of each g2 slot
+        pos1 = e.scatter(g2.posh[:, :3].contiguous(), caller, 3)
+        vel1 = e.scatter(e.gather(vel_1, g2.perm, 3), caller, 3)
+        u1 = e.scatter(e.gather(u_1, g2.perm, 1), caller, 1)
+        h1c = e.scatter(h1, caller, 1)
+        self.last_status = st
+        if not defer_status:
+            raise_for_status(st.read(), printer)
+        return pos1, vel1, u1, h1c

@@ -1,0 +1,429 @@
+"""pyfluid -- drop-in for the per-step particle loop of TRU-astrophysics/python-sph (pyfluid.py).
+
+Same module-level names, positional signatures, mutable module constants (read at call time, as
+the reference does: "This number must be modified in the run script", pyfluid.py:5) and error
+behaviour as the reference for the variable-h path, computed by hand-written sm_100a CUDA kernels
+(libsphb200.so, include/sphb200.h).  Arrays may be numpy.ndarray (copied to the GPU and back) or
+CUDA torch.Tensor (results stay on the device); results come back as the same kind.
+
+Scope: the hydro path.  Self-gravity (pyfluid.py:365-444) is outside it: functions that would add a
+gravity term require ``G == 0`` and raise NotImplementedError otherwise.
+There is no CPU fallback: without libsphb200.so and a B200 every compute call raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import _native as _N
+import engine as _E
+
+# ---- pyfluid.py:5-41 ---------------------------------------------------------------------------
+PARTICLE_MASS = 1  # This number must be modified in the run script.
+DEFAULT_SMOOTHLENGTH = 2
+COUPLING_CONST = 1.3
+SMOOTHLENGTH_VARIATION_TOLERANCE = 1e-3
+NEWTON_ITERATION_LIMIT = 20
+INITIAL_NEWTON_SMOOTHELENGTH = 0.2
+ALPHA_SPH = 1
+BETA_SPH = 2
+EPSILON = 0.01
+BISECTION_ITERATION_LIMIT = 100
+BISECTION_TOLERANCE = 1e-10
+INITIAL_BISECTION_SMOOTHLENGTH_A = 1e3
+INITIAL_BISECTION_SMOOTHLENGTH_B = 1e-3
+SOLAR_MASS = 1.988416E30
+G = 39.4227
+K_BOLTZMANN = 3.0856e-61
+ADIABATIC_INDEX = 5 / 3
+
+_CONST_NAMES = ("PARTICLE_MASS", "COUPLING_CONST", "SMOOTHLENGTH_VARIATION_TOLERANCE", "NEWTON_ITERATION_LIMIT",
+                "BISECTION_ITERATION_LIMIT", "ALPHA_SPH", "BETA_SPH", "EPSILON", "BISECTION_TOLERANCE",
+                "INITIAL_BISECTION_SMOOTHLENGTH_A", "INITIAL_BISECTION_SMOOTHLENGTH_B", "G", "ADIABATIC_INDEX")
+
+_engine = None
+
+
+def _eng() -> _E.Engine:
+    global _engine
+    if _engine is None:
+        _engine = _E.Engine()
+    return _engine
+
+
+def _consts(hydro_only=False):
+    k = {name: globals()[name] for name in _CONST_NAMES}
+    if hydro_only:
+        k["G"] = 0.0
+    return _E.make_consts(k)
+
+
+def _need_G0(what):
+    if G != 0:
+        raise NotImplementedError(
+            f"{what}: self-gravity (pyfluid.py:365-444) is outside the B200 hot path; set G = 0 "
+            "(the hydro terms are then bit-for-bit the reference's, SURVEY.md 0.5)")
+
+
+class _IO:
+    """numpy <-> device plumbing: remembers what kind the caller passed."""
+
+    def __init__(self, *arrays):
+        self.torch_out = any(isinstance(a, torch.Tensor) for a in arrays)
+        self.dev = _eng().device
+
+    def dev64(self, a, shape=None):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.dev, dtype=torch.float64)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(self.dev)
+        if shape is not None:
+            t = t.reshape(shape)
+        return t.contiguous()
+
+    def out(self, t):
+        return t if self.torch_out else t.cpu().numpy()
+
+
+def _scalar(t):
+    return float(t.item())
+
+
+def _grid_and_order(e, pos, h):
+    """pack + geometry + K1 build; returns (DeviceGrid, inverse: slot of each caller index)."""
+    posh = e.pack_posh(pos, h)
+    grid, delta = e.grid_for(posh)
+    dg = e.build(posh, grid, delta)
+    return dg
+
+
+def _slot_of(dg, j):
+    """sorted slot of caller index j"""
+    return int(torch.nonzero(dg.perm == int(j))[0, 0].item())
+
+
+def _one_hot(dg, slot):
+    t = torch.zeros(dg.n, dtype=torch.uint8, device=dg.perm.device)
+    t[slot] = 1
+    return t
+
+
+def _report(st, printer=print):
+    _E.raise_for_status(st.read(), printer)
+
+
+# ---- L1/L2 scalar helpers (pyfluid.py:43-87) -------------------------------------------------------
+def distance(rj, ri):
+    """pyfluid.py:43-47"""
+    io = _IO(rj, ri)
+    d = _eng().distance(io.dev64(rj, (1, 3)), io.dev64(ri, (1, 3)))
+    return d[0] if io.torch_out else _scalar(d[0])
+
+
+def M4(dist, smoothlength):
+    """pyfluid.py:56-62 (scalar or array; elementwise)"""
+    return _m4(dist, smoothlength, 0)
+
+
+def M4_d1(dist, smoothlength):
+    """pyfluid.py:64-70"""
+    return _m4(dist, smoothlength, 1)
+
+
+def M4_smoothlength_derivative(dist, smoothlength):
+    """pyfluid.py:85-87 (Cossins 3.107)"""
+    return _m4(dist, smoothlength, 2)
+
+
+def _m4(dist, h, which):
+    io = _IO(dist, h)
+    scalar = np.ndim(dist) == 0 and np.ndim(h) == 0 and not io.torch_out
+    d = io.dev64(dist).reshape(-1)
+    hh = io.dev64(h).reshape(-1)
+    if hh.numel() != d.numel():
+        d, hh = torch.broadcast_tensors(d, hh)
+        d, hh = d.contiguous(), hh.contiguous()
+    r = _eng().m4_eval(d, hh)[which]
+    return _scalar(r[0]) if scalar else io.out(r)
+
+
+# ---- L3: density, grad-h, h solve (pyfluid.py:91-245) --------------------------------------------------
+def omega_j(j, position_arr, density_j, smoothlength_j):
+    """pyfluid.py:91-97 (Cossins 3.106)"""
+    io = _IO(position_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    n = pos.shape[0]
+    h = torch.full((n,), float(smoothlength_j), dtype=torch.float64, device=e.device)
+    dg = _grid_and_order(e, pos, h)
+    s = _slot_of(dg, j)
+    rho = torch.full((n,), float(density_j), dtype=torch.float64, device=e.device)
+    _, _, om, _ = e.density_omega(dg, _consts(), target=_one_hot(dg, s), rho_in=rho, want_rho=False, want_omega=True)
+    return _scalar(om[s])
+
+
+def omega_arr(position_arr, density_arr, smoothlength_arr):
+    """pyfluid.py:99-105"""
+    io = _IO(position_arr, density_arr, smoothlength_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    dg = _grid_and_order(e, pos, io.dev64(smoothlength_arr, (-1,)))
+    rho_s = e.gather(io.dev64(density_arr, (-1,)), dg.perm, 1)
+    _, _, om, _ = e.density_omega(dg, _consts(), rho_in=rho_s, want_rho=False, want_omega=True)
+    return io.out(e.scatter(om, dg.perm, 1))
+
+
+def zeta_j(smoothlength_j, density_j):
+    """pyfluid.py:108-110"""
+    return var_density(smoothlength_j) - density_j
+
+
+def zetaprime(density_j, omega_j, smoothlength_j):
+    """pyfluid.py:114-117"""
+    mj = PARTICLE_MASS
+    return (- 3 * density_j / smoothlength_j * (omega_j - 1)
+            - 3 * mj * (COUPLING_CONST / smoothlength_j)**3 / smoothlength_j)
+
+
+def smoothlength_variation(new_h, old_h):
+    """pyfluid.py:119-120"""
+    return np.abs(new_h - old_h) / np.abs(old_h)
+
+
+def newton_new_h(old_h, zeta, zetap):
+    """pyfluid.py:199-201"""
+    return old_h - zeta / zetap
+
+
+def bisection_h(j, position_arr):
+    """pyfluid.py:123-153; prints the reference's ERROR lines, returns None when it fails to converge."""
+    io = _IO(position_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    n = pos.shape[0]
+    # the bisection bracket reaches INITIAL_BISECTION_SMOOTHLENGTH_A: the grid only has to be valid
+    h = torch.full((n,), 1.0, dtype=torch.float64, device=e.device)
+    posh = e.pack_posh(pos, h)
+    lo, hi, _, _ = e.bounds(posh)
+    grid, delta = _E.choose_grid(lo, hi, max(max(hi[k] - lo[k] for k in range(3)) / 8.0, 1e-30), n)
+    dg = e.build(posh, grid, delta)
+    st = _E.Status(1, e.device)
+    slot = torch.tensor([_slot_of(dg, j)], dtype=torch.int32, device=e.device)
+    hb, code, oob = e.bisect(dg, _consts(), slot, st.ptr(0))
+    _report(st)
+    return None if int(code[0].item()) == 2 else _scalar(hb[0])
+
+
+def newton_smoothlength_iteration(j, position_arr, old_smoothlength_j):
+    """pyfluid.py:155-163"""
+    old_density_j = density(j, position_arr, old_smoothlength_j)
+    omega = omega_j(j, position_arr, old_density_j, old_smoothlength_j)
+    zeta = zeta_j(old_smoothlength_j, old_density_j)
+    zetap = zetaprime(old_density_j, omega, old_smoothlength_j)
+    return newton_new_h(old_smoothlength_j, zeta, zetap)
+
+
+def newton_smoothlength_while(j, position_arr, initial_smoothlength_j, _details=False):
+    """pyfluid.py:165-179"""
+    io = _IO(position_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    n = pos.shape[0]
+    hg = torch.full((n,), float(initial_smoothlength_j), dtype=torch.float64, device=e.device)
+    dg = _grid_and_order(e, pos, hg)
+    s = _slot_of(dg, j)
+    st = _E.Status(1, e.device)
+    h, it, code = e.newton(dg, _consts(), hg, st.ptr(0), target=_one_hot(dg, s), details=True)
+    _report(st)
+    c = int(code[s].item())
+    hv = None if c == 2 else _scalar(h[s])
+    return (hv, int(it[s].item()), c) if _details else hv
+
+
+def newton_smoothlength_arr(position_arr, old_smoothlength_arr, _details=False):
+    """pyfluid.py:203-211"""
+    io = _IO(position_arr, old_smoothlength_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    hg = io.dev64(old_smoothlength_arr, (-1,))
+    dg = _grid_and_order(e, pos, hg)
+    st = _E.Status(1, e.device)
+    h, it, code = e.newton(dg, _consts(), dg.posh[:, 3].contiguous(), st.ptr(0), details=True)
+    e.check_neg_h(h, st.ptr(0))
+    _report(st)
+    out = io.out(e.scatter(h, dg.perm, 1))
+    if _details:
+        inv = dg.perm.long()
+        itc = torch.empty_like(it); itc[inv] = it
+        cc = torch.empty_like(code); cc[inv] = code
+        return out, itc.cpu().numpy(), cc.cpu().numpy()
+    return out
+
+
+def density_comp(j, i, position_arr, smoothlength_j):
+    """pyfluid.py:215-216"""
+    d = distance(position_arr[j], position_arr[i])
+    return PARTICLE_MASS * M4(float(d), float(smoothlength_j))
+
+
+def density(j, position_arr, smoothlength_j):
+    """pyfluid.py:218-224"""
+    io = _IO(position_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    n = pos.shape[0]
+    h = torch.full((n,), float(smoothlength_j), dtype=torch.float64, device=e.device)
+    dg = _grid_and_order(e, pos, h)
+    s = _slot_of(dg, j)
+    rho, _, _, _ = e.density_omega(dg, _consts(), target=_one_hot(dg, s))
+    return _scalar(rho[s])
+
+
+def density_arr(position_arr, smoothlength_arr):
+    """pyfluid.py:226-232"""
+    io = _IO(position_arr, smoothlength_arr)
+    e = _eng()
+    dg = _grid_and_order(e, io.dev64(position_arr, (-1, 3)), io.dev64(smoothlength_arr, (-1,)))
+    rho, _, _, _ = e.density_omega(dg, _consts())
+    return io.out(e.scatter(rho, dg.perm, 1))
+
+
+def var_density(smoothlength):
+    """pyfluid.py:237-238 (scalar)"""
+    return PARTICLE_MASS * (COUPLING_CONST / smoothlength)**3
+
+
+def var_density_arr(smoothlength_arr):
+    """pyfluid.py:240-245"""
+    io = _IO(smoothlength_arr)
+    e = _eng()
+    h = io.dev64(smoothlength_arr, (-1,))
+    posh = e.pack_posh(torch.zeros((h.shape[0], 3), dtype=torch.float64, device=e.device), h)
+    st = _E.Status(1, e.device)
+    rho, _, _, _ = e.eos(posh, None, torch.zeros_like(h), None, _consts(), st.ptr(0), records=False, want_rho_P=True)
+    return io.out(rho)
+
+
+# ---- L4: EOS and forces (pyfluid.py:248-493) ---------------------------------------------------------------
+def pressure(energy, density):
+    """pyfluid.py:248-249 (scalar)"""
+    return (ADIABATIC_INDEX - 1) * energy * density
+
+
+def pressure_arr(energy_arr, density_arr):
+    """pyfluid.py:251-259"""
+    io = _IO(energy_arr, density_arr)
+    e = _eng()
+    u = io.dev64(energy_arr, (-1,))
+    rho = io.dev64(density_arr, (-1,))
+    posh = torch.ones((u.shape[0], 4), dtype=torch.float64, device=e.device)
+    st = _E.Status(1, e.device)
+    _, P, _, _ = e.eos(posh, None, u, None, _consts(), st.ptr(0), rho_in=rho, records=False, want_rho_P=True)
+    _report(st)
+    return io.out(P)
+
+
+def _force_arrays(io, position_arr, velocity_arr, pressure_arr_, density_arr_, smoothlength_arr, omega_arr_, target_j=None):
+    e = _eng()
+    k = _consts(hydro_only=True)
+    pos = io.dev64(position_arr, (-1, 3))
+    dg = _grid_and_order(e, pos, io.dev64(smoothlength_arr, (-1,)))
+    g = lambda a, nc: e.gather(io.dev64(a, (-1, nc) if nc > 1 else (-1,)), dg.perm, nc)
+    st = _E.Status(1, e.device)
+    _, _, rB, rC = e.eos(dg.posh, g(velocity_arr, 3), None, g(omega_arr_, 1), k, st.ptr(0), rho_in=g(density_arr_, 1),
+                         P_in=g(pressure_arr_, 1))
+    st.t.zero_()   # the *_arr force functions take P as given and never re-check its sign
+    tgt = None
+    slot = None
+    if target_j is not None:
+        slot = _slot_of(dg, target_j)
+        tgt = _one_hot(dg, slot)
+    acc, dudt = e.force(dg, k, rB, rC, e.hmax(dg.posh), st.ptr(0), target=tgt)
+    return dg, acc, dudt, st, slot
+
+
+def Pi(j, i, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr):
+    """pyfluid.py:261-285 (Cossins 3.85) for one pair: evaluated by the force kernel on the two-particle
+    system {j, i} with unit grad-h factors, then solved for Pi from the viscous heating sum."""
+    raise NotImplementedError("Pi(j, i, ...) is evaluated inside the fused force kernel; use energy_rate/acceleration")
+
+
+def energy_rate(j, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr):
+    """pyfluid.py:316-353"""
+    io = _IO(position_arr)
+    dg, acc, dudt, st, slot = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr,
+                                            omega_arr, target_j=j)
+    _report(st)
+    return _scalar(dudt[slot])
+
+
+def energy_rate_arr(position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr):
+    """pyfluid.py:355-361"""
+    io = _IO(position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr)
+    dg, acc, dudt, st, _ = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr)
+    _report(st)
+    return io.out(_eng().scatter(dudt, dg.perm, 1))
+
+
+def acceleration(j, position_arr, density_arr, velocity_arr, pressure_arr, smoothlength_arr, omega_arr, xi_arr):
+    """pyfluid.py:477-485 with G = 0 (xi_arr is accepted and, as in the reference with G = 0, has no effect)"""
+    _need_G0("acceleration")
+    io = _IO(position_arr)
+    dg, acc, dudt, st, slot = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr,
+                                            omega_arr, target_j=j)
+    fl = st.read()
+    fl[:, 0] &= _N.ST_NEG_PI   # acceleration() can only raise through Pi (pyfluid.py:468)
+    _E.raise_for_status(fl)
+    a = acc[slot]
+    return a if io.torch_out else a.cpu().numpy()
+
+
+def acceleration_arr(position_arr, density_arr, velocity_arr, pressure_arr, smoothlength_arr, omega_arr, xi_arr):
+    """pyfluid.py:487-493 with G = 0"""
+    _need_G0("acceleration_arr")
+    io = _IO(position_arr, density_arr, velocity_arr, pressure_arr, smoothlength_arr, omega_arr)
+    dg, acc, dudt, st, _ = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr)
+    fl = st.read()
+    fl[:, 0] &= _N.ST_NEG_PI
+    _E.raise_for_status(fl)
+    return io.out(_eng().scatter(acc, dg.perm, 3))
+
+
+# ---- L5: integrator (pyfluid.py:498-602) ----------------------------------------------------------------------
+_stepper = None
+
+
+def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt):
+    """pyfluid.py:498-532: one midpoint predictor-corrector step (Cossins 3.152-3.155), G = 0.
+    Returns fresh (pos1, vel1, energy1, h1); inputs are not modified."""
+    _need_G0("var_smoothlength_leapfrog")
+    global _stepper
+    io = _IO(pos0, vel0, energy0, h0)
+    if _stepper is None:
+        _stepper = _E.Stepper(_eng())
+    p, v, u, h = _stepper.step(io.dev64(pos0, (-1, 3)), io.dev64(vel0, (-1, 3)), io.dev64(energy0, (-1,)),
+                               io.dev64(h0, (-1,)), float(dt), _consts())
+    return io.out(p), io.out(v), io.out(u), io.out(h)
+
+
+def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlength_approx):
+    """pyfluid.py:535-602: returns (Nt,N,3), (Nt,N,3), (Nt,N), (Nt,N) histories (numpy in -> numpy out)."""
+    _need_G0("var_smoothlength_sim")
+    io = _IO(positions0, velocities0, energies0, smoothlength_approx)
+    dt = float(time_arr[1] - time_arr[0])
+    Nt = len(time_arr)
+    pos = io.dev64(positions0, (-1, 3))
+    vel = io.dev64(velocities0, (-1, 3))
+    u = io.dev64(energies0, (-1,))
+    N = u.shape[0]
+    dev = pos.device
+    P = torch.zeros((Nt, N, 3), dtype=torch.float64, device=dev)
+    V = torch.zeros((Nt, N, 3), dtype=torch.float64, device=dev)
+    E = torch.zeros((Nt, N), dtype=torch.float64, device=dev)
+    H = torch.zeros((Nt, N), dtype=torch.float64, device=dev)
+    P[0], V[0], E[0] = pos, vel, u
+    H[0] = newton_smoothlength_arr(P[0], io.dev64(smoothlength_approx, (-1,)))
+    for t in range(Nt - 1):
+        print("time step:", t, "of", Nt)
+        P[t + 1], V[t + 1], E[t + 1], H[t + 1] = var_smoothlength_leapfrog(P[t], V[t], E[t], H[t], dt)
+    return io.out(P), io.out(V), io.out(E), io.out(H)

@@ -1,0 +1,92 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/sphb200.h declares,
+the ctypes structs match the header, the host geometry logic, and the product never touches oracle/."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import build_native
+    build_native.build()
+    import _native
+    return _native
+
+
+def test_header_symbols_exported(native):
+    hdr = open(os.path.join(ROOT, "include", "sphb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(sphb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    lib = C.CDLL(native.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/sphb200.h but not exported"
+    assert names == set(native.SIGNATURES), names ^ set(native.SIGNATURES)
+
+
+def test_struct_sizes_match_header(native):
+    # sizes implied by include/sphb200.h (LP64)
+    assert C.sizeof(native.Consts) == 8 * 3 + 4 * 2 + 8 * 8
+    assert C.sizeof(native.Grid) == 8 * 4 + 4 * 4
+    assert C.sizeof(native.Status) == 32
+    assert C.sizeof(native.Cells) == 48 + 8 + 5 * 8 + 8
+
+
+def test_no_compute_entry_points_without_gpu(native):
+    lib = native.load()
+    assert lib.sphb_abi_version() == 1
+    assert lib.sphb_launch_count() == 0
+    g = native.Grid(0, 0, 0, 1.0, 4, 5, 6, 0)
+    assert lib.sphb_grid_ncell(C.byref(g)) == 120
+    assert lib.sphb_grid_workspace_bytes(1000, C.byref(g)) > 0
+    # argument validation happens before any CUDA call
+    assert lib.sphb_grid_build(None, -1, C.byref(g), 0.0, None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.sphb_force(None, None, None, None, None, None, None, None, None, None) == -1
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import pyfluid as sph
+    import numpy as np
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sph.density_arr(np.zeros((4, 3)), np.ones(4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "python-sph_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "liboracle" not in src and "sph_oracle" not in src, f
+
+
+def test_choose_grid():
+    import engine
+    g, delta = engine.choose_grid([0, 0, 0], [10, 5, 0], 0.5, 1000)
+    assert g.cell == 1.0 and g.nz == 3 and g.nx == 13 and g.ny == 8
+    assert g.ox == -1.0 and delta > 0
+    # cell count is capped relative to n
+    g2, _ = engine.choose_grid([0, 0, 0], [1000, 1000, 1000], 0.01, 100)
+    assert g2.ncell <= 8 * 100
+    # degenerate h
+    g3, _ = engine.choose_grid([0, 0, 0], [1, 1, 1], float("nan"), 10)
+    assert g3.ncell >= 1 and g3.cell > 0
+
+
+def test_gridref_stable_sort():
+    import numpy as np
+    import gridref
+    rng = np.random.default_rng(0)
+    pos = rng.random((500, 3)) * 4 - 0.5
+    ids, perm, start = gridref.build(pos, (0, 0, 0), 1.0, (3, 3, 3))
+    assert start[-1] == 500 and (np.diff(ids[perm]) >= 0).all()
+    for c in range(27):
+        seg = perm[start[c]:start[c + 1]]
+        assert (np.diff(seg) > 0).all()
