@@ -253,6 +253,10 @@ class Oracle:
         self.L.oracle_step_work_sample(C.byref(self.c), _p(pos), _p(vel), _p(e), _p(h), C.c_int64(len(pos)), _p(jl), C.c_int64(len(jl)), _p(sink))
         return sink
 
+    def set_wide(self, on):
+        """bench.py only: split each per-particle O(N) loop over the OpenMP threads"""
+        self.L.oracle_set_wide(C.c_int(1 if on else 0))
+
     def num_threads(self):
         return int(self.L.oracle_num_threads())
 

@@ -59,6 +59,12 @@ enum {
 
 #define PI_D 3.141592653589793 /* np.pi */
 
+/* "wide" mode (bench.py only): the O(N) inner loop of each per-particle function is split over the
+ * OpenMP threads, so that a handful of sampled particles keeps every host core busy at N = 16 M.
+ * It changes the summation order (chunked partial sums), nothing else; tests run with it off. */
+static int g_wide = 0;
+void oracle_set_wide(int on) { g_wide = on; }
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP
@@ -164,6 +170,7 @@ static inline double var_density(const oracle_consts *c, double h)
 static double density_j(const oracle_consts *c, const double *pos, int64_t n, int64_t j, double h)
 {
     double rho = 0.0;
+#pragma omp parallel for reduction(+ : rho) schedule(static) if (g_wide)
     for (int64_t i = 0; i < n; ++i)
         rho += c->particle_mass * oracle_M4(oracle_distance(pos + 3 * j, pos + 3 * i), h);
     return rho;
@@ -173,6 +180,7 @@ static double density_j(const oracle_consts *c, const double *pos, int64_t n, in
 static double omega_j(const oracle_consts *c, const double *pos, int64_t n, int64_t j, double rho, double h)
 {
     double sum = 0.0;
+#pragma omp parallel for reduction(+ : sum) schedule(static) if (g_wide)
     for (int64_t i = 0; i < n; ++i)
         sum += c->particle_mass * oracle_M4_dh(oracle_distance(pos + 3 * j, pos + 3 * i), h);
     return 1.0 + h / (3.0 * rho) * sum;
@@ -355,6 +363,8 @@ static double energy_rate_j(const oracle_consts *c, int64_t j, const double *pos
                             const double *rho, const double *h, const double *omega, int64_t n, int32_t *status)
 {
     double density_change = 0.0, viscosity_sum = 0.0;
+    int32_t stl = 0;
+#pragma omp parallel for reduction(+ : density_change, viscosity_sum) reduction(| : stl) schedule(static) if (g_wide)
     for (int64_t i = 0; i < n; ++i) {
         double vji[3] = { vel[3 * j] - vel[3 * i], vel[3 * j + 1] - vel[3 * i + 1], vel[3 * j + 2] - vel[3 * i + 2] };
         double gj[3], gi[3], mean[3];
@@ -362,8 +372,9 @@ static double energy_rate_j(const oracle_consts *c, int64_t j, const double *pos
         dellM4(pos + 3 * j, pos + 3 * i, h[i], gi);
         density_change += c->particle_mass * dot3(vji, gj);
         for (int k = 0; k < 3; ++k) mean[k] = 0.5 * (gj[k] + gi[k]);
-        viscosity_sum += (c->particle_mass * Pi_ji(c, j, i, pos, vel, P, rho, h, status) * dot3(vji, mean));
+        viscosity_sum += (c->particle_mass * Pi_ji(c, j, i, pos, vel, P, rho, h, &stl) * dot3(vji, mean));
     }
+    *status |= stl;
     viscosity_sum *= 0.5;
     if (viscosity_sum < 0.0) *status |= ORC_NEG_VISC;
     return (P[j] / (pow(rho[j], 2.0) * omega[j]) * density_change + viscosity_sum);
@@ -413,8 +424,10 @@ static void acceleration_j(const oracle_consts *c, int64_t j, const double *pos,
                            const double *P, const double *h, const double *omega, const double *xi, int64_t n,
                            double *acc, int32_t *status)
 {
-    acc[0] = acc[1] = acc[2] = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    int32_t stl = 0;
     const double m = c->particle_mass;
+#pragma omp parallel for reduction(+ : a0, a1, a2) reduction(| : stl) schedule(static) if (g_wide)
     for (int64_t i = 0; i < n; ++i) {
         double term[3] = { 0.0, 0.0, 0.0 };
         const double *rj = pos + 3 * j, *ri = pos + 3 * i;
@@ -427,7 +440,7 @@ static void acceleration_j(const oracle_consts *c, int64_t j, const double *pos,
         if (!same) {
             double aj = P[j] / (omega[j] * pow(rho[j], 2.0));
             double ai = P[i] / (omega[i] * pow(rho[i], 2.0));
-            double pi_half = Pi_ji(c, j, i, pos, vel, P, rho, h, status) * 0.5;
+            double pi_half = Pi_ji(c, j, i, pos, vel, P, rho, h, &stl) * 0.5;
             for (int k = 0; k < 3; ++k) {
                 double accel = aj * gj[k] + ai * gi[k];
                 double visc = pi_half * (gj[k] + gi[k]);
@@ -449,10 +462,14 @@ static void acceleration_j(const oracle_consts *c, int64_t j, const double *pos,
                 term[k] = (term[k] + g1[k]) + g2;
             }
         }
-        acc[0] += term[0];
-        acc[1] += term[1];
-        acc[2] += term[2];
+        a0 += term[0];
+        a1 += term[1];
+        a2 += term[2];
     }
+    acc[0] = a0;
+    acc[1] = a1;
+    acc[2] = a2;
+    *status |= stl;
 }
 
 /* pyfluid.py:316 energy_rate(j, ...) for a list of j */
@@ -597,7 +614,7 @@ void oracle_step_work_sample(const oracle_consts *c, const double *pos, const do
         omega[i] = 1.0; /* frozen stand-in for the neighbours' omega; the cost does not depend on it */
         xi[i] = 0.0;
     }
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) if (!g_wide)
     for (int64_t t = 0; t < nj; ++t) {
         int64_t j = jlist[t];
         double acc[3], s = 0.0;

@@ -126,20 +126,45 @@ class Engine:
         self.lib = require_cuda()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._ws = None
+        self.prof = None
         self._bws = torch.empty(int(self.lib.sphb_bounds_workspace_bytes(0)), dtype=torch.uint8, device=self.device)
         self._b8 = torch.empty(8, dtype=F64, device=self.device)
+
+    def _run(self, name, fn, *args):
+        """call one C-ABI entry point; with profiling on, bracket it with CUDA events on the launch stream"""
+        if self.prof is None:
+            N.check(fn(*args), name)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        N.check(fn(*args), name)
+        e1.record()
+        self.prof.append((name, e0, e1))
+
+    def prof_start(self):
+        self.prof = []
+
+    def prof_stop(self):
+        """-> {name: (calls, total ms)}; synchronises"""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.prof or []:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        self.prof = None
+        return out
 
     # -- K1 ------------------------------------------------------------------------------------
     def pack_posh(self, pos, h):
         n = pos.shape[0]
         posh = torch.empty((n, 4), dtype=F64, device=self.device)
-        N.check(self.lib.sphb_pack_posh(_ptr(pos), _ptr(h), n, _ptr(posh), _stream()), "pack_posh")
+        self._run("pack_posh", self.lib.sphb_pack_posh, _ptr(pos), _ptr(h), n, _ptr(posh), _stream())
         return posh
 
     def bounds(self, posh):
         """-> (lo[3], hi[3], hmax, hmean) as python floats (one tiny D2H sync)."""
         n = posh.shape[0]
-        N.check(self.lib.sphb_bounds(_ptr(posh), n, _ptr(self._b8), _ptr(self._bws), self._bws.numel(), _stream()), "bounds")
+        self._run("bounds", self.lib.sphb_bounds, _ptr(posh), n, _ptr(self._b8), _ptr(self._bws), self._bws.numel(), _stream())
         b = self._b8.cpu().tolist()
         return b[0:3], b[3:6], b[6], b[7] / n
 
@@ -155,30 +180,30 @@ class Engine:
         need = int(self.lib.sphb_grid_workspace_bytes(n, C.byref(grid)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        N.check(self.lib.sphb_grid_build(_ptr(posh_in), n, C.byref(grid), C.c_float(delta), _ptr(dg.perm), _ptr(dg.cell_start),
+        self._run("grid_build", self.lib.sphb_grid_build, _ptr(posh_in), n, C.byref(grid), C.c_float(delta), _ptr(dg.perm), _ptr(dg.cell_start),
                                          _ptr(dg.cell_hmax), _ptr(dg.cell_id), _ptr(dg.posh), _ptr(dg.frec),
-                                         _ptr(self._ws), self._ws.numel(), _stream()), "grid_build")
+                                         _ptr(self._ws), self._ws.numel(), _stream())
         return dg
 
     def set_h(self, dg: DeviceGrid, h_sorted):
-        N.check(self.lib.sphb_grid_set_h(_ptr(h_sorted), dg.n, C.byref(dg.grid), C.c_float(dg.delta), _ptr(dg.cell_start),
-                                         _ptr(dg.cell_hmax), _ptr(dg.posh), _ptr(dg.frec), _stream()), "grid_set_h")
+        self._run("grid_set_h", self.lib.sphb_grid_set_h, _ptr(h_sorted), dg.n, C.byref(dg.grid), C.c_float(dg.delta), _ptr(dg.cell_start),
+                                         _ptr(dg.cell_hmax), _ptr(dg.posh), _ptr(dg.frec), _stream())
 
     def gather(self, src, perm, ncomp):
         n = perm.shape[0]
         dst = torch.empty((n, ncomp) if ncomp > 1 else (n,), dtype=F64, device=self.device)
-        N.check(self.lib.sphb_gather_f64(_ptr(src), _ptr(perm), n, ncomp, _ptr(dst), _stream()), "gather")
+        self._run("gather", self.lib.sphb_gather_f64, _ptr(src), _ptr(perm), n, ncomp, _ptr(dst), _stream())
         return dst
 
     def scatter(self, src, perm, ncomp):
         n = perm.shape[0]
         dst = torch.empty((n, ncomp) if ncomp > 1 else (n,), dtype=F64, device=self.device)
-        N.check(self.lib.sphb_scatter_f64(_ptr(src), _ptr(perm), n, ncomp, _ptr(dst), _stream()), "scatter")
+        self._run("scatter", self.lib.sphb_scatter_f64, _ptr(src), _ptr(perm), n, ncomp, _ptr(dst), _stream())
         return dst
 
     def gather_u32(self, src, perm):
         dst = torch.empty(perm.shape[0], dtype=torch.int32, device=self.device)
-        N.check(self.lib.sphb_gather_u32(_ptr(src), _ptr(perm), perm.shape[0], _ptr(dst), _stream()), "gather_u32")
+        self._run("gather_u32", self.lib.sphb_gather_u32, _ptr(src), _ptr(perm), perm.shape[0], _ptr(dst), _stream())
         return dst
 
     # -- K2 ------------------------------------------------------------------------------------
@@ -189,8 +214,8 @@ class Engine:
         dw = torch.empty(n, dtype=F64, device=self.device) if want_dwdh else None
         om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
         ng = torch.empty(n, dtype=torch.int32, device=self.device) if want_ngb else None
-        N.check(self.lib.sphb_density_omega(dg.cells(), C.byref(consts), _ptr(target), _ptr(h_target), _ptr(rho_in), _ptr(rho),
-                                            _ptr(dw), _ptr(om), _ptr(ng), _stream()), "density_omega")
+        self._run("density_omega", self.lib.sphb_density_omega, dg.cells(), C.byref(consts), _ptr(target), _ptr(h_target), _ptr(rho_in), _ptr(rho),
+                                            _ptr(dw), _ptr(om), _ptr(ng), _stream())
         return rho, dw, om, ng
 
     # -- K3 ------------------------------------------------------------------------------------
@@ -201,8 +226,8 @@ class Engine:
         it = torch.zeros(n, dtype=torch.int32, device=self.device) if details else None
         code = torch.zeros(n, dtype=torch.int32, device=self.device) if details else None
         fail = torch.empty(n, dtype=torch.int32, device=self.device)
-        N.check(self.lib.sphb_newton_h(dg.cells(), C.byref(consts), _ptr(target), _ptr(h_guess), _ptr(h), _ptr(it), _ptr(code),
-                                       _ptr(fail), status_ptr, _stream()), "newton_h")
+        self._run("newton_h", self.lib.sphb_newton_h, dg.cells(), C.byref(consts), _ptr(target), _ptr(h_guess), _ptr(h), _ptr(it), _ptr(code),
+                                       _ptr(fail), status_ptr, _stream())
         return (h, it, code) if details else h
 
     def bisect(self, dg, consts, slots, status_ptr):
@@ -210,13 +235,13 @@ class Engine:
         h = torch.empty(m, dtype=F64, device=self.device)
         code = torch.empty(m, dtype=torch.int32, device=self.device)
         oob = torch.empty(m, dtype=torch.int32, device=self.device)
-        N.check(self.lib.sphb_bisect_h(dg.cells(), C.byref(consts), _ptr(slots), m, _ptr(h), _ptr(code), _ptr(oob), 0,
-                                       status_ptr, _stream()), "bisect_h")
+        self._run("bisect_h", self.lib.sphb_bisect_h, dg.cells(), C.byref(consts), _ptr(slots), m, _ptr(h), _ptr(code), _ptr(oob), 0,
+                                       status_ptr, _stream())
         return h, code, oob
 
     def hmax(self, posh):
         out = torch.empty(1, dtype=torch.float32, device=self.device)
-        N.check(self.lib.sphb_hmax(_ptr(posh), posh.shape[0], _ptr(out), _stream()), "hmax")
+        self._run("hmax", self.lib.sphb_hmax, _ptr(posh), posh.shape[0], _ptr(out), _stream())
         return out
 
     def neighbours(self, dg, query_slots, cap, symmetric=False):
@@ -224,8 +249,8 @@ class Engine:
         out = torch.empty((m, cap), dtype=torch.int32, device=self.device)
         cnt = torch.empty(m, dtype=torch.int32, device=self.device)
         hm = self.hmax(dg.posh) if symmetric else None
-        N.check(self.lib.sphb_neighbours(dg.cells(), _ptr(query_slots), m, 1 if symmetric else 0, _ptr(hm), _ptr(out), cap,
-                                         _ptr(cnt), _stream()), "neighbours")
+        self._run("neighbours", self.lib.sphb_neighbours, dg.cells(), _ptr(query_slots), m, 1 if symmetric else 0, _ptr(hm), _ptr(out), cap,
+                                         _ptr(cnt), _stream())
         return out, cnt
 
     # -- K4 ------------------------------------------------------------------------------------
@@ -235,8 +260,8 @@ class Engine:
         P = torch.empty(n, dtype=F64, device=self.device) if want_rho_P else None
         recB = torch.empty((n, 4), dtype=F64, device=self.device) if records else None
         recC = torch.empty((n, 4), dtype=F64, device=self.device) if records else None
-        N.check(self.lib.sphb_eos(_ptr(posh), _ptr(vel), _ptr(u), _ptr(omega), _ptr(rho_in), _ptr(P_in), n, C.byref(consts),
-                                  _ptr(rho), _ptr(P), _ptr(recB), _ptr(recC), status_ptr, _stream()), "eos")
+        self._run("eos", self.lib.sphb_eos, _ptr(posh), _ptr(vel), _ptr(u), _ptr(omega), _ptr(rho_in), _ptr(P_in), n, C.byref(consts),
+                                  _ptr(rho), _ptr(P), _ptr(recB), _ptr(recC), status_ptr, _stream())
         return rho, P, recB, recC
 
     def force(self, dg, consts, recB, recC, hmax, status_ptr, target=None):
@@ -245,8 +270,8 @@ class Engine:
             torch.empty((n, 3), dtype=F64, device=self.device)
         dudt = torch.zeros(n, dtype=F64, device=self.device) if target is not None else \
             torch.empty(n, dtype=F64, device=self.device)
-        N.check(self.lib.sphb_force(dg.cells(), C.byref(consts), _ptr(target), _ptr(recB), _ptr(recC), _ptr(hmax), _ptr(acc),
-                                    _ptr(dudt), status_ptr, _stream()), "force")
+        self._run("force", self.lib.sphb_force, dg.cells(), C.byref(consts), _ptr(target), _ptr(recB), _ptr(recC), _ptr(hmax), _ptr(acc),
+                                    _ptr(dudt), status_ptr, _stream())
         return acc, dudt
 
     # -- K5 ------------------------------------------------------------------------------------
@@ -255,8 +280,8 @@ class Engine:
         posh = torch.empty((n, 4), dtype=F64, device=self.device)
         vel = torch.empty((n, 3), dtype=F64, device=self.device)
         u = torch.empty(n, dtype=F64, device=self.device)
-        N.check(self.lib.sphb_predict(_ptr(posh0), _ptr(vel0), _ptr(u0), _ptr(acc0), _ptr(dudt0), float(dt), n, _ptr(posh),
-                                      _ptr(vel), _ptr(u), status_ptr, _stream()), "predict")
+        self._run("predict", self.lib.sphb_predict, _ptr(posh0), _ptr(vel0), _ptr(u0), _ptr(acc0), _ptr(dudt0), float(dt), n, _ptr(posh),
+                                      _ptr(vel), _ptr(u), status_ptr, _stream())
         return posh, vel, u
 
     def correct(self, posh0, vel0, u0, acc_mid, dudt_mid, dt, status_ptr):
@@ -264,28 +289,28 @@ class Engine:
         posh = torch.empty((n, 4), dtype=F64, device=self.device)
         vel = torch.empty((n, 3), dtype=F64, device=self.device)
         u = torch.empty(n, dtype=F64, device=self.device)
-        N.check(self.lib.sphb_correct(_ptr(posh0), _ptr(vel0), _ptr(u0), _ptr(acc_mid), _ptr(dudt_mid), float(dt), n, _ptr(posh),
-                                      _ptr(vel), _ptr(u), status_ptr, _stream()), "correct")
+        self._run("correct", self.lib.sphb_correct, _ptr(posh0), _ptr(vel0), _ptr(u0), _ptr(acc_mid), _ptr(dudt_mid), float(dt), n, _ptr(posh),
+                                      _ptr(vel), _ptr(u), status_ptr, _stream())
         return posh, vel, u
 
     def check_neg_h(self, h, status_ptr):
-        N.check(self.lib.sphb_check_neg_h(_ptr(h), h.shape[0], status_ptr, _stream()), "check_neg_h")
+        self._run("check_neg_h", self.lib.sphb_check_neg_h, _ptr(h), h.shape[0], status_ptr, _stream())
 
     def distance(self, rj, ri):
         n = rj.shape[0]
         out = torch.empty(n, dtype=F64, device=self.device)
-        N.check(self.lib.sphb_distance(_ptr(rj), _ptr(ri), n, _ptr(out), _stream()), "distance")
+        self._run("distance", self.lib.sphb_distance, _ptr(rj), _ptr(ri), n, _ptr(out), _stream())
         return out
 
     def m4_eval(self, dist, h):
         n = dist.shape[0]
         W, dW, dWdh = (torch.empty(n, dtype=F64, device=self.device) for _ in range(3))
-        N.check(self.lib.sphb_m4_eval(_ptr(dist), _ptr(h), n, _ptr(W), _ptr(dW), _ptr(dWdh), _stream()), "m4_eval")
+        self._run("m4_eval", self.lib.sphb_m4_eval, _ptr(dist), _ptr(h), n, _ptr(W), _ptr(dW), _ptr(dWdh), _stream())
         return W, dW, dWdh
 
     def fp64_peak(self, blocks=148 * 8, iters=20000):
         ms, fl = C.c_double(), C.c_double()
-        N.check(self.lib.sphb_fp64_peak(blocks, iters, C.byref(ms), C.byref(fl)), "fp64_peak")
+        self._run("fp64_peak", self.lib.sphb_fp64_peak, blocks, iters, C.byref(ms), C.byref(fl))
         return fl.value / (ms.value * 1e-3) / 1e12   # TFLOP/s
 
 
