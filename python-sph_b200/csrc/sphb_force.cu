@@ -69,11 +69,11 @@ struct SphbForceAcc {
 };
 
 __device__ __forceinline__ void sphb_force_flush(const double *posh, const double *recB, const double *recC,
-                                                 const uint32_t *list, int lane, int cnt, const sphb_consts &k,
+                                                 const SphbWarpShared &ws, int lane, int cnt, const sphb_consts &k,
                                                  SphbForceAcc &a)
 {
     for (int n_ = 0; n_ < cnt; ++n_) {
-        const uint32_t i = list[n_ * 32 + lane];
+        const uint32_t i = sphb_list_get(ws, lane, n_);
         double x, y, z, hi;
         sphb_load4(posh, i, x, y, z, hi);
         const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
@@ -146,10 +146,11 @@ __global__ void __launch_bounds__(SPHB_THREADS)
     a.negpi = 0;
     const float Rj = sphb_radius_of_h(a.hj, g.delta), thr = f.w;
     const float RH = sphb_radius_of_h((double)hmax_global[0], g.delta);
-    int cnt = 0;
-    auto flush = [&](int n_) { sphb_force_flush(c.posh, recB, recC, ws.list, lane, n_, k, a); };
-    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, RH, cnt, flush);
-    flush(cnt);
+    SphbList L;
+    L.init(ws, lane);
+    auto flush = [&](int n_) { sphb_force_flush(c.posh, recB, recC, ws, lane, n_, k, a); };
+    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, RH, L, flush);
+    flush(L.count());
     if (tgt) {
         const double m = k.particle_mass;
         acc[3 * j] = m * a.ax;

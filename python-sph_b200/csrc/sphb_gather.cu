@@ -25,11 +25,12 @@ struct SphbOwnAcc {
     int nn;
 };
 
-__device__ __forceinline__ void sphb_own_flush(const double *posh, const uint32_t *list, int lane, int cnt, SphbOwnAcc &a)
+__device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWarpShared &ws, int lane, int cnt,
+                                               SphbOwnAcc &a)
 {
 #pragma unroll 2
     for (int k = 0; k < cnt; ++k) {
-        const uint32_t i = list[k * 32 + lane];
+        const uint32_t i = sphb_list_get(ws, lane, k);
         double x, y, z, h;
         sphb_load_posh(posh, i, x, y, z, h);
         const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
@@ -76,11 +77,12 @@ __global__ void __launch_bounds__(SPHB_THREADS)
     a.sumF = a.sumG = 0.0;
     a.nn = 0;
     const float Rj = sphb_radius_of_h(h, g.delta), thr = sphb_thr_of_h(h, g.delta);
-    int cnt = 0;
     SphbWarpShared &ws = sh[warp];
-    auto flush = [&](int n_) { sphb_own_flush(c.posh, ws.list, lane, n_, a); };
-    sphb_warp_scan<false>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, 0.f, cnt, flush);
-    flush(cnt);
+    SphbList L;
+    L.init(ws, lane);
+    auto flush = [&](int n_) { sphb_own_flush(c.posh, ws, lane, n_, a); };
+    sphb_warp_scan<false>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
+    flush(L.count());
     if (tgt) {
         const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
         const double rs = pref * a.sumF;
@@ -131,10 +133,12 @@ __global__ void __launch_bounds__(SPHB_THREADS)
         a.sumF = a.sumG = 0.0;
         a.nn = 0;
         const float Rj = sphb_radius_of_h(h_old, g.delta), thr = sphb_thr_of_h(h_old, g.delta);
-        int cnt = 0;
-        auto flush = [&](int n_) { sphb_own_flush(c.posh, ws.list, lane, n_, a); };
-        sphb_warp_scan<false>(g, ws, lane, active, f.x, f.y, f.z, Rj, thr, row, 0.f, cnt, flush);
-        flush(cnt);
+        SphbList L;
+        L.init(ws, lane);
+        auto flush = [&](int n_) { sphb_own_flush(c.posh, ws, lane, n_, a); };
+        sphb_warp_scan<false>(g, ws, lane, active, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
+        flush(L.count());
+        __syncwarp();
         if (active) {
             // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
             const double pref = k.particle_mass / (SPHB_PI * (h_old * h_old * h_old));

@@ -1,29 +1,37 @@
 // sphb_scan.cuh -- the candidate scan shared by every gather kernel (K2 density/omega, K3 Newton,
-// K4 force, neighbour sets).
+// K4 force).
 //
 // Mapping: one lane = one target particle, one warp = 32 consecutive slots of the cell-sorted
 // particle array.  For each group of lanes that share a cell row, the warp
 //   1. takes the group's bounding box + search radius and turns it into rows of cells; every row is ONE
-//      contiguous span of the sorted array (x is the fastest cell axis), found by all lanes in parallel;
-//   2. stages the span's fp32 prefilter records through a 32-entry shared-memory tile (coalesced
-//      float4 loads) and lets every lane test every staged candidate in FP32 (broadcast LDS);
-//   3. appends survivors to a per-lane index list in shared memory ([k][lane]: conflict free); when a
-//      list is about to overflow, or at the end, `flush(cnt)` evaluates the listed pairs in FP64.
+//      contiguous span of the sorted array (x is the fastest cell axis), resolved by all lanes in parallel;
+//   2. stages the span through a 32-entry shared-memory tile: each lane loads one fp32 prefilter record
+//      (coalesced float4), re-centres it on the group's box centre O and stores (c', |c'|^2); then every
+//      lane tests every staged candidate with 3 FFMA + 1 compare:
+//          |c' - t'|^2 <= thr   <=>   |c'|^2 - 2 c'.t'  <=  thr - |t'|^2   (+ rounding allowance)
+//      (broadcast LDS.128, no bank conflicts);
+//   3. appends survivors as 16-bit (segment, offset) codes to a per-lane list in shared memory
+//      ([k][lane]); `flush(cnt)` evaluates the listed pairs in FP64 when a list is about to overflow, when
+//      the 32-entry segment table is full, and at the end.
 // The FP32 test only has to be conservative (positions carry an absolute error <= delta, thresholds are
-// rounded up); membership is decided in FP64 by the consumer.  Candidates are always visited in
-// ascending sorted-slot order, so every per-target sum has one fixed order regardless of how targets
-// are grouped into warps or ranks.
+// rounded up, `err` covers the re-centred arithmetic); membership is decided in FP64 by the consumer.
+// Candidates are always visited in ascending sorted-slot order, so every per-target sum has one fixed
+// order regardless of how targets are grouped into warps or ranks.
 #pragma once
 #include "sphb_common.cuh"
 
 #ifndef SPHB_LIST
-#define SPHB_LIST 64 /* per-lane list capacity */
+#define SPHB_LIST 128 /* per-lane list capacity (16-bit entries) */
 #endif
-#define SPHB_SUB 8 /* candidates filtered between two overflow checks */
+#define SPHB_SUB 8        /* candidates filtered between two overflow checks */
+#define SPHB_SEG_BITS 11  /* list code = (segment slot << 11) | offset in segment */
+#define SPHB_SEG_LEN (1u << SPHB_SEG_BITS)
 
 struct SphbWarpShared {
-    float4 tile[32];
-    uint32_t list[SPHB_LIST * 32];
+    float4 tile[32];      // x', y', z', |c'|^2 of the staged candidates (NaN-padded)
+    float tthr[32];       // SYM: the candidates' own squared support thresholds
+    uint32_t segbase[32]; // first sorted slot of each live segment
+    uint16_t list[SPHB_LIST * 32];
 };
 
 struct SphbScanCtx {
@@ -74,18 +82,46 @@ __device__ __forceinline__ double sphb_axis_gap(double lo, double hi, int c, int
     return g;
 }
 
+// per-lane list cursor: 32-bit shared-window addresses (a generic 64-bit pointer would cost two more
+// integer instructions per accepted candidate)
+struct SphbList {
+    uint32_t p;    // address of the lane's next free entry (stride 32 entries = 64 bytes)
+    uint32_t p0;   // address of list[lane]
+    __device__ __forceinline__ void init(const SphbWarpShared &ws, int lane)
+    {
+        p0 = (uint32_t)__cvta_generic_to_shared(ws.list + lane);
+        p = p0;
+    }
+    __device__ __forceinline__ int count() const { return (int)((p - p0) >> 6); }
+    __device__ __forceinline__ void reset() { p = p0; }
+    __device__ __forceinline__ void push(uint32_t code)
+    {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(p), "h"((uint16_t)code) : "memory");
+        p += 64;
+    }
+};
+
+// decode entry k of the calling lane's list
+__device__ __forceinline__ uint32_t sphb_list_get(const SphbWarpShared &ws, int lane, int k)
+{
+    const uint32_t code = ws.list[k * 32 + lane];
+    return ws.segbase[code >> SPHB_SEG_BITS] + (code & (SPHB_SEG_LEN - 1u));
+}
+
 // One full scan for the calling warp.  Every lane must call it (inactive lanes pass tgt = false).
 //   fx,fy,fz : the lane's own fp32 record position;  Rj: its search radius (float, rounded up, may be +inf)
 //   thr      : its squared threshold (float, rounded up, may be +inf)
 //   row      : its cell row id (cell_id / nx), used to group lanes
 //   SYM      : also accept candidates whose own support reaches the target (frec.w), using RH =
 //              radius of the global h_max to bound the cells that can hold such candidates
-//   cnt      : per-lane list fill, in/out;  flush(cnt) must consume ws.list[k*32+lane], k < cnt
+//   flush(n) : consume entries 0..n-1 of the lane's list (sphb_list_get); called warp-uniformly
+// The caller must call flush(L.count()) once more after the scan returns (lists persist across groups).
 template <bool SYM, class Flush>
 __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpShared &ws, int lane, bool tgt, float fx,
                                                float fy, float fz, float Rj, float thr, uint32_t row, float RH,
-                                               int &cnt, Flush &&flush)
+                                               SphbList &L, Flush &&flush)
 {
+    int nseg = 0;   // live entries of ws.segbase (warp-uniform)
     unsigned remaining = __ballot_sync(SPHB_FULL, tgt);
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
@@ -96,12 +132,24 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
 
         // bounding box and largest radius of the group
         const float inf = CUDART_INF_F;
-        const double xmin = sphb_warp_min(ing ? fx : inf), xmax = sphb_warp_max(ing ? fx : -inf);
-        const double ymin = sphb_warp_min(ing ? fy : inf), ymax = sphb_warp_max(ing ? fy : -inf);
-        const double zmin = sphb_warp_min(ing ? fz : inf), zmax = sphb_warp_max(ing ? fz : -inf);
+        const float xmin_f = sphb_warp_min(ing ? fx : inf), xmax_f = sphb_warp_max(ing ? fx : -inf);
+        const float ymin_f = sphb_warp_min(ing ? fy : inf), ymax_f = sphb_warp_max(ing ? fy : -inf);
+        const float zmin_f = sphb_warp_min(ing ? fz : inf), zmax_f = sphb_warp_max(ing ? fz : -inf);
+        const double xmin = xmin_f, xmax = xmax_f, ymin = ymin_f, ymax = ymax_f, zmin = zmin_f, zmax = zmax_f;
         const double Rg = sphb_warp_max(ing ? Rj : 0.f);
         const double Rw = SYM ? fmax(Rg, (double)RH) : Rg;
-        const float thr_l = ing ? thr : -1.f;
+
+        // group-local frame: centre of the box; err bounds the fp32 rounding of the re-centred test
+        const float ox = 0.5f * (xmin_f + xmax_f), oy = 0.5f * (ymin_f + ymax_f), oz = 0.5f * (zmin_f + zmax_f);
+        const float tx = fx - ox, ty = fy - oy, tz = fz - oz;
+        const float tt = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+        const float hdx = xmax_f - xmin_f, hdy = ymax_f - ymin_f, hdz = zmax_f - zmin_f;
+        const float dmax = 0.5f * (hdx + hdy + hdz) + (float)Rw + 1.8f * (float)g.cell;   // >= |c'| of anything in range
+        const float err = 4e-6f * dmax * dmax;
+        const float m2x = -2.f * tx, m2y = -2.f * ty, m2z = -2.f * tz;
+        // pass  <=>  |c'|^2 - 2 c'.t' <= thr - |t'|^2 + err ; lanes outside the group never pass
+        const float thrp = ing ? (thr - tt + err) : -inf;
+        const float offp = ing ? (err - tt) : -inf;   // SYM: candidate threshold + offp
 
         const int cyl = sphb_cell_lo(ymin - Rw, g.inv_cell, g.ny), cyh = sphb_cell_hi(ymax + Rw, g.inv_cell, g.ny);
         const int czl = sphb_cell_lo(zmin - Rw, g.inv_cell, g.nz), czh = sphb_cell_hi(zmax + Rw, g.inv_cell, g.nz);
@@ -156,34 +204,50 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                 }
             }
             const int nb = (int)((nrows - rb) < 32 ? (nrows - rb) : 32);
-            // ---- walk the spans ---------------------------------------------------------------------
+            // ---- walk the spans, one segment (<= 2048 slots) at a time -----------------------------
             for (int k = 0; k < nb; ++k) {
                 const uint32_t sk = __shfl_sync(SPHB_FULL, s, k), ek = __shfl_sync(SPHB_FULL, e, k);
-                for (uint32_t t = sk; t < ek; t += 32) {
-                    const uint32_t ci = t + lane;
-                    if (ci < ek) ws.tile[lane] = __ldg(g.frec + ci);
-                    __syncwarp();
-                    const int nt = (int)((ek - t) < 32u ? (ek - t) : 32u);
-                    for (int c0 = 0; c0 < nt; c0 += SPHB_SUB) {
-                        if (__any_sync(SPHB_FULL, cnt > SPHB_LIST - SPHB_SUB)) {
-                            flush(cnt);
-                            cnt = 0;
-                        }
-#pragma unroll
-                        for (int c = 0; c < SPHB_SUB; ++c) {
-                            if (c0 + c < nt) {
-                                const float4 f = ws.tile[c0 + c];
-                                const float dx = f.x - fx, dy = f.y - fy, dz = f.z - fz;
-                                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                                const float th = SYM ? fmaxf(thr_l, f.w) : thr_l;
-                                if (ing && d2 <= th) {
-                                    ws.list[cnt * 32 + lane] = t + (uint32_t)(c0 + c);
-                                    ++cnt;
-                                }
-                            }
-                        }
+                for (uint32_t t0 = sk; t0 < ek; t0 += SPHB_SEG_LEN) {
+                    if (nseg == 32) {   // segment table full: drain the lists that reference it
+                        flush(L.count());
+                        L.reset();
+                        nseg = 0;
                     }
                     __syncwarp();
+                    if (lane == 0) ws.segbase[nseg] = t0;
+                    uint32_t code = (uint32_t)nseg << SPHB_SEG_BITS;
+                    ++nseg;
+                    const uint32_t t1 = (ek - t0) < SPHB_SEG_LEN ? ek : t0 + SPHB_SEG_LEN;
+                    for (uint32_t t = t0; t < t1; t += 32) {
+                        const uint32_t ci = t + lane;
+                        float4 rec = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+                        if (ci < t1) {
+                            const float4 f = __ldg(g.frec + ci);
+                            rec.x = f.x - ox;
+                            rec.y = f.y - oy;
+                            rec.z = f.z - oz;
+                            rec.w = fmaf(rec.z, rec.z, fmaf(rec.y, rec.y, rec.x * rec.x));
+                            if (SYM) ws.tthr[lane] = f.w;
+                        }
+                        ws.tile[lane] = rec;
+                        __syncwarp();
+                        const int nt = (int)((t1 - t) < 32u ? (t1 - t) : 32u);
+                        for (int c0 = 0; c0 < nt; c0 += SPHB_SUB) {
+                            if (__any_sync(SPHB_FULL, L.count() > SPHB_LIST - SPHB_SUB)) {
+                                flush(L.count());
+                                L.reset();
+                            }
+#pragma unroll
+                            for (int c = 0; c < SPHB_SUB; ++c) {
+                                const float4 f = ws.tile[c0 + c];
+                                const float sv = fmaf(f.x, m2x, fmaf(f.y, m2y, fmaf(f.z, m2z, f.w)));
+                                const float th = SYM ? fmaxf(thrp, ws.tthr[c0 + c] + offp) : thrp;
+                                if (sv <= th) L.push(code + c);
+                            }
+                            code += SPHB_SUB;
+                        }
+                        __syncwarp();
+                    }
                 }
             }
         }
