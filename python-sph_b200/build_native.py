@@ -23,7 +23,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, f) for f in SOURCES]
+    extra = os.environ.get("SPHB_NVCC_EXTRA", "").split()   # tuning sweeps only (e.g. -DSPHB_LIST=96)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         print(r.stderr)

@@ -68,6 +68,13 @@ __device__ __forceinline__ double sphb_rcp(double x)
     return fma(y, t, y);
 }
 
+// one 32-byte record (4 doubles) with a single 256-bit read-only load (LDG.E.256, sm_100+): a gathered
+// record costs one L1 wavefront per touched line instead of two
+__device__ __forceinline__ void sphb_ld4(const double *rec, size_t i, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(rec + 4 * i));
+}
+
 // ---------------------------------------------------------------------------------------------
 // M4 cubic spline, dimensionless parts (pyfluid.py:56-70): W = f(q)/(pi h^3), W' = fp(q)/(pi h^4)
 // np.piecewise semantics: q >= 2 -> 0, 1 <= q < 2 -> middle, q < 1 -> inner (also negative q), NaN -> 0

@@ -5,16 +5,14 @@
 #include "sphb_scan.cuh"
 
 #define SPHB_WARPS 4
+#ifndef SPHB_MINB_FORCE
+#define SPHB_MINB_FORCE 5
+#endif
 #define SPHB_THREADS (SPHB_WARPS * 32)
 
 __device__ __forceinline__ void sphb_load4(const double *rec, size_t i, double &a, double &b, double &c, double &d)
 {
-    const double2 *p = reinterpret_cast<const double2 *>(rec) + 2 * i;
-    const double2 u = __ldg(p), v = __ldg(p + 1);
-    a = u.x;
-    b = u.y;
-    c = v.x;
-    d = v.y;
+    sphb_ld4(rec, i, a, b, c, d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -113,7 +111,7 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
     }
 }
 
-__global__ void __launch_bounds__(SPHB_THREADS)
+__global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     k_force(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ recB,
             const double *__restrict__ recC, const float *__restrict__ hmax_global, double *__restrict__ acc,
             double *__restrict__ dudt, sphb_status *__restrict__ status)

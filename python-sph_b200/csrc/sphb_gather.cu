@@ -5,16 +5,14 @@
 #include "sphb_scan.cuh"
 
 #define SPHB_WARPS 4
+#ifndef SPHB_MINB_OWN
+#define SPHB_MINB_OWN 6
+#endif
 #define SPHB_THREADS (SPHB_WARPS * 32)
 
 __device__ __forceinline__ void sphb_load_posh(const double *posh, size_t i, double &x, double &y, double &z, double &h)
 {
-    const double2 *p = reinterpret_cast<const double2 *>(posh) + 2 * i;
-    const double2 a = __ldg(p), b = __ldg(p + 1);
-    x = a.x;
-    y = a.y;
-    z = b.x;
-    h = b.y;
+    sphb_ld4(posh, i, x, y, z, h);
 }
 
 // One evaluation of sumF = sum f(q), sumG = sum (q f'(q) + 3 f(q)) over the lane's list.
@@ -48,7 +46,7 @@ __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWar
 // ------------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPHB_THREADS)
+__global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_density_omega(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_target,
                     const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
                     double *__restrict__ omega, int32_t *__restrict__ ngb_count)
@@ -100,7 +98,7 @@ __global__ void __launch_bounds__(SPHB_THREADS)
 // ------------------------------------------------------------------------------------------------
 // K3: per-lane Newton loop with warp-vote convergence mask (pyfluid.py:155-179)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPHB_THREADS)
+__global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_newton_h(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_guess,
                double *__restrict__ h_out, int32_t *__restrict__ iters, int32_t *__restrict__ code,
                uint32_t *__restrict__ fail_list, sphb_status *__restrict__ status)

@@ -23,7 +23,9 @@
 #ifndef SPHB_LIST
 #define SPHB_LIST 128 /* per-lane list capacity (16-bit entries) */
 #endif
-#define SPHB_SUB 8        /* candidates filtered between two overflow checks */
+#ifndef SPHB_SUB
+#define SPHB_SUB 8 /* candidates filtered between two overflow checks */
+#endif
 #define SPHB_SEG_BITS 11  /* list code = (segment slot << 11) | offset in segment */
 #define SPHB_SEG_LEN (1u << SPHB_SEG_BITS)
 
@@ -237,12 +239,22 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                                 flush(L.count());
                                 L.reset();
                             }
+                            // all loads of the sub-tile first (independent LDS.128), then the tests
+                            float4 f[SPHB_SUB];
+                            float tq[SPHB_SUB];
 #pragma unroll
                             for (int c = 0; c < SPHB_SUB; ++c) {
-                                const float4 f = ws.tile[c0 + c];
-                                const float sv = fmaf(f.x, m2x, fmaf(f.y, m2y, fmaf(f.z, m2z, f.w)));
-                                const float th = SYM ? fmaxf(thrp, ws.tthr[c0 + c] + offp) : thrp;
-                                if (sv <= th) L.push(code + c);
+                                f[c] = ws.tile[c0 + c];
+                                if (SYM) tq[c] = ws.tthr[c0 + c];
+                            }
+                            float sv[SPHB_SUB];
+#pragma unroll
+                            for (int c = 0; c < SPHB_SUB; ++c)
+                                sv[c] = fmaf(f[c].x, m2x, fmaf(f[c].y, m2y, fmaf(f[c].z, m2z, f[c].w)));
+#pragma unroll
+                            for (int c = 0; c < SPHB_SUB; ++c) {
+                                const float th = SYM ? fmaxf(thrp, tq[c] + offp) : thrp;
+                                if (sv[c] <= th) L.push(code + c);
                             }
                             code += SPHB_SUB;
                         }
