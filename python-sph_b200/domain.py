@@ -1,0 +1,300 @@
+"""Slab decomposition of the per-step particle loop over the GPUs of one box.
+
+One process per GPU.  Rank r owns the particles with cuts[r] <= x < cuts[r+1] (cut planes chosen so
+that ranks own equal particle counts).  The reference has no distributed code; the only data-parallel
+axis is "every particle's sums are independent given a frozen snapshot" (pyfluid.py:203-207,:487-491),
+so each gather phase needs exactly one exchange of ghost particles:
+
+    halo(pos, h, vel, u)   before every cell-list build      all_to_all_single (NCCL over NVLink)
+    halo(h_new)            after a Newton solve               same send lists
+    halo(omega)            after an Omega pass (force needs Omega_i of ghost neighbours)
+    migration              after the corrector                full 64-byte records + global id
+    allreduce(max/min/sum) h_max, bounding box, status words  a few scalars
+
+Ghost width = 2 h_max (1 + margin): the force support is 2 max(h_i, h_j).  Local arrays are kept sorted
+by global particle id before each build, so the stable cell sort visits neighbours in the same order as
+a single-GPU run with the same grid geometry: k-rank results are bit-identical to 1-rank results.
+
+`HaloExchanger` is pure plumbing on torch tensors (any device, any backend) and is what the world-size-2
+gloo tests on CPU exercise; `SlabRunner` drives the CUDA kernels through engine.Engine.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+import engine as E
+
+F64 = torch.float64
+
+
+def equal_count_cuts(x_sorted_sample, world):
+    """Cut planes from a sorted sample of x coordinates: world+1 values, ends at -inf/+inf."""
+    n = x_sorted_sample.numel()
+    cuts = [-math.inf]
+    for r in range(1, world):
+        k = (n * r) // world
+        # midway between neighbours so that equal coordinates (lattice planes) stay on one side
+        a, b = float(x_sorted_sample[max(k - 1, 0)]), float(x_sorted_sample[min(k, n - 1)])
+        cuts.append(0.5 * (a + b))
+    cuts.append(math.inf)
+    return cuts
+
+
+class HaloExchanger:
+    """Send lists + all_to_all plumbing for one snapshot of owned x coordinates."""
+
+    def __init__(self, cuts, rank, world, group=None):
+        self.cuts, self.rank, self.world, self.group = list(cuts), rank, world, group
+
+    def owner_of(self, x):
+        inner = torch.tensor(self.cuts[1:-1], dtype=x.dtype, device=x.device)
+        return torch.bucketize(x, inner, right=True)
+
+    def plan(self, x_owned, width):
+        """indices (into the owned arrays) to send to every other rank: everything within `width` of its slab"""
+        self.send_idx = []
+        for q in range(self.world):
+            if q == self.rank:
+                self.send_idx.append(torch.empty(0, dtype=torch.int64, device=x_owned.device))
+                continue
+            m = (x_owned >= self.cuts[q] - width) & (x_owned < self.cuts[q + 1] + width)
+            self.send_idx.append(torch.nonzero(m).flatten())
+        self._counts(x_owned.device)
+        return self
+
+    def plan_migration(self, x_owned):
+        own = self.owner_of(x_owned)
+        self.send_idx = [torch.nonzero(own == q).flatten() if q != self.rank
+                         else torch.empty(0, dtype=torch.int64, device=x_owned.device) for q in range(self.world)]
+        self.stay = torch.nonzero(own == self.rank).flatten()
+        self._counts(x_owned.device)
+        return self
+
+    def _counts(self, device):
+        send = torch.tensor([int(i.numel()) for i in self.send_idx], dtype=torch.int64, device=device)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        self.send_counts = send.tolist()
+        self.recv_counts = recv.tolist()
+        self.all_idx = torch.cat(self.send_idx) if self.world > 1 else self.send_idx[0]
+
+    @property
+    def n_recv(self):
+        return int(sum(self.recv_counts))
+
+    def exchange(self, arrays):
+        """arrays: list of (n_owned, k) or (n_owned,) float64 tensors -> list of received arrays, sources in rank
+        order, each source's particles in the sender's owned order (deterministic)."""
+        cols = [a.reshape(a.shape[0], -1) for a in arrays]
+        widths = [c.shape[1] for c in cols]
+        K = sum(widths)
+        packed = torch.cat(cols, dim=1).index_select(0, self.all_idx).contiguous() if K else None
+        out = torch.empty((self.n_recv, K), dtype=packed.dtype, device=packed.device)
+        dist.all_to_all_single(out, packed, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
+                               group=self.group)
+        res, o = [], 0
+        for a, wd in zip(arrays, widths):
+            r = out[:, o:o + wd]
+            res.append(r.reshape(-1) if a.dim() == 1 else r.contiguous())
+            o += wd
+        return [r.contiguous() for r in res]
+
+
+class SlabRunner:
+    """var_smoothlength_leapfrog on a slab-decomposed particle set (one rank per GPU)."""
+
+    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05):
+        self.e, self.consts, self.world, self.rank, self.margin = eng, consts, world, rank, margin
+        self.dev = eng.device
+        self.statuses = []
+        self.geom = None
+        self.h_width_factor = 1.0
+
+    # ---- setup -------------------------------------------------------------------------------------
+    def scatter_initial(self, w):
+        """every rank generates the same synthetic workload and keeps its slab"""
+        import numpy as np
+        x = w["pos"][:, 0]
+        xs = np.sort(x[:: max(1, len(x) // 1000000)])
+        self.cuts = equal_count_cuts(torch.from_numpy(xs), self.world)
+        own = (x >= self.cuts[self.rank]) & (x < self.cuts[self.rank + 1])
+        idx = np.nonzero(own)[0]
+        self.n_total = len(x)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a[idx])).to(self.dev)
+        return dict(gid=torch.from_numpy(idx.astype(np.int64)).to(self.dev), pos=to(w["pos"]), vel=to(w["vel"]), u=to(w["u"]),
+                    h=to(w["h_guess"]))
+
+    def _global_geom(self, pos, h):
+        lo = pos.min(dim=0).values
+        hi = pos.max(dim=0).values
+        s = torch.stack([h.sum(), torch.tensor(float(h.numel()), dtype=F64, device=self.dev)])
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        lo, hi, s = lo.tolist(), hi.tolist(), s.tolist()
+        return E.choose_grid(lo, hi, s[0] / s[1], int(s[1]))
+
+    def _hmax(self, h):
+        t = h.max().reshape(1).clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- one snapshot: ghosts + cell list ------------------------------------------------------------
+    def _snapshot(self, st, width, fields):
+        """exchange ghosts of `fields` (names in st), build the cell list over owned+ghost sorted by global id.
+        returns a dict with the grid, index maps and the local (gid-sorted) arrays."""
+        hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width)
+        recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in fields])
+        gid_all = torch.cat([st["gid"], recv[0].to(torch.int64)])
+        order = torch.argsort(gid_all)                       # local order L: ascending global id
+        n_own = st["gid"].numel()
+        loc = torch.empty_like(order)
+        loc[order] = torch.arange(order.numel(), device=self.dev)
+        snap = dict(hx=hx, order=order, loc_own=loc[:n_own], loc_ghost=loc[n_own:], n_own=n_own, n_loc=order.numel())
+        for f, g in zip(fields, recv[1:]):
+            snap[f] = torch.cat([st[f], g]).index_select(0, order).contiguous()
+        owned_L = torch.zeros(order.numel(), dtype=torch.uint8, device=self.dev)
+        owned_L[snap["loc_own"]] = 1
+        posh = self.e.pack_posh(snap["pos"], snap["h"])
+        dg = self.e.build(posh, *self.geom)
+        snap["dg"] = dg
+        snap["target"] = owned_L.index_select(0, dg.perm.long()).contiguous()   # grid order
+        return snap
+
+    def _to_grid(self, snap, arr_L, ncomp):
+        return self.e.gather(arr_L, snap["dg"].perm, ncomp)
+
+    def _owned_from_grid(self, snap, arr_S, ncomp):
+        arr_L = self.e.scatter(arr_S, snap["dg"].perm, ncomp)
+        return arr_L.index_select(0, snap["loc_own"]).contiguous()
+
+    def _fill_ghosts(self, snap, owned_vals):
+        """owned values (owned order) -> local array L with the ghosts' values fetched from their owners"""
+        g = snap["hx"].exchange([owned_vals])[0]
+        out = torch.empty((snap["n_loc"],) + tuple(owned_vals.shape[1:]), dtype=F64, device=self.dev)
+        out[snap["loc_own"]] = owned_vals
+        out[snap["loc_ghost"]] = g
+        return out
+
+    # ---- physics stages -----------------------------------------------------------------------------------
+    def _stage(self, snap, status_ptr):
+        """the six calls of pyfluid.py:502-507 for the owned particles -> acc, dudt (owned order)"""
+        e, dg = self.e, snap["dg"]
+        _, _, om_S, _ = e.density_omega(dg, self.consts, target=snap["target"], want_rho=False, want_omega=True)
+        om_L = self._fill_ghosts(snap, self._owned_from_grid(snap, om_S, 1))
+        vel_S = self._to_grid(snap, snap["vel"], 3)
+        u_S = self._to_grid(snap, snap["u"], 1)
+        _, _, rB, rC = e.eos(dg.posh, vel_S, u_S, self._to_grid(snap, om_L, 1), self.consts, status_ptr)
+        acc_S, dudt_S = e.force(dg, self.consts, rB, rC, e.hmax(dg.posh), status_ptr, target=snap["target"])
+        return self._owned_from_grid(snap, acc_S, 3), self._owned_from_grid(snap, dudt_S, 1)
+
+    def _newton(self, snap, status_ptr):
+        e, dg = self.e, snap["dg"]
+        h_S = e.newton(dg, self.consts, dg.posh[:, 3].contiguous(), status_ptr, target=snap["target"])
+        h_own = self._owned_from_grid(snap, h_S, 1)
+        e.check_neg_h(h_own, status_ptr)
+        return h_own
+
+    def cold_solve(self, st):
+        self.geom = self._global_geom(st["pos"], st["h"])
+        hmax = self._hmax(st["h"])
+        stt = E.Status(1, self.dev)
+        snap = self._snapshot(st, 2.0 * hmax * 1.6, ["pos", "h"])     # generous: the guess is an under-estimate
+        st = dict(st)
+        st["h"] = self._newton(snap, stt.ptr(0))
+        self.statuses.append(stt)
+        self.geom = self._global_geom(st["pos"], st["h"])
+        return st
+
+    def step(self, st, dt):
+        e = self.e
+        stt = E.Status(E.S_COUNT, self.dev)
+        width = lambda h: 2.0 * self._hmax(h) * (1.0 + self.margin) + 4.0 * self.geom[1]
+        # stage 0
+        s0 = self._snapshot(st, width(st["h"]), ["pos", "h", "vel", "u"])
+        acc0, dudt0 = self._stage(s0, stt.ptr(E.S_STAGE0))
+        # predictor (owned only)
+        posh0 = e.pack_posh(st["pos"], st["h"])
+        posh_m, vel_m, u_m = e.predict(posh0, st["vel"], st["u"], acc0, dudt0, dt, stt.ptr(E.S_PRED))
+        mid = dict(gid=st["gid"], pos=posh_m[:, :3].contiguous(), h=st["h"], vel=vel_m, u=u_m)
+        # h_mid
+        s1 = self._snapshot(mid, width(st["h"]) * 1.02, ["pos", "h", "vel", "u"])
+        w1 = width(st["h"]) * 1.02
+        h_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID))
+        if 2.0 * self._hmax(h_mid) > w1:
+            raise RuntimeError("halo too narrow for the new smoothing lengths; increase SlabRunner(margin=...)")
+        h_mid_L = self._fill_ghosts(s1, h_mid)
+        e.set_h(s1["dg"], self._to_grid(s1, h_mid_L, 1))
+        acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID))
+        # corrector (owned only, t0 state is still in owned order)
+        posh_1, vel_1, u_1 = e.correct(posh0, st["vel"], st["u"], acc1, dudt1, dt, stt.ptr(E.S_CORR))
+        new = dict(gid=st["gid"], pos=posh_1[:, :3].contiguous(), h=h_mid, vel=vel_1, u=u_1)
+        # migration, then h1
+        new = self._migrate(new)
+        s2 = self._snapshot(new, width(new["h"]) * 1.02, ["pos", "h"])
+        new["h"] = self._newton(s2, stt.ptr(E.S_NEWTON_1))
+        self.statuses.append(stt)
+        return new
+
+    def _migrate(self, st):
+        hx = HaloExchanger(self.cuts, self.rank, self.world).plan_migration(st["pos"][:, 0].contiguous())
+        names = ["pos", "h", "vel", "u"]
+        recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in names])
+        out = dict(gid=torch.cat([st["gid"].index_select(0, hx.stay), recv[0].to(torch.int64)]))
+        for f, g in zip(names, recv[1:]):
+            out[f] = torch.cat([st[f].index_select(0, hx.stay), g]).contiguous()
+        return out
+
+    def check_status(self, printer=lambda *_: None):
+        """OR the flag words / sum the counters of every step since the last call, over all ranks"""
+        acc = torch.zeros((E.S_COUNT, 8), dtype=torch.int32, device=self.dev)
+        for s in self.statuses:
+            t = s.t if s.t.shape[0] == E.S_COUNT else torch.cat([s.t, torch.zeros((E.S_COUNT - s.t.shape[0], 8),
+                                                                                  dtype=torch.int32, device=self.dev)])
+            acc[:, 0] |= t[:, 0]
+            acc[:, 1:] += t[:, 1:]
+        self.statuses = []
+        allr = [torch.empty_like(acc) for _ in range(self.world)]
+        dist.all_gather(allr, acc)
+        tot = allr[0].clone()
+        for t in allr[1:]:
+            tot[:, 0] |= t[:, 0]
+            tot[:, 1:] += t[:, 1:]
+        E.raise_for_status(tot.cpu().numpy(), printer=printer)
+
+    def gather_state(self, st):
+        """all particles in global-id order on every rank (tests / small runs)"""
+        names = ["pos", "h", "vel", "u"]
+        n = torch.tensor([st["gid"].numel()], dtype=torch.int64, device=self.dev)
+        ns = [torch.empty_like(n) for _ in range(self.world)]
+        dist.all_gather(ns, n)
+        ns = [int(t.item()) for t in ns]
+        packed = torch.cat([st["gid"].to(F64).reshape(-1, 1)] + [st[f].reshape(st[f].shape[0], -1) for f in names], dim=1)
+        bufs = [torch.empty((k, packed.shape[1]), dtype=F64, device=self.dev) for k in ns]
+        dist.all_gather(bufs, packed.contiguous())
+        allp = torch.cat(bufs)
+        allp = allp.index_select(0, torch.argsort(allp[:, 0].to(torch.int64)))
+        return dict(pos=allp[:, 1:4].contiguous(), h=allp[:, 4].contiguous(), vel=allp[:, 5:8].contiguous(), u=allp[:, 8].contiguous())
+
+    def e2e(self, st, dt, steps):
+        """public-API-style step with host buffers on every rank: H2D of the owned state, step, D2H"""
+        import time
+        host = {k: v.cpu().pin_memory() for k, v in st.items()}
+        nb = sum(v.numel() * v.element_size() for v in host.values())
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            d = {k: v.to(self.dev, non_blocking=True) for k, v in host.items()}
+            r = self.step(d, dt)
+            host = {k: v.cpu() for k, v in r.items()}
+            torch.cuda.synchronize()
+        dist.barrier()
+        el = torch.tensor([time.perf_counter() - t0], dtype=F64, device=self.dev)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([float(nb)], dtype=F64, device=self.dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        return {"value": self.n_total * steps / float(el.item()), "unit": "particle-steps/s",
+                "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(tot.item()), "steps": steps}

@@ -359,47 +359,45 @@ class Stepper:
 
     def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print):
         e = self.e
-        n = pos0.shape[0]
         st = Status(S_COUNT, e.device)
-        posh_c = e.pack_posh(pos0, h0)
-        grid, delta = self.geom if self.geom is not None else e.grid_for(posh_c)
+        posh0 = e.pack_posh(pos0, h0)
+        grid, delta = self.geom if self.geom is not None else e.grid_for(posh0)
+
+        # State stays in CALLER order between stages; every cell list is built from caller-order positions, so
+        # ties inside a cell are always broken by the caller index and every sum has one fixed order (the
+        # multi-GPU runner does the same with global ids: k-rank results equal 1-rank results bit for bit).
+        def stage(dg, vel_c, u_c, sidx):
+            """the six calls at pyfluid.py:502-507 / :517-522 -> acc, dudt in caller order"""
+            _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
+            _, _, rB, rC = e.eos(dg.posh, e.gather(vel_c, dg.perm, 3), e.gather(u_c, dg.perm, 1), om, consts, st.ptr(sidx))
+            acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx))
+            return e.scatter(acc, dg.perm, 3), e.scatter(dudt, dg.perm, 1)
+
+        def solve_h(dg, sidx):
+            """newton_smoothlength_arr(pos, guess = the h carried in the snapshot), caller order"""
+            h_s = e.newton(dg, consts, dg.posh[:, 3].contiguous(), st.ptr(sidx))
+            e.check_neg_h(h_s, st.ptr(sidx))
+            return h_s
 
         # ---- stage 0 at (pos0, h0): pyfluid.py:502-507 ------------------------------------------
-        g0 = e.build(posh_c, grid, delta)
-        vel0_s = e.gather(vel0, g0.perm, 3)
-        u0_s = e.gather(u0, g0.perm, 1)
-        _, _, om0, _ = e.density_omega(g0, consts, want_rho=False, want_omega=True)
-        _, _, rB, rC = e.eos(g0.posh, vel0_s, u0_s, om0, consts, st.ptr(S_STAGE0))
-        acc0, dudt0 = e.force(g0, consts, rB, rC, e.hmax(g0.posh), st.ptr(S_STAGE0))
+        g0 = e.build(posh0, grid, delta)
+        acc0, dudt0 = stage(g0, vel0, u0, S_STAGE0)
         # ---- predictor: pyfluid.py:511-515 ---------------------------------------------------------
-        posh_m, vel_m, u_m = e.predict(g0.posh, vel0_s, u0_s, acc0, dudt0, dt, st.ptr(S_PRED))
-        # ---- h_mid = newton(pos_mid, h0): pyfluid.py:516 --------------------------------------------
+        posh_m, vel_m, u_m = e.predict(posh0, vel0, u0, acc0, dudt0, dt, st.ptr(S_PRED))
+        # ---- h_mid = newton(pos_mid, h0), stage mid: pyfluid.py:516-522 -------------------------------
         g1 = e.build(posh_m, grid, delta)
-        h_mid = e.newton(g1, consts, g1.posh[:, 3].contiguous(), st.ptr(S_NEWTON_MID))
-        e.check_neg_h(h_mid, st.ptr(S_NEWTON_MID))
-        e.set_h(g1, h_mid)
-        # ---- stage mid: pyfluid.py:517-522 -----------------------------------------------------------
-        vel_m1 = e.gather(vel_m, g1.perm, 3)
-        u_m1 = e.gather(u_m, g1.perm, 1)
-        _, _, om1, _ = e.density_omega(g1, consts, want_rho=False, want_omega=True)
-        _, _, rB, rC = e.eos(g1.posh, vel_m1, u_m1, om1, consts, st.ptr(S_STAGE_MID))
-        acc1, dudt1 = e.force(g1, consts, rB, rC, e.hmax(g1.posh), st.ptr(S_STAGE_MID))
-        # ---- corrector: pyfluid.py:524-528 (needs the t0 state in g1 order) -----------------------
-        posh0_1 = e.gather(g0.posh, g1.perm, 4)
-        vel0_1 = e.gather(vel0_s, g1.perm, 3)
-        u0_1 = e.gather(u0_s, g1.perm, 1)
-        posh_1, vel_1, u_1 = e.correct(posh0_1, vel0_1, u0_1, acc1, dudt1, dt, st.ptr(S_CORR))
-        # ---- h1 = newton(pos1, h_mid): pyfluid.py:530 --------------------------------------------------
+        h_mid_s = solve_h(g1, S_NEWTON_MID)
+        e.set_h(g1, h_mid_s)
+        acc1, dudt1 = stage(g1, vel_m, u_m, S_STAGE_MID)
+        h_mid = e.scatter(h_mid_s, g1.perm, 1)
+        # ---- corrector: pyfluid.py:524-528 ---------------------------------------------------------------
+        posh_1, vel1, u1 = e.correct(posh0, vel0, u0, acc1, dudt1, dt, st.ptr(S_CORR))
+        # ---- h1 = newton(pos1, h_mid): pyfluid.py:530 ------------------------------------------------------
+        posh_1 = e.pack_posh(posh_1[:, :3].contiguous(), h_mid)
         g2 = e.build(posh_1, grid, delta)
-        h1 = e.newton(g2, consts, e.gather(h_mid, g2.perm, 1), st.ptr(S_NEWTON_1))
-        e.check_neg_h(h1, st.ptr(S_NEWTON_1))
-        # ---- back to caller order ------------------------------------------------------------------------
-        caller = e.gather_u32(e.gather_u32(g0.perm, g1.perm), g2.perm)   # caller index of each g2 slot
-        pos1 = e.scatter(g2.posh[:, :3].contiguous(), caller, 3)
-        vel1 = e.scatter(e.gather(vel_1, g2.perm, 3), caller, 3)
-        u1 = e.scatter(e.gather(u_1, g2.perm, 1), caller, 1)
-        h1c = e.scatter(h1, caller, 1)
+        h1 = e.scatter(solve_h(g2, S_NEWTON_1), g2.perm, 1)
+        pos1 = posh_1[:, :3].contiguous()
         self.last_status = st
         if not defer_status:
             raise_for_status(st.read(), printer)
-        return pos1, vel1, u1, h1c
+        return pos1, vel1, u1, h1

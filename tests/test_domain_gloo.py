@@ -1,0 +1,84 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: cut planes, halo send lists, the all_to_all
+exchange and particle migration (python-sph_b200/domain.py).  No kernels run here."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import domain
+        rng = np.random.default_rng(0)
+        n = 4000
+        pos = rng.random((n, 3)) * np.array([10.0, 2.0, 2.0])
+        val = rng.random(n)
+        xs = torch.from_numpy(np.sort(pos[:, 0]))
+        cuts = domain.equal_count_cuts(xs, world)
+        own = np.nonzero((pos[:, 0] >= cuts[rank]) & (pos[:, 0] < cuts[rank + 1]))[0]
+        gid = torch.from_numpy(own.astype(np.int64))
+        p = torch.from_numpy(pos[own])
+        v = torch.from_numpy(val[own])
+        w = 0.7
+        hx = domain.HaloExchanger(cuts, rank, world).plan(p[:, 0], w)
+        g_gid, g_pos, g_val = hx.exchange([gid.to(torch.float64), p, v])
+        g_gid = g_gid.to(torch.int64).numpy()
+        # every particle of another rank within w of my slab arrived, exactly once, with the right payload
+        lo, hi = cuts[rank], cuts[rank + 1]
+        others = np.setdiff1d(np.arange(n), own)
+        need = others[(pos[others, 0] >= lo - w) & (pos[others, 0] < hi + w)]
+        ok = (np.sort(g_gid) == np.sort(need)).all() and (g_pos.numpy() == pos[g_gid]).all() and (g_val.numpy() == val[g_gid]).all()
+        # second exchange with the same plan returns values in the same order
+        g2 = hx.exchange([v * 2.0])[0]
+        ok = ok and (g2.numpy() == 2.0 * val[g_gid]).all()
+        # migration conserves the particle set
+        p_moved = p.clone()
+        p_moved[:, 0] += 1.5
+        mg = domain.HaloExchanger(cuts, rank, world).plan_migration(p_moved[:, 0])
+        r_gid, r_pos = mg.exchange([gid.to(torch.float64), p_moved])
+        mine = torch.cat([gid[mg.stay], r_gid.to(torch.int64)])
+        mine_x = torch.cat([p_moved[mg.stay, 0], r_pos[:, 0]])
+        ok = ok and bool(((mine_x >= lo) & (mine_x < hi)).all())
+        cnt = torch.tensor([mine.numel()])
+        dist.all_reduce(cnt)
+        ok = ok and int(cnt.item()) == n
+        q.put((rank, bool(ok), int(len(need))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_and_migration_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(nneed > 0 for _, _, nneed in res)
+
+
+def test_equal_count_cuts():
+    import domain
+    x = torch.sort(torch.rand(1000, dtype=torch.float64)).values
+    c = domain.equal_count_cuts(x, 4)
+    assert len(c) == 5 and c[0] == -np.inf and c[-1] == np.inf
+    counts = [int(((x >= c[r]) & (x < c[r + 1])).sum()) for r in range(4)]
+    assert counts == [250] * 4
