@@ -169,6 +169,12 @@ int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *tar
                const double *recC, const float *hmax_global, double *acc, double *dudt, sphb_status *status,
                void *stream);
 
+/* Per-pair terms for explicit (j, i) slot pairs (pairs[2*p], pairs[2*p+1]), same records as sphb_force:
+ * pi_out[p] = Pi(j, i, ...) (pyfluid.py:261-285); acc_out[3*p..] = fluid_accel_viscosity_comp(j, i, ...)
+ * (pyfluid.py:459-474; zero for identical positions).  Either output may be NULL. */
+int sphb_pair_terms(const double *posh, const double *recB, const double *recC, const uint32_t *pairs, int64_t n_pairs,
+                    const sphb_consts *k, double *pi_out, double *acc_out, sphb_status *status, void *stream);
+
 /* ---- K5: integrator updates (pyfluid.py:511-515 predictor, :524-528 corrector) ------------------- */
 int sphb_predict(const double *posh0, const double *vel0, const double *u0, const double *acc0, const double *dudt0,
                  double dt, int64_t n, double *posh_mid, double *vel_mid, double *u_mid, sphb_status *status,

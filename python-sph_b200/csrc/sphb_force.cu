@@ -163,6 +163,64 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     }
 }
 
+// Pi(j,i) and fluid_accel_viscosity_comp(j,i) for explicit pairs, written in the reference's own form
+// (pyfluid.py:261-285, :459-474): this is the per-pair entry point, not the hot loop.
+__global__ void k_pair_terms(const double *__restrict__ posh, const double *__restrict__ recB,
+                             const double *__restrict__ recC, const uint32_t *__restrict__ pairs, long long n_pairs,
+                             sphb_consts k, double *__restrict__ pi_out, double *__restrict__ acc_out,
+                             sphb_status *__restrict__ status)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint32_t j = pairs[2 * p], i = pairs[2 * p + 1];
+    double xj, yj, zj, hj, xi, yi, zi, hi, vxj, vyj, vzj, Aj, vxi, vyi, vzi, Ai, rhoj, csj, hinvj, gj, rhoi, csi, hinvi, gi;
+    sphb_load4(posh, j, xj, yj, zj, hj);
+    sphb_load4(posh, i, xi, yi, zi, hi);
+    sphb_load4(recB, j, vxj, vyj, vzj, Aj);
+    sphb_load4(recB, i, vxi, vyi, vzi, Ai);
+    sphb_load4(recC, j, rhoj, csj, hinvj, gj);
+    sphb_load4(recC, i, rhoi, csi, hinvi, gi);
+    const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    const double vdr = sphb_dot3(dx, dy, dz, vxj - vxi, vyj - vyi, vzj - vzi);
+    const double dist = __dsqrt_rn(sphb_d2(dx, dy, dz));
+    double pi = 0.0;
+    if (vdr < 0.0) {
+        const double mean_h = 0.5 * (hj + hi);
+        const double mu = mean_h * vdr / (dist * dist + k.epsilon * (mean_h * mean_h));
+        const double cs = 0.5 * (csi + csj);
+        const double mean_rho = 0.5 * (rhoj + rhoi);
+        pi = (-k.alpha * cs * mu + k.beta * (mu * mu)) / mean_rho;
+        if (pi < 0.0) atomicOr(&status->flags, SPHB_ST_NEG_PI);
+    }
+    if (pi_out) pi_out[p] = pi;
+    if (acc_out) {
+        double a[3] = {0.0, 0.0, 0.0};
+        if (!(dx == 0.0 && dy == 0.0 && dz == 0.0)) {
+            const double wj = sphb_m4_fp(dist / hj) * gj, wi = sphb_m4_fp(dist / hi) * gi;   // M4_d1
+            const double d[3] = {dx / dist, dy / dist, dz / dist};                            // direction_i_j
+            for (int c = 0; c < 3; ++c) {
+                const double gJ = wj * d[c], gI = wi * d[c];
+                a[c] = -k.particle_mass * ((Aj * gJ + Ai * gI) + pi * 0.5 * (gJ + gI));
+            }
+        }
+        acc_out[3 * p] = a[0];
+        acc_out[3 * p + 1] = a[1];
+        acc_out[3 * p + 2] = a[2];
+    }
+}
+
+extern "C" int sphb_pair_terms(const double *posh, const double *recB, const double *recC, const uint32_t *pairs,
+                               int64_t n_pairs, const sphb_consts *k, double *pi_out, double *acc_out,
+                               sphb_status *status, void *stream)
+{
+    if (n_pairs < 0 || !k || !status || (n_pairs > 0 && (!posh || !recB || !recC || !pairs))) return SPHB_E_ARG;
+    if (n_pairs == 0) return SPHB_OK;
+    k_pair_terms<<<(unsigned)((n_pairs + 127) / 128), 128, 0, sphb_stream(stream)>>>(posh, recB, recC, pairs, n_pairs, *k,
+                                                                                     pi_out, acc_out, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: predictor (pyfluid.py:511-515) and corrector (:524-528); arithmetic in the reference's order
 // ------------------------------------------------------------------------------------------------

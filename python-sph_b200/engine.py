@@ -274,6 +274,15 @@ class Engine:
                                     _ptr(dudt), status_ptr, _stream())
         return acc, dudt
 
+    def pair_terms(self, posh, recB, recC, pairs, consts, status_ptr):
+        """pairs: int32 (m,2) slot pairs -> Pi (m), fluid_accel_viscosity_comp (m,3)"""
+        m = pairs.shape[0]
+        pi = torch.empty(m, dtype=F64, device=self.device)
+        acc = torch.empty((m, 3), dtype=F64, device=self.device)
+        self._run("pair_terms", self.lib.sphb_pair_terms, _ptr(posh), _ptr(recB), _ptr(recC), _ptr(pairs), m, C.byref(consts),
+                  _ptr(pi), _ptr(acc), status_ptr, _stream())
+        return pi, acc
+
     # -- K5 ------------------------------------------------------------------------------------
     def predict(self, posh0, vel0, u0, acc0, dudt0, dt, status_ptr):
         n = posh0.shape[0]

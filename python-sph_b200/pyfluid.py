@@ -342,10 +342,39 @@ def _force_arrays(io, position_arr, velocity_arr, pressure_arr_, density_arr_, s
     return dg, acc, dudt, st, slot
 
 
+def _pair(io, j, i, position_arr, velocity_arr, pressure_arr_, density_arr_, smoothlength_arr, omega_arr_):
+    e = _eng()
+    k = _consts(hydro_only=True)
+    pos = io.dev64(position_arr, (-1, 3))
+    posh = e.pack_posh(pos, io.dev64(smoothlength_arr, (-1,)))
+    n = pos.shape[0]
+    om = io.dev64(omega_arr_, (-1,)) if omega_arr_ is not None else torch.ones(n, dtype=torch.float64, device=e.device)
+    st = _E.Status(1, e.device)
+    _, _, rB, rC = e.eos(posh, io.dev64(velocity_arr, (-1, 3)), None, om, k, st.ptr(0), rho_in=io.dev64(density_arr_, (-1,)),
+                         P_in=io.dev64(pressure_arr_, (-1,)))
+    st.t.zero_()
+    pairs = torch.tensor([[int(j), int(i)]], dtype=torch.int32, device=e.device)
+    pi, acc = e.pair_terms(posh, rB, rC, pairs, k, st.ptr(0))
+    _report(st)
+    return pi, acc
+
+
 def Pi(j, i, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr):
-    """pyfluid.py:261-285 (Cossins 3.85) for one pair: evaluated by the force kernel on the two-particle
-    system {j, i} with unit grad-h factors, then solved for Pi from the viscous heating sum."""
-    raise NotImplementedError("Pi(j, i, ...) is evaluated inside the fused force kernel; use energy_rate/acceleration")
+    """pyfluid.py:261-285 (Cossins 3.85)"""
+    io = _IO(position_arr)
+    pi, _ = _pair(io, j, i, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, None)
+    v = _scalar(pi[0])
+    return v if v != 0.0 else 0
+
+
+def fluid_accel_viscosity_comp(j, i, position_arr, velocity_arr, density_arr, pressure_arr, smoothlength_arr, omega_arr):
+    """pyfluid.py:459-474; the reference returns the int 0 for identical positions"""
+    io = _IO(position_arr)
+    pos = io.dev64(position_arr, (-1, 3))
+    if bool(torch.equal(pos[int(j)], pos[int(i)])):
+        return 0
+    _, acc = _pair(io, j, i, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr)
+    return acc[0] if io.torch_out else acc[0].cpu().numpy()
 
 
 def energy_rate(j, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr):

@@ -160,6 +160,14 @@ def main():
         out["C_" + k] = v
     meta["C_sim_stdout"] = txt
 
+    # ---- case P: per-pair functions Pi (pyfluid.py:261) and fluid_accel_viscosity_comp (:459) on case C ----
+    pairs = np.array([[0, 1], [3, 17], [5, 5], [10, 42], [63, 0], [7, 8], [20, 21], [33, 2]])
+    sph.G = 0.0
+    out["P_pairs"] = pairs
+    out["P_Pi"] = np.array([float(sph.Pi(j, i, pos, vel, P, den, hC)) for j, i in pairs])
+    out["P_acc"] = np.array([np.zeros(3) + sph.fluid_accel_viscosity_comp(j, i, pos, vel, den, P, hC, om) for j, i in pairs])
+    sph.G = G_DEFAULT
+
     # ---- case D: pyfluidex2d_var_h.py:10-25 settings (planar z=0, u=1e-59, h guess 1, dt 0.1),
     #      seeded, with the (N,3) layout var_smoothlength_sim actually takes (pyfluid.py:544) -----
     rng = np.random.default_rng(3)

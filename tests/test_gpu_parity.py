@@ -350,3 +350,17 @@ def test_conservation_properties(sph):
     assert rel(h[js], o.newton_smoothlength_while(js, pos, 0.8)[0]) < RTOL
     assert rel(om[js], o.omega_j(js, pos, rho[js], h[js])) < RTOL
     assert vrel(acc[js], o.acceleration_arr(pos, rho, vel, P, h, om, np.zeros(n), j=js)) < RTOL
+
+
+def test_golden_P_pair_functions(sph, golden):
+    g = golden
+    pos, vel, h, P, den, om = g["C_pos"], g["C_vel"], g["C_h"], g["C_P"], g["C_den"], g["C_omega"]
+    for (j, i), pi_ref, acc_ref in zip(g["P_pairs"], g["P_Pi"], g["P_acc"]):
+        pi = sph.Pi(int(j), int(i), pos, vel, P, den, h)
+        assert pi == pytest.approx(pi_ref, rel=RTOL, abs=0.0)
+        a = sph.fluid_accel_viscosity_comp(int(j), int(i), pos, vel, den, P, h, om)
+        if j == i:
+            assert isinstance(a, int) and a == 0
+        else:
+            assert vrel(a, acc_ref) < RTOL or np.abs(acc_ref).max() == 0.0
+    assert (g["P_Pi"] > 0).any() and (g["P_Pi"] == 0).any()
