@@ -135,15 +135,17 @@ int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint
  * replaces newton_smoothlength_iteration/_while/_arr (pyfluid.py:155-179, 203-211) and
  * bisection_h (pyfluid.py:123-153).  h_out[j]: converged h, or the bisection result, or NaN when
  * bisection returned None.  iters[j]: Newton iterations performed.  code[j]: 0 Newton converged,
- * 1 bisection converged, 2 bisection returned None.  Counters/flags land in *status. */
+ * 1 bisection converged, 2 bisection returned None.  Counters/flags land in *status.
+ * omega_out (optional): Omega_j = 1 + h/(3 rho) sum_i m dW/dh at the RETURNED h with rho = m (eta/h)^3 -- what the step
+ * computes next (pyfluid.py:517-518); it comes from one more pass over the converged iteration's neighbour list. */
 int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *h_guess,
-                  double *h_out, int32_t *iters, int32_t *code, uint32_t *fail_list, sphb_status *status,
-                  void *stream);
+                  double *h_out, double *omega_out, int32_t *iters, int32_t *code, uint32_t *fail_list,
+                  sphb_status *status, void *stream);
 /* bisection for an explicit list of target slots (also used for bisection_h(j, pos) itself);
  * n_list < 0: take the list length from status->nfail (device side).  oob (optional, per list entry) */
 int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, const uint32_t *list, int64_t n_list,
-                  double *h_out, int32_t *code, int32_t *oob, int32_t indexed_by_slot, sphb_status *status,
-                  void *stream);
+                  double *h_out, double *omega_out, int32_t *code, int32_t *oob, int32_t indexed_by_slot,
+                  sphb_status *status, void *stream);
 
 /* ---- neighbour sets (SURVEY.md 8(c) oracle: NB(j) = {i : distance(r_j, r_i)/h_j < 2}) -------------
  * exact reference arithmetic (fma-ordered dot, IEEE sqrt and divide).  Writes, for each of the

@@ -6,7 +6,7 @@
 
 #define SPHB_WARPS 4
 #ifndef SPHB_MINB_FORCE
-#define SPHB_MINB_FORCE 5
+#define SPHB_MINB_FORCE 4
 #endif
 #define SPHB_THREADS (SPHB_WARPS * 32)
 
@@ -66,48 +66,72 @@ struct SphbForceAcc {
     int negpi;
 };
 
+// one pair, given the candidate's position record; the other two records are only fetched for real pairs
+__device__ __forceinline__ void sphb_force_pair(const double *recB, const double *recC, uint32_t i, double x, double y,
+                                                double z, double hi, const sphb_consts &k, SphbForceAcc &a)
+{
+    const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
+    const double d2 = sphb_d2(dx, dy, dz);
+    if (!sphb_nonzero(d2)) return;   // coincident positions contribute exactly 0 (pyfluid.py:51-52,461)
+    double rhoi, csi, hinvi, gi;
+    sphb_load4(recC, i, rhoi, csi, hinvi, gi);
+    const double rinv = sphb_rsqrt(d2);
+    const double r = d2 * rinv;
+    const double qj = r * a.hinvj, qi = r * hinvi;
+    if (!(qj < 2.0) && !(qi < 2.0)) return;   // prefilter false positive
+    double vxi, vyi, vzi, Ai;
+    sphb_load4(recB, i, vxi, vyi, vzi, Ai);
+    const double sj = sphb_m4c_fp(qj) * a.gj * rinv;
+    const double si = sphb_m4c_fp(qi) * gi * rinv;
+    const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
+    const double vdr = sphb_dot3(dx, dy, dz, dvx, dvy, dvz);
+    a.dens = fma(sj, vdr, a.dens);
+    const double sm = sj + si;
+    double pi_half = 0.0;
+    if (vdr < 0.0) {
+        const double mean_h = 0.5 * (a.hj + hi);
+        const double den = fma(k.epsilon * mean_h, mean_h, d2);
+        const double mean_rho = 0.5 * (a.rhoj + rhoi);
+        const double inv = sphb_rcp(den * mean_rho);
+        const double mu = (mean_h * vdr) * (inv * mean_rho);
+        const double cs = 0.5 * (csi + a.csj);
+        const double pi = (mu * fma(k.beta, mu, -k.alpha * cs)) * (inv * den);
+        if (pi < 0.0) a.negpi = 1;
+        pi_half = 0.5 * pi;
+    }
+    const double coef = fma(a.Aj, sj, fma(Ai, si, pi_half * sm));
+    a.ax = fma(-coef, dx, a.ax);
+    a.ay = fma(-coef, dy, a.ay);
+    a.az = fma(-coef, dz, a.az);
+    a.visc = fma(pi_half * sm, vdr, a.visc);
+}
+
+// drain the lane's list with the next position record in flight (two buffers, unrolled by two)
 __device__ __forceinline__ void sphb_force_flush(const double *posh, const double *recB, const double *recC,
                                                  const SphbWarpShared &ws, int lane, int cnt, const sphb_consts &k,
                                                  SphbForceAcc &a)
 {
-    for (int n_ = 0; n_ < cnt; ++n_) {
-        const uint32_t i = sphb_list_get(ws, lane, n_);
-        double x, y, z, hi;
-        sphb_load4(posh, i, x, y, z, hi);
-        const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
-        const double d2 = sphb_d2(dx, dy, dz);
-        if (!(d2 > 0.0)) continue;
-        double rhoi, csi, hinvi, gi;
-        sphb_load4(recC, i, rhoi, csi, hinvi, gi);
-        const double rinv = sphb_rsqrt(d2);
-        const double r = d2 * rinv;
-        const double qj = r * a.hinvj, qi = r * hinvi;
-        if (!(qj < 2.0) && !(qi < 2.0)) continue;   // prefilter false positive
-        double vxi, vyi, vzi, Ai;
-        sphb_load4(recB, i, vxi, vyi, vzi, Ai);
-        const double sj = sphb_m4_fp(qj) * a.gj * rinv;
-        const double si = sphb_m4_fp(qi) * gi * rinv;
-        const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
-        const double vdr = sphb_dot3(dx, dy, dz, dvx, dvy, dvz);
-        a.dens = fma(sj, vdr, a.dens);
-        const double sm = sj + si;
-        double pi_half = 0.0;
-        if (vdr < 0.0) {
-            const double mean_h = 0.5 * (a.hj + hi);
-            const double den = fma(k.epsilon * mean_h, mean_h, d2);
-            const double mean_rho = 0.5 * (a.rhoj + rhoi);
-            const double inv = sphb_rcp(den * mean_rho);
-            const double mu = (mean_h * vdr) * (inv * mean_rho);
-            const double cs = 0.5 * (csi + a.csj);
-            const double pi = (mu * fma(k.beta, mu, -k.alpha * cs)) * (inv * den);
-            if (pi < 0.0) a.negpi = 1;
-            pi_half = 0.5 * pi;
+    double ax, ay, az, ah, bx, by, bz, bh;
+    uint32_t ia = 0, ib = 0;
+    if (cnt > 0) {
+        ia = sphb_list_get(ws, lane, 0);
+        sphb_load4(posh, ia, ax, ay, az, ah);
+    }
+    int n_ = 0;
+    while (n_ < cnt) {
+        if (n_ + 1 < cnt) {
+            ib = sphb_list_get(ws, lane, n_ + 1);
+            sphb_load4(posh, ib, bx, by, bz, bh);
         }
-        const double coef = fma(a.Aj, sj, fma(Ai, si, pi_half * sm));
-        a.ax = fma(-coef, dx, a.ax);
-        a.ay = fma(-coef, dy, a.ay);
-        a.az = fma(-coef, dz, a.az);
-        a.visc = fma(pi_half * sm, vdr, a.visc);
+        sphb_force_pair(recB, recC, ia, ax, ay, az, ah, k, a);
+        ++n_;
+        if (n_ >= cnt) break;
+        if (n_ + 1 < cnt) {
+            ia = sphb_list_get(ws, lane, n_ + 1);
+            sphb_load4(posh, ia, ax, ay, az, ah);
+        }
+        sphb_force_pair(recB, recC, ib, bx, by, bz, bh, k, a);
+        ++n_;
     }
 }
 

@@ -6,7 +6,7 @@
 
 #define SPHB_WARPS 4
 #ifndef SPHB_MINB_OWN
-#define SPHB_MINB_OWN 6
+#define SPHB_MINB_OWN 4
 #endif
 #define SPHB_THREADS (SPHB_WARPS * 32)
 
@@ -23,23 +23,35 @@ struct SphbOwnAcc {
     int nn;
 };
 
+__device__ __forceinline__ void sphb_own_pair(double x, double y, double z, SphbOwnAcc &a)
+{
+    const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
+    const double d2 = sphb_d2(dx, dy, dz);
+    const double r = sphb_nonzero(d2) ? d2 * sphb_rsqrt(d2) : 0.0;
+    const double q = r * a.hinv;
+    double f, fp;
+    sphb_m4c(q, f, fp);
+    a.sumF += f;
+    a.sumG += fma(q, fp, 3.0 * f);
+    a.nn += (q < 2.0) ? 1 : 0;
+}
+
+// drain the lane's list: the record of entry k+1 is in flight while entry k is evaluated (two register
+// buffers, loop unrolled by two so that no copies are needed)
 __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWarpShared &ws, int lane, int cnt,
                                                SphbOwnAcc &a)
 {
-#pragma unroll 2
-    for (int k = 0; k < cnt; ++k) {
-        const uint32_t i = sphb_list_get(ws, lane, k);
-        double x, y, z, h;
-        sphb_load_posh(posh, i, x, y, z, h);
-        const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
-        const double d2 = sphb_d2(dx, dy, dz);
-        const double r = d2 > 0.0 ? d2 * sphb_rsqrt(d2) : 0.0;
-        const double q = r * a.hinv;
-        double f, fp;
-        sphb_m4(q, f, fp);
-        a.sumF += f;
-        a.sumG += fma(q, fp, 3.0 * f);
-        a.nn += (q < 2.0) ? 1 : 0;
+    double ax, ay, az, ah, bx, by, bz, bh;
+    if (cnt > 0) sphb_load_posh(posh, sphb_list_get(ws, lane, 0), ax, ay, az, ah);
+    int k = 0;
+    while (k < cnt) {
+        if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), bx, by, bz, bh);
+        sphb_own_pair(ax, ay, az, a);
+        ++k;
+        if (k >= cnt) break;
+        if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), ax, ay, az, ah);
+        sphb_own_pair(bx, by, bz, a);
+        ++k;
     }
 }
 
@@ -96,12 +108,25 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: per-lane Newton loop with warp-vote convergence mask (pyfluid.py:155-179)
+// K3: per-lane Newton loop with warp-vote convergence mask (pyfluid.py:155-179).
+// With omega_out != NULL the kernel also returns Omega at the converged h (pyfluid.py:91-97 with the algebraic
+// density, as the step uses it at :503/:518): the scan radius carries a 1.1e-3 margin, so when a lane converges
+// (|h_old - h_new| < 1e-3 |h_new|) its neighbour list already covers the support of h_new and the sum
+// sum_i m dW/dh(r, h_new) is one more pass over the SAME list -- no second cell scan, no extra launch.
 // ------------------------------------------------------------------------------------------------
+#define SPHB_NEWTON_MARGIN 1.1e-3
+
+__device__ __forceinline__ double sphb_omega_from_sumG(const sphb_consts &k, double h, double sumG)
+{
+    const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
+    const double ds = -(pref / h) * sumG;                       // sum_i m dW/dh
+    return 1.0 + h / (3.0 * sphb_var_density(k, h)) * ds;       // pyfluid.py:97 with rho = m (eta/h)^3
+}
+
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_newton_h(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_guess,
-               double *__restrict__ h_out, int32_t *__restrict__ iters, int32_t *__restrict__ code,
-               uint32_t *__restrict__ fail_list, sphb_status *__restrict__ status)
+               double *__restrict__ h_out, double *__restrict__ omega_out, int32_t *__restrict__ iters,
+               int32_t *__restrict__ code, uint32_t *__restrict__ fail_list, sphb_status *__restrict__ status)
 {
     __shared__ SphbWarpShared sh[SPHB_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,6 +137,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     const bool tgt = valid && (target == nullptr || target[j] != 0);
     const SphbScanCtx g = sphb_make_ctx(c);
     SphbWarpShared &ws = sh[warp];
+    const double rmargin = omega_out ? 1.0 + SPHB_NEWTON_MARGIN : 1.0;
 
     SphbOwnAcc a;
     a.xj = a.yj = a.zj = 0.0;
@@ -124,19 +150,25 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
         row = c.cell_id[j] / (uint32_t)g.nx;
     }
     if (tgt) h_old = h_guess[j];
-    bool active = tgt;
+    bool active = tgt, need_scan = false;
+    double h_fin = 1.0;
     int it = 0;
     while (__any_sync(SPHB_FULL, active)) {
         a.hinv = 1.0 / h_old;
         a.sumF = a.sumG = 0.0;
         a.nn = 0;
-        const float Rj = sphb_radius_of_h(h_old, g.delta), thr = sphb_thr_of_h(h_old, g.delta);
+        const double hs = h_old * rmargin;
+        const float Rj = sphb_radius_of_h(hs, g.delta), thr = sphb_thr_of_h(hs, g.delta);
         SphbList L;
         L.init(ws, lane);
-        auto flush = [&](int n_) { sphb_own_flush(c.posh, ws, lane, n_, a); };
+        bool flushed = false;   // warp-uniform: did a list overflow during this scan?
+        auto flush = [&](int n_) {
+            flushed = true;
+            sphb_own_flush(c.posh, ws, lane, n_, a);
+        };
         sphb_warp_scan<false>(g, ws, lane, active, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
-        flush(L.count());
-        __syncwarp();
+        const int cnt = L.count();
+        sphb_own_flush(c.posh, ws, lane, cnt, a);
         if (active) {
             // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
             const double pref = k.particle_mass / (SPHB_PI * (h_old * h_old * h_old));
@@ -153,6 +185,18 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                 if (iters) iters[j] = it;
                 if (code) code[j] = 0;
                 active = false;
+                if (omega_out) {
+                    if (!flushed) {
+                        SphbOwnAcc b = a;
+                        b.hinv = 1.0 / h_new;
+                        b.sumF = b.sumG = 0.0;
+                        sphb_own_flush(c.posh, ws, lane, cnt, b);
+                        omega_out[j] = sphb_omega_from_sumG(k, h_new, b.sumG);
+                    } else {
+                        need_scan = true;
+                        h_fin = h_new;
+                    }
+                }
             } else {
                 h_old = h_new;
                 if (it >= k.newton_limit) {
@@ -161,12 +205,26 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                     const int slot = atomicAdd(&status->nfail, 1);
                     fail_list[slot] = (uint32_t)j;
                     h_out[j] = CUDART_NAN;
+                    if (omega_out) omega_out[j] = CUDART_NAN;
                     if (iters) iters[j] = it;
                     if (code) code[j] = 1;
                     active = false;
                 }
             }
         }
+        __syncwarp();
+    }
+    // lanes whose list overflowed: one more scan at the final h
+    if (__any_sync(SPHB_FULL, need_scan)) {
+        a.hinv = 1.0 / h_fin;
+        a.sumF = a.sumG = 0.0;
+        const float Rj = sphb_radius_of_h(h_fin, g.delta), thr = sphb_thr_of_h(h_fin, g.delta);
+        SphbList L;
+        L.init(ws, lane);
+        auto flush = [&](int n_) { sphb_own_flush(c.posh, ws, lane, n_, a); };
+        sphb_warp_scan<false>(g, ws, lane, need_scan, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
+        flush(L.count());
+        if (need_scan) omega_out[j] = sphb_omega_from_sumG(k, h_fin, a.sumG);
     }
 }
 
@@ -175,7 +233,8 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
 // of the block call it; returns the same value in every thread.
 // ------------------------------------------------------------------------------------------------
 __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, double xj, double yj, double zj,
-                                     double fxj, double fyj, double fzj, double h, double *red /*[SPHB_WARPS]*/)
+                                     double fxj, double fyj, double fzj, double h, double *red /*[2*SPHB_WARPS]*/,
+                                     double *sumG_out = nullptr)
 {
     const SphbScanCtx g = sphb_make_ctx(c);
     const double R = (h > 0.0) ? (2.0 * h * 1.000001 + (double)g.delta) * 1.00001 : (double)CUDART_INF_F;
@@ -185,7 +244,7 @@ __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, 
     const bool fullx = (cxl == 0 && cxh == g.nx - 1);
     const bool fully = fullx && (cyl == 0 && cyh == g.ny - 1);
     const double hinv = 1.0 / h;
-    double sum = 0.0;
+    double sum = 0.0, sumg = 0.0;
     // spans: merge rows when the x range (and the y range) cover the whole axis
     const int nzs = fully ? 1 : (czh - czl + 1);
     const int nys = fullx ? 1 : (cyh - cyl + 1);
@@ -213,25 +272,34 @@ __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, 
                 double f, fp;
                 sphb_m4(q, f, fp);
                 sum += f;
+                sumg += fma(q, fp, 3.0 * f);
             }
         }
     }
     sum = sphb_warp_sum(sum);
+    sumg = sphb_warp_sum(sumg);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = sum;
+        red[SPHB_WARPS + (threadIdx.x >> 5)] = sumg;
+    }
     __syncthreads();
-    double tot = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    double tot = 0.0, totg = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        tot += red[w];
+        totg += red[SPHB_WARPS + w];
+    }
+    if (sumG_out) *sumG_out = totg;
     return k.particle_mass / (SPHB_PI * (h * h * h)) * tot;
 }
 
 // bisection_h, pyfluid.py:123-153 (density at h_a / h_b is re-used instead of recomputed: same value)
 __global__ void __launch_bounds__(SPHB_THREADS)
     k_bisect_h(sphb_cells c, sphb_consts k, const uint32_t *__restrict__ list, long long n_list_arg,
-               double *__restrict__ h_out, int32_t *__restrict__ code, int32_t *__restrict__ oob_out,
-               int indexed_by_slot, sphb_status *__restrict__ status)
+               double *__restrict__ h_out, double *__restrict__ omega_out, int32_t *__restrict__ code,
+               int32_t *__restrict__ oob_out, int indexed_by_slot, sphb_status *__restrict__ status)
 {
-    __shared__ double red[SPHB_WARPS];
+    __shared__ double red[2 * SPHB_WARPS];
     const long long n_list = n_list_arg >= 0 ? n_list_arg : (long long)status->nfail;
     for (long long e = blockIdx.x; e < n_list; e += gridDim.x) {
         const uint32_t j = list[e];
@@ -262,9 +330,16 @@ __global__ void __launch_bounds__(SPHB_THREADS)
             }
             ++i;
         }
+        double om = CUDART_NAN;
+        if (omega_out && res == 1) {   // Omega at the bisection root (algebraic density, like the step)
+            double sg = 0.0;
+            sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, root, red, &sg);
+            om = sphb_omega_from_sumG(k, root, sg);
+        }
         if (threadIdx.x == 0) {
             const long long o = indexed_by_slot ? (long long)j : e;
             h_out[o] = root;
+            if (omega_out) omega_out[o] = om;
             if (code) code[o] = res;
             if (oob_out) oob_out[o] = oob;
             if (oob) atomicAdd(&status->bisect_oob, oob);
@@ -348,32 +423,32 @@ extern "C" int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k,
 }
 
 extern "C" int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, const uint32_t *list, int64_t n_list,
-                             double *h_out, int32_t *code, int32_t *oob, int32_t indexed_by_slot, sphb_status *status,
-                             void *stream)
+                             double *h_out, double *omega_out, int32_t *code, int32_t *oob, int32_t indexed_by_slot,
+                             sphb_status *status, void *stream)
 {
     if (!sphb_cells_ok(cells) || !k || !list || !h_out || !status) return SPHB_E_ARG;
     if (n_list == 0 || cells->n == 0) return SPHB_OK;
     long long blocks = n_list > 0 ? n_list : 296;
     if (blocks > 1184) blocks = 1184;
     k_bisect_h<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, list, (long long)n_list, h_out,
-                                                                           code, oob, indexed_by_slot, status);
+                                                                           omega_out, code, oob, indexed_by_slot, status);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
 
 extern "C" int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target,
-                             const double *h_guess, double *h_out, int32_t *iters, int32_t *code, uint32_t *fail_list,
-                             sphb_status *status, void *stream)
+                             const double *h_guess, double *h_out, double *omega_out, int32_t *iters, int32_t *code,
+                             uint32_t *fail_list, sphb_status *status, void *stream)
 {
     if (!sphb_cells_ok(cells) || !k || !h_guess || !h_out || !fail_list || !status) return SPHB_E_ARG;
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
     SPHB_CUDA(cudaMemsetAsync(&status->nfail, 0, sizeof(int32_t), sphb_stream(stream)));
-    k_newton_h<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out, iters,
-                                                                           code, fail_list, status);
+    k_newton_h<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out, omega_out,
+                                                                           iters, code, fail_list, status);
     SPHB_LAUNCHED();
     // the fallback reads its list length from status->nfail on the device: no host round trip
-    return sphb_bisect_h(cells, k, fail_list, -1, h_out, code, nullptr, 1, status, stream);
+    return sphb_bisect_h(cells, k, fail_list, -1, h_out, omega_out, code, nullptr, 1, status, stream);
 }
 
 extern "C" int sphb_neighbours(const sphb_cells *cells, const uint32_t *query, int64_t n_query, int32_t symmetric,

@@ -180,23 +180,25 @@ class SlabRunner:
         return out
 
     # ---- physics stages -----------------------------------------------------------------------------------
-    def _stage(self, snap, status_ptr):
+    def _stage(self, snap, status_ptr, om_own=None):
         """the six calls of pyfluid.py:502-507 for the owned particles -> acc, dudt (owned order)"""
         e, dg = self.e, snap["dg"]
-        _, _, om_S, _ = e.density_omega(dg, self.consts, target=snap["target"], want_rho=False, want_omega=True)
-        om_L = self._fill_ghosts(snap, self._owned_from_grid(snap, om_S, 1))
+        if om_own is None:
+            _, _, om_S, _ = e.density_omega(dg, self.consts, target=snap["target"], want_rho=False, want_omega=True)
+            om_own = self._owned_from_grid(snap, om_S, 1)
+        om_L = self._fill_ghosts(snap, om_own)
         vel_S = self._to_grid(snap, snap["vel"], 3)
         u_S = self._to_grid(snap, snap["u"], 1)
         _, _, rB, rC = e.eos(dg.posh, vel_S, u_S, self._to_grid(snap, om_L, 1), self.consts, status_ptr)
         acc_S, dudt_S = e.force(dg, self.consts, rB, rC, e.hmax(dg.posh), status_ptr, target=snap["target"])
         return self._owned_from_grid(snap, acc_S, 3), self._owned_from_grid(snap, dudt_S, 1)
 
-    def _newton(self, snap, status_ptr):
+    def _newton(self, snap, status_ptr, want_omega=False):
         e, dg = self.e, snap["dg"]
-        h_S = e.newton(dg, self.consts, dg.posh[:, 3].contiguous(), status_ptr, target=snap["target"])
-        h_own = self._owned_from_grid(snap, h_S, 1)
+        r = e.newton(dg, self.consts, dg.posh[:, 3].contiguous(), status_ptr, target=snap["target"], want_omega=want_omega)
+        h_own = self._owned_from_grid(snap, r[0] if want_omega else r, 1)
         e.check_neg_h(h_own, status_ptr)
-        return h_own
+        return (h_own, self._owned_from_grid(snap, r[1], 1)) if want_omega else h_own
 
     def cold_solve(self, st):
         self.geom = self._global_geom(st["pos"], st["h"])
@@ -223,12 +225,12 @@ class SlabRunner:
         # h_mid
         s1 = self._snapshot(mid, width(st["h"]) * 1.02, ["pos", "h", "vel", "u"])
         w1 = width(st["h"]) * 1.02
-        h_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID))
+        h_mid, om_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID), want_omega=True)
         if 2.0 * self._hmax(h_mid) > w1:
             raise RuntimeError("halo too narrow for the new smoothing lengths; increase SlabRunner(margin=...)")
         h_mid_L = self._fill_ghosts(s1, h_mid)
         e.set_h(s1["dg"], self._to_grid(s1, h_mid_L, 1))
-        acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID))
+        acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID), om_own=om_mid)
         # corrector (owned only, t0 state is still in owned order)
         posh_1, vel_1, u_1 = e.correct(posh0, st["vel"], st["u"], acc1, dudt1, dt, stt.ptr(E.S_CORR))
         new = dict(gid=st["gid"], pos=posh_1[:, :3].contiguous(), h=h_mid, vel=vel_1, u=u_1)

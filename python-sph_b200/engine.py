@@ -92,7 +92,7 @@ def make_consts(k) -> N.Consts:
 
 
 # cell edge = CELL_FACTOR * 2 * mean(h): one cell ~ one support radius of a typical particle
-CELL_FACTOR = 1.0
+CELL_FACTOR = float(__import__('os').environ.get('SPHB_CELL_FACTOR', '0.9'))
 MAX_CELLS_PER_PARTICLE = 8
 
 
@@ -219,23 +219,28 @@ class Engine:
         return rho, dw, om, ng
 
     # -- K3 ------------------------------------------------------------------------------------
-    def newton(self, dg, consts, h_guess, status_ptr, target=None, details=False):
+    def newton(self, dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False):
+        """-> h (, iters, code) (, omega at the returned h when want_omega)"""
         n = dg.n
+        om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
         h = torch.full((n,), float("nan"), dtype=F64, device=self.device) if target is not None else \
             torch.empty(n, dtype=F64, device=self.device)
         it = torch.zeros(n, dtype=torch.int32, device=self.device) if details else None
         code = torch.zeros(n, dtype=torch.int32, device=self.device) if details else None
         fail = torch.empty(n, dtype=torch.int32, device=self.device)
-        self._run("newton_h", self.lib.sphb_newton_h, dg.cells(), C.byref(consts), _ptr(target), _ptr(h_guess), _ptr(h), _ptr(it), _ptr(code),
+        self._run("newton_h", self.lib.sphb_newton_h, dg.cells(), C.byref(consts), _ptr(target), _ptr(h_guess), _ptr(h), _ptr(om), _ptr(it), _ptr(code),
                                        _ptr(fail), status_ptr, _stream())
-        return (h, it, code) if details else h
+        out = (h, it, code) if details else (h,)
+        if want_omega:
+            out = out + (om,)
+        return out if len(out) > 1 else out[0]
 
     def bisect(self, dg, consts, slots, status_ptr):
         m = slots.shape[0]
         h = torch.empty(m, dtype=F64, device=self.device)
         code = torch.empty(m, dtype=torch.int32, device=self.device)
         oob = torch.empty(m, dtype=torch.int32, device=self.device)
-        self._run("bisect_h", self.lib.sphb_bisect_h, dg.cells(), C.byref(consts), _ptr(slots), m, _ptr(h), _ptr(code), _ptr(oob), 0,
+        self._run("bisect_h", self.lib.sphb_bisect_h, dg.cells(), C.byref(consts), _ptr(slots), m, _ptr(h), None, _ptr(code), _ptr(oob), 0,
                                        status_ptr, _stream())
         return h, code, oob
 
@@ -375,18 +380,20 @@ class Stepper:
         # State stays in CALLER order between stages; every cell list is built from caller-order positions, so
         # ties inside a cell are always broken by the caller index and every sum has one fixed order (the
         # multi-GPU runner does the same with global ids: k-rank results equal 1-rank results bit for bit).
-        def stage(dg, vel_c, u_c, sidx):
-            """the six calls at pyfluid.py:502-507 / :517-522 -> acc, dudt in caller order"""
-            _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
+        def stage(dg, vel_c, u_c, sidx, om=None):
+            """the six calls at pyfluid.py:502-507 / :517-522 -> acc, dudt in caller order
+            (om: Omega already produced by the Newton kernel for this snapshot)"""
+            if om is None:
+                _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
             _, _, rB, rC = e.eos(dg.posh, e.gather(vel_c, dg.perm, 3), e.gather(u_c, dg.perm, 1), om, consts, st.ptr(sidx))
             acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx))
             return e.scatter(acc, dg.perm, 3), e.scatter(dudt, dg.perm, 1)
 
-        def solve_h(dg, sidx):
-            """newton_smoothlength_arr(pos, guess = the h carried in the snapshot), caller order"""
-            h_s = e.newton(dg, consts, dg.posh[:, 3].contiguous(), st.ptr(sidx))
-            e.check_neg_h(h_s, st.ptr(sidx))
-            return h_s
+        def solve_h(dg, sidx, want_omega=False):
+            """newton_smoothlength_arr(pos, guess = the h carried in the snapshot), grid order"""
+            r = e.newton(dg, consts, dg.posh[:, 3].contiguous(), st.ptr(sidx), want_omega=want_omega)
+            e.check_neg_h(r[0] if want_omega else r, st.ptr(sidx))
+            return r
 
         # ---- stage 0 at (pos0, h0): pyfluid.py:502-507 ------------------------------------------
         g0 = e.build(posh0, grid, delta)
@@ -395,9 +402,9 @@ class Stepper:
         posh_m, vel_m, u_m = e.predict(posh0, vel0, u0, acc0, dudt0, dt, st.ptr(S_PRED))
         # ---- h_mid = newton(pos_mid, h0), stage mid: pyfluid.py:516-522 -------------------------------
         g1 = e.build(posh_m, grid, delta)
-        h_mid_s = solve_h(g1, S_NEWTON_MID)
+        h_mid_s, om_mid = solve_h(g1, S_NEWTON_MID, want_omega=True)
         e.set_h(g1, h_mid_s)
-        acc1, dudt1 = stage(g1, vel_m, u_m, S_STAGE_MID)
+        acc1, dudt1 = stage(g1, vel_m, u_m, S_STAGE_MID, om=om_mid)
         h_mid = e.scatter(h_mid_s, g1.perm, 1)
         # ---- corrector: pyfluid.py:524-528 ---------------------------------------------------------------
         posh_1, vel1, u1 = e.correct(posh0, vel0, u0, acc1, dudt1, dt, st.ptr(S_CORR))

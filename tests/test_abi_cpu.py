@@ -69,7 +69,7 @@ def test_product_never_imports_oracle():
 
 def test_choose_grid():
     import engine
-    g, delta = engine.choose_grid([0, 0, 0], [10, 5, 0], 0.5, 1000)
+    g, delta = engine.choose_grid([0, 0, 0], [10, 5, 0], 0.5, 1000, cell=1.0)
     assert g.cell == 1.0 and g.nz == 3 and g.nx == 13 and g.ny == 8
     assert g.ox == -1.0 and delta > 0
     # cell count is capped relative to n

@@ -364,3 +364,24 @@ def test_golden_P_pair_functions(sph, golden):
         else:
             assert vrel(a, acc_ref) < RTOL or np.abs(acc_ref).max() == 0.0
     assert (g["P_Pi"] > 0).any() and (g["P_Pi"] == 0).any()
+
+
+@pytest.mark.parametrize("guess", [0.8, 0.45, 1.15])
+def test_newton_fused_omega(sph, orc, guess):
+    """Omega returned by the Newton kernel (one more pass over the converged iteration's neighbour list, or the
+    bisection kernel's own sum) equals omega_arr at the solved h"""
+    import torch
+    import engine as E
+    n = 3000
+    pos, vel, e, L = uniform_cloud(n, 41)
+    eng = sph._eng()
+    dg = sph._grid_and_order(eng, torch.from_numpy(pos).cuda(), torch.full((n,), guess, dtype=torch.float64, device="cuda"))
+    st = E.Status(1, eng.device)
+    h_s, om_s = eng.newton(dg, sph._consts(), dg.posh[:, 3].contiguous(), st.ptr(0), want_omega=True)
+    h = eng.scatter(h_s, dg.perm, 1).cpu().numpy()
+    om = eng.scatter(om_s, dg.perm, 1).cpu().numpy()
+    assert rel(h, orc.newton_smoothlength_arr(pos, np.full(n, guess))) < RTOL
+    ok = np.isfinite(h)
+    rho = orc.var_density_arr(h[ok])
+    om_ref = orc.omega_j(np.flatnonzero(ok), pos, rho, h[ok])
+    assert rel(om[ok], om_ref) < RTOL
