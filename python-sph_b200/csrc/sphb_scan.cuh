@@ -31,7 +31,6 @@
 
 struct SphbWarpShared {
     float4 tile[32];      // x', y', z', |c'|^2 of the staged candidates (NaN-padded)
-    float tthr[32];       // SYM: the candidates' own squared support thresholds
     uint32_t segbase[32]; // first sorted slot of each live segment
     uint16_t list[SPHB_LIST * 32];
 };
@@ -223,15 +222,24 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                     for (uint32_t t = t0; t < t1; t += 32) {
                         const uint32_t ci = t + lane;
                         float4 rec = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
+                        float wthr = 0.f;
                         if (ci < t1) {
                             const float4 f = __ldg(g.frec + ci);
                             rec.x = f.x - ox;
                             rec.y = f.y - oy;
                             rec.z = f.z - oz;
                             rec.w = fmaf(rec.z, rec.z, fmaf(rec.y, rec.y, rec.x * rec.x));
-                            if (SYM) ws.tthr[lane] = f.w;
+                            wthr = f.w;
                         }
                         ws.tile[lane] = rec;
+                        // SYM: the candidates' own supports enter through the largest threshold of the tile (one
+                        // warp reduction per 32 candidates instead of a load + max per candidate; thresholds are
+                        // non-negative floats, so their bit patterns order like integers)
+                        float th = thrp;
+                        if (SYM) {
+                            const float ttile = __int_as_float(__reduce_max_sync(SPHB_FULL, __float_as_int(wthr)));
+                            th = fmaxf(thrp, ttile + offp);
+                        }
                         __syncwarp();
                         const int nt = (int)((t1 - t) < 32u ? (t1 - t) : 32u);
                         for (int c0 = 0; c0 < nt; c0 += SPHB_SUB) {
@@ -241,21 +249,15 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                             }
                             // all loads of the sub-tile first (independent LDS.128), then the tests
                             float4 f[SPHB_SUB];
-                            float tq[SPHB_SUB];
 #pragma unroll
-                            for (int c = 0; c < SPHB_SUB; ++c) {
-                                f[c] = ws.tile[c0 + c];
-                                if (SYM) tq[c] = ws.tthr[c0 + c];
-                            }
+                            for (int c = 0; c < SPHB_SUB; ++c) f[c] = ws.tile[c0 + c];
                             float sv[SPHB_SUB];
 #pragma unroll
                             for (int c = 0; c < SPHB_SUB; ++c)
                                 sv[c] = fmaf(f[c].x, m2x, fmaf(f[c].y, m2y, fmaf(f[c].z, m2z, f[c].w)));
 #pragma unroll
-                            for (int c = 0; c < SPHB_SUB; ++c) {
-                                const float th = SYM ? fmaxf(thrp, tq[c] + offp) : thrp;
+                            for (int c = 0; c < SPHB_SUB; ++c)
                                 if (sv[c] <= th) L.push(code + c);
-                            }
                             code += SPHB_SUB;
                         }
                         __syncwarp();
