@@ -55,31 +55,31 @@ class HaloExchanger:
 
     def plan(self, x_owned, width):
         """indices (into the owned arrays) to send to every other rank: everything within `width` of its slab"""
-        self.send_idx = []
-        for q in range(self.world):
-            if q == self.rank:
-                self.send_idx.append(torch.empty(0, dtype=torch.int64, device=x_owned.device))
-                continue
-            m = (x_owned >= self.cuts[q] - width) & (x_owned < self.cuts[q + 1] + width)
-            self.send_idx.append(torch.nonzero(m).flatten())
-        self._counts(x_owned.device)
+        lo = torch.tensor([c - width for c in self.cuts[:-1]], dtype=x_owned.dtype, device=x_owned.device)
+        hi = torch.tensor([c + width for c in self.cuts[1:]], dtype=x_owned.dtype, device=x_owned.device)
+        m = (x_owned[None, :] >= lo[:, None]) & (x_owned[None, :] < hi[:, None])   # (world, n_owned)
+        m[self.rank] = False
+        self._from_mask(m)
         return self
 
     def plan_migration(self, x_owned):
         own = self.owner_of(x_owned)
-        self.send_idx = [torch.nonzero(own == q).flatten() if q != self.rank
-                         else torch.empty(0, dtype=torch.int64, device=x_owned.device) for q in range(self.world)]
-        self.stay = torch.nonzero(own == self.rank).flatten()
-        self._counts(x_owned.device)
+        q = torch.arange(self.world, device=x_owned.device)
+        m = own[None, :] == q[:, None]
+        self.stay = torch.nonzero(m[self.rank]).flatten()
+        m[self.rank] = False
+        self._from_mask(m)
         return self
 
-    def _counts(self, device):
-        send = torch.tensor([int(i.numel()) for i in self.send_idx], dtype=torch.int64, device=device)
+    def _from_mask(self, m):
+        """send lists from a (world, n_owned) membership mask: destination-major, owned order within a destination;
+        one count exchange, one D2H of 2*world integers"""
+        send = m.sum(dim=1)
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, group=self.group)
-        self.send_counts = send.tolist()
-        self.recv_counts = recv.tolist()
-        self.all_idx = torch.cat(self.send_idx) if self.world > 1 else self.send_idx[0]
+        self.all_idx = torch.nonzero(m)[:, 1].contiguous()   # row-major: sorted by destination, then owned index
+        both = torch.stack([send, recv]).tolist()
+        self.send_counts, self.recv_counts = both[0], both[1]
 
     @property
     def n_recv(self):
@@ -111,7 +111,8 @@ class SlabRunner:
         self.dev = eng.device
         self.statuses = []
         self.geom = None
-        self.h_width_factor = 1.0
+        self._hmax_t = None      # device scalar: global max h after the last solve (all-reduced, read lazily)
+        self._halo_viol = None   # device flag: a solved h outgrew the halo it was computed with
 
     # ---- setup -------------------------------------------------------------------------------------
     def scatter_initial(self, w):
@@ -141,6 +142,17 @@ class SlabRunner:
         t = h.max().reshape(1).clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def _post_hmax(self, h):
+        """start the all-reduce of max(h); the value is only read (one tiny D2H) when the next step needs it"""
+        t = h.max().reshape(1).clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self._hmax_t = t
+
+    def _note_halo(self, h_new, width):
+        """device-side check that the halo a solve ran with still covers 2 h_new (reported by check_status)"""
+        bad = (2.0 * h_new.max() > width).to(torch.int32).reshape(1)
+        self._halo_viol = bad if self._halo_viol is None else torch.maximum(self._halo_viol, bad)
 
     # ---- one snapshot: ghosts + cell list ------------------------------------------------------------
     def _snapshot(self, st, width, fields):
@@ -209,25 +221,27 @@ class SlabRunner:
         st["h"] = self._newton(snap, stt.ptr(0))
         self.statuses.append(stt)
         self.geom = self._global_geom(st["pos"], st["h"])
+        self._post_hmax(st["h"])
         return st
 
     def step(self, st, dt):
         e = self.e
         stt = E.Status(E.S_COUNT, self.dev)
-        width = lambda h: 2.0 * self._hmax(h) * (1.0 + self.margin) + 4.0 * self.geom[1]
+        if self._hmax_t is None:
+            self._post_hmax(st["h"])
+        w0 = 2.0 * float(self._hmax_t.item()) * (1.0 + self.margin) + 4.0 * self.geom[1]   # one scalar D2H per step
+        w1, w2 = w0 * 1.02, w0 * 1.04
         # stage 0
-        s0 = self._snapshot(st, width(st["h"]), ["pos", "h", "vel", "u"])
+        s0 = self._snapshot(st, w0, ["pos", "h", "vel", "u"])
         acc0, dudt0 = self._stage(s0, stt.ptr(E.S_STAGE0))
         # predictor (owned only)
         posh0 = e.pack_posh(st["pos"], st["h"])
         posh_m, vel_m, u_m = e.predict(posh0, st["vel"], st["u"], acc0, dudt0, dt, stt.ptr(E.S_PRED))
         mid = dict(gid=st["gid"], pos=posh_m[:, :3].contiguous(), h=st["h"], vel=vel_m, u=u_m)
         # h_mid
-        s1 = self._snapshot(mid, width(st["h"]) * 1.02, ["pos", "h", "vel", "u"])
-        w1 = width(st["h"]) * 1.02
+        s1 = self._snapshot(mid, w1, ["pos", "h", "vel", "u"])
         h_mid, om_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID), want_omega=True)
-        if 2.0 * self._hmax(h_mid) > w1:
-            raise RuntimeError("halo too narrow for the new smoothing lengths; increase SlabRunner(margin=...)")
+        self._note_halo(h_mid, w1)
         h_mid_L = self._fill_ghosts(s1, h_mid)
         e.set_h(s1["dg"], self._to_grid(s1, h_mid_L, 1))
         acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID), om_own=om_mid)
@@ -236,8 +250,9 @@ class SlabRunner:
         new = dict(gid=st["gid"], pos=posh_1[:, :3].contiguous(), h=h_mid, vel=vel_1, u=u_1)
         # migration, then h1
         new = self._migrate(new)
-        s2 = self._snapshot(new, width(new["h"]) * 1.02, ["pos", "h"])
+        s2 = self._snapshot(new, w2, ["pos", "h"])
         new["h"] = self._newton(s2, stt.ptr(E.S_NEWTON_1))
+        self._post_hmax(new["h"])
         self.statuses.append(stt)
         return new
 
@@ -265,6 +280,12 @@ class SlabRunner:
         for t in allr[1:]:
             tot[:, 0] |= t[:, 0]
             tot[:, 1:] += t[:, 1:]
+        if self._halo_viol is not None:
+            v = self._halo_viol.clone()
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            self._halo_viol = None
+            if int(v.item()):
+                raise RuntimeError("halo too narrow for the new smoothing lengths; increase SlabRunner(margin=...)")
         E.raise_for_status(tot.cpu().numpy(), printer=printer)
 
     def gather_state(self, st):
@@ -282,21 +303,31 @@ class SlabRunner:
         return dict(pos=allp[:, 1:4].contiguous(), h=allp[:, 4].contiguous(), vel=allp[:, 5:8].contiguous(), u=allp[:, 8].contiguous())
 
     def e2e(self, st, dt, steps):
-        """public-API-style step with host buffers on every rank: H2D of the owned state, step, D2H"""
+        """public-API-style step with HOST buffers on every rank: H2D of the owned state from pinned memory, step,
+        D2H of the result into pinned memory, every step (buffers have 10 % headroom for migration)"""
         import time
-        host = {k: v.cpu().pin_memory() for k, v in st.items()}
-        nb = sum(v.numel() * v.element_size() for v in host.values())
+        n0 = st["gid"].numel()
+        cap = int(n0 * 1.1) + 1024
+        pinned = {k: torch.empty((cap,) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in st.items()}
+        for k, v in st.items():
+            pinned[k][:n0].copy_(v)
+        n = n0
+        nbytes = 0
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
-            d = {k: v.to(self.dev, non_blocking=True) for k, v in host.items()}
+            d = {k: v[:n].to(self.dev, non_blocking=True) for k, v in pinned.items()}
+            nbytes += sum(v.numel() * v.element_size() for v in d.values())
             r = self.step(d, dt)
-            host = {k: v.cpu() for k, v in r.items()}
+            n = r["gid"].numel()
+            assert n <= cap, "migration exceeded the host buffer headroom"
+            for k, v in r.items():
+                pinned[k][:n].copy_(v, non_blocking=True)
             torch.cuda.synchronize()
         dist.barrier()
         el = torch.tensor([time.perf_counter() - t0], dtype=F64, device=self.dev)
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        tot = torch.tensor([float(nb)], dtype=F64, device=self.dev)
+        tot = torch.tensor([float(nbytes) / steps], dtype=F64, device=self.dev)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         return {"value": self.n_total * steps / float(el.item()), "unit": "particle-steps/s",
                 "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(tot.item()), "steps": steps}
