@@ -8,8 +8,11 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsphb200.so")
 SOURCES = ["sphb_grid.cu", "sphb_gather.cu", "sphb_force.cu"]
 HEADERS = ["sphb_common.cuh", "sphb_scan.cuh", os.path.join("..", "..", "include", "sphb200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared"]
+# -fmad=false: only the fma() calls written in the sources are fused.  Implicit contraction would let two inlined
+# copies of the same pair function (list drained inside the scan / after it, even / odd unrolled slot) round
+# differently, and per-particle sums would then depend on how targets are chunked into warps and ranks.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-shared"]
 
 
 def stale():

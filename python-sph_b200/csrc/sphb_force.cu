@@ -64,7 +64,44 @@ struct SphbForceAcc {
     double rhoj, csj, hinvj, gj;
     double ax, ay, az, dens, visc;
     int negpi;
+#ifdef SPHB_DEBUG_FORCE
+    long long jslot;
+#endif
 };
+
+#ifdef SPHB_DEBUG_FORCE
+// debug aid (not built by default): record the contributing candidates of one target slot, in evaluation order
+__device__ long long g_dbg_target = -1;
+__device__ int g_dbg_count = 0;
+__device__ uint32_t g_dbg_list[4096];
+__device__ double g_dbg_val[4096];
+extern "C" int sphb_debug_force_set(long long t)
+{
+    int z = 0;
+    cudaMemcpyToSymbol(g_dbg_target, &t, sizeof(t));
+    cudaMemcpyToSymbol(g_dbg_count, &z, sizeof(z));
+    return 0;
+}
+extern "C" int sphb_debug_force_get(uint32_t *list_host, double *val_host)
+{
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_dbg_count, sizeof(n));
+    cudaMemcpyFromSymbol(list_host, g_dbg_list, sizeof(uint32_t) * 4096);
+    cudaMemcpyFromSymbol(val_host, g_dbg_val, sizeof(double) * 4096);
+    return n;
+}
+#define SPHB_DBG(jslot, islot, v)                                   \
+    if ((long long)(jslot) == g_dbg_target) {                       \
+        const int p_ = atomicAdd(&g_dbg_count, 1);                  \
+        if (p_ < 4096) {                                            \
+            g_dbg_list[p_] = (islot);                               \
+            g_dbg_val[p_] = (v);                                    \
+        }                                                           \
+    }
+#else
+#define SPHB_DBG(jslot, islot, v)
+#endif
 
 // one pair, given the candidate's position record; the other two records are only fetched for real pairs
 __device__ __forceinline__ void sphb_force_pair(const double *recB, const double *recC, uint32_t i, double x, double y,
@@ -100,6 +137,7 @@ __device__ __forceinline__ void sphb_force_pair(const double *recB, const double
         pi_half = 0.5 * pi;
     }
     const double coef = fma(a.Aj, sj, fma(Ai, si, pi_half * sm));
+    SPHB_DBG(a.jslot, i, coef * dx);
     a.ax = fma(-coef, dx, a.ax);
     a.ay = fma(-coef, dy, a.ay);
     a.az = fma(-coef, dz, a.az);
@@ -166,6 +204,9 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     }
     a.ax = a.ay = a.az = a.dens = a.visc = 0.0;
     a.negpi = 0;
+#ifdef SPHB_DEBUG_FORCE
+    a.jslot = tgt ? j : -2;
+#endif
     const float Rj = sphb_radius_of_h(a.hj, g.delta), thr = f.w;
     const float RH = sphb_radius_of_h((double)hmax_global[0], g.delta);
     SphbList L;

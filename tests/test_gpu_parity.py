@@ -385,3 +385,53 @@ def test_newton_fused_omega(sph, orc, guess):
     rho = orc.var_density_arr(h[ok])
     om_ref = orc.omega_j(np.flatnonzero(ok), pos, rho, h[ok])
     assert rel(om[ok], om_ref) < RTOL
+
+
+def test_sums_do_not_depend_on_warp_chunking(sph):
+    """every per-particle sum has ONE order and ONE rounding: prepending far-away particles (which shifts how
+    targets fall into warps) or masking targets must not change a single bit of rho, Omega, a, du/dt.
+    This is what makes k-rank runs bit-identical to 1-rank runs."""
+    import torch
+    import engine as E
+    import workloads
+    eng = sph._eng()
+    w = workloads.sod_tube(48)
+    sph.PARTICLE_MASS = w["m"]
+    try:
+        c = sph._consts()
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        pos, vel, u = to(w["pos"]), to(w["vel"]), to(w["u"])
+        h0 = to(w["h_guess"] * 1.0843)
+        lo, hi, hmax, hmean = eng.bounds(eng.pack_posh(pos, h0))
+        grid, delta = E.choose_grid(lo, hi, hmean, pos.shape[0])
+
+        def run(shift=0, mask_every=0):
+            p, hh, vv, uu = pos, h0, vel, u
+            if shift:
+                far = torch.full((shift, 3), -10.0, dtype=torch.float64, device="cuda")
+                far += torch.arange(shift, device="cuda", dtype=torch.float64)[:, None] * 1e-3
+                p = torch.cat([far, p]); hh = torch.cat([h0[:shift], hh]); vv = torch.cat([vel[:shift] * 0, vv]); uu = torch.cat([u[:shift], uu])
+            dg = eng.build(eng.pack_posh(p, hh), grid, delta)
+            st = E.Status(1, eng.device)
+            tgt = None
+            if mask_every:
+                tgt = torch.ones(p.shape[0], dtype=torch.uint8, device="cuda")
+                tgt[::mask_every] = 0
+                tgt = tgt[dg.perm.long()].contiguous()
+            rho, _, om, _ = eng.density_omega(dg, c, target=tgt, want_rho=True, want_omega=True)
+            _, _, om_all, _ = eng.density_omega(dg, c, want_rho=False, want_omega=True)
+            _, _, rB, rC = eng.eos(dg.posh, eng.gather(vv, dg.perm, 3), eng.gather(uu, dg.perm, 1), om_all, c, st.ptr(0))
+            acc, dudt = eng.force(dg, c, rB, rC, eng.hmax(dg.posh), st.ptr(0), target=tgt)
+            hs, oms = eng.newton(dg, c, dg.posh[:, 3].contiguous(), st.ptr(0), target=tgt, want_omega=True)
+            return [eng.scatter(x, dg.perm, k)[shift:] for x, k in ((acc, 3), (dudt, 1), (rho, 1), (om, 1), (hs, 1), (oms, 1))]
+
+        ref = run()
+        for shift, me in ((5, 0), (17, 0), (0, 3)):
+            got = run(shift, me)
+            keep = torch.ones(pos.shape[0], dtype=torch.bool, device="cuda")
+            if me:
+                keep[::me] = False
+            for name, a, b in zip(("acc", "dudt", "rho", "omega", "h", "omega_fused"), ref, got):
+                assert torch.equal(a[keep], b[keep]), (name, shift, me)
+    finally:
+        sph.PARTICLE_MASS = 1
