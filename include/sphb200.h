@@ -104,9 +104,10 @@ int64_t sphb_grid_workspace_bytes(int64_t n, const sphb_grid *g);
 /* pack caller-order AoS (pos (n,3), h (n)) into posh (n,4) */
 int sphb_pack_posh(const double *pos, const double *h, int64_t n, double *posh, void *stream);
 /* Sort `posh_in` (any order) into grid order.  Outputs: perm[s] = index into posh_in of sorted
- * slot s (stable: ties in cell id keep ascending input index), cell_start, cell_hmax, cell_id,
- * posh_sorted, frec_sorted.  delta = fp32 position error bound to bake into frec.w. */
-int sphb_grid_build(const double *posh_in, int64_t n, const sphb_grid *g, float delta, uint32_t *perm,
+ * slot s, cell_start, cell_hmax, cell_id, posh_sorted, frec_sorted.  Ties in cell id are ordered by
+ * ascending tie_key[input index] (unique keys, e.g. global particle ids), or by ascending input index when
+ * tie_key is NULL (stable sort).  delta = fp32 position error bound to bake into frec.w. */
+int sphb_grid_build(const double *posh_in, const int64_t *tie_key, int64_t n, const sphb_grid *g, float delta, uint32_t *perm,
                     uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id, double *posh_sorted,
                     float *frec_sorted, void *workspace, int64_t workspace_bytes, void *stream);
 /* refresh h in posh/frec/cell_hmax of an existing grid (positions unchanged) */

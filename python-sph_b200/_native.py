@@ -63,7 +63,7 @@ SIGNATURES = {
     "sphb_grid_ncell": (I64, [C.POINTER(Grid)]),
     "sphb_grid_workspace_bytes": (I64, [I64, C.POINTER(Grid)]),
     "sphb_pack_posh": (C.c_int, [P, P, I64, P, P]),
-    "sphb_grid_build": (C.c_int, [P, I64, C.POINTER(Grid), C.c_float, P, P, P, P, P, P, P, I64, P]),
+    "sphb_grid_build": (C.c_int, [P, P, I64, C.POINTER(Grid), C.c_float, P, P, P, P, P, P, P, I64, P]),
     "sphb_grid_set_h": (C.c_int, [P, I64, C.POINTER(Grid), C.c_float, P, P, P, P, P]),
     "sphb_gather_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_scatter_f64": (C.c_int, [P, P, I64, I32, P, P]),

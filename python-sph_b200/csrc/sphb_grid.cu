@@ -211,7 +211,8 @@ __device__ __forceinline__ void sphb_emit_records(const double *__restrict__ pos
 }
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-    k_cell_finish(const double *__restrict__ posh_in, sphb_grid g, long long ncell, float delta,
+    k_cell_finish(const double *__restrict__ posh_in, const long long *__restrict__ tie_key, sphb_grid g, long long ncell,
+                  float delta,
                   const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ perm_tmp,
                   uint32_t *__restrict__ perm, uint32_t *__restrict__ cell_id, float *__restrict__ cell_hmax,
                   double *__restrict__ posh, float *__restrict__ frec)
@@ -228,17 +229,22 @@ __global__ void __launch_bounds__(FIN_WARPS * 32)
     }
     if (cnt <= 32) {
         const uint32_t v = lane < cnt ? perm_tmp[s + lane] : 0xffffffffu;
+        const long long key = (lane < cnt) ? (tie_key ? tie_key[v] : (long long)v) : 0x7fffffffffffffffll;
         uint32_t rank = 0;
         for (uint32_t k = 0; k < cnt; ++k) {
-            const uint32_t o = __shfl_sync(SPHB_FULL, v, k);
-            rank += (o < v) ? 1u : 0u;
+            const long long o = __shfl_sync(SPHB_FULL, key, k);
+            rank += (o < key) ? 1u : 0u;
         }
         if (lane < cnt) sphb_emit_records(posh_in, v, s + rank, g, delta, (uint32_t)cell, perm, cell_id, posh, frec, hm);
     } else if (cnt <= FIN_SORT_MAX) {
         for (uint32_t a = lane; a < cnt; a += 32) {
             const uint32_t v = perm_tmp[s + a];
+            const long long key = tie_key ? tie_key[v] : (long long)v;
             uint32_t rank = 0;
-            for (uint32_t k = 0; k < cnt; ++k) rank += (perm_tmp[s + k] < v) ? 1u : 0u;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const uint32_t o = perm_tmp[s + k];
+                rank += ((tie_key ? tie_key[o] : (long long)o) < key) ? 1u : 0u;
+            }
             sphb_emit_records(posh_in, v, s + rank, g, delta, (uint32_t)cell, perm, cell_id, posh, frec, hm);
         }
     } else {
@@ -303,7 +309,8 @@ extern "C" int sphb_pack_posh(const double *pos, const double *h, int64_t n, dou
     return SPHB_OK;
 }
 
-extern "C" int sphb_grid_build(const double *posh_in, int64_t n, const sphb_grid *g, float delta, uint32_t *perm,
+extern "C" int sphb_grid_build(const double *posh_in, const int64_t *tie_key, int64_t n, const sphb_grid *g, float delta,
+                               uint32_t *perm,
                                uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id, double *posh_sorted,
                                float *frec_sorted, void *workspace, int64_t workspace_bytes, void *stream)
 {
@@ -340,7 +347,8 @@ extern "C" int sphb_grid_build(const double *posh_in, int64_t n, const sphb_grid
         k_cell_scatter<<<nblk(n, 256), 256, 0, st>>>(cell_tmp, n, cell_start, cursor, perm_tmp);
         SPHB_LAUNCHED();
     }
-    k_cell_finish<<<nblk(ncell, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(posh_in, *g, ncell, delta, cell_start, perm_tmp,
+    k_cell_finish<<<nblk(ncell, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(posh_in, (const long long *)tie_key, *g, ncell, delta,
+                                                                     cell_start, perm_tmp,
                                                                      perm, cell_id, cell_hmax, posh_sorted, frec_sorted);
     SPHB_LAUNCHED();
     return SPHB_OK;

@@ -106,8 +106,9 @@ class HaloExchanger:
 class SlabRunner:
     """var_smoothlength_leapfrog on a slab-decomposed particle set (one rank per GPU)."""
 
-    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05):
+    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05, balance=True):
         self.e, self.consts, self.world, self.rank, self.margin = eng, consts, world, rank, margin
+        self.balance = balance
         self.dev = eng.device
         self.statuses = []
         self.geom = None
@@ -156,40 +157,30 @@ class SlabRunner:
 
     # ---- one snapshot: ghosts + cell list ------------------------------------------------------------
     def _snapshot(self, st, width, fields):
-        """exchange ghosts of `fields` (names in st), build the cell list over owned+ghost sorted by global id.
-        returns a dict with the grid, index maps and the local (gid-sorted) arrays."""
+        """exchange ghosts of `fields` (names in st) and build the cell list over [owned..., ghosts...]; ties inside a
+        cell are broken by global particle id, so the neighbour order does not depend on the decomposition."""
         hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width)
         recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in fields])
-        gid_all = torch.cat([st["gid"], recv[0].to(torch.int64)])
-        order = torch.argsort(gid_all)                       # local order L: ascending global id
         n_own = st["gid"].numel()
-        loc = torch.empty_like(order)
-        loc[order] = torch.arange(order.numel(), device=self.dev)
-        snap = dict(hx=hx, order=order, loc_own=loc[:n_own], loc_ghost=loc[n_own:], n_own=n_own, n_loc=order.numel())
+        gid_all = torch.cat([st["gid"], recv[0].to(torch.int64)])
+        snap = dict(hx=hx, n_own=n_own, n_loc=gid_all.numel())
         for f, g in zip(fields, recv[1:]):
-            snap[f] = torch.cat([st[f], g]).index_select(0, order).contiguous()
-        owned_L = torch.zeros(order.numel(), dtype=torch.uint8, device=self.dev)
-        owned_L[snap["loc_own"]] = 1
+            snap[f] = torch.cat([st[f], g])
         posh = self.e.pack_posh(snap["pos"], snap["h"])
-        dg = self.e.build(posh, *self.geom)
+        dg = self.e.build(posh, *self.geom, tie_key=gid_all)
         snap["dg"] = dg
-        snap["target"] = owned_L.index_select(0, dg.perm.long()).contiguous()   # grid order
+        snap["target"] = (dg.perm < n_own).to(torch.uint8)   # grid order: owned particles are the targets
         return snap
 
     def _to_grid(self, snap, arr_L, ncomp):
         return self.e.gather(arr_L, snap["dg"].perm, ncomp)
 
     def _owned_from_grid(self, snap, arr_S, ncomp):
-        arr_L = self.e.scatter(arr_S, snap["dg"].perm, ncomp)
-        return arr_L.index_select(0, snap["loc_own"]).contiguous()
+        return self.e.scatter(arr_S, snap["dg"].perm, ncomp)[:snap["n_own"]].contiguous()
 
     def _fill_ghosts(self, snap, owned_vals):
-        """owned values (owned order) -> local array L with the ghosts' values fetched from their owners"""
-        g = snap["hx"].exchange([owned_vals])[0]
-        out = torch.empty((snap["n_loc"],) + tuple(owned_vals.shape[1:]), dtype=F64, device=self.dev)
-        out[snap["loc_own"]] = owned_vals
-        out[snap["loc_ghost"]] = g
-        return out
+        """owned values (owned order) -> local array [owned..., ghosts...] with the ghosts' values from their owners"""
+        return torch.cat([owned_vals, snap["hx"].exchange([owned_vals])[0]])
 
     # ---- physics stages -----------------------------------------------------------------------------------
     def _stage(self, snap, status_ptr, om_own=None):
@@ -212,6 +203,34 @@ class SlabRunner:
         e.check_neg_h(h_own, status_ptr)
         return (h_own, self._owned_from_grid(snap, r[1], 1)) if want_omega else h_own
 
+    # cost model of one particle-step, fitted on B200 (profiles/): a fixed part plus the cells its search box
+    # covers; sparse particles (large h on a grid sized for the dense majority) cost ~1.65x a dense one
+    COST_A, COST_B = 5.2, 0.032
+
+    def rebalance(self, st, nbins=16384):
+        """work-balanced cut planes: equalise the summed per-particle cost model between ranks,
+        then migrate.  One all-reduce of a weighted x-histogram."""
+        cell = self.geom[0].cell
+        wgt = self.COST_A + self.COST_B * (4.0 * st["h"] / cell + 1.0) ** 3
+        x = st["pos"][:, 0].contiguous()
+        ext = torch.stack([x.min(), -x.max()])
+        dist.all_reduce(ext, op=dist.ReduceOp.MIN)
+        xlo, xhi = float(ext[0].item()), float(-ext[1].item())
+        span = max(xhi - xlo, 1e-300)
+        b = ((x - xlo) * (nbins / span)).long().clamp_(0, nbins - 1)
+        hist = torch.bincount(b, weights=wgt, minlength=nbins)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        cum = torch.cumsum(hist, 0).cpu()
+        total = float(cum[-1])
+        cuts = [-math.inf]
+        for r in range(1, self.world):
+            k = int(torch.searchsorted(cum, torch.tensor(total * r / self.world, dtype=cum.dtype)).item())
+            # cut at the upper edge of bin k, nudged off any lattice plane by half a bin
+            cuts.append(xlo + (min(k, nbins - 1) + 1) * span / nbins)
+        cuts.append(math.inf)
+        self.cuts = cuts
+        return self._migrate(st)
+
     def cold_solve(self, st):
         self.geom = self._global_geom(st["pos"], st["h"])
         hmax = self._hmax(st["h"])
@@ -221,6 +240,8 @@ class SlabRunner:
         st["h"] = self._newton(snap, stt.ptr(0))
         self.statuses.append(stt)
         self.geom = self._global_geom(st["pos"], st["h"])
+        if self.balance:
+            st = self.rebalance(st)
         self._post_hmax(st["h"])
         return st
 

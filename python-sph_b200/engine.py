@@ -174,13 +174,13 @@ class Engine:
             raise ValueError("non-finite particle positions")
         return choose_grid(lo, hi, hmean if math.isfinite(hmean) and hmean > 0 else hmax, posh.shape[0], cell=cell)
 
-    def build(self, posh_in, grid, delta) -> DeviceGrid:
+    def build(self, posh_in, grid, delta, tie_key=None) -> DeviceGrid:
         n = posh_in.shape[0]
         dg = DeviceGrid(n, grid, delta, self.device)
         need = int(self.lib.sphb_grid_workspace_bytes(n, C.byref(grid)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        self._run("grid_build", self.lib.sphb_grid_build, _ptr(posh_in), n, C.byref(grid), C.c_float(delta), _ptr(dg.perm), _ptr(dg.cell_start),
+        self._run("grid_build", self.lib.sphb_grid_build, _ptr(posh_in), _ptr(tie_key), n, C.byref(grid), C.c_float(delta), _ptr(dg.perm), _ptr(dg.cell_start),
                                          _ptr(dg.cell_hmax), _ptr(dg.cell_id), _ptr(dg.posh), _ptr(dg.frec),
                                          _ptr(self._ws), self._ws.numel(), _stream())
         return dg

@@ -28,6 +28,11 @@ torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 prof = eng.prof_stop()
 kern = sum(v[1] for v in prof.values())
+allk = [None] * world
+dist.all_gather_object(allk, {"rank": rank, "n_own": int(st["gid"].numel()), "kernel_ms": round(kern, 2), "wall_ms": round(wall * 1e3, 2),
+                              "force": round(prof["force"][1], 2), "newton": round(prof["newton_h"][1], 2)})
+if rank == 0:
+    print(json.dumps(allk))
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as p:
     st = r.step(st, w["dt"])
