@@ -106,9 +106,10 @@ class HaloExchanger:
 class SlabRunner:
     """var_smoothlength_leapfrog on a slab-decomposed particle set (one rank per GPU)."""
 
-    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05, balance=True):
+    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05, balance=True, calib_steps=2):
         self.e, self.consts, self.world, self.rank, self.margin = eng, consts, world, rank, margin
         self.balance = balance
+        self.calib_left = calib_steps if balance else 0   # first steps are timed per rank and the cuts re-balanced
         self.dev = eng.device
         self.statuses = []
         self.geom = None
@@ -127,7 +128,7 @@ class SlabRunner:
         self.n_total = len(x)
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a[idx])).to(self.dev)
         return dict(gid=torch.from_numpy(idx.astype(np.int64)).to(self.dev), pos=to(w["pos"]), vel=to(w["vel"]), u=to(w["u"]),
-                    h=to(w["h_guess"]))
+                    h=to(w["h_guess"]), wfac=torch.ones(len(idx), dtype=F64, device=self.dev))
 
     def _global_geom(self, pos, h):
         lo = pos.min(dim=0).values
@@ -211,7 +212,7 @@ class SlabRunner:
         """work-balanced cut planes: equalise the summed per-particle cost model between ranks,
         then migrate.  One all-reduce of a weighted x-histogram."""
         cell = self.geom[0].cell
-        wgt = self.COST_A + self.COST_B * (4.0 * st["h"] / cell + 1.0) ** 3
+        wgt = (self.COST_A + self.COST_B * (4.0 * st["h"] / cell + 1.0) ** 3) * st["wfac"]
         x = st["pos"][:, 0].contiguous()
         ext = torch.stack([x.min(), -x.max()])
         dist.all_reduce(ext, op=dist.ReduceOp.MIN)
@@ -231,6 +232,21 @@ class SlabRunner:
         self.cuts = cuts
         return self._migrate(st)
 
+    def _calibrate(self, st, my_ms):
+        """feedback: scale every owned particle's weight by (measured time / modelled weight) of its rank, normalised
+        over the job, then re-balance (the weight factor travels with the particle)"""
+        cell = self.geom[0].cell
+        w_model = float(((self.COST_A + self.COST_B * (4.0 * st["h"] / cell + 1.0) ** 3) * st["wfac"]).sum().item())
+        v = torch.tensor([my_ms, w_model], dtype=F64, device=self.dev)
+        allv = [torch.empty_like(v) for _ in range(self.world)]
+        dist.all_gather(allv, v)
+        tt = sum(float(a[0]) for a in allv)
+        ww = sum(float(a[1]) for a in allv)
+        fac = (my_ms / max(w_model, 1e-300)) / (tt / max(ww, 1e-300))
+        st = dict(st)
+        st["wfac"] = st["wfac"] * min(max(fac, 0.5), 2.0)
+        return self.rebalance(st)
+
     def cold_solve(self, st):
         self.geom = self._global_geom(st["pos"], st["h"])
         hmax = self._hmax(st["h"])
@@ -246,6 +262,15 @@ class SlabRunner:
         return st
 
     def step(self, st, dt):
+        if self.calib_left > 0 and self.e.prof is None:
+            self.calib_left -= 1
+            self.e.prof_start()
+            new = self._step(st, dt)
+            ms = sum(v[1] for v in self.e.prof_stop().values())
+            return self._calibrate(new, ms)
+        return self._step(st, dt)
+
+    def _step(self, st, dt):
         e = self.e
         stt = E.Status(E.S_COUNT, self.dev)
         if self._hmax_t is None:
@@ -259,6 +284,9 @@ class SlabRunner:
         posh0 = e.pack_posh(st["pos"], st["h"])
         posh_m, vel_m, u_m = e.predict(posh0, st["vel"], st["u"], acc0, dudt0, dt, stt.ptr(E.S_PRED))
         mid = dict(gid=st["gid"], pos=posh_m[:, :3].contiguous(), h=st["h"], vel=vel_m, u=u_m)
+        wfac = st.get("wfac")
+        if wfac is None:
+            wfac = torch.ones_like(st["h"])
         # h_mid
         s1 = self._snapshot(mid, w1, ["pos", "h", "vel", "u"])
         h_mid, om_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID), want_omega=True)
@@ -268,7 +296,7 @@ class SlabRunner:
         acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID), om_own=om_mid)
         # corrector (owned only, t0 state is still in owned order)
         posh_1, vel_1, u_1 = e.correct(posh0, st["vel"], st["u"], acc1, dudt1, dt, stt.ptr(E.S_CORR))
-        new = dict(gid=st["gid"], pos=posh_1[:, :3].contiguous(), h=h_mid, vel=vel_1, u=u_1)
+        new = dict(gid=st["gid"], pos=posh_1[:, :3].contiguous(), h=h_mid, vel=vel_1, u=u_1, wfac=wfac)
         # migration, then h1
         new = self._migrate(new)
         s2 = self._snapshot(new, w2, ["pos", "h"])
@@ -279,7 +307,7 @@ class SlabRunner:
 
     def _migrate(self, st):
         hx = HaloExchanger(self.cuts, self.rank, self.world).plan_migration(st["pos"][:, 0].contiguous())
-        names = ["pos", "h", "vel", "u"]
+        names = ["pos", "h", "vel", "u", "wfac"]
         recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in names])
         out = dict(gid=torch.cat([st["gid"].index_select(0, hx.stay), recv[0].to(torch.int64)]))
         for f, g in zip(names, recv[1:]):
