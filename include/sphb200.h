@@ -59,13 +59,15 @@ typedef struct sphb_consts {
     double gamma;          /* ADIABATIC_INDEX                   :41 */
 } sphb_consts;
 
-/* Uniform cell grid.  Cell of a point: c = clamp(floor((x - origin)/cell), 0, dim-1) per axis,
- * linear id = (cz*ny + cy)*nx + cx.  (The reference has no cell list; SURVEY.md 8(c) "self-oracle".) */
+/* Cell grid: edge `cell` in y and z, edge cell/xdiv in x (x is the fastest axis: finer x cells make the row
+ * spans of a search tighter).  Cell of a point: cx = clamp(floor((x - ox)/(cell/xdiv)), 0, nx-1),
+ * cy = clamp(floor((y - oy)/cell), 0, ny-1), cz likewise; linear id = (cz*ny + cy)*nx + cx.
+ * (The reference has no cell list; SURVEY.md 8(c) "self-oracle".) */
 typedef struct sphb_grid {
     double ox, oy, oz; /* origin */
-    double cell;       /* cell edge */
+    double cell;       /* cell edge in y and z */
     int32_t nx, ny, nz;
-    int32_t pad_;
+    int32_t xdiv;      /* x edge = cell / xdiv; values < 1 mean 1 */
 } sphb_grid;
 
 /* device status block, zeroed by sphb_status_reset */

@@ -29,7 +29,7 @@ class Consts(C.Structure):
 
 class Grid(C.Structure):
     _fields_ = [("ox", C.c_double), ("oy", C.c_double), ("oz", C.c_double), ("cell", C.c_double),
-                ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("pad_", C.c_int32)]
+                ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("xdiv", C.c_int32)]
 
     @property
     def ncell(self):

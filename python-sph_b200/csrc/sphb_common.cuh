@@ -32,6 +32,12 @@ extern long long g_sphb_launches;
 
 static inline cudaStream_t sphb_stream(void *s) { return (cudaStream_t)s; }
 
+// x edge of a cell: cell / xdiv (IEEE division, the same on host and device)
+__host__ __device__ __forceinline__ double sphb_cellx(const sphb_grid &g)
+{
+    return g.cell / (double)(g.xdiv > 0 ? g.xdiv : 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // exact reference geometry (membership tests, pyfluid.py:43-47): d.dot(d) is
 // fma(dz,dz,fma(dy,dy,dx*dx)) on the reference's numpy (tests/golden/make_golden.py self-test)

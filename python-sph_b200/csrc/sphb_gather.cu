@@ -238,7 +238,7 @@ __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, 
 {
     const SphbScanCtx g = sphb_make_ctx(c);
     const double R = (h > 0.0) ? (2.0 * h * 1.000001 + (double)g.delta) * 1.00001 : (double)CUDART_INF_F;
-    const int cxl = sphb_cell_lo(fxj - R, g.inv_cell, g.nx), cxh = sphb_cell_hi(fxj + R, g.inv_cell, g.nx);
+    const int cxl = sphb_cell_lo(fxj - R, g.inv_cellx, g.nx), cxh = sphb_cell_hi(fxj + R, g.inv_cellx, g.nx);
     const int cyl = sphb_cell_lo(fyj - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fyj + R, g.inv_cell, g.ny);
     const int czl = sphb_cell_lo(fzj - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fzj + R, g.inv_cell, g.nz);
     const bool fullx = (cxl == 0 && cxh == g.nx - 1);
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(SPHB_THREADS)
     double hr = hj;
     if (symmetric && hmax_global && !((double)hmax_global[0] <= hr)) hr = (double)hmax_global[0];
     const double R = (hr > 0.0) ? (2.0 * hr * 1.000001 + (double)g.delta) * 1.00001 : (double)CUDART_INF_F;
-    const int cxl = sphb_cell_lo(fj.x - R, g.inv_cell, g.nx), cxh = sphb_cell_hi(fj.x + R, g.inv_cell, g.nx);
+    const int cxl = sphb_cell_lo(fj.x - R, g.inv_cellx, g.nx), cxh = sphb_cell_hi(fj.x + R, g.inv_cellx, g.nx);
     const int cyl = sphb_cell_lo(fj.y - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fj.y + R, g.inv_cell, g.ny);
     const int czl = sphb_cell_lo(fj.z - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fj.z + R, g.inv_cell, g.nz);
     long long total = 0;

@@ -67,7 +67,7 @@ extern "C" int64_t sphb_grid_workspace_bytes(int64_t n, const sphb_grid *g)
 __device__ __forceinline__ uint32_t sphb_cell_of(const sphb_grid &g, double x, double y, double z)
 {
     // c = clamp(floor((x - origin)/cell), 0, dim-1); IEEE subtract and divide, no contraction
-    double cx = floor(__ddiv_rn(__dsub_rn(x, g.ox), g.cell));
+    double cx = floor(__ddiv_rn(__dsub_rn(x, g.ox), sphb_cellx(g)));
     double cy = floor(__ddiv_rn(__dsub_rn(y, g.oy), g.cell));
     double cz = floor(__ddiv_rn(__dsub_rn(z, g.oz), g.cell));
     cx = fmin(fmax(cx, 0.0), (double)(g.nx - 1));   // NaN -> 0

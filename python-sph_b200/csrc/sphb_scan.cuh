@@ -40,7 +40,8 @@ struct SphbScanCtx {
     const float *cell_hmax;
     const float4 *frec;
     int nx, ny, nz;
-    double cell, inv_cell;
+    double cell, inv_cell;     // y,z edge
+    double cellx, inv_cellx;   // x edge = cell / xdiv
     float delta;
 };
 
@@ -55,6 +56,8 @@ __device__ __forceinline__ SphbScanCtx sphb_make_ctx(const sphb_cells &c)
     s.nz = c.grid.nz;
     s.cell = c.grid.cell;
     s.inv_cell = 1.0 / c.grid.cell;
+    s.cellx = sphb_cellx(c.grid);
+    s.inv_cellx = 1.0 / s.cellx;
     s.delta = c.delta;
     return s;
 }
@@ -169,19 +172,19 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                 int lo = 0x7fffffff, hi = -1;
                 if (g2 < Rg * Rg) {
                     const double hx = sqrt(Rg * Rg - g2);   // +inf stays +inf
-                    lo = sphb_cell_lo(xmin - hx, g.inv_cell, g.nx);
-                    hi = sphb_cell_hi(xmax + hx, g.inv_cell, g.nx);
+                    lo = sphb_cell_lo(xmin - hx, g.inv_cellx, g.nx);
+                    hi = sphb_cell_hi(xmax + hx, g.inv_cellx, g.nx);
                 }
                 const size_t rowbase = ((size_t)rz * g.ny + ry) * (size_t)g.nx;
                 if (SYM && g2 < Rw * Rw) {
                     const double hxw = sqrt(Rw * Rw - g2);
-                    const int wl = sphb_cell_lo(xmin - hxw, g.inv_cell, g.nx);
-                    const int wh = sphb_cell_hi(xmax + hxw, g.inv_cell, g.nx);
+                    const int wl = sphb_cell_lo(xmin - hxw, g.inv_cellx, g.nx);
+                    const int wh = sphb_cell_hi(xmax + hxw, g.inv_cellx, g.nx);
                     // extend the tight range outwards to the farthest cell whose h_max reaches the group
                     for (int cx = wl; cx < lo && cx <= wh; ++cx) {
                         const double hm = (double)g.cell_hmax[rowbase + cx];
                         const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
-                        const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cell);
+                        const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cellx);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             lo = cx;
                             if (hi < lo) hi = lo;
@@ -191,7 +194,7 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                     for (int cx = wh; cx > hi && cx >= wl; --cx) {
                         const double hm = (double)g.cell_hmax[rowbase + cx];
                         const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
-                        const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cell);
+                        const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cellx);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             hi = cx;
                             if (lo > hi) lo = hi;

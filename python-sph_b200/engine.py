@@ -91,30 +91,37 @@ def make_consts(k) -> N.Consts:
         float(k["G"]), float(k["ADIABATIC_INDEX"]))
 
 
-# cell edge = CELL_FACTOR * 2 * mean(h): one cell ~ one support radius of a typical particle
+# cell edge (y,z) = CELL_FACTOR * 2 * mean(h): one cell ~ one support radius of a typical particle; x edge = that / XDIV
 CELL_FACTOR = float(__import__('os').environ.get('SPHB_CELL_FACTOR', '0.9'))
+XDIV = int(__import__('os').environ.get('SPHB_XDIV', '1'))
 MAX_CELLS_PER_PARTICLE = 8
 
 
-def choose_grid(lo, hi, h_mean, n, pad_cells=1.0, cell=None):
+def choose_grid(lo, hi, h_mean, n, pad_cells=1.0, cell=None, xdiv=None):
     """Grid geometry from the bounding box [lo, hi] (3-vectors of python floats) and the mean h.
     Outliers are legal (they are clamped into border cells), so the box only affects speed."""
+    xdiv = max(1, int(xdiv if xdiv is not None else XDIV))
     ext = [max(hi[k] - lo[k], 0.0) for k in range(3)]
     if cell is None:
         cell = 2.0 * h_mean * CELL_FACTOR
     if not (cell > 0.0) or not math.isfinite(cell):
         cell = max(max(ext), 1.0)
-    cell = max(cell, max(ext) * 1e-4, 1e-300)   # at most 1e4 cells per axis
+    cell = max(cell, max(ext) * 1e-4, 1e-300)   # at most 1e4 cells per axis (y,z)
     max_cells = max(64, MAX_CELLS_PER_PARTICLE * n)
     while True:
-        dims = [int(math.floor((ext[k] + 2 * pad_cells * cell) / cell)) + 1 for k in range(3)]
+        dims = [int(math.floor((ext[0] + 2 * pad_cells * cell) / (cell / xdiv))) + 1,
+                int(math.floor((ext[1] + 2 * pad_cells * cell) / cell)) + 1,
+                int(math.floor((ext[2] + 2 * pad_cells * cell) / cell)) + 1]
         if dims[0] * dims[1] * dims[2] <= max_cells:
             break
-        cell *= 1.26
-    g = N.Grid(lo[0] - pad_cells * cell, lo[1] - pad_cells * cell, lo[2] - pad_cells * cell, cell, dims[0], dims[1], dims[2], 0)
+        if xdiv > 1:
+            xdiv //= 2
+        else:
+            cell *= 1.26
+    g = N.Grid(lo[0] - pad_cells * cell, lo[1] - pad_cells * cell, lo[2] - pad_cells * cell, cell, dims[0], dims[1], dims[2], xdiv)
     # fp32 positions relative to the origin: |x| <= L  ->  error <= 2^-24 L per coordinate; 4*2^-23*L covers a
     # three-component difference with room; 2x slack for particles that drift outside the box
-    L = max(dims) * cell
+    L = max(dims[0] / xdiv, dims[1], dims[2]) * cell
     delta = 2.0 * 4.0 * 2.0 ** -23 * L
     return g, delta
 

@@ -69,8 +69,8 @@ def test_product_never_imports_oracle():
 
 def test_choose_grid():
     import engine
-    g, delta = engine.choose_grid([0, 0, 0], [10, 5, 0], 0.5, 1000, cell=1.0)
-    assert g.cell == 1.0 and g.nz == 3 and g.nx == 13 and g.ny == 8
+    g, delta = engine.choose_grid([0, 0, 0], [10, 5, 0], 0.5, 1000, cell=1.0, xdiv=2)
+    assert g.cell == 1.0 and g.xdiv == 2 and g.nz == 3 and g.nx == 25 and g.ny == 8
     assert g.ox == -1.0 and delta > 0
     # cell count is capped relative to n
     g2, _ = engine.choose_grid([0, 0, 0], [1000, 1000, 1000], 0.01, 100)
@@ -85,8 +85,8 @@ def test_gridref_stable_sort():
     import gridref
     rng = np.random.default_rng(0)
     pos = rng.random((500, 3)) * 4 - 0.5
-    ids, perm, start = gridref.build(pos, (0, 0, 0), 1.0, (3, 3, 3))
+    ids, perm, start = gridref.build(pos, (0, 0, 0), 1.0, (6, 3, 3), xdiv=2)
     assert start[-1] == 500 and (np.diff(ids[perm]) >= 0).all()
-    for c in range(27):
+    for c in range(54):
         seg = perm[start[c]:start[c + 1]]
         assert (np.diff(seg) > 0).all()

@@ -85,7 +85,7 @@ def test_grid_build_bit_exact(sph, n, seed, planar):
     grid, delta = e.grid_for(posh)
     dg = e.build(posh, grid, delta)
     dims = (grid.nx, grid.ny, grid.nz)
-    ids, perm, start = gridref.build(pos, (grid.ox, grid.oy, grid.oz), grid.cell, dims)
+    ids, perm, start = gridref.build(pos, (grid.ox, grid.oy, grid.oz), grid.cell, dims, grid.xdiv)
     assert (dg.perm.cpu().numpy().astype(np.int64) == perm).all()
     assert (dg.cell_start.cpu().numpy().astype(np.int64) == start).all()
     assert (dg.cell_id.cpu().numpy().astype(np.int64) == ids[perm]).all()
