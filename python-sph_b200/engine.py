@@ -378,7 +378,10 @@ class Stepper:
         self.last_status = None
         self.geom = None   # (grid, delta) reused across steps when set by the caller
 
-    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print):
+    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, omega0=None, want_omega1=False):
+        """omega0 (caller order, optional): Omega(pos0, h0) if the caller already has it -- the time loop does, because
+        the previous step's last Newton kernel returns it (want_omega1=True appends omega1 to the result).  Without
+        it the step computes Omega0 itself, exactly like a stand-alone var_smoothlength_leapfrog call."""
         e = self.e
         st = Status(S_COUNT, e.device)
         posh0 = e.pack_posh(pos0, h0)
@@ -404,7 +407,7 @@ class Stepper:
 
         # ---- stage 0 at (pos0, h0): pyfluid.py:502-507 ------------------------------------------
         g0 = e.build(posh0, grid, delta)
-        acc0, dudt0 = stage(g0, vel0, u0, S_STAGE0)
+        acc0, dudt0 = stage(g0, vel0, u0, S_STAGE0, om=None if omega0 is None else e.gather(omega0, g0.perm, 1))
         # ---- predictor: pyfluid.py:511-515 ---------------------------------------------------------
         posh_m, vel_m, u_m = e.predict(posh0, vel0, u0, acc0, dudt0, dt, st.ptr(S_PRED))
         # ---- h_mid = newton(pos_mid, h0), stage mid: pyfluid.py:516-522 -------------------------------
@@ -418,9 +421,12 @@ class Stepper:
         # ---- h1 = newton(pos1, h_mid): pyfluid.py:530 ------------------------------------------------------
         posh_1 = e.pack_posh(posh_1[:, :3].contiguous(), h_mid)
         g2 = e.build(posh_1, grid, delta)
-        h1 = e.scatter(solve_h(g2, S_NEWTON_1), g2.perm, 1)
+        r = solve_h(g2, S_NEWTON_1, want_omega=want_omega1)
+        h1 = e.scatter(r[0] if want_omega1 else r, g2.perm, 1)
         pos1 = posh_1[:, :3].contiguous()
         self.last_status = st
         if not defer_status:
             raise_for_status(st.read(), printer)
+        if want_omega1:
+            return pos1, vel1, u1, h1, e.scatter(r[1], g2.perm, 1)
         return pos1, vel1, u1, h1

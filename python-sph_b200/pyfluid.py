@@ -436,8 +436,11 @@ def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt):
 
 
 def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlength_approx):
-    """pyfluid.py:535-602: returns (Nt,N,3), (Nt,N,3), (Nt,N), (Nt,N) histories (numpy in -> numpy out)."""
+    """pyfluid.py:535-602: returns (Nt,N,3), (Nt,N,3), (Nt,N), (Nt,N) histories (numpy in -> numpy out).
+    Inside the loop Omega at (pos[t+1], h[t+1]) comes out of step t's last Newton kernel and is handed to step
+    t+1, which would otherwise recompute exactly that sum (pyfluid.py:503); the results are unchanged."""
     _need_G0("var_smoothlength_sim")
+    global _stepper
     io = _IO(positions0, velocities0, energies0, smoothlength_approx)
     dt = float(time_arr[1] - time_arr[0])
     Nt = len(time_arr)
@@ -452,7 +455,12 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
     H = torch.zeros((Nt, N), dtype=torch.float64, device=dev)
     P[0], V[0], E[0] = pos, vel, u
     H[0] = newton_smoothlength_arr(P[0], io.dev64(smoothlength_approx, (-1,)))
+    if _stepper is None:
+        _stepper = _E.Stepper(_eng())
+    om = None
     for t in range(Nt - 1):
         print("time step:", t, "of", Nt)
-        P[t + 1], V[t + 1], E[t + 1], H[t + 1] = var_smoothlength_leapfrog(P[t], V[t], E[t], H[t], dt)
+        P[t + 1], V[t + 1], E[t + 1], H[t + 1], om = _stepper.step(P[t].contiguous(), V[t].contiguous(), E[t].contiguous(),
+                                                                  H[t].contiguous(), dt, _consts(), omega0=om,
+                                                                  want_omega1=True)
     return io.out(P), io.out(V), io.out(E), io.out(H)
