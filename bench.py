@@ -323,8 +323,11 @@ def run_ours(a):
         flops_force = FLOP_FORCE * n_sym
         ach = flops_force / (f_ms * 1e-3) / 1e12
         bytes_force = 104.0 * n_total
+        # DRAM bytes per launch: dram__bytes_read+write of k_force from the committed ncu --set full capture
+        # (profiles/r01_ncu_final_summary.txt: 292.1 MB for 1 990 656 particles), scaled per particle
+        traffic_force = 292.089e6 / 1990656 * n_total
         roof = {"kernel": "k_force", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                "traffic": None, "peak_source": "DFMA microbenchmark in this run (sphb_fp64_peak); not in MEASURED_PEAKS.json",
+                "traffic": traffic_force, "traffic_source": "ncu capture at 1 990 656 particles scaled per particle (profiles/)", "peak_source": "DFMA microbenchmark in this run (sphb_fp64_peak); not in MEASURED_PEAKS.json",
                 "launch_ms": f_ms, "share_of_step": prof["force"][1] / step_ms,
                 "hbm": {"achieved": bytes_force / (f_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_force / (f_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},

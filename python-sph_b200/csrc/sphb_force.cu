@@ -384,17 +384,27 @@ __global__ void __launch_bounds__(RED_THREADS)
 
 __global__ void k_bounds_final(const double *__restrict__ part, int nb, double *__restrict__ out8, float *__restrict__ hmax_f)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double v[8];
-    for (int k = 0; k < 8; ++k) v[k] = part[k];
-    for (int b = 1; b < nb; ++b) {
+    // one warp folds the per-block partials
+    const int lane = threadIdx.x;
+    double v[8] = {CUDART_INF, CUDART_INF, CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, 0.0};
+    for (int b = lane; b < nb; b += 32) {
         for (int k = 0; k < 3; ++k) v[k] = fmin(v[k], part[(size_t)b * 8 + k]);
         for (int k = 3; k < 7; ++k) v[k] = fmax(v[k], part[(size_t)b * 8 + k]);
         v[7] += part[(size_t)b * 8 + 7];
     }
-    if (out8)
-        for (int k = 0; k < 8; ++k) out8[k] = v[k];
-    if (hmax_f) hmax_f[0] = sphb_f_up(v[6]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = fmin(v[k], __shfl_xor_sync(SPHB_FULL, v[k], o));
+#pragma unroll
+        for (int k = 3; k < 7; ++k) v[k] = fmax(v[k], __shfl_xor_sync(SPHB_FULL, v[k], o));
+        v[7] += __shfl_xor_sync(SPHB_FULL, v[7], o);
+    }
+    if (lane == 0) {
+        if (out8)
+            for (int k = 0; k < 8; ++k) out8[k] = v[k];
+        if (hmax_f) hmax_f[0] = sphb_f_up(v[6]);
+    }
 }
 
 #define BOUNDS_BLOCKS 592
