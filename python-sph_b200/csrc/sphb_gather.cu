@@ -123,6 +123,7 @@ __device__ __forceinline__ double sphb_omega_from_sumG(const sphb_consts &k, dou
     return 1.0 + h / (3.0 * sphb_var_density(k, h)) * ds;       // pyfluid.py:97 with rho = m (eta/h)^3
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_newton_h(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_guess,
                double *__restrict__ h_out, double *__restrict__ omega_out, int32_t *__restrict__ iters,
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     const bool tgt = valid && (target == nullptr || target[j] != 0);
     const SphbScanCtx g = sphb_make_ctx(c);
     SphbWarpShared &ws = sh[warp];
-    const double rmargin = omega_out ? 1.0 + SPHB_NEWTON_MARGIN : 1.0;
+    const double rmargin = FUSED ? 1.0 + SPHB_NEWTON_MARGIN : 1.0;
 
     SphbOwnAcc a;
     a.xj = a.yj = a.zj = 0.0;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                 if (iters) iters[j] = it;
                 if (code) code[j] = 0;
                 active = false;
-                if (omega_out) {
+                if (FUSED) {
                     if (!flushed) {
                         SphbOwnAcc b = a;
                         b.hinv = 1.0 / h_new;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                     const int slot = atomicAdd(&status->nfail, 1);
                     fail_list[slot] = (uint32_t)j;
                     h_out[j] = CUDART_NAN;
-                    if (omega_out) omega_out[j] = CUDART_NAN;
+                    if (FUSED) omega_out[j] = CUDART_NAN;
                     if (iters) iters[j] = it;
                     if (code) code[j] = 1;
                     active = false;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
         __syncwarp();
     }
     // lanes whose list overflowed: one more scan at the final h
-    if (__any_sync(SPHB_FULL, need_scan)) {
+    if (FUSED && __any_sync(SPHB_FULL, need_scan)) {
         a.hinv = 1.0 / h_fin;
         a.sumF = a.sumG = 0.0;
         const float Rj = sphb_radius_of_h(h_fin, g.delta), thr = sphb_thr_of_h(h_fin, g.delta);
@@ -444,8 +445,12 @@ extern "C" int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, cons
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
     SPHB_CUDA(cudaMemsetAsync(&status->nfail, 0, sizeof(int32_t), sphb_stream(stream)));
-    k_newton_h<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out, omega_out,
-                                                                           iters, code, fail_list, status);
+    if (omega_out)
+        k_newton_h<true><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out,
+                                                                                     omega_out, iters, code, fail_list, status);
+    else
+        k_newton_h<false><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out,
+                                                                                      omega_out, iters, code, fail_list, status);
     SPHB_LAUNCHED();
     // the fallback reads its list length from status->nfail on the device: no host round trip
     return sphb_bisect_h(cells, k, fail_list, -1, h_out, omega_out, code, nullptr, 1, status, stream);
