@@ -110,8 +110,11 @@ __device__ __forceinline__ void sphb_force_pair(const double *recB, const double
     const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
     const double d2 = sphb_d2(dx, dy, dz);
     if (!sphb_nonzero(d2)) return;   // coincident positions contribute exactly 0 (pyfluid.py:51-52,461)
-    double rhoi, csi, hinvi, gi;
-    sphb_load4(recC, i, rhoi, csi, hinvi, gi);
+    // 1/h_i and 1/(pi h_i^4) are recomputed (7 FP64 instructions) rather than gathered: the third record is then
+    // only needed by the viscous branch, i.e. for about half of the pairs
+    const double hinvi = sphb_rcp(hi);
+    const double hi2 = hinvi * hinvi;
+    const double gi = (hi2 * hi2) * 0.3183098861837907;   // 1/pi
     const double rinv = sphb_rsqrt(d2);
     const double r = d2 * rinv;
     const double qj = r * a.hinvj, qi = r * hinvi;
@@ -126,6 +129,8 @@ __device__ __forceinline__ void sphb_force_pair(const double *recB, const double
     const double sm = sj + si;
     double pi_half = 0.0;
     if (vdr < 0.0) {
+        double rhoi, csi, hinv_unused, g_unused;
+        sphb_load4(recC, i, rhoi, csi, hinv_unused, g_unused);
         const double mean_h = 0.5 * (a.hj + hi);
         const double den = fma(k.epsilon * mean_h, mean_h, d2);
         const double mean_rho = 0.5 * (a.rhoj + rhoi);

@@ -435,3 +435,21 @@ def test_sums_do_not_depend_on_warp_chunking(sph):
                 assert torch.equal(a[keep], b[keep]), (name, shift, me)
     finally:
         sph.PARTICLE_MASS = 1
+
+
+def test_omega_carry_does_not_change_a_bit(sph):
+    """the time loop hands Omega(pos1, h1) from one step's last Newton kernel to the next step (var_smoothlength_sim);
+    a step that receives it must return exactly what a stand-alone step returns"""
+    import torch
+    import engine as E
+    n = 5000
+    pos, vel, e, L = uniform_cloud(n, 77, vscale=0.7)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    h = to(sph.newton_smoothlength_arr(pos, np.full(n, 0.8)))
+    stp = E.Stepper(sph._eng())
+    c = sph._consts()
+    s1 = stp.step(to(pos), to(vel), to(e), h, 2e-3, c, want_omega1=True)
+    plain = stp.step(s1[0], s1[1], s1[2], s1[3], 2e-3, c)
+    carried = stp.step(s1[0], s1[1], s1[2], s1[3], 2e-3, c, omega0=s1[4])
+    for a, b in zip(plain, carried):
+        assert torch.equal(a, b)
