@@ -129,10 +129,12 @@ int sphb_gather_u32(const uint32_t *src, const uint32_t *perm, int64_t n, uint32
  *   omega[j]    = 1 + h_j/(3 rho_j) dwdh_sum[j]                    (if omega non-NULL; rho_j = rho_in[j], or
  *                                                                   var_density(h_j) = m (eta/h_j)^3 when rho_in is NULL,
  *                                                                   which is what the step uses, pyfluid.py:502-503)
+ *   xi[j]       = -h_j/(3 rho_j) sum_i m dphi/dh(|r_j - r_i|, h_j)    (optional; xi/xi_arr, pyfluid.py:401-418 -- the
+ *                                                                   grad-h term of the softened gravity, compact support)
  * h_j is cells->posh[j][3] unless h_target != NULL.  ngb_count (optional) = #{i : q < 2}. */
 int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *h_target,
-                       const double *rho_in, double *rho_sum, double *dwdh_sum, double *omega, int32_t *ngb_count,
-                       void *stream);
+                       const double *rho_in, double *rho_sum, double *dwdh_sum, double *omega, double *xi,
+                       int32_t *ngb_count, void *stream);
 
 /* ---- K3: Newton-Raphson smoothing-length solve ---------------------------------------------------
  * replaces newton_smoothlength_iteration/_while/_arr (pyfluid.py:155-179, 203-211) and
@@ -163,22 +165,36 @@ int sphb_neighbours(const sphb_cells *cells, const uint32_t *query, int64_t n_qu
  * recB[j] = {vx, vy, vz, A}; recC[j] = {rho, cs, 1/h, 1/(pi h^4)}.
  * rho_in / P_in (optional): take density / pressure from the caller instead (energy_rate_arr and
  * acceleration_arr receive them as arguments, pyfluid.py:355,487); u may then be NULL.
- * recB/recC may be NULL (var_density_arr / pressure_arr only). */
+ * recB/recC may be NULL (var_density_arr / pressure_arr only).
+ * bgrav (optional, needs omega): (G/2) xi/omega per particle -- the factor of the compact grad-h gravity correction
+ * (smoothed_gravity_correction_comp, pyfluid.py:434-437); zeros when xi is NULL. */
 int sphb_eos(const double *posh, const double *vel, const double *u, const double *omega, const double *rho_in,
-             const double *P_in, int64_t n, const sphb_consts *k, double *rho, double *P, double *recB, double *recC,
-             sphb_status *status, void *stream);
+             const double *P_in, const double *xi, int64_t n, const sphb_consts *k, double *rho, double *P, double *recB,
+             double *recC, double *bgrav, sphb_status *status, void *stream);
 /* sphb_force: replaces energy_rate/_arr (pyfluid.py:316-361), Pi (:261-285),
- * fluid_accel_viscosity_comp (:459-474) and acceleration/_arr (:477-493) with G = 0.
+ * fluid_accel_viscosity_comp (:459-474) and the compact terms of acceleration/_arr (:477-493): with bgrav != NULL
+ * the grad-h gravity correction (:434-437) is included; the long-range gravity sum is sphb_gravity_direct.
  * acc (n,3) and dudt (n) for target slots. */
 int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *recB,
-               const double *recC, const float *hmax_global, double *acc, double *dudt, sphb_status *status,
-               void *stream);
+               const double *recC, const double *bgrav, const float *hmax_global, double *acc, double *dudt,
+               sphb_status *status, void *stream);
+/* Softened self-gravity, the long-range part (smoothed_gravity_acceleration_comp, pyfluid.py:420-432): exact all-pairs
+ * fp64 sum, acc (n,3) (+)= sum_i -G/2 m (grav_force(d,h_j) + grav_force(d,h_i)) (r_j - r_i)/d.  O(n^2).  posh in any
+ * order; acc in the same order. */
+int sphb_gravity_direct(const double *posh, int64_t n, const sphb_consts *k, int32_t accumulate, double *acc,
+                        void *stream);
+/* grav_potential, grav_force, grav_potential_smoothlength_derivative elementwise (pyfluid.py:365-399) */
+int sphb_grav_eval(const double *dist, const double *h, int64_t n, double *phi, double *force, double *dphidh,
+                   void *stream);
 
 /* Per-pair terms for explicit (j, i) slot pairs (pairs[2*p], pairs[2*p+1]), same records as sphb_force:
  * pi_out[p] = Pi(j, i, ...) (pyfluid.py:261-285); acc_out[3*p..] = fluid_accel_viscosity_comp(j, i, ...)
- * (pyfluid.py:459-474; zero for identical positions).  Either output may be NULL. */
+ * (pyfluid.py:459-474; zero for identical positions); grav_out[3*p..] = smoothed_gravity_acceleration_comp(j, i, ...)
+ * (:420-432); corr_out[3*p..] = smoothed_gravity_correction_comp(j, i, ...) (:434-437, needs bgrav from sphb_eos).
+ * Any output may be NULL. */
 int sphb_pair_terms(const double *posh, const double *recB, const double *recC, const uint32_t *pairs, int64_t n_pairs,
-                    const sphb_consts *k, double *pi_out, double *acc_out, sphb_status *status, void *stream);
+                    const sphb_consts *k, double *pi_out, double *acc_out, const double *bgrav, double *grav_out,
+                    double *corr_out, sphb_status *status, void *stream);
 
 /* ---- K5: integrator updates (pyfluid.py:511-515 predictor, :524-528 corrector) ------------------- */
 int sphb_predict(const double *posh0, const double *vel0, const double *u0, const double *acc0, const double *dudt0,

@@ -68,13 +68,15 @@ SIGNATURES = {
     "sphb_gather_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_scatter_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_gather_u32": (C.c_int, [P, P, I64, P, P]),
-    "sphb_density_omega": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
+    "sphb_density_omega": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
     "sphb_newton_h": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
     "sphb_bisect_h": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, I64, P, P, P, P, I32, P, P]),
     "sphb_neighbours": (C.c_int, [C.POINTER(Cells), P, I64, I32, P, P, I64, P, P]),
-    "sphb_eos": (C.c_int, [P, P, P, P, P, P, I64, C.POINTER(Consts), P, P, P, P, P, P]),
-    "sphb_force": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
-    "sphb_pair_terms": (C.c_int, [P, P, P, P, I64, C.POINTER(Consts), P, P, P, P]),
+    "sphb_eos": (C.c_int, [P, P, P, P, P, P, P, I64, C.POINTER(Consts), P, P, P, P, P, P, P]),
+    "sphb_force": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
+    "sphb_gravity_direct": (C.c_int, [P, I64, C.POINTER(Consts), I32, P, P]),
+    "sphb_grav_eval": (C.c_int, [P, P, I64, P, P, P, P]),
+    "sphb_pair_terms": (C.c_int, [P, P, P, P, I64, C.POINTER(Consts), P, P, P, P, P, P, P]),
     "sphb_predict": (C.c_int, [P, P, P, P, P, C.c_double, I64, P, P, P, P, P]),
     "sphb_correct": (C.c_int, [P, P, P, P, P, C.c_double, I64, P, P, P, P, P]),
     "sphb_bounds": (C.c_int, [P, I64, P, P, I64, P]),

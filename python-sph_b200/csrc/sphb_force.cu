@@ -22,9 +22,9 @@ __device__ __forceinline__ void sphb_load4(const double *rec, size_t i, double &
 // ------------------------------------------------------------------------------------------------
 __global__ void k_eos(const double *__restrict__ posh, const double *__restrict__ vel, const double *__restrict__ u,
                       const double *__restrict__ omega, const double *__restrict__ rho_in,
-                      const double *__restrict__ P_in, long long n, sphb_consts k, double *__restrict__ rho_out,
-                      double *__restrict__ P_out, double *__restrict__ recB, double *__restrict__ recC,
-                      sphb_status *__restrict__ status)
+                      const double *__restrict__ P_in, const double *__restrict__ xi, long long n, sphb_consts k,
+                      double *__restrict__ rho_out, double *__restrict__ P_out, double *__restrict__ recB,
+                      double *__restrict__ recC, double *__restrict__ bgrav, sphb_status *__restrict__ status)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -35,6 +35,7 @@ __global__ void k_eos(const double *__restrict__ posh, const double *__restrict_
     if (P < 0.0) atomicOr(&status->flags, SPHB_ST_NEG_P);
     if (rho_out) rho_out[i] = rho;
     if (P_out) P_out[i] = P;
+    if (bgrav) bgrav[i] = xi ? (k.G / 2.0) * (xi[i] / omega[i]) : 0.0;   // (G/2) xi/Omega, pyfluid.py:436
     if (!recB || !recC) return;
     const double om = omega[i];
     const double A = P / (om * (rho * rho));
@@ -63,6 +64,7 @@ struct SphbForceAcc {
     double vxj, vyj, vzj, Aj;
     double rhoj, csj, hinvj, gj;
     double ax, ay, az, dens, visc;
+    double Bj;   // GRAV: (G/2) xi_j / Omega_j
     int negpi;
 #ifdef SPHB_DEBUG_FORCE
     long long jslot;
@@ -103,9 +105,14 @@ extern "C" int sphb_debug_force_get(uint32_t *list_host, double *val_host)
 #define SPHB_DBG(jslot, islot, v)
 #endif
 
-// one pair, given the candidate's position record; the other two records are only fetched for real pairs
-__device__ __forceinline__ void sphb_force_pair(const double *recB, const double *recC, uint32_t i, double x, double y,
-                                                double z, double hi, const sphb_consts &k, SphbForceAcc &a)
+// one pair, given the candidate's position record; the other two records are only fetched for real pairs.
+// GRAV: the compact grad-h correction of the softened gravity (smoothed_gravity_correction_comp, pyfluid.py:434-437)
+// has the same shape as the pressure term, -m (B_j gradW(h_j) + B_i gradW(h_i)) with B = (G/2) xi/Omega, and rides
+// in the acceleration coefficient only (du/dt keeps the pure A_j).
+template <bool GRAV>
+__device__ __forceinline__ void sphb_force_pair(const double *recB, const double *recC, const double *bgrav, uint32_t i,
+                                                double x, double y, double z, double hi, const sphb_consts &k,
+                                                SphbForceAcc &a)
 {
     const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
     const double d2 = sphb_d2(dx, dy, dz);
@@ -141,7 +148,8 @@ __device__ __forceinline__ void sphb_force_pair(const double *recB, const double
         if (pi < 0.0) a.negpi = 1;
         pi_half = 0.5 * pi;
     }
-    const double coef = fma(a.Aj, sj, fma(Ai, si, pi_half * sm));
+    double coef = fma(a.Aj, sj, fma(Ai, si, pi_half * sm));
+    if (GRAV) coef = fma(a.Bj, sj, fma(__ldg(bgrav + i), si, coef));
     SPHB_DBG(a.jslot, i, coef * dx);
     a.ax = fma(-coef, dx, a.ax);
     a.ay = fma(-coef, dy, a.ay);
@@ -150,9 +158,10 @@ __device__ __forceinline__ void sphb_force_pair(const double *recB, const double
 }
 
 // drain the lane's list with the next position record in flight (two buffers, unrolled by two)
+template <bool GRAV>
 __device__ __forceinline__ void sphb_force_flush(const double *posh, const double *recB, const double *recC,
-                                                 const SphbWarpShared &ws, int lane, int cnt, const sphb_consts &k,
-                                                 SphbForceAcc &a)
+                                                 const double *bgrav, const SphbWarpShared &ws, int lane, int cnt,
+                                                 const sphb_consts &k, SphbForceAcc &a)
 {
     double ax, ay, az, ah, bx, by, bz, bh;
     uint32_t ia = 0, ib = 0;
@@ -166,22 +175,23 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
             ib = sphb_list_get(ws, lane, n_ + 1);
             sphb_load4(posh, ib, bx, by, bz, bh);
         }
-        sphb_force_pair(recB, recC, ia, ax, ay, az, ah, k, a);
+        sphb_force_pair<GRAV>(recB, recC, bgrav, ia, ax, ay, az, ah, k, a);
         ++n_;
         if (n_ >= cnt) break;
         if (n_ + 1 < cnt) {
             ia = sphb_list_get(ws, lane, n_ + 1);
             sphb_load4(posh, ia, ax, ay, az, ah);
         }
-        sphb_force_pair(recB, recC, ib, bx, by, bz, bh, k, a);
+        sphb_force_pair<GRAV>(recB, recC, bgrav, ib, bx, by, bz, bh, k, a);
         ++n_;
     }
 }
 
+template <bool GRAV>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     k_force(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ recB,
-            const double *__restrict__ recC, const float *__restrict__ hmax_global, double *__restrict__ acc,
-            double *__restrict__ dudt, sphb_status *__restrict__ status)
+            const double *__restrict__ recC, const double *__restrict__ bgrav, const float *__restrict__ hmax_global,
+            double *__restrict__ acc, double *__restrict__ dudt, sphb_status *__restrict__ status)
 {
     __shared__ SphbWarpShared sh[SPHB_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -209,6 +219,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     }
     a.ax = a.ay = a.az = a.dens = a.visc = 0.0;
     a.negpi = 0;
+    a.Bj = (GRAV && valid) ? bgrav[j] : 0.0;
 #ifdef SPHB_DEBUG_FORCE
     a.jslot = tgt ? j : -2;
 #endif
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     const float RH = sphb_radius_of_h((double)hmax_global[0], g.delta);
     SphbList L;
     L.init(ws, lane);
-    auto flush = [&](int n_) { sphb_force_flush(c.posh, recB, recC, ws, lane, n_, k, a); };
+    auto flush = [&](int n_) { sphb_force_flush<GRAV>(c.posh, recB, recC, bgrav, ws, lane, n_, k, a); };
     sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, RH, L, flush);
     flush(L.count());
     if (tgt) {
@@ -235,10 +246,14 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
 
 // Pi(j,i) and fluid_accel_viscosity_comp(j,i) for explicit pairs, written in the reference's own form
 // (pyfluid.py:261-285, :459-474): this is the per-pair entry point, not the hot loop.
+// forward declarations of the softened-gravity scalar functions (defined further down)
+__device__ __forceinline__ double sphb_grav_force(double dist, double h);
+
 __global__ void k_pair_terms(const double *__restrict__ posh, const double *__restrict__ recB,
                              const double *__restrict__ recC, const uint32_t *__restrict__ pairs, long long n_pairs,
                              sphb_consts k, double *__restrict__ pi_out, double *__restrict__ acc_out,
-                             sphb_status *__restrict__ status)
+                             const double *__restrict__ bgrav, double *__restrict__ grav_out,
+                             double *__restrict__ corr_out, sphb_status *__restrict__ status)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
@@ -277,16 +292,147 @@ __global__ void k_pair_terms(const double *__restrict__ posh, const double *__re
         acc_out[3 * p + 1] = a[1];
         acc_out[3 * p + 2] = a[2];
     }
+    const bool same = (dx == 0.0 && dy == 0.0 && dz == 0.0);
+    if (grav_out) {   // smoothed_gravity_acceleration_comp, pyfluid.py:420-432
+        double gq[3] = {0.0, 0.0, 0.0};
+        if (!same) {
+            const double f = sphb_grav_force(dist, hj) + sphb_grav_force(dist, hi);
+            const double d[3] = {dx / dist, dy / dist, dz / dist};
+            for (int c = 0; c < 3; ++c) gq[c] = -k.G / 2.0 * k.particle_mass * (f * d[c]);
+        }
+        for (int c = 0; c < 3; ++c) grav_out[3 * p + c] = gq[c];
+    }
+    if (corr_out) {   // smoothed_gravity_correction_comp, pyfluid.py:434-437 (bgrav = (G/2) xi/omega)
+        double cq[3] = {0.0, 0.0, 0.0};
+        if (!same && bgrav) {
+            const double wj = sphb_m4_fp(dist / hj) * gj, wi = sphb_m4_fp(dist / hi) * gi;
+            const double d[3] = {dx / dist, dy / dist, dz / dist};
+            for (int c = 0; c < 3; ++c) cq[c] = -k.particle_mass * (bgrav[j] * (wj * d[c]) + bgrav[i] * (wi * d[c]));
+        }
+        for (int c = 0; c < 3; ++c) corr_out[3 * p + c] = cq[c];
+    }
 }
 
 extern "C" int sphb_pair_terms(const double *posh, const double *recB, const double *recC, const uint32_t *pairs,
                                int64_t n_pairs, const sphb_consts *k, double *pi_out, double *acc_out,
-                               sphb_status *status, void *stream)
+                               const double *bgrav, double *grav_out, double *corr_out, sphb_status *status,
+                               void *stream)
 {
     if (n_pairs < 0 || !k || !status || (n_pairs > 0 && (!posh || !recB || !recC || !pairs))) return SPHB_E_ARG;
     if (n_pairs == 0) return SPHB_OK;
-    k_pair_terms<<<(unsigned)((n_pairs + 127) / 128), 128, 0, sphb_stream(stream)>>>(posh, recB, recC, pairs, n_pairs, *k,
-                                                                                     pi_out, acc_out, status);
+    k_pair_terms<<<(unsigned)((n_pairs + 127) / 128), 128, 0, sphb_stream(stream)>>>(
+        posh, recB, recC, pairs, n_pairs, *k, pi_out, acc_out, bgrav, grav_out, corr_out, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Softened self-gravity (pyfluid.py:378-389, :420-432).  The pair force is 1/r^2 beyond 2h: it has
+// no compact support, so this is an exact all-pairs sum in fp64, tiled through shared memory (one thread per target,
+// 128 candidates per tile, candidates in index order).  O(N^2): meant for the N <~ 1e6 runs where the reference's
+// default G is kept; the 16 M benchmark path runs with G = 0.
+// ------------------------------------------------------------------------------------------------
+// grav_force(dist, h), pyfluid.py:378-389; np.piecewise order [x < 1, 1 <= x < 2, x >= 2], NaN -> 0
+__device__ __forceinline__ double sphb_grav_force(double dist, double h)
+{
+    const double x = dist / h;
+    const double ih2 = 1.0 / (h * h);
+    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+    const double in = ih2 * (4.0 / 3.0 * x - 6.0 / 5.0 * x3 + 0.5 * x4);
+    const double mid = ih2 * (8.0 / 3.0 * x - 3.0 * x2 + 6.0 / 5.0 * x3 - 1.0 / 6.0 * x4 - 1.0 / (15.0 * x2));
+    const double far = 1.0 / (dist * dist);
+    return (x < 1.0) ? in : ((x >= 1.0 && x < 2.0) ? mid : ((x >= 2.0) ? far : 0.0));
+}
+// grav_potential(dist, h), pyfluid.py:365-376
+__device__ __forceinline__ double sphb_grav_potential(double dist, double h)
+{
+    const double x = dist / h;
+    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2, x5 = x4 * x;
+    const double in = 1.0 / h * (2.0 / 3.0 * x2 - 3.0 / 10.0 * x3 + 1.0 / 10.0 * x5 - 7.0 / 5.0);
+    const double mid = 1.0 / h * (4.0 / 3.0 * x2 - x3 + 3.0 / 10.0 * x4 - 1.0 / 30.0 * x5 - 8.0 / 5.0 + 1.0 / (15.0 * x));
+    return (x < 1.0) ? in : ((x >= 1.0 && x < 2.0) ? mid : ((x >= 2.0) ? -1.0 / dist : 0.0));
+}
+// grav_potential_smoothlength_derivative(dist, h), pyfluid.py:391-399
+__device__ __forceinline__ double sphb_grav_dphidh(double dist, double h)
+{
+    const double x = dist / h;
+    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2, x5 = x4 * x;
+    const double in = -1.0 / (h * h) * (2.0 * x2 - 12.0 / 10.0 * x3 + 6.0 / 10.0 * x5 - 7.0 / 5.0);
+    const double mid = -1.0 / (h * h) * (4.0 * x2 - 4.0 * x3 + 3.0 / 2.0 * x4 - 1.0 / 5.0 * x5 - 8.0 / 5.0);
+    return (x < 1.0) ? in : ((x >= 1.0 && x < 2.0) ? mid : 0.0);
+}
+
+#define GRAV_TILE 128
+// acc[j] (+)= sum_i -G/2 m (grav_force(d, h_j) + grav_force(d, h_i)) (r_j - r_i)/d   for r_i != r_j
+__global__ void __launch_bounds__(GRAV_TILE)
+    k_gravity_direct(const double *__restrict__ posh, long long n, sphb_consts k, int accumulate, double *__restrict__ acc)
+{
+    __shared__ double4 tile[GRAV_TILE];
+    const long long j = (long long)blockIdx.x * GRAV_TILE + threadIdx.x;
+    double xj = 0.0, yj = 0.0, zj = 0.0, hj = 1.0;
+    if (j < n) sphb_load4(posh, (size_t)j, xj, yj, zj, hj);
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (long long t0 = 0; t0 < n; t0 += GRAV_TILE) {
+        const long long i = t0 + threadIdx.x;
+        double4 c = make_double4(0.0, 0.0, 0.0, 1.0);
+        if (i < n) sphb_load4(posh, (size_t)i, c.x, c.y, c.z, c.w);
+        __syncthreads();
+        tile[threadIdx.x] = c;
+        __syncthreads();
+        const int nt = (int)((n - t0) < GRAV_TILE ? (n - t0) : GRAV_TILE);
+        for (int q = 0; q < nt; ++q) {
+            const double4 p = tile[q];
+            const double dx = xj - p.x, dy = yj - p.y, dz = zj - p.z;
+            if (dx == 0.0 && dy == 0.0 && dz == 0.0) continue;   // np.array_equal(rj, ri) -> 0, pyfluid.py:422
+            const double d = __dsqrt_rn(sphb_d2(dx, dy, dz));
+            const double f = sphb_grav_force(d, hj) + sphb_grav_force(d, p.w);
+            const double s = f / d;
+            ax = fma(s, dx, ax);
+            ay = fma(s, dy, ay);
+            az = fma(s, dz, az);
+        }
+    }
+    if (j < n) {
+        const double w = -k.G / 2.0 * k.particle_mass;
+        if (accumulate) {
+            acc[3 * j] += w * ax;
+            acc[3 * j + 1] += w * ay;
+            acc[3 * j + 2] += w * az;
+        } else {
+            acc[3 * j] = w * ax;
+            acc[3 * j + 1] = w * ay;
+            acc[3 * j + 2] = w * az;
+        }
+    }
+}
+
+extern "C" int sphb_gravity_direct(const double *posh, int64_t n, const sphb_consts *k, int32_t accumulate, double *acc,
+                                   void *stream)
+{
+    if (n < 0 || !k || (n > 0 && (!posh || !acc))) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_gravity_direct<<<(unsigned)((n + GRAV_TILE - 1) / GRAV_TILE), GRAV_TILE, 0, sphb_stream(stream)>>>(posh, n, *k,
+                                                                                                      accumulate, acc);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+__global__ void k_grav_eval(const double *__restrict__ dist, const double *__restrict__ h, long long n,
+                            double *__restrict__ phi, double *__restrict__ force, double *__restrict__ dphidh)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (phi) phi[i] = sphb_grav_potential(dist[i], h[i]);
+    if (force) force[i] = sphb_grav_force(dist[i], h[i]);
+    if (dphidh) dphidh[i] = sphb_grav_dphidh(dist[i], h[i]);
+}
+
+extern "C" int sphb_grav_eval(const double *dist, const double *h, int64_t n, double *phi, double *force, double *dphidh,
+                              void *stream)
+{
+    if (n < 0 || (n > 0 && (!dist || !h))) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_grav_eval<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(dist, h, n, phi, force, dphidh);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
@@ -562,32 +708,38 @@ extern "C" int sphb_fp64_peak(int32_t blocks, int32_t iters, double *ms_host, do
 // C-ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" int sphb_eos(const double *posh, const double *vel, const double *u, const double *omega,
-                        const double *rho_in, const double *P_in, int64_t n, const sphb_consts *k, double *rho, double *P,
-                        double *recB, double *recC, sphb_status *status, void *stream)
+                        const double *rho_in, const double *P_in, const double *xi, int64_t n, const sphb_consts *k,
+                        double *rho, double *P, double *recB, double *recC, double *bgrav, sphb_status *status,
+                        void *stream)
 {
     if (n < 0 || !k || !status) return SPHB_E_ARG;
     if (n > 0 && (!posh || (!u && !P_in))) return SPHB_E_ARG;
     if ((recB != nullptr) != (recC != nullptr)) return SPHB_E_ARG;
     if (n > 0 && recB && (!vel || !omega)) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
-    k_eos<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh, vel, u, omega, rho_in, P_in, n, *k, rho, P,
-                                                                        recB, recC, status);
+    if (bgrav && !omega) return SPHB_E_ARG;
+    k_eos<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh, vel, u, omega, rho_in, P_in, xi, n, *k, rho,
+                                                                        P, recB, recC, bgrav, status);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
 
 extern "C" int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *recB,
-                          const double *recC, const float *hmax_global, double *acc, double *dudt, sphb_status *status,
-                          void *stream)
+                          const double *recC, const double *bgrav, const float *hmax_global, double *acc, double *dudt,
+                          sphb_status *status, void *stream)
 {
     if (!cells || !k || !recB || !recC || !hmax_global || !acc || !dudt || !status) return SPHB_E_ARG;
     if (cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh || !cells->frec)
         return SPHB_E_ARG;
-    if (k->G != 0.0) return SPHB_E_ARG;   // self-gravity is outside this path
+    if (k->G != 0.0 && !bgrav) return SPHB_E_ARG;   // with gravity on, the grad-h correction factors are required
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
-    k_force<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, hmax_global, acc,
-                                                                        dudt, status);
+    if (bgrav)
+        k_force<true><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, bgrav,
+                                                                                  hmax_global, acc, dudt, status);
+    else
+        k_force<false><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, bgrav,
+                                                                                   hmax_global, acc, dudt, status);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -19,10 +19,21 @@ __device__ __forceinline__ void sphb_load_posh(const double *posh, size_t i, dou
 // rho_sum = m sumF/(pi h^3) (pyfluid.py:218-224), sum m dW/dh = -m sumG/(pi h^4) (pyfluid.py:85-87,91-97).
 struct SphbOwnAcc {
     double xj, yj, zj, hinv;
-    double sumF, sumG;
+    double sumF, sumG, sumX;
     int nn;
 };
 
+// -h^2 dphi/dh of the softened potential, dimensionless: grav_potential_smoothlength_derivative(dist, h) =
+// -(1/h^2) pX(x), x = dist/h (pyfluid.py:391-399); np.piecewise order [x < 1, 1 <= x < 2, x >= 2], NaN -> 0
+__device__ __forceinline__ double sphb_grav_pX(double x)
+{
+    const double x2 = x * x, x3 = x2 * x;
+    const double in = fma(0.6, x2 * x3, fma(-1.2, x3, fma(2.0, x2, -1.4)));
+    const double mid = fma(-0.2, x2 * x3, fma(1.5, x2 * x2, fma(-4.0, x3, fma(4.0, x2, -1.6))));
+    return (x < 1.0) ? in : ((x >= 1.0 && x < 2.0) ? mid : 0.0);
+}
+
+template <bool XI = false>
 __device__ __forceinline__ void sphb_own_pair(double x, double y, double z, SphbOwnAcc &a)
 {
     const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
@@ -34,10 +45,12 @@ __device__ __forceinline__ void sphb_own_pair(double x, double y, double z, Sphb
     a.sumF += f;
     a.sumG += fma(q, fp, 3.0 * f);
     a.nn += (q < 2.0) ? 1 : 0;
+    if (XI) a.sumX += sphb_grav_pX(q);
 }
 
 // drain the lane's list: the record of entry k+1 is in flight while entry k is evaluated (two register
 // buffers, loop unrolled by two so that no copies are needed)
+template <bool XI = false>
 __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWarpShared &ws, int lane, int cnt,
                                                SphbOwnAcc &a)
 {
@@ -46,11 +59,11 @@ __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWar
     int k = 0;
     while (k < cnt) {
         if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), bx, by, bz, bh);
-        sphb_own_pair(ax, ay, az, a);
+        sphb_own_pair<XI>(ax, ay, az, a);
         ++k;
         if (k >= cnt) break;
         if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), ax, ay, az, ah);
-        sphb_own_pair(bx, by, bz, a);
+        sphb_own_pair<XI>(bx, by, bz, a);
         ++k;
     }
 }
@@ -58,10 +71,11 @@ __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWar
 // ------------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------------
+template <bool XI>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_density_omega(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_target,
                     const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
-                    double *__restrict__ omega, int32_t *__restrict__ ngb_count)
+                    double *__restrict__ omega, double *__restrict__ xi_out, int32_t *__restrict__ ngb_count)
 {
     __shared__ SphbWarpShared sh[SPHB_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,13 +98,13 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
         row = c.cell_id[j] / (uint32_t)g.nx;
     }
     a.hinv = 1.0 / h;
-    a.sumF = a.sumG = 0.0;
+    a.sumF = a.sumG = a.sumX = 0.0;
     a.nn = 0;
     const float Rj = sphb_radius_of_h(h, g.delta), thr = sphb_thr_of_h(h, g.delta);
     SphbWarpShared &ws = sh[warp];
     SphbList L;
     L.init(ws, lane);
-    auto flush = [&](int n_) { sphb_own_flush(c.posh, ws, lane, n_, a); };
+    auto flush = [&](int n_) { sphb_own_flush<XI>(c.posh, ws, lane, n_, a); };
     sphb_warp_scan<false>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
     flush(L.count());
     if (tgt) {
@@ -99,9 +113,12 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
         const double ds = -(pref / h) * a.sumG;
         if (rho_sum) rho_sum[j] = rs;
         if (dwdh_sum) dwdh_sum[j] = ds;
-        if (omega) {
-            const double rho = rho_in ? rho_in[j] : sphb_var_density(k, h);
-            omega[j] = 1.0 + h / (3.0 * rho) * ds;   // pyfluid.py:97
+        const double rho = rho_in ? rho_in[j] : sphb_var_density(k, h);
+        if (omega) omega[j] = 1.0 + h / (3.0 * rho) * ds;   // pyfluid.py:97
+        if (XI) {
+            // xi_j = -h/(3 rho) sum_i m dphi/dh = -h/(3 rho) * (-(m/h^2) sum pX), pyfluid.py:401-410
+            const double sx = k.particle_mass * (-(1.0 / (h * h)) * a.sumX);
+            xi_out[j] = -h / (3.0 * rho) * sx;
         }
         if (ngb_count) ngb_count[j] = a.nn;
     }
@@ -156,7 +173,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     int it = 0;
     while (__any_sync(SPHB_FULL, active)) {
         a.hinv = 1.0 / h_old;
-        a.sumF = a.sumG = 0.0;
+        a.sumF = a.sumG = a.sumX = 0.0;
         a.nn = 0;
         const double hs = h_old * rmargin;
         const float Rj = sphb_radius_of_h(hs, g.delta), thr = sphb_thr_of_h(hs, g.delta);
@@ -412,13 +429,17 @@ static inline int sphb_cells_ok(const sphb_cells *c)
 
 extern "C" int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target,
                                   const double *h_target, const double *rho_in, double *rho_sum, double *dwdh_sum,
-                                  double *omega, int32_t *ngb_count, void *stream)
+                                  double *omega, double *xi_out, int32_t *ngb_count, void *stream)
 {
     if (!sphb_cells_ok(cells) || !k) return SPHB_E_ARG;
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
-    k_density_omega<<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_target, rho_in,
-                                                                                rho_sum, dwdh_sum, omega, ngb_count);
+    if (xi_out)
+        k_density_omega<true><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(
+            *cells, *k, target, h_target, rho_in, rho_sum, dwdh_sum, omega, xi_out, ngb_count);
+    else
+        k_density_omega<false><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(
+            *cells, *k, target, h_target, rho_in, rho_sum, dwdh_sum, omega, xi_out, ngb_count);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

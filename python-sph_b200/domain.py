@@ -107,6 +107,8 @@ class SlabRunner:
     """var_smoothlength_leapfrog on a slab-decomposed particle set (one rank per GPU)."""
 
     def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05, balance=True, calib_steps=2):
+        if consts.G != 0.0:
+            raise NotImplementedError("SlabRunner: the all-pairs gravity sum is single-GPU only; run with G = 0")
         self.e, self.consts, self.world, self.rank, self.margin = eng, consts, world, rank, margin
         self.balance = balance
         self.calib_left = calib_steps if balance else 0   # first steps are timed per rank and the cuts re-balanced

@@ -215,15 +215,17 @@ class Engine:
 
     # -- K2 ------------------------------------------------------------------------------------
     def density_omega(self, dg, consts, target=None, h_target=None, rho_in=None, want_rho=True, want_dwdh=False,
-                      want_omega=False, want_ngb=False):
+                      want_omega=False, want_ngb=False, want_xi=False):
+        """-> rho_sum, dwdh_sum, omega, ngb_count (, xi when want_xi); entries not asked for are None"""
         n = dg.n
+        xi = torch.empty(n, dtype=F64, device=self.device) if want_xi else None
         rho = torch.empty(n, dtype=F64, device=self.device) if want_rho else None
         dw = torch.empty(n, dtype=F64, device=self.device) if want_dwdh else None
         om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
         ng = torch.empty(n, dtype=torch.int32, device=self.device) if want_ngb else None
         self._run("density_omega", self.lib.sphb_density_omega, dg.cells(), C.byref(consts), _ptr(target), _ptr(h_target), _ptr(rho_in), _ptr(rho),
-                                            _ptr(dw), _ptr(om), _ptr(ng), _stream())
-        return rho, dw, om, ng
+                                            _ptr(dw), _ptr(om), _ptr(xi), _ptr(ng), _stream())
+        return (rho, dw, om, ng, xi) if want_xi else (rho, dw, om, ng)
 
     # -- K3 ------------------------------------------------------------------------------------
     def newton(self, dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False):
@@ -266,34 +268,54 @@ class Engine:
         return out, cnt
 
     # -- K4 ------------------------------------------------------------------------------------
-    def eos(self, posh, vel, u, omega, consts, status_ptr, rho_in=None, P_in=None, records=True, want_rho_P=False):
+    def eos(self, posh, vel, u, omega, consts, status_ptr, rho_in=None, P_in=None, records=True, want_rho_P=False, xi=None,
+            want_bgrav=False):
+        """-> rho, P, recB, recC (, bgrav = (G/2) xi/omega when want_bgrav)"""
         n = posh.shape[0]
+        bg = torch.empty(n, dtype=F64, device=self.device) if want_bgrav else None
         rho = torch.empty(n, dtype=F64, device=self.device) if want_rho_P else None
         P = torch.empty(n, dtype=F64, device=self.device) if want_rho_P else None
         recB = torch.empty((n, 4), dtype=F64, device=self.device) if records else None
         recC = torch.empty((n, 4), dtype=F64, device=self.device) if records else None
-        self._run("eos", self.lib.sphb_eos, _ptr(posh), _ptr(vel), _ptr(u), _ptr(omega), _ptr(rho_in), _ptr(P_in), n, C.byref(consts),
-                                  _ptr(rho), _ptr(P), _ptr(recB), _ptr(recC), status_ptr, _stream())
-        return rho, P, recB, recC
+        self._run("eos", self.lib.sphb_eos, _ptr(posh), _ptr(vel), _ptr(u), _ptr(omega), _ptr(rho_in), _ptr(P_in), _ptr(xi), n, C.byref(consts),
+                                  _ptr(rho), _ptr(P), _ptr(recB), _ptr(recC), _ptr(bg), status_ptr, _stream())
+        return (rho, P, recB, recC, bg) if want_bgrav else (rho, P, recB, recC)
 
-    def force(self, dg, consts, recB, recC, hmax, status_ptr, target=None):
+    def gravity_direct(self, posh, consts, acc=None):
+        """long-range softened gravity (all pairs, fp64); adds into `acc` (n,3) when given (same order as posh)"""
+        n = posh.shape[0]
+        out = acc if acc is not None else torch.empty((n, 3), dtype=F64, device=self.device)
+        self._run("gravity_direct", self.lib.sphb_gravity_direct, _ptr(posh), n, C.byref(consts), 1 if acc is not None else 0,
+                  _ptr(out), _stream())
+        return out
+
+    def grav_eval(self, dist, h):
+        n = dist.shape[0]
+        phi, f, dp = (torch.empty(n, dtype=F64, device=self.device) for _ in range(3))
+        self._run("grav_eval", self.lib.sphb_grav_eval, _ptr(dist), _ptr(h), n, _ptr(phi), _ptr(f), _ptr(dp), _stream())
+        return phi, f, dp
+
+    def force(self, dg, consts, recB, recC, hmax, status_ptr, target=None, bgrav=None):
         n = dg.n
         acc = torch.zeros((n, 3), dtype=F64, device=self.device) if target is not None else \
             torch.empty((n, 3), dtype=F64, device=self.device)
         dudt = torch.zeros(n, dtype=F64, device=self.device) if target is not None else \
             torch.empty(n, dtype=F64, device=self.device)
-        self._run("force", self.lib.sphb_force, dg.cells(), C.byref(consts), _ptr(target), _ptr(recB), _ptr(recC), _ptr(hmax), _ptr(acc),
+        self._run("force", self.lib.sphb_force, dg.cells(), C.byref(consts), _ptr(target), _ptr(recB), _ptr(recC), _ptr(bgrav), _ptr(hmax), _ptr(acc),
                                     _ptr(dudt), status_ptr, _stream())
         return acc, dudt
 
-    def pair_terms(self, posh, recB, recC, pairs, consts, status_ptr):
-        """pairs: int32 (m,2) slot pairs -> Pi (m), fluid_accel_viscosity_comp (m,3)"""
+    def pair_terms(self, posh, recB, recC, pairs, consts, status_ptr, bgrav=None, want_grav=False):
+        """pairs: int32 (m,2) slot pairs -> Pi (m), fluid_accel_viscosity_comp (m,3)
+        (, smoothed_gravity_acceleration_comp (m,3), smoothed_gravity_correction_comp (m,3) when want_grav)"""
         m = pairs.shape[0]
         pi = torch.empty(m, dtype=F64, device=self.device)
         acc = torch.empty((m, 3), dtype=F64, device=self.device)
+        gr = torch.empty((m, 3), dtype=F64, device=self.device) if want_grav else None
+        co = torch.empty((m, 3), dtype=F64, device=self.device) if want_grav else None
         self._run("pair_terms", self.lib.sphb_pair_terms, _ptr(posh), _ptr(recB), _ptr(recC), _ptr(pairs), m, C.byref(consts),
-                  _ptr(pi), _ptr(acc), status_ptr, _stream())
-        return pi, acc
+                  _ptr(pi), _ptr(acc), _ptr(bgrav), _ptr(gr), _ptr(co), status_ptr, _stream())
+        return (pi, acc, gr, co) if want_grav else (pi, acc)
 
     # -- K5 ------------------------------------------------------------------------------------
     def predict(self, posh0, vel0, u0, acc0, dudt0, dt, status_ptr):
@@ -390,13 +412,24 @@ class Stepper:
         # State stays in CALLER order between stages; every cell list is built from caller-order positions, so
         # ties inside a cell are always broken by the caller index and every sum has one fixed order (the
         # multi-GPU runner does the same with global ids: k-rank results equal 1-rank results bit for bit).
+        grav = consts.G != 0.0
+
         def stage(dg, vel_c, u_c, sidx, om=None):
             """the six calls at pyfluid.py:502-507 / :517-522 -> acc, dudt in caller order
             (om: Omega already produced by the Newton kernel for this snapshot)"""
-            if om is None:
-                _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
-            _, _, rB, rC = e.eos(dg.posh, e.gather(vel_c, dg.perm, 3), e.gather(u_c, dg.perm, 1), om, consts, st.ptr(sidx))
-            acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx))
+            vel_s, u_s = e.gather(vel_c, dg.perm, 3), e.gather(u_c, dg.perm, 1)
+            if grav:
+                # xi_arr (:504) rides in the Omega pass; its compact correction (:434-437) rides in the force kernel;
+                # the long-range pair force (:420-432) is an exact all-pairs sum
+                _, _, om, _, xi = e.density_omega(dg, consts, want_rho=False, want_omega=True, want_xi=True)
+                _, _, rB, rC, bg = e.eos(dg.posh, vel_s, u_s, om, consts, st.ptr(sidx), xi=xi, want_bgrav=True)
+                acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx), bgrav=bg)
+                e.gravity_direct(dg.posh, consts, acc=acc)
+            else:
+                if om is None:
+                    _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
+                _, _, rB, rC = e.eos(dg.posh, vel_s, u_s, om, consts, st.ptr(sidx))
+                acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx))
             return e.scatter(acc, dg.perm, 3), e.scatter(dudt, dg.perm, 1)
 
         def solve_h(dg, sidx, want_omega=False):

@@ -6,8 +6,10 @@ behaviour as the reference for the variable-h path, computed by hand-written sm_
 (libsphb200.so, include/sphb200.h).  Arrays may be numpy.ndarray (copied to the GPU and back) or
 CUDA torch.Tensor (results stay on the device); results come back as the same kind.
 
-Scope: the hydro path.  Self-gravity (pyfluid.py:365-444) is outside it: functions that would add a
-gravity term require ``G == 0`` and raise NotImplementedError otherwise.
+Scope: the hydro path plus the reference's softened self-gravity (pyfluid.py:365-444):
+the grad-h terms (xi, its correction) have compact support and ride in the cell-list kernels; the 1/r^2 pair
+force is an exact all-pairs fp64 sum (O(N^2): fine for the N <~ 1e6 runs that keep the default G; the multi-GPU
+runner and the 16 M benchmark run with G = 0).
 There is no CPU fallback: without libsphb200.so and a B200 every compute call raises.
 """
 from __future__ import annotations
@@ -56,13 +58,6 @@ def _consts(hydro_only=False):
     if hydro_only:
         k["G"] = 0.0
     return _E.make_consts(k)
-
-
-def _need_G0(what):
-    if G != 0:
-        raise NotImplementedError(
-            f"{what}: self-gravity (pyfluid.py:365-444) is outside the B200 hot path; set G = 0 "
-            "(the hydro terms are then bit-for-bit the reference's, SURVEY.md 0.5)")
 
 
 class _IO:
@@ -323,22 +318,80 @@ def pressure_arr(energy_arr, density_arr):
     return io.out(P)
 
 
-def _force_arrays(io, position_arr, velocity_arr, pressure_arr_, density_arr_, smoothlength_arr, omega_arr_, target_j=None):
+# ---- gravity helpers (pyfluid.py:365-418) --------------------------------------------------------------------
+def _grav(dist, h, which):
+    io = _IO(dist, h)
+    scalar = np.ndim(dist) == 0 and np.ndim(h) == 0 and not io.torch_out
+    d = io.dev64(dist).reshape(-1)
+    hh = io.dev64(h).reshape(-1)
+    if hh.numel() != d.numel():
+        d, hh = torch.broadcast_tensors(d, hh)
+        d, hh = d.contiguous(), hh.contiguous()
+    r = _eng().grav_eval(d, hh)[which]
+    return _scalar(r[0]) if scalar else io.out(r)
+
+
+def grav_potential(dist, smoothlength):
+    """pyfluid.py:365-376 (Cossins 3.149)"""
+    return _grav(dist, smoothlength, 0)
+
+
+def grav_force(dist, smoothlength):
+    """pyfluid.py:378-389 (Cossins 3.148)"""
+    return _grav(dist, smoothlength, 1)
+
+
+def grav_potential_smoothlength_derivative(dist, smoothlength):
+    """pyfluid.py:391-399"""
+    return _grav(dist, smoothlength, 2)
+
+
+def xi(j, position_arr, density_j, smoothlength_j):
+    """pyfluid.py:401-410"""
+    io = _IO(position_arr)
     e = _eng()
-    k = _consts(hydro_only=True)
+    pos = io.dev64(position_arr, (-1, 3))
+    n = pos.shape[0]
+    h = torch.full((n,), float(smoothlength_j), dtype=torch.float64, device=e.device)
+    dg = _grid_and_order(e, pos, h)
+    s = _slot_of(dg, j)
+    rho = torch.full((n,), float(density_j), dtype=torch.float64, device=e.device)
+    r = e.density_omega(dg, _consts(), target=_one_hot(dg, s), rho_in=rho, want_rho=False, want_xi=True)
+    return _scalar(r[4][s])
+
+
+def xi_arr(density_arr, smoothlength_arr, position_arr):
+    """pyfluid.py:412-418"""
+    io = _IO(position_arr, density_arr, smoothlength_arr)
+    e = _eng()
+    dg = _grid_and_order(e, io.dev64(position_arr, (-1, 3)), io.dev64(smoothlength_arr, (-1,)))
+    rho_s = e.gather(io.dev64(density_arr, (-1,)), dg.perm, 1)
+    r = e.density_omega(dg, _consts(), rho_in=rho_s, want_rho=False, want_xi=True)
+    return io.out(e.scatter(r[4], dg.perm, 1))
+
+
+def _force_arrays(io, position_arr, velocity_arr, pressure_arr_, density_arr_, smoothlength_arr, omega_arr_, target_j=None,
+                  xi_arr_=None):
+    """xi_arr_ != None: include the gravity terms of acceleration() (pyfluid.py:481-483) when G != 0"""
+    e = _eng()
+    grav = xi_arr_ is not None and G != 0
+    k = _consts(hydro_only=not grav)
     pos = io.dev64(position_arr, (-1, 3))
     dg = _grid_and_order(e, pos, io.dev64(smoothlength_arr, (-1,)))
     g = lambda a, nc: e.gather(io.dev64(a, (-1, nc) if nc > 1 else (-1,)), dg.perm, nc)
     st = _E.Status(1, e.device)
-    _, _, rB, rC = e.eos(dg.posh, g(velocity_arr, 3), None, g(omega_arr_, 1), k, st.ptr(0), rho_in=g(density_arr_, 1),
-                         P_in=g(pressure_arr_, 1))
+    r = e.eos(dg.posh, g(velocity_arr, 3), None, g(omega_arr_, 1), k, st.ptr(0), rho_in=g(density_arr_, 1),
+              P_in=g(pressure_arr_, 1), xi=g(xi_arr_, 1) if grav else None, want_bgrav=grav)
+    rB, rC, bg = r[2], r[3], (r[4] if grav else None)
     st.t.zero_()   # the *_arr force functions take P as given and never re-check its sign
     tgt = None
     slot = None
     if target_j is not None:
         slot = _slot_of(dg, target_j)
         tgt = _one_hot(dg, slot)
-    acc, dudt = e.force(dg, k, rB, rC, e.hmax(dg.posh), st.ptr(0), target=tgt)
+    acc, dudt = e.force(dg, k, rB, rC, e.hmax(dg.posh), st.ptr(0), target=tgt, bgrav=bg)
+    if grav:
+        e.gravity_direct(dg.posh, k, acc=acc)
     return dg, acc, dudt, st, slot
 
 
@@ -357,6 +410,41 @@ def _pair(io, j, i, position_arr, velocity_arr, pressure_arr_, density_arr_, smo
     pi, acc = e.pair_terms(posh, rB, rC, pairs, k, st.ptr(0))
     _report(st)
     return pi, acc
+
+
+def smoothed_gravity_acceleration_comp(j, i, position_arr, smoothlength_arr):
+    """pyfluid.py:420-432; the reference returns the int 0 for identical positions"""
+    io = _IO(position_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    if bool(torch.equal(pos[int(j)], pos[int(i)])):
+        return 0
+    n = pos.shape[0]
+    posh = e.pack_posh(pos, io.dev64(smoothlength_arr, (-1,)))
+    one = torch.ones(n, dtype=torch.float64, device=e.device)
+    st = _E.Status(1, e.device)
+    k = _consts()
+    _, _, rB, rC = e.eos(posh, torch.zeros((n, 3), dtype=torch.float64, device=e.device), None, one, k, st.ptr(0), rho_in=one, P_in=one)
+    pairs = torch.tensor([[int(j), int(i)]], dtype=torch.int32, device=e.device)
+    r = e.pair_terms(posh, rB, rC, pairs, k, st.ptr(0), want_grav=True)
+    return r[2][0] if io.torch_out else r[2][0].cpu().numpy()
+
+
+def smoothed_gravity_correction_comp(j, i, position_arr, smoothlength_arr, omega_arr, xi_arr):
+    """pyfluid.py:434-437"""
+    io = _IO(position_arr)
+    e = _eng()
+    pos = io.dev64(position_arr, (-1, 3))
+    n = pos.shape[0]
+    posh = e.pack_posh(pos, io.dev64(smoothlength_arr, (-1,)))
+    one = torch.ones(n, dtype=torch.float64, device=e.device)
+    st = _E.Status(1, e.device)
+    k = _consts()
+    r = e.eos(posh, torch.zeros((n, 3), dtype=torch.float64, device=e.device), None, io.dev64(omega_arr, (-1,)), k, st.ptr(0),
+              rho_in=one, P_in=one, xi=io.dev64(xi_arr, (-1,)), want_bgrav=True)
+    pairs = torch.tensor([[int(j), int(i)]], dtype=torch.int32, device=e.device)
+    out = e.pair_terms(posh, r[2], r[3], pairs, k, st.ptr(0), bgrav=r[4], want_grav=True)
+    return out[3][0] if io.torch_out else out[3][0].cpu().numpy()
 
 
 def Pi(j, i, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr):
@@ -395,11 +483,10 @@ def energy_rate_arr(position_arr, velocity_arr, pressure_arr, density_arr, smoot
 
 
 def acceleration(j, position_arr, density_arr, velocity_arr, pressure_arr, smoothlength_arr, omega_arr, xi_arr):
-    """pyfluid.py:477-485 with G = 0 (xi_arr is accepted and, as in the reference with G = 0, has no effect)"""
-    _need_G0("acceleration")
+    """pyfluid.py:477-485 (fluid + softened gravity + its grad-h correction)"""
     io = _IO(position_arr)
     dg, acc, dudt, st, slot = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr,
-                                            omega_arr, target_j=j)
+                                            omega_arr, target_j=j, xi_arr_=xi_arr)
     fl = st.read()
     fl[:, 0] &= _N.ST_NEG_PI   # acceleration() can only raise through Pi (pyfluid.py:468)
     _E.raise_for_status(fl)
@@ -408,10 +495,10 @@ def acceleration(j, position_arr, density_arr, velocity_arr, pressure_arr, smoot
 
 
 def acceleration_arr(position_arr, density_arr, velocity_arr, pressure_arr, smoothlength_arr, omega_arr, xi_arr):
-    """pyfluid.py:487-493 with G = 0"""
-    _need_G0("acceleration_arr")
+    """pyfluid.py:487-493"""
     io = _IO(position_arr, density_arr, velocity_arr, pressure_arr, smoothlength_arr, omega_arr)
-    dg, acc, dudt, st, _ = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr)
+    dg, acc, dudt, st, _ = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr,
+                                         xi_arr_=xi_arr)
     fl = st.read()
     fl[:, 0] &= _N.ST_NEG_PI
     _E.raise_for_status(fl)
@@ -425,7 +512,6 @@ _stepper = None
 def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt):
     """pyfluid.py:498-532: one midpoint predictor-corrector step (Cossins 3.152-3.155), G = 0.
     Returns fresh (pos1, vel1, energy1, h1); inputs are not modified."""
-    _need_G0("var_smoothlength_leapfrog")
     global _stepper
     io = _IO(pos0, vel0, energy0, h0)
     if _stepper is None:
@@ -439,7 +525,6 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
     """pyfluid.py:535-602: returns (Nt,N,3), (Nt,N,3), (Nt,N), (Nt,N) histories (numpy in -> numpy out).
     Inside the loop Omega at (pos[t+1], h[t+1]) comes out of step t's last Newton kernel and is handed to step
     t+1, which would otherwise recompute exactly that sum (pyfluid.py:503); the results are unchanged."""
-    _need_G0("var_smoothlength_sim")
     global _stepper
     io = _IO(positions0, velocities0, energies0, smoothlength_approx)
     dt = float(time_arr[1] - time_arr[0])

@@ -167,6 +167,18 @@ def main():
     out["P_Pi"] = np.array([float(sph.Pi(j, i, pos, vel, P, den, hC)) for j, i in pairs])
     out["P_acc"] = np.array([np.zeros(3) + sph.fluid_accel_viscosity_comp(j, i, pos, vel, den, P, hC, om) for j, i in pairs])
     sph.G = G_DEFAULT
+    #      gravity pieces on the same pairs with the default G (pyfluid.py:401-437)
+    xiC = sph.xi_arr(den, hC, pos)
+    out["C_xi"] = xiC
+    out["P_grav"] = np.array([np.zeros(3) + sph.smoothed_gravity_acceleration_comp(j, i, pos, hC) for j, i in pairs])
+    out["P_corr"] = np.array([np.zeros(3) + sph.smoothed_gravity_correction_comp(j, i, pos, hC, om, xiC) for j, i in pairs])
+    out["C_acc_G"] = sph.acceleration_arr(pos, den, vel, P, hC, om, xiC)
+    kd2 = np.array([0.0, 0.3, 0.999, 1.0, 1.5, 1.999, 2.0, 2.5, 7.0])
+    with np.errstate(all="ignore"):
+        out["kat_grav_dist"] = kd2
+        out["kat_grav_phi"] = np.array([float(sph.grav_potential(np.float64(d), np.float64(1.3))) for d in kd2 * 1.3])
+        out["kat_grav_force"] = np.array([float(sph.grav_force(np.float64(d), np.float64(1.3))) for d in kd2 * 1.3])
+        out["kat_grav_dphidh"] = np.array([float(sph.grav_potential_smoothlength_derivative(np.float64(d), np.float64(1.3))) for d in kd2 * 1.3])
 
     # ---- case D: pyfluidex2d_var_h.py:10-25 settings (planar z=0, u=1e-59, h guess 1, dt 0.1),
     #      seeded, with the (N,3) layout var_smoothlength_sim actually takes (pyfluid.py:544) -----

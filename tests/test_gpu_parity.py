@@ -227,12 +227,6 @@ def test_error_conventions(sph, golden):
         sph.var_smoothlength_leapfrog(g["B_pos"], g["B_vel"] * 5.0, np.full(24, 1e-3), g["B_h"], 0.5)
     with pytest.raises(RuntimeError, match="Obtained negative pressure."):
         sph.pressure_arr(np.array([1.0, -1.0]), np.array([1.0, 1.0]))
-    sph.G = 39.4227
-    try:
-        with pytest.raises(NotImplementedError):
-            sph.var_smoothlength_leapfrog(g["B_pos"], g["B_vel"], g["B_e"], g["B_h"], 1e-3)
-    finally:
-        sph.G = 0.0
 
 
 def test_constants_read_at_call_time(sph, golden, oracle_mod):
@@ -453,3 +447,56 @@ def test_omega_carry_does_not_change_a_bit(sph):
     carried = stp.step(s1[0], s1[1], s1[2], s1[3], 2e-3, c, omega0=s1[4])
     for a, b in zip(plain, carried):
         assert torch.equal(a, b)
+
+
+# ---- softened self-gravity: the reference's default G -------------------------------------
+def test_gravity_kats_and_golden(sph, golden):
+    g = golden
+    d = g["kat_grav_dist"] * 1.3
+    h = np.full(len(d), 1.3)
+    with np.errstate(all="ignore"):
+        for fn, key in ((sph.grav_potential, "kat_grav_phi"), (sph.grav_force, "kat_grav_force"),
+                        (sph.grav_potential_smoothlength_derivative, "kat_grav_dphidh")):
+            got, ref = fn(d, h), g[key]
+            ok = np.isclose(got, ref, rtol=1e-13, atol=1e-13) | (np.isinf(got) & np.isinf(ref)) | (np.isnan(got) & np.isnan(ref))
+            assert ok.all(), (key, got, ref)
+    sph.G = 39.4227
+    try:
+        pos, vel, h, P, den, om = g["C_pos"], g["C_vel"], g["C_h"], g["C_P"], g["C_den"], g["C_omega"]
+        xi = sph.xi_arr(den, h, pos)
+        assert rel(xi, g["C_xi"]) < RTOL
+        assert sph.xi(5, pos, den[5], h[5]) == pytest.approx(g["C_xi"][5], rel=RTOL)
+        assert vrel(sph.acceleration_arr(pos, den, vel, P, h, om, xi), g["C_acc_G"]) < RTOL
+        assert vrel(sph.acceleration(9, pos, den, vel, P, h, om, xi), g["C_acc_G"][9]) < RTOL
+        for (j, i), gr, co in zip(g["P_pairs"], g["P_grav"], g["P_corr"]):
+            a = sph.smoothed_gravity_acceleration_comp(int(j), int(i), pos, h)
+            b = sph.smoothed_gravity_correction_comp(int(j), int(i), pos, h, om, xi)
+            if j == i:
+                assert isinstance(a, int) and a == 0
+            else:
+                assert np.abs(a - gr).max() <= RTOL * max(np.abs(gr).max(), 1e-300)
+            assert np.abs(b - co).max() <= RTOL * max(np.abs(co).max(), 1e-300) or np.abs(co).max() == 0.0
+        # case B: stage and one leapfrog step with the default G
+        pos, vel, e, h = g["B_pos"], g["B_vel"], g["B_e"], g["B_h"]
+        xi = sph.xi_arr(g["B_den"], h, pos)
+        assert rel(xi, g["B_xi"]) < RTOL
+        assert vrel(sph.acceleration_arr(pos, g["B_den"], vel, g["B_P"], h, g["B_omega"], xi), g["B_acc_G"]) < RTOL
+        p1, v1, e1, h1 = sph.var_smoothlength_leapfrog(pos, vel, e, h, 1e-3)
+        assert rel(p1, g["B_lf_G_pos"]) < RTOL and vrel(v1, g["B_lf_G_vel"]) < RTOL
+        assert rel(e1, g["B_lf_G_e"]) < RTOL and rel(h1, g["B_lf_G_h"]) < RTOL
+    finally:
+        sph.G = 0.0
+
+
+def test_gravity_leapfrog_vs_oracle(sph, oracle_mod):
+    n = 1500
+    pos, vel, e, L = uniform_cloud(n, 91, vscale=0.5)
+    o = oracle_mod.Oracle()   # default G = 39.4227
+    h = o.newton_smoothlength_arr(pos, np.full(n, 0.8))
+    sph.G = 39.4227
+    try:
+        p1, v1, e1, h1 = sph.var_smoothlength_leapfrog(pos, vel, e, h, 1e-3)
+    finally:
+        sph.G = 0.0
+    q1, w1, f1, g1 = o.var_smoothlength_leapfrog(pos, vel, e, h, 1e-3)
+    assert rel(p1, q1) < RTOL and vrel(v1, w1) < RTOL and rel(e1, f1) < RTOL and rel(h1, g1) < RTOL

@@ -98,6 +98,14 @@ def test_case_B_default_gravity(golden, oracle_mod):
     assert g["B_lf_G_h"][0] == 1.0562858987682495 and g["B_lf_G_e"][0] == 1.408523737660402
 
 
+def test_case_C_gravity_pieces(golden, oracle_mod):
+    g = golden
+    o = oracle_mod.Oracle()   # default G
+    xi = o.xi_arr(g["C_den"], g["C_h"], g["C_pos"])
+    close(xi, g["C_xi"])
+    vclose(o.acceleration_arr(g["C_pos"], g["C_den"], g["C_vel"], g["C_P"], g["C_h"], g["C_omega"], xi), g["C_acc_G"], 1e-12)
+
+
 def test_case_C_sim_and_neighbours(golden, oracle_mod):
     g = golden
     o = oracle_mod.Oracle(G=0.0)
