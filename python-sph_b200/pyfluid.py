@@ -465,6 +465,35 @@ def fluid_accel_viscosity_comp(j, i, position_arr, velocity_arr, density_arr, pr
     return acc[0] if io.torch_out else acc[0].cpu().numpy()
 
 
+def energy_evolve(j, position_arr, velocity_arr, energy_arr, pressure_arr, density_arr, smoothlength_j, dt):
+    """pyfluid.py:292-306 (deprecated in the reference, still used by its static-h path): Euler step of the
+    fixed-h, inviscid energy equation (Cossins 3.74) for particle j"""
+    h = np.full(len(np.asarray(energy_arr.cpu() if isinstance(energy_arr, torch.Tensor) else energy_arr)), float(smoothlength_j))
+    return float(_io_np(energy_evolve_arr(position_arr, velocity_arr, energy_arr, pressure_arr, density_arr, h, None, dt))[int(j)])
+
+
+def _io_np(x):
+    return x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def energy_evolve_arr(position_arr, velocity_arr, energies_initial, pressure_arr, density_arr, smoothlength_arr, omega_arr, dt):
+    """pyfluid.py:308-314: e + P_j/rho_j^2 sum_i m v_ji . gradW(h_j) dt (omega_arr is ignored, as in the reference).
+    Same pair kernel as energy_rate_arr with Omega = 1 and the viscosity switched off."""
+    global ALPHA_SPH, BETA_SPH
+    io = _IO(position_arr, velocity_arr, energies_initial, pressure_arr, density_arr, smoothlength_arr)
+    e = _eng()
+    u0 = io.dev64(energies_initial, (-1,))
+    a0, b0 = ALPHA_SPH, BETA_SPH
+    ALPHA_SPH, BETA_SPH = 0, 0
+    try:
+        dg, acc, dudt, st, _ = _force_arrays(io, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr,
+                                             torch.ones_like(u0))
+    finally:
+        ALPHA_SPH, BETA_SPH = a0, b0
+    rate = e.scatter(dudt, dg.perm, 1)
+    return io.out(u0 + rate * float(dt))
+
+
 def energy_rate(j, position_arr, velocity_arr, pressure_arr, density_arr, smoothlength_arr, omega_arr):
     """pyfluid.py:316-353"""
     io = _IO(position_arr)
@@ -519,6 +548,40 @@ def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt):
     p, v, u, h = _stepper.step(io.dev64(pos0, (-1, 3)), io.dev64(vel0, (-1, 3)), io.dev64(energy0, (-1,)),
                                io.dev64(h0, (-1,)), float(dt), _consts())
     return io.out(p), io.out(v), io.out(u), io.out(h)
+
+
+def static_smoothlength_leapfrog(pos0, vel0, energy0, dt):
+    """pyfluid.py:607-621, REPAIRED.  As shipped it cannot run (acceleration_arr is called with 4 arguments but takes 7,
+    energy_evolve_arr with 7 but takes 8; the authors say so at :605-606).  The minimal repair of SURVEY.md 8(f) #3 is
+    used: acceleration_arr(pos, den, vel0, press, h, ones, zeros) -- no grad-h terms at fixed h -- and
+    energy_evolve_arr(pos0, vel0, energy0, press0, den0, h, None, dt).  This is a repair, not reference behaviour;
+    tests/golden/make_golden.py applies the same shim to the reference's own functions."""
+    io = _IO(pos0, vel0, energy0)
+    pos0_t, vel0_t, e0_t = io.dev64(pos0, (-1, 3)), io.dev64(vel0, (-1, 3)), io.dev64(energy0, (-1,))
+    n = e0_t.shape[0]
+    h = torch.full((n,), float(DEFAULT_SMOOTHLENGTH), dtype=torch.float64, device=e0_t.device)
+    ones, zeros = torch.ones_like(h), torch.zeros_like(h)
+    dt = float(dt)
+    den0 = density_arr(pos0_t, h)
+    press0 = pressure_arr(e0_t, den0)
+    acc0 = acceleration_arr(pos0_t, den0, vel0_t, press0, h, ones, zeros)
+    pos1 = pos0_t + vel0_t * dt + 0.5 * acc0 * dt**2
+    energy1 = energy_evolve_arr(pos0_t, vel0_t, e0_t, press0, den0, h, None, dt)
+    den1 = density_arr(pos1, h)
+    press1 = pressure_arr(energy1, den1)
+    acc1 = acceleration_arr(pos1, den1, vel0_t, press1, h, ones, zeros)
+    vel1 = vel0_t + 0.5 * (acc0 + acc1) * dt
+    return io.out(pos1), io.out(vel1), io.out(energy1)
+
+
+def static_smoothlength_sim(time, positions_with_time, velocities_with_time, energies_with_time):
+    """pyfluid.py:623-630: fills the caller's [particle][dim][time] arrays in place (numpy), like the reference"""
+    dt = time[1] - time[0]
+    for t in range(len(time) - 1):
+        (positions_with_time[:, :, t + 1], velocities_with_time[:, :, t + 1],
+         energies_with_time[:, t + 1]) = static_smoothlength_leapfrog(np.ascontiguousarray(positions_with_time[:, :, t]),
+                                                                      np.ascontiguousarray(velocities_with_time[:, :, t]),
+                                                                      np.ascontiguousarray(energies_with_time[:, t]), dt)
 
 
 def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlength_approx):

@@ -234,6 +234,44 @@ def main():
     for k, v in dict(pos=pos, vel=vel, e=e, h=hG_, omega=om, dudt=dudt, acc_G0=accg).items():
         out["G_" + k] = v
 
+    # ---- case S: BASELINE config 1, pyfluidex2d_static_h.py:10-31 settings (N=20 planar, u=10, h=2, dt=0.1, two fast
+    #      intruders), seeded, through the MINIMAL REPAIR of the static path (the shipped
+    #      static_smoothlength_leapfrog calls acceleration_arr / energy_evolve_arr with the wrong arity, pyfluid.py:605-621).
+    #      Every arithmetic step below is a call of an unmodified reference function.
+    def static_leapfrog_repaired(pos0, vel0, energy0, dt):
+        N = pos0.shape[0]
+        hs = sph.DEFAULT_SMOOTHLENGTH * np.ones(N)
+        one, zero = np.ones(N), np.zeros(N)
+        den0 = sph.density_arr(pos0, hs)
+        press0 = sph.pressure_arr(energy0, den0)
+        acc0 = sph.acceleration_arr(pos0, den0, vel0, press0, hs, one, zero)
+        pos1 = pos0 + vel0 * dt + 0.5 * acc0 * dt**2
+        energy1 = sph.energy_evolve_arr(pos0, vel0, energy0, press0, den0, hs, None, dt)
+        den1 = sph.density_arr(pos1, hs)
+        press1 = sph.pressure_arr(energy1, den1)
+        acc1 = sph.acceleration_arr(pos1, den1, vel0, press1, hs, one, zero)
+        vel1 = vel0 + 0.5 * (acc0 + acc1) * dt
+        return pos1, vel1, energy1
+
+    rng = np.random.default_rng(0)
+    N = 20
+    posS = np.zeros((N, 3)); posS[:, :2] = rng.random((N, 2)) * 10
+    velS = np.zeros((N, 3))
+    posS[0] = [10, 0, 0]; velS[0] = [0, 10, 0]
+    posS[1] = [0, 10, 0]; velS[1] = [-10, 0, 0]
+    eS = np.full(N, 10.0)
+    for gname, gval in (("G", G_DEFAULT), ("G0", 0.0)):
+        sph.G = gval
+        p, v, e_ = posS, velS, eS
+        hist = [(p, v, e_)]
+        for _ in range(3):
+            p, v, e_ = static_leapfrog_repaired(p, v, e_, 0.1)
+            hist.append((p, v, e_))
+        out["S_%s_pos" % gname] = np.array([hh[0] for hh in hist])
+        out["S_%s_vel" % gname] = np.array([hh[1] for hh in hist])
+        out["S_%s_e" % gname] = np.array([hh[2] for hh in hist])
+    sph.G = G_DEFAULT
+
     # ---- error convention: negative energy at the predictor (pyfluid.py:514-515) -------------
     sph.G = 0.0
     try:

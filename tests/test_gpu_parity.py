@@ -500,3 +500,30 @@ def test_gravity_leapfrog_vs_oracle(sph, oracle_mod):
         sph.G = 0.0
     q1, w1, f1, g1 = o.var_smoothlength_leapfrog(pos, vel, e, h, 1e-3)
     assert rel(p1, q1) < RTOL and vrel(v1, w1) < RTOL and rel(e1, f1) < RTOL and rel(h1, g1) < RTOL
+
+
+def test_golden_S_static_h_config1(sph, golden):
+    """BASELINE config 1 (pyfluidex2d_static_h.py settings) through the repaired static path:
+    three steps against the same shim applied to the reference's own functions, with G = 0 and with the default G"""
+    g = golden
+    for gname, gval in (("G0", 0.0), ("G", 39.4227)):
+        sph.G = gval
+        try:
+            p, v, e = g["S_%s_pos" % gname][0], g["S_%s_vel" % gname][0], g["S_%s_e" % gname][0]
+            for t in range(1, 4):
+                p, v, e = sph.static_smoothlength_leapfrog(p, v, e, 0.1)
+                assert rel(p, g["S_%s_pos" % gname][t]) < RTOL, (gname, t)
+                assert vrel(v, g["S_%s_vel" % gname][t]) < RTOL, (gname, t)
+                assert rel(e, g["S_%s_e" % gname][t]) < RTOL, (gname, t)
+        finally:
+            sph.G = 0.0
+    # the in-place [particle][dim][time] driver of the reference (pyfluid.py:623-630)
+    n, nt = 20, 3
+    P = np.zeros((n, 3, nt)); V = np.zeros((n, 3, nt)); E = np.zeros((n, nt))
+    P[:, :, 0], V[:, :, 0], E[:, 0] = g["S_G0_pos"][0], g["S_G0_vel"][0], g["S_G0_e"][0]
+    sph.static_smoothlength_sim(np.array([0.0, 0.1, 0.2]), P, V, E)
+    assert rel(P[:, :, 2], g["S_G0_pos"][2]) < RTOL and rel(E[:, 2], g["S_G0_e"][2]) < RTOL
+    e_one = sph.energy_evolve(3, g["S_G0_pos"][0], g["S_G0_vel"][0], g["S_G0_e"][0],
+                              sph.pressure_arr(g["S_G0_e"][0], sph.density_arr(g["S_G0_pos"][0], np.full(20, 2.0))),
+                              sph.density_arr(g["S_G0_pos"][0], np.full(20, 2.0)), 2.0, 0.1)
+    assert e_one == pytest.approx(g["S_G0_e"][1][3], rel=RTOL)
