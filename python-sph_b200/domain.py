@@ -106,12 +106,12 @@ class HaloExchanger:
 class SlabRunner:
     """var_smoothlength_leapfrog on a slab-decomposed particle set (one rank per GPU)."""
 
-    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05, balance=True, calib_steps=2):
+    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05, balance=True, calib_steps=0):
         if consts.G != 0.0:
             raise NotImplementedError("SlabRunner: the all-pairs gravity sum is single-GPU only; run with G = 0")
         self.e, self.consts, self.world, self.rank, self.margin = eng, consts, world, rank, margin
         self.balance = balance
-        self.calib_left = calib_steps if balance else 0   # first steps are timed per rank and the cuts re-balanced
+        self.calib_left = calib_steps if balance else 0   # optional: time the first steps per rank and re-balance
         self.dev = eng.device
         self.statuses = []
         self.geom = None
@@ -248,6 +248,20 @@ class SlabRunner:
         st = dict(st)
         st["wfac"] = st["wfac"] * min(max(fac, 0.5), 2.0)
         return self.rebalance(st)
+
+    def calibrate(self, st, dt, rounds=2):
+        """setup-time load balancing: run `rounds` throw-away steps from `st`, time this rank's kernels in each, fold the
+        measured time into the per-particle cost factors and re-cut.  Returns `st` (unchanged physics) redistributed."""
+        if not self.balance or self.world == 1:
+            return st
+        for _ in range(rounds):
+            self.e.prof_start()
+            self._step(st, dt)
+            ms = sum(v[1] for v in self.e.prof_stop().values())
+            self.statuses.pop()          # the throw-away step's status block
+            st = self._calibrate(st, ms)
+            self._post_hmax(st["h"])
+        return st
 
     def cold_solve(self, st):
         self.geom = self._global_geom(st["pos"], st["h"])

@@ -17,6 +17,7 @@ k = dict(PARTICLE_MASS=w["m"], COUPLING_CONST=1.3, SMOOTHLENGTH_VARIATION_TOLERA
 consts = E.make_consts(k)
 r = domain.SlabRunner(eng, consts, world, rank)
 st = r.cold_solve(r.scatter_initial(w))
+st = r.calibrate(st, w["dt"])
 for _ in range(2):
     st = r.step(st, w["dt"])
 torch.cuda.synchronize(); dist.barrier()
