@@ -8,10 +8,12 @@ so each gather phase needs exactly one exchange of ghost particles:
     halo(pos, h, vel, u)   before every cell-list build      all_to_all_single (NCCL over NVLink)
     halo(h_new)            after a Newton solve               same send lists
     halo(omega)            after an Omega pass (force needs Omega_i of ghost neighbours)
-    migration              after the corrector                full 64-byte records + global id
-    allreduce(max/min/sum) h_max, bounding box, status words  a few scalars
+    migration + re-plan    every `replan_every` steps         full 64-byte records + global id, new send lists
+    allreduce(max/min/sum) h_max, bounding box, status words  a few scalars, only at a re-plan / status check
 
-Ghost width = 2 h_max (1 + margin): the force support is 2 max(h_i, h_j).  Local arrays are kept sorted
+The send lists (the halo "plan") are made with a skin and reused for every snapshot until the next re-plan, so a
+steady-state step contains no device->host read; drift and h growth are checked against the plan on the device.
+Ghost width = 2 h_max (1 + margin) + skin: the force support is 2 max(h_i, h_j).  Local arrays are kept sorted
 by global particle id before each build, so the stable cell sort visits neighbours in the same order as
 a single-GPU run with the same grid geometry: k-rank results are bit-identical to 1-rank results.
 
@@ -115,8 +117,13 @@ class SlabRunner:
         self.dev = eng.device
         self.statuses = []
         self.geom = None
-        self._hmax_t = None      # device scalar: global max h after the last solve (all-reduced, read lazily)
-        self._halo_viol = None   # device flag: a solved h outgrew the halo it was computed with
+        self._halo_viol = None   # device flag: a solved h / the accumulated drift outgrew the halo plan
+        # Halo plan (send lists + ghost ids), reused for every snapshot until the next re-plan: in steady state a step
+        # then has NO device->host read at all.  The plan is made with a skin; the drift since it was made and the
+        # current h_max are checked against it on the device, and check_status() reports a violation.
+        self.plan = None
+        self.replan_every = 8     # steps between migrations / re-plans
+        self.skin = 0.1           # extra halo width, in units of h_max, that particles may drift before a re-plan
 
     # ---- setup -------------------------------------------------------------------------------------
     def scatter_initial(self, w):
@@ -147,27 +154,33 @@ class SlabRunner:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def _post_hmax(self, h):
-        """start the all-reduce of max(h); the value is only read (one tiny D2H) when the next step needs it"""
-        t = h.max().reshape(1).clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        self._hmax_t = t
+    def _make_plan(self, st, extra=1.0):
+        """migrate, then fix the halo send lists and the ghost ids until the next re-plan (the only place with
+        device->host reads: send counts and h_max)"""
+        st = self._migrate(st)
+        hm = self._hmax(st["h"])
+        width = 2.0 * hm * (1.0 + self.margin) * extra + 2.0 * self.skin * hm + 4.0 * self.geom[1]
+        hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width)
+        gid_recv = hx.exchange([st["gid"].to(F64)])[0].to(torch.int64)
+        self.plan = dict(hx=hx, width=width, gid_all=torch.cat([st["gid"], gid_recv]), pos_ref=st["pos"].clone(), age=0)
+        return st
 
-    def _note_halo(self, h_new, width):
-        """device-side check that the halo a solve ran with still covers 2 h_new (reported by check_status)"""
-        bad = (2.0 * h_new.max() > width).to(torch.int32).reshape(1)
+    def _note_plan_use(self, pos, h):
+        """device-side validity check of the current plan: 2 h_max + 2 drift must stay inside the planned width"""
+        drift = (pos - self.plan["pos_ref"]).abs().amax()
+        bad = (2.0 * h.max() + 2.0 * drift > self.plan["width"]).to(torch.int32).reshape(1)
         self._halo_viol = bad if self._halo_viol is None else torch.maximum(self._halo_viol, bad)
 
-    # ---- one snapshot: ghosts + cell list ------------------------------------------------------------
-    def _snapshot(self, st, width, fields):
-        """exchange ghosts of `fields` (names in st) and build the cell list over [owned..., ghosts...]; ties inside a
-        cell are broken by global particle id, so the neighbour order does not depend on the decomposition."""
-        hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width)
-        recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in fields])
+    def _snapshot(self, st, fields):
+        """exchange ghosts of `fields` (names in st) along the current plan and build the cell list over
+        [owned..., ghosts...]; ties inside a cell are broken by global particle id, so the neighbour order does not
+        depend on the decomposition."""
+        hx = self.plan["hx"]
+        recv = hx.exchange([st[f] for f in fields])
         n_own = st["gid"].numel()
-        gid_all = torch.cat([st["gid"], recv[0].to(torch.int64)])
+        gid_all = self.plan["gid_all"]
         snap = dict(hx=hx, n_own=n_own, n_loc=gid_all.numel())
-        for f, g in zip(fields, recv[1:]):
+        for f, g in zip(fields, recv):
             snap[f] = torch.cat([st[f], g])
         posh = self.e.pack_posh(snap["pos"], snap["h"])
         dg = self.e.build(posh, *self.geom, tie_key=gid_all)
@@ -232,6 +245,7 @@ class SlabRunner:
             cuts.append(xlo + (min(k, nbins - 1) + 1) * span / nbins)
         cuts.append(math.inf)
         self.cuts = cuts
+        self.plan = None
         return self._migrate(st)
 
     def _calibrate(self, st, my_ms):
@@ -260,21 +274,33 @@ class SlabRunner:
             ms = sum(v[1] for v in self.e.prof_stop().values())
             self.statuses.pop()          # the throw-away step's status block
             st = self._calibrate(st, ms)
-            self._post_hmax(st["h"])
         return st
 
     def cold_solve(self, st):
         self.geom = self._global_geom(st["pos"], st["h"])
-        hmax = self._hmax(st["h"])
-        stt = E.Status(1, self.dev)
-        snap = self._snapshot(st, 2.0 * hmax * 1.6, ["pos", "h"])     # generous: the guess is an under-estimate
-        st = dict(st)
-        st["h"] = self._newton(snap, stt.ptr(0))
+        # the guess is usually an under-estimate and the halo must cover the support of the SOLVED h: widen and
+        # repeat until the plan's own validity check passes (setup path: host reads are fine here)
+        extra, guess = 1.6, st["h"]
+        while True:
+            stt = E.Status(1, self.dev)
+            st = self._make_plan(dict(st, h=guess), extra=extra)
+            guess = st["h"]
+            snap = self._snapshot(st, ["pos", "h"])
+            h_new = self._newton(snap, stt.ptr(0))
+            self._halo_viol = None
+            self._note_plan_use(st["pos"], h_new)
+            bad = self._halo_viol.clone()
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            self._halo_viol = None
+            if not int(bad.item()):
+                break
+            extra *= 1.6
+        st["h"] = h_new
         self.statuses.append(stt)
         self.geom = self._global_geom(st["pos"], st["h"])
+        self.plan = None
         if self.balance:
             st = self.rebalance(st)
-        self._post_hmax(st["h"])
         return st
 
     def step(self, st, dt):
@@ -289,12 +315,11 @@ class SlabRunner:
     def _step(self, st, dt):
         e = self.e
         stt = E.Status(E.S_COUNT, self.dev)
-        if self._hmax_t is None:
-            self._post_hmax(st["h"])
-        w0 = 2.0 * float(self._hmax_t.item()) * (1.0 + self.margin) + 4.0 * self.geom[1]   # one scalar D2H per step
-        w1, w2 = w0 * 1.02, w0 * 1.04
+        if self.plan is None or self.plan["age"] >= self.replan_every:
+            st = self._make_plan(st)
+        self.plan["age"] += 1
         # stage 0
-        s0 = self._snapshot(st, w0, ["pos", "h", "vel", "u"])
+        s0 = self._snapshot(st, ["pos", "h", "vel", "u"])
         acc0, dudt0 = self._stage(s0, stt.ptr(E.S_STAGE0))
         # predictor (owned only)
         posh0 = e.pack_posh(st["pos"], st["h"])
@@ -304,20 +329,19 @@ class SlabRunner:
         if wfac is None:
             wfac = torch.ones_like(st["h"])
         # h_mid
-        s1 = self._snapshot(mid, w1, ["pos", "h", "vel", "u"])
+        s1 = self._snapshot(mid, ["pos", "h", "vel", "u"])
         h_mid, om_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID), want_omega=True)
-        self._note_halo(h_mid, w1)
+        self._note_plan_use(mid["pos"], h_mid)
         h_mid_L = self._fill_ghosts(s1, h_mid)
         e.set_h(s1["dg"], self._to_grid(s1, h_mid_L, 1))
         acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID), om_own=om_mid)
         # corrector (owned only, t0 state is still in owned order)
         posh_1, vel_1, u_1 = e.correct(posh0, st["vel"], st["u"], acc1, dudt1, dt, stt.ptr(E.S_CORR))
         new = dict(gid=st["gid"], pos=posh_1[:, :3].contiguous(), h=h_mid, vel=vel_1, u=u_1, wfac=wfac)
-        # migration, then h1
-        new = self._migrate(new)
-        s2 = self._snapshot(new, w2, ["pos", "h"])
+        # h1 (migration happens at the next re-plan)
+        s2 = self._snapshot(new, ["pos", "h"])
         new["h"] = self._newton(s2, stt.ptr(E.S_NEWTON_1))
-        self._post_hmax(new["h"])
+        self._note_plan_use(new["pos"], new["h"])
         self.statuses.append(stt)
         return new
 
@@ -350,7 +374,8 @@ class SlabRunner:
             dist.all_reduce(v, op=dist.ReduceOp.MAX)
             self._halo_viol = None
             if int(v.item()):
-                raise RuntimeError("halo too narrow for the new smoothing lengths; increase SlabRunner(margin=...)")
+                raise RuntimeError("the halo plan was outgrown (h or particle drift): lower SlabRunner.replan_every or raise "
+                                   ".margin / .skin")
         E.raise_for_status(tot.cpu().numpy(), printer=printer)
 
     def gather_state(self, st):
