@@ -273,22 +273,21 @@ def run_ours(a):
     # ---- e2e: public API semantics on pinned host buffers (H2D + step + D2H each step) ----------------
     e2e = None
     if not a.no_e2e and runner is None:
+        # the public call with pinned host tensors: pyfluid.var_smoothlength_leapfrog(pos, vel, u, h, dt)
+        import pyfluid as sph
+        sph.G = 0.0
+        sph.PARTICLE_MASS = w["m"]
         hin = [t.cpu().pin_memory() for t in state]
-        hout = [torch.empty_like(t).pin_memory() for t in hin]
         nb = sum(t.numel() * 8 for t in hin)
         ke = max(1, min(a.steps, 3))
+        hin = list(sph.var_smoothlength_leapfrog(hin[0], hin[1], hin[2], hin[3], dt))   # warm-up (allocations, streams)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(ke):
-            d = [t.to(dev, non_blocking=True) for t in hin]
-            r = stepper.step(d[0], d[1], d[2], d[3], dt, consts, defer_status=False, printer=lambda *_: None)
-            for o_, r_ in zip(hout, r):
-                o_.copy_(r_, non_blocking=True)
-            torch.cuda.synchronize()
-            hin, hout = hout, hin
+            hin = list(sph.var_smoothlength_leapfrog(hin[0], hin[1], hin[2], hin[3], dt))
         el = time.perf_counter() - t0
         e2e = {"value": n_total * ke / el, "unit": "particle-steps/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
-               "steps": ke}
+               "steps": ke, "api": "pyfluid.var_smoothlength_leapfrog on pinned host tensors (transfers overlapped with kernels)"}
     elif runner is not None and not a.no_e2e:
         e2e = runner.e2e(state, dt, max(1, min(a.steps, 3)))
 

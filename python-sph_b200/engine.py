@@ -400,7 +400,8 @@ class Stepper:
         self.last_status = None
         self.geom = None   # (grid, delta) reused across steps when set by the caller
 
-    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, omega0=None, want_omega1=False):
+    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, omega0=None, want_omega1=False,
+             hooks=None):
         """omega0 (caller order, optional): Omega(pos0, h0) if the caller already has it -- the time loop does, because
         the previous step's last Newton kernel returns it (want_omega1=True appends omega1 to the result).  Without
         it the step computes Omega0 itself, exactly like a stand-alone var_smoothlength_leapfrog call."""
@@ -417,6 +418,10 @@ class Stepper:
         def stage(dg, vel_c, u_c, sidx, om=None):
             """the six calls at pyfluid.py:502-507 / :517-522 -> acc, dudt in caller order
             (om: Omega already produced by the Newton kernel for this snapshot)"""
+            if not grav and om is None:
+                _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
+            if hooks is not None and sidx == S_STAGE0:
+                hooks.before_vel_u()          # velocities and energies are first needed here
             vel_s, u_s = e.gather(vel_c, dg.perm, 3), e.gather(u_c, dg.perm, 1)
             if grav:
                 # xi_arr (:504) rides in the Omega pass; its compact correction (:434-437) rides in the force kernel;
@@ -426,8 +431,6 @@ class Stepper:
                 acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx), bgrav=bg)
                 e.gravity_direct(dg.posh, consts, acc=acc)
             else:
-                if om is None:
-                    _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
                 _, _, rB, rC = e.eos(dg.posh, vel_s, u_s, om, consts, st.ptr(sidx))
                 acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx))
             return e.scatter(acc, dg.perm, 3), e.scatter(dudt, dg.perm, 1)
@@ -451,6 +454,8 @@ class Stepper:
         h_mid = e.scatter(h_mid_s, g1.perm, 1)
         # ---- corrector: pyfluid.py:524-528 ---------------------------------------------------------------
         posh_1, vel1, u1 = e.correct(posh0, vel0, u0, acc1, dudt1, dt, st.ptr(S_CORR))
+        if hooks is not None:
+            hooks.after_corrector(posh_1, vel1, u1)   # pos1, vel1, u1 are final: their copy-out can start now
         # ---- h1 = newton(pos1, h_mid): pyfluid.py:530 ------------------------------------------------------
         posh_1 = e.pack_posh(posh_1[:, :3].contiguous(), h_mid)
         g2 = e.build(posh_1, grid, delta)
@@ -463,3 +468,56 @@ class Stepper:
         if want_omega1:
             return pos1, vel1, u1, h1, e.scatter(r[1], g2.perm, 1)
         return pos1, vel1, u1, h1
+
+
+class _PinnedHooks:
+    """stream choreography of Stepper.step_pinned"""
+
+    def __init__(self, copy_stream, ev_vel_u, out):
+        self.cs, self.ev, self.out = copy_stream, ev_vel_u, out
+        self.ev_out = torch.cuda.Event()
+
+    def before_vel_u(self):
+        torch.cuda.current_stream().wait_event(self.ev)
+
+    def after_corrector(self, posh_1, vel1, u1):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        pos1 = posh_1[:, :3]
+        with torch.cuda.stream(self.cs):
+            self.cs.wait_event(ev)
+            self.out[0].copy_(pos1, non_blocking=True)
+            self.out[1].copy_(vel1, non_blocking=True)
+            self.out[2].copy_(u1, non_blocking=True)
+            self.ev_out.record(self.cs)
+        for t in (posh_1, vel1, u1):
+            t.record_stream(self.cs)
+
+
+def step_pinned(stepper, pos_h, vel_h, u_h, h_h, dt, consts, out=None, printer=print):
+    """var_smoothlength_leapfrog for HOST tensors (pinned memory): the step with its transfers overlapped.
+    pos and h go up first; vel and u follow on a copy stream while the cell list and the Omega pass run; pos1, vel1, u1
+    come down while the last Newton solve runs; h1 follows.  Returns pinned host tensors (`out` is reused if given)."""
+    e = stepper.e
+    dev = e.device
+    main = torch.cuda.current_stream()
+    cs = torch.cuda.Stream(device=dev)
+    if out is None:
+        out = [torch.empty_like(t).pin_memory() for t in (pos_h, vel_h, u_h, h_h)]
+    pos_d = pos_h.to(dev, non_blocking=True)
+    h_d = h_h.to(dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    with torch.cuda.stream(cs):
+        vel_d = vel_h.to(dev, non_blocking=True)
+        u_d = u_h.to(dev, non_blocking=True)
+        ev.record(cs)
+    vel_d.record_stream(main)
+    u_d.record_stream(main)
+    hooks = _PinnedHooks(cs, ev, out)
+    r = stepper.step(pos_d, vel_d, u_d, h_d, dt, consts, defer_status=True, hooks=hooks)
+    out[3].copy_(r[3], non_blocking=True)
+    main.wait_event(hooks.ev_out)
+    torch.cuda.synchronize(dev)
+    raise_for_status(stepper.last_status.read(), printer)
+    return out

@@ -545,6 +545,11 @@ def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt):
     io = _IO(pos0, vel0, energy0, h0)
     if _stepper is None:
         _stepper = _E.Stepper(_eng())
+    host = [t for t in (pos0, vel0, energy0, h0) if isinstance(t, torch.Tensor) and not t.is_cuda]
+    if len(host) == 4 and all(t.is_pinned() and t.dtype == torch.float64 and t.is_contiguous() for t in host):
+        # pinned host tensors in -> pinned host tensors out, transfers overlapped with the kernels
+        return tuple(_E.step_pinned(_stepper, pos0.reshape(-1, 3), vel0.reshape(-1, 3), energy0.reshape(-1), h0.reshape(-1),
+                                    float(dt), _consts()))
     p, v, u, h = _stepper.step(io.dev64(pos0, (-1, 3)), io.dev64(vel0, (-1, 3)), io.dev64(energy0, (-1,)),
                                io.dev64(h0, (-1,)), float(dt), _consts())
     return io.out(p), io.out(v), io.out(u), io.out(h)
@@ -596,19 +601,24 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
     vel = io.dev64(velocities0, (-1, 3))
     u = io.dev64(energies0, (-1,))
     N = u.shape[0]
-    dev = pos.device
-    P = torch.zeros((Nt, N, 3), dtype=torch.float64, device=dev)
-    V = torch.zeros((Nt, N, 3), dtype=torch.float64, device=dev)
-    E = torch.zeros((Nt, N), dtype=torch.float64, device=dev)
-    H = torch.zeros((Nt, N), dtype=torch.float64, device=dev)
-    P[0], V[0], E[0] = pos, vel, u
-    H[0] = newton_smoothlength_arr(P[0], io.dev64(smoothlength_approx, (-1,)))
+    if io.torch_out:
+        mk = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=pos.device)
+        put = lambda arr, t, x: arr.__setitem__(t, x)
+    else:
+        # numpy callers get numpy histories: each snapshot goes to host memory as it is produced, so the (Nt,N,.)
+        # history never has to fit in HBM (the reference's own TODO at pyfluid.py:585-588)
+        mk = lambda *shape: np.zeros(shape)
+        put = lambda arr, t, x: arr.__setitem__(t, x.cpu().numpy())
+    P, V, E, H = mk(Nt, N, 3), mk(Nt, N, 3), mk(Nt, N), mk(Nt, N)
+    h = newton_smoothlength_arr(pos, io.dev64(smoothlength_approx, (-1,)))
+    for arr, x in ((P, pos), (V, vel), (E, u), (H, h)):
+        put(arr, 0, x)
     if _stepper is None:
         _stepper = _E.Stepper(_eng())
     om = None
     for t in range(Nt - 1):
         print("time step:", t, "of", Nt)
-        P[t + 1], V[t + 1], E[t + 1], H[t + 1], om = _stepper.step(P[t].contiguous(), V[t].contiguous(), E[t].contiguous(),
-                                                                  H[t].contiguous(), dt, _consts(), omega0=om,
-                                                                  want_omega1=True)
-    return io.out(P), io.out(V), io.out(E), io.out(H)
+        pos, vel, u, h, om = _stepper.step(pos, vel, u, h, dt, _consts(), omega0=om, want_omega1=True)
+        for arr, x in ((P, pos), (V, vel), (E, u), (H, h)):
+            put(arr, t + 1, x)
+    return P, V, E, H

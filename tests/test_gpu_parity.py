@@ -527,3 +527,18 @@ def test_golden_S_static_h_config1(sph, golden):
                               sph.pressure_arr(g["S_G0_e"][0], sph.density_arr(g["S_G0_pos"][0], np.full(20, 2.0))),
                               sph.density_arr(g["S_G0_pos"][0], np.full(20, 2.0)), 2.0, 0.1)
     assert e_one == pytest.approx(g["S_G0_e"][1][3], rel=RTOL)
+
+
+def test_pinned_host_tensors_overlapped_path(sph, golden):
+    """pinned CPU tensors in -> pinned CPU tensors out (transfers overlapped with the kernels): same bits as the
+    device-tensor path"""
+    import torch
+    n = 20000
+    pos, vel, e, L = uniform_cloud(n, 55, vscale=0.6)
+    h = sph.newton_smoothlength_arr(pos, np.full(n, 0.8))
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (pos, vel, e, h)]
+    ref = sph.var_smoothlength_leapfrog(*dev, 1e-3)
+    host = [t.cpu().pin_memory() for t in dev]
+    out = sph.var_smoothlength_leapfrog(*host, 1e-3)
+    for a, b in zip(ref, out):
+        assert (not b.is_cuda) and b.is_pinned() and torch.equal(a.cpu(), b)
