@@ -209,13 +209,13 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     a.vxj = a.vyj = a.vzj = a.Aj = 0.0;
     a.rhoj = a.csj = a.hinvj = a.gj = 0.0;
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t row = 0xffffffffu;
+    uint32_t cid = 0xffffffffu;
     if (valid) {
         sphb_load4(c.posh, (size_t)j, a.xj, a.yj, a.zj, a.hj);
         sphb_load4(recB, (size_t)j, a.vxj, a.vyj, a.vzj, a.Aj);
         sphb_load4(recC, (size_t)j, a.rhoj, a.csj, a.hinvj, a.gj);
         f = __ldg(g.frec + j);
-        row = c.cell_id[j] / (uint32_t)g.nx;
+        cid = c.cell_id[j];
     }
     a.ax = a.ay = a.az = a.dens = a.visc = 0.0;
     a.negpi = 0;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     SphbList L;
     L.init(ws, lane);
     auto flush = [&](int n_) { sphb_force_flush<GRAV>(c.posh, recB, recC, bgrav, ws, lane, n_, k, a); };
-    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, RH, L, flush);
+    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush);
     flush(L.count());
     if (tgt) {
         const double m = k.particle_mass;

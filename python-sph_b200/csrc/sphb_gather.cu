@@ -90,12 +90,12 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     double h = 1.0;
     a.xj = a.yj = a.zj = 0.0;
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t row = 0xffffffffu;
+    uint32_t cid = 0xffffffffu;
     if (valid) {
         sphb_load_posh(c.posh, (size_t)j, a.xj, a.yj, a.zj, h);
         if (h_target) h = h_target[j];
         f = __ldg(g.frec + j);
-        row = c.cell_id[j] / (uint32_t)g.nx;
+        cid = c.cell_id[j];
     }
     a.hinv = 1.0 / h;
     a.sumF = a.sumG = a.sumX = 0.0;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     SphbList L;
     L.init(ws, lane);
     auto flush = [&](int n_) { sphb_own_flush<XI>(c.posh, ws, lane, n_, a); };
-    sphb_warp_scan<false>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
+    sphb_warp_scan<false>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
     flush(L.count());
     if (tgt) {
         const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
@@ -126,12 +126,16 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
 
 // ------------------------------------------------------------------------------------------------
 // K3: per-lane Newton loop with warp-vote convergence mask (pyfluid.py:155-179).
-// With omega_out != NULL the kernel also returns Omega at the converged h (pyfluid.py:91-97 with the algebraic
-// density, as the step uses it at :503/:518): the scan radius carries a 1.1e-3 margin, so when a lane converges
-// (|h_old - h_new| < 1e-3 |h_new|) its neighbour list already covers the support of h_new and the sum
-// sum_i m dW/dh(r, h_new) is one more pass over the SAME list -- no second cell scan, no extra launch.
+// The cell scan runs at the guess with a small radius margin and leaves each lane a neighbour list that covers
+// every h up to (1 + margin) * guess.  Each further evaluation the lane needs -- the sums of the next Newton
+// iterate, or (omega_out != NULL) the sum m dW/dh at the converged h that Omega is made of (pyfluid.py:91-97 with
+// the algebraic density, as the step uses it at :503/:518) -- is one more pass over the SAME list while the new h
+// stays inside that cover; entries beyond the support of the new h add exact zeros.  Only a lane whose h leaves
+// the cover (cold solves, bad guesses), or whose list overflowed, makes the warp scan again.
 // ------------------------------------------------------------------------------------------------
-#define SPHB_NEWTON_MARGIN 1.1e-3
+#ifndef SPHB_NEWTON_MARGIN
+#define SPHB_NEWTON_MARGIN 4e-3
+#endif
 
 __device__ __forceinline__ double sphb_omega_from_sumG(const sphb_consts &k, double h, double sumG)
 {
@@ -155,95 +159,99 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     const bool tgt = valid && (target == nullptr || target[j] != 0);
     const SphbScanCtx g = sphb_make_ctx(c);
     SphbWarpShared &ws = sh[warp];
-    const double rmargin = FUSED ? 1.0 + SPHB_NEWTON_MARGIN : 1.0;
+    const double rmargin = 1.0 + SPHB_NEWTON_MARGIN;
 
     SphbOwnAcc a;
     a.xj = a.yj = a.zj = 0.0;
-    double h_old = 1.0, hdummy;
+    double h_cur = 1.0, hdummy;
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t row = 0xffffffffu;
+    uint32_t cid = 0xffffffffu;
     if (valid) {
         sphb_load_posh(c.posh, (size_t)j, a.xj, a.yj, a.zj, hdummy);
         f = __ldg(g.frec + j);
-        row = c.cell_id[j] / (uint32_t)g.nx;
+        cid = c.cell_id[j];
     }
-    if (tgt) h_old = h_guess[j];
-    bool active = tgt, need_scan = false;
-    double h_fin = 1.0;
-    int it = 0;
-    while (__any_sync(SPHB_FULL, active)) {
-        a.hinv = 1.0 / h_old;
+    if (tgt) h_cur = h_guess[j];
+    // what the lane needs next: 1 = the sums of a Newton iterate at h_cur, 2 = sum m dW/dh at the converged h_cur
+    // (FUSED), 0 = nothing
+    int want = tgt ? 1 : 0;
+    double h_cover = 0.0;    // the lane's list holds every neighbour of any h <= h_cover
+    bool have_lists = false; // warp-uniform: the lists of the last scan are intact (no overflow flush)
+    int cnt = 0, it = 0;
+#ifdef SPHB_NEWTON_TRACE
+    const long long trace_t0 = clock64();
+    int trace_scans = 0, trace_rounds = 0;
+#endif
+    while (__any_sync(SPHB_FULL, want != 0)) {
+        const bool pend = want != 0;
+        a.hinv = 1.0 / h_cur;
         a.sumF = a.sumG = a.sumX = 0.0;
         a.nn = 0;
-        const double hs = h_old * rmargin;
-        const float Rj = sphb_radius_of_h(hs, g.delta), thr = sphb_thr_of_h(hs, g.delta);
-        SphbList L;
-        L.init(ws, lane);
-        bool flushed = false;   // warp-uniform: did a list overflow during this scan?
-        auto flush = [&](int n_) {
-            flushed = true;
-            sphb_own_flush(c.posh, ws, lane, n_, a);
-        };
-        sphb_warp_scan<false>(g, ws, lane, active, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
-        const int cnt = L.count();
-        sphb_own_flush(c.posh, ws, lane, cnt, a);
-        if (active) {
+        const bool covered = have_lists && h_cur > 0.0 && h_cur <= h_cover;
+        if (__any_sync(SPHB_FULL, pend && !covered)) {
+            // scan (again) for every lane that still needs something
+#ifdef SPHB_NEWTON_TRACE
+            ++trace_scans;
+#endif
+            const double hs = h_cur * rmargin;
+            const float Rj = sphb_radius_of_h(hs, g.delta), thr = sphb_thr_of_h(hs, g.delta);
+            SphbList L;
+            L.init(ws, lane);
+            bool flushed = false;   // warp-uniform: did a list overflow during this scan?
+            auto flush = [&](int n_) {
+                flushed = true;
+                sphb_own_flush(c.posh, ws, lane, n_, a);
+            };
+            sphb_warp_scan<false>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
+            cnt = L.count();   // 0 for lanes that were not scanned for
+            have_lists = !flushed;
+            h_cover = pend ? hs : 0.0;
+        }
+        sphb_own_flush(c.posh, ws, lane, pend ? cnt : 0, a);
+        if (want == 1) {
             // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
-            const double pref = k.particle_mass / (SPHB_PI * (h_old * h_old * h_old));
+            const double pref = k.particle_mass / (SPHB_PI * (h_cur * h_cur * h_cur));
             const double rho = pref * a.sumF;
-            const double sdh = -(pref / h_old) * a.sumG;
-            const double vd = sphb_var_density(k, h_old);
+            const double sdh = -(pref / h_cur) * a.sumG;
+            const double vd = sphb_var_density(k, h_cur);
             const double zeta = vd - rho;
-            const double zetap = -sdh - 3.0 * vd / h_old;
-            const double h_new = h_old - zeta / zetap;
+            const double zetap = -sdh - 3.0 * vd / h_cur;
+            const double h_new = h_cur - zeta / zetap;
             ++it;
             // smoothlength_variation(old, new) = |old - new| / |new|, pyfluid.py:119-120,172
-            if (fabs(h_old - h_new) / fabs(h_new) < k.h_tol && h_new > 0.0) {
+            if (fabs(h_cur - h_new) / fabs(h_new) < k.h_tol && h_new > 0.0) {
                 h_out[j] = h_new;
                 if (iters) iters[j] = it;
                 if (code) code[j] = 0;
-                active = false;
-                if (FUSED) {
-                    if (!flushed) {
-                        SphbOwnAcc b = a;
-                        b.hinv = 1.0 / h_new;
-                        b.sumF = b.sumG = 0.0;
-                        sphb_own_flush(c.posh, ws, lane, cnt, b);
-                        omega_out[j] = sphb_omega_from_sumG(k, h_new, b.sumG);
-                    } else {
-                        need_scan = true;
-                        h_fin = h_new;
-                    }
-                }
-            } else {
-                h_old = h_new;
-                if (it >= k.newton_limit) {
-                    // "WARNING: Failure to converge in newton_new_h." -> bisection_h(j, pos), pyfluid.py:178-179
-                    atomicAdd(&status->newton_warn, 1);
-                    const int slot = atomicAdd(&status->nfail, 1);
-                    fail_list[slot] = (uint32_t)j;
-                    h_out[j] = CUDART_NAN;
-                    if (FUSED) omega_out[j] = CUDART_NAN;
-                    if (iters) iters[j] = it;
-                    if (code) code[j] = 1;
-                    active = false;
-                }
+                want = FUSED ? 2 : 0;
+            } else if (it >= k.newton_limit) {
+                // "WARNING: Failure to converge in newton_new_h." -> bisection_h(j, pos), pyfluid.py:178-179
+                atomicAdd(&status->newton_warn, 1);
+                const int slot = atomicAdd(&status->nfail, 1);
+                fail_list[slot] = (uint32_t)j;
+                h_out[j] = CUDART_NAN;
+                if (FUSED) omega_out[j] = CUDART_NAN;
+                if (iters) iters[j] = it;
+                if (code) code[j] = 1;
+                want = 0;
             }
+            h_cur = h_new;
+        } else if (want == 2) {
+            omega_out[j] = sphb_omega_from_sumG(k, h_cur, a.sumG);
+            want = 0;
         }
         __syncwarp();
+#ifdef SPHB_NEWTON_TRACE
+        ++trace_rounds;
+#endif
     }
-    // lanes whose list overflowed: one more scan at the final h
-    if (FUSED && __any_sync(SPHB_FULL, need_scan)) {
-        a.hinv = 1.0 / h_fin;
-        a.sumF = a.sumG = 0.0;
-        const float Rj = sphb_radius_of_h(h_fin, g.delta), thr = sphb_thr_of_h(h_fin, g.delta);
-        SphbList L;
-        L.init(ws, lane);
-        auto flush = [&](int n_) { sphb_own_flush(c.posh, ws, lane, n_, a); };
-        sphb_warp_scan<false>(g, ws, lane, need_scan, f.x, f.y, f.z, Rj, thr, row, 0.f, L, flush);
-        flush(L.count());
-        if (need_scan) omega_out[j] = sphb_omega_from_sumG(k, h_fin, a.sumG);
+#ifdef SPHB_NEWTON_TRACE
+    // tuning aid (scripts/newton_phase.py): per-warp cost and what it was spent on, in place of iters / code
+    if (valid && iters && code) {
+        iters[j] = it | (trace_scans << 8) | (trace_rounds << 16) | (cnt << 24 & 0x7f000000);
+        code[j] = (int)((clock64() - trace_t0) >> 4);
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -26,12 +26,15 @@
 #ifndef SPHB_SUB
 #define SPHB_SUB 8 /* candidates filtered between two overflow checks */
 #endif
-#define SPHB_SEG_BITS 11  /* list code = (segment slot << 11) | offset in segment */
+#ifndef SPHB_SEG_BITS
+#define SPHB_SEG_BITS 9   /* list code = (segment slot << 9) | offset in segment */
+#endif
 #define SPHB_SEG_LEN (1u << SPHB_SEG_BITS)
+#define SPHB_NSEG (1 << (16 - SPHB_SEG_BITS)) /* live segments a 16-bit code can address */
 
 struct SphbWarpShared {
     float4 tile[32];      // x', y', z', |c'|^2 of the staged candidates (NaN-padded)
-    uint32_t segbase[32]; // first sorted slot of each live segment
+    uint32_t segbase[SPHB_NSEG]; // first sorted slot of each live segment
     uint16_t list[SPHB_LIST * 32];
 };
 
@@ -115,22 +118,39 @@ __device__ __forceinline__ uint32_t sphb_list_get(const SphbWarpShared &ws, int 
 // One full scan for the calling warp.  Every lane must call it (inactive lanes pass tgt = false).
 //   fx,fy,fz : the lane's own fp32 record position;  Rj: its search radius (float, rounded up, may be +inf)
 //   thr      : its squared threshold (float, rounded up, may be +inf)
-//   row      : its cell row id (cell_id / nx), used to group lanes
+//   cid      : its linear cell id, used to group lanes (0xffffffff for lanes without a particle)
 //   SYM      : also accept candidates whose own support reaches the target (frec.w), using RH =
 //              radius of the global h_max to bound the cells that can hold such candidates
 //   flush(n) : consume entries 0..n-1 of the lane's list (sphb_list_get); called warp-uniformly
 // The caller must call flush(L.count()) once more after the scan returns (lists persist across groups).
+//
+// Lanes are grouped into runs of consecutive slots that share a row of cells AND follow each other closely in x:
+// a lane whose cell lies more than one search diameter beyond its predecessor's starts a new group.  (Merging two
+// lanes costs the cells between them on every row, splitting costs one more diameter: the break-even gap.  Without
+// the rule a warp over a nearly empty row -- a few strays at both ends of a boundary layer -- would scan the whole
+// row for all of them.)
 template <bool SYM, class Flush>
 __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpShared &ws, int lane, bool tgt, float fx,
-                                               float fy, float fz, float Rj, float thr, uint32_t row, float RH,
+                                               float fy, float fz, float Rj, float thr, uint32_t cid, float RH,
                                                SphbList &L, Flush &&flush)
 {
     int nseg = 0;   // live entries of ws.segbase (warp-uniform)
     unsigned remaining = __ballot_sync(SPHB_FULL, tgt);
+    // group key: number of breaks at or before the lane
+    const uint32_t row = cid / (uint32_t)g.nx, cx = cid - row * (uint32_t)g.nx;
+    uint32_t gkey;
+    {
+        const float rmax = fmaxf(sphb_warp_max(tgt ? Rj : 0.f), SYM ? RH : 0.f);
+        const float gapf = ceilf(2.f * rmax * (float)g.inv_cellx);               // +inf, NaN -> no x breaks
+        const uint32_t gap = (gapf < 1e9f) ? (uint32_t)fmaxf(gapf, 1.f) : 0xffffffffu;
+        const uint32_t prow = __shfl_up_sync(SPHB_FULL, row, 1), pcx = __shfl_up_sync(SPHB_FULL, cx, 1);
+        const bool brk = (lane == 0) || (row != prow) || (cx > pcx && cx - pcx > gap);
+        gkey = (uint32_t)__popc(__ballot_sync(SPHB_FULL, brk) & (0xffffffffu >> (31 - lane)));
+    }
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
-        const uint32_t lrow = __shfl_sync(SPHB_FULL, row, leader);
-        const bool ing = tgt && (row == lrow);
+        const uint32_t lkey = __shfl_sync(SPHB_FULL, gkey, leader);
+        const bool ing = tgt && (gkey == lkey);
         const unsigned grp = __ballot_sync(SPHB_FULL, ing);
         remaining &= ~grp;
 
@@ -208,11 +228,11 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                 }
             }
             const int nb = (int)((nrows - rb) < 32 ? (nrows - rb) : 32);
-            // ---- walk the spans, one segment (<= 2048 slots) at a time -----------------------------
+            // ---- walk the spans, one segment (<= SPHB_SEG_LEN slots) at a time -----------------------------
             for (int k = 0; k < nb; ++k) {
                 const uint32_t sk = __shfl_sync(SPHB_FULL, s, k), ek = __shfl_sync(SPHB_FULL, e, k);
                 for (uint32_t t0 = sk; t0 < ek; t0 += SPHB_SEG_LEN) {
-                    if (nseg == 32) {   // segment table full: drain the lists that reference it
+                    if (nseg == SPHB_NSEG) {   // segment table full: drain the lists that reference it
                         flush(L.count());
                         L.reset();
                         nseg = 0;

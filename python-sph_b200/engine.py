@@ -181,9 +181,14 @@ class Engine:
             raise ValueError("non-finite particle positions")
         return choose_grid(lo, hi, hmean if math.isfinite(hmean) and hmean > 0 else hmax, posh.shape[0], cell=cell)
 
-    def build(self, posh_in, grid, delta, tie_key=None) -> DeviceGrid:
+    def build(self, posh_in, grid, delta, tie_key=None, out=None) -> DeviceGrid:
+        """out: a DeviceGrid of the same n and cell count to rebuild in place (the Stepper's per-stage pool)"""
         n = posh_in.shape[0]
-        dg = DeviceGrid(n, grid, delta, self.device)
+        if out is not None and out.n == n and out.grid.ncell == grid.ncell:
+            dg = out
+            dg.grid, dg.delta, dg._cells = grid, float(delta), None
+        else:
+            dg = DeviceGrid(n, grid, delta, self.device)
         need = int(self.lib.sphb_grid_workspace_bytes(n, C.byref(grid)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -399,6 +404,7 @@ class Stepper:
         self.e = engine
         self.last_status = None
         self.geom = None   # (grid, delta) reused across steps when set by the caller
+        self._pool = [None, None, None]   # the three cell lists of a step, rebuilt in place while n and the grid size hold
 
     def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, omega0=None, want_omega1=False,
              hooks=None):
@@ -442,12 +448,13 @@ class Stepper:
             return r
 
         # ---- stage 0 at (pos0, h0): pyfluid.py:502-507 ------------------------------------------
-        g0 = e.build(posh0, grid, delta)
+        pool = self._pool
+        g0 = pool[0] = e.build(posh0, grid, delta, out=pool[0])
         acc0, dudt0 = stage(g0, vel0, u0, S_STAGE0, om=None if omega0 is None else e.gather(omega0, g0.perm, 1))
         # ---- predictor: pyfluid.py:511-515 ---------------------------------------------------------
         posh_m, vel_m, u_m = e.predict(posh0, vel0, u0, acc0, dudt0, dt, st.ptr(S_PRED))
         # ---- h_mid = newton(pos_mid, h0), stage mid: pyfluid.py:516-522 -------------------------------
-        g1 = e.build(posh_m, grid, delta)
+        g1 = pool[1] = e.build(posh_m, grid, delta, out=pool[1])
         h_mid_s, om_mid = solve_h(g1, S_NEWTON_MID, want_omega=True)
         e.set_h(g1, h_mid_s)
         acc1, dudt1 = stage(g1, vel_m, u_m, S_STAGE_MID, om=om_mid)
@@ -458,7 +465,7 @@ class Stepper:
             hooks.after_corrector(posh_1, vel1, u1)   # pos1, vel1, u1 are final: their copy-out can start now
         # ---- h1 = newton(pos1, h_mid): pyfluid.py:530 ------------------------------------------------------
         posh_1 = e.pack_posh(posh_1[:, :3].contiguous(), h_mid)
-        g2 = e.build(posh_1, grid, delta)
+        g2 = pool[2] = e.build(posh_1, grid, delta, out=pool[2])
         r = solve_h(g2, S_NEWTON_1, want_omega=want_omega1)
         h1 = e.scatter(r[0] if want_omega1 else r, g2.perm, 1)
         pos1 = posh_1[:, :3].contiguous()
@@ -504,7 +511,7 @@ def step_pinned(stepper, pos_h, vel_h, u_h, h_h, dt, consts, out=None, printer=p
     main = torch.cuda.current_stream()
     cs = torch.cuda.Stream(device=dev)
     if out is None:
-        out = [torch.empty_like(t).pin_memory() for t in (pos_h, vel_h, u_h, h_h)]
+        out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (pos_h, vel_h, u_h, h_h)]
     pos_d = pos_h.to(dev, non_blocking=True)
     h_d = h_h.to(dev, non_blocking=True)
     ev = torch.cuda.Event()
