@@ -9,6 +9,9 @@
 #define SPHB_MINB_FORCE 4
 #endif
 #define SPHB_THREADS (SPHB_WARPS * 32)
+#ifndef SPHB_FORCE_FLUSH_ROWS
+#define SPHB_FORCE_FLUSH_ROWS 0
+#endif
 
 __device__ __forceinline__ void sphb_load4(const double *rec, size_t i, double &a, double &b, double &c, double &d)
 {
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     SphbList L;
     L.init(ws, lane);
     auto flush = [&](int n_) { sphb_force_flush<GRAV>(c.posh, recB, recC, bgrav, ws, lane, n_, k, a); };
-    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush);
+    sphb_warp_scan<true, SPHB_FORCE_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush);
     flush(L.count());
     if (tgt) {
         const double m = k.particle_mass;

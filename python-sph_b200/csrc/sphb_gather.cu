@@ -9,6 +9,9 @@
 #define SPHB_MINB_OWN 4
 #endif
 #define SPHB_THREADS (SPHB_WARPS * 32)
+#ifndef SPHB_OWN_FLUSH_ROWS
+#define SPHB_OWN_FLUSH_ROWS 0
+#endif
 
 __device__ __forceinline__ void sphb_load_posh(const double *posh, size_t i, double &x, double &y, double &z, double &h)
 {
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     SphbList L;
     L.init(ws, lane);
     auto flush = [&](int n_) { sphb_own_flush<XI>(c.posh, ws, lane, n_, a); };
-    sphb_warp_scan<false>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
+    sphb_warp_scan<false, SPHB_OWN_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
     flush(L.count());
     if (tgt) {
         const double pref = k.particle_mass / (SPHB_PI * (h * h * h));

@@ -129,7 +129,10 @@ __device__ __forceinline__ uint32_t sphb_list_get(const SphbWarpShared &ws, int 
 // lanes costs the cells between them on every row, splitting costs one more diameter: the break-even gap.  Without
 // the rule a warp over a nearly empty row -- a few strays at both ends of a boundary layer -- would scan the whole
 // row for all of them.)
-template <bool SYM, class Flush>
+//   FLUSH_ROWS: 0 = drain only when a list fills up; n > 0 = also after every n rows of cells; -1 = after every z layer
+//              of rows.  Early drains keep the lanes of the warp inside the same few rows while they gather their
+//              neighbours' records (shorter reuse distance in L1, fewer distinct lines per gather).
+template <bool SYM, int FLUSH_ROWS = 0, class Flush>
 __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpShared &ws, int lane, bool tgt, float fx,
                                                float fy, float fz, float Rj, float thr, uint32_t cid, float RH,
                                                SphbList &L, Flush &&flush)
@@ -230,6 +233,15 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
             const int nb = (int)((nrows - rb) < 32 ? (nrows - rb) : 32);
             // ---- walk the spans, one segment (<= SPHB_SEG_LEN slots) at a time -----------------------------
             for (int k = 0; k < nb; ++k) {
+                if (FLUSH_ROWS != 0) {
+                    const long long r = rb + k;
+                    const int every = FLUSH_ROWS > 0 ? FLUSH_ROWS : nry;
+                    if (r > 0 && r % every == 0 && __any_sync(SPHB_FULL, L.count() > 0)) {
+                        flush(L.count());
+                        L.reset();
+                        nseg = 0;
+                    }
+                }
                 const uint32_t sk = __shfl_sync(SPHB_FULL, s, k), ek = __shfl_sync(SPHB_FULL, e, k);
                 for (uint32_t t0 = sk; t0 < ek; t0 += SPHB_SEG_LEN) {
                     if (nseg == SPHB_NSEG) {   // segment table full: drain the lists that reference it

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -448,7 +449,7 @@ class Stepper:
             return r
 
         # ---- stage 0 at (pos0, h0): pyfluid.py:502-507 ------------------------------------------
-        pool = self._pool
+        pool = self._pool if os.environ.get("SPHB_NO_POOL") is None else [None, None, None]
         g0 = pool[0] = e.build(posh0, grid, delta, out=pool[0])
         acc0, dudt0 = stage(g0, vel0, u0, S_STAGE0, om=None if omega0 is None else e.gather(omega0, g0.perm, 1))
         # ---- predictor: pyfluid.py:511-515 ---------------------------------------------------------
