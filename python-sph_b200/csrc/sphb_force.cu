@@ -160,12 +160,158 @@ __device__ __forceinline__ void sphb_force_pair(const double *recB, const double
     a.visc = fma(pi_half * sm, vdr, a.visc);
 }
 
-// drain the lane's list with the next position record in flight (two buffers, unrolled by two)
+// ---- two list entries side by side ---------------------------------------------------------------------
+// The same operations per pair as sphb_force_pair, arranged as straight-line code for two candidates so that two
+// independent FP64 dependency chains are in flight per lane; the accumulators are then updated in list order, which
+// keeps every sum bit-identical to the one-at-a-time loop.  `ok` replaces the early returns.
+struct SphbPairTerms {
+    double dx, dy, dz, d2, hi, sj, si, vdr, Ai, pism, coef;
+    bool ok;
+};
+
+__device__ __forceinline__ void sphb_force_geom(const double *recB, uint32_t i, const double (&p)[4], bool present,
+                                                const SphbForceAcc &a, SphbPairTerms &t)
+{
+    t.dx = a.xj - p[0];
+    t.dy = a.yj - p[1];
+    t.dz = a.zj - p[2];
+    t.hi = p[3];
+    t.d2 = sphb_d2(t.dx, t.dy, t.dz);
+    const double hinvi = sphb_rcp(t.hi);
+    const double hi2 = hinvi * hinvi;
+    const double gi = (hi2 * hi2) * 0.3183098861837907;   // 1/pi
+    const double rinv = sphb_rsqrt(t.d2);
+    const double r = t.d2 * rinv;
+    const double qj = r * a.hinvj, qi = r * hinvi;
+    t.ok = present && sphb_nonzero(t.d2) && ((qj < 2.0) || (qi < 2.0));
+    double vxi = 0.0, vyi = 0.0, vzi = 0.0;
+    t.Ai = 0.0;
+    if (t.ok) sphb_load4(recB, i, vxi, vyi, vzi, t.Ai);
+    t.sj = sphb_m4c_fp(qj) * a.gj * rinv;
+    t.si = sphb_m4c_fp(qi) * gi * rinv;
+    const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
+    t.vdr = sphb_dot3(t.dx, t.dy, t.dz, dvx, dvy, dvz);
+}
+
+__device__ __forceinline__ double sphb_force_pi(const sphb_consts &k, const SphbForceAcc &a, const SphbPairTerms &t,
+                                                double rhoi, double csi)
+{
+    const double mean_h = 0.5 * (a.hj + t.hi);
+    const double den = fma(k.epsilon * mean_h, mean_h, t.d2);
+    const double mean_rho = 0.5 * (a.rhoj + rhoi);
+    const double inv = sphb_rcp(den * mean_rho);
+    const double mu = (mean_h * t.vdr) * (inv * mean_rho);
+    const double cs = 0.5 * (csi + a.csj);
+    return (mu * fma(k.beta, mu, -k.alpha * cs)) * (inv * den);
+}
+
+template <bool GRAV>
+__device__ __forceinline__ void sphb_force_accumulate(const double *bgrav, uint32_t i, double pi_half,
+                                                      const SphbPairTerms &t, SphbForceAcc &a)
+{
+    if (!t.ok) return;
+    a.dens = fma(t.sj, t.vdr, a.dens);
+    const double sm = t.sj + t.si;
+    double coef = fma(a.Aj, t.sj, fma(t.Ai, t.si, pi_half * sm));
+    if (GRAV) coef = fma(a.Bj, t.sj, fma(__ldg(bgrav + i), t.si, coef));
+    SPHB_DBG(a.jslot, i, coef * t.dx);
+    a.ax = fma(-coef, t.dx, a.ax);
+    a.ay = fma(-coef, t.dy, a.ay);
+    a.az = fma(-coef, t.dz, a.az);
+    a.visc = fma(pi_half * sm, t.vdr, a.visc);
+}
+
+template <bool GRAV>
+__device__ __forceinline__ void sphb_force_pair2(const double *recB, const double *recC, const double *bgrav, uint32_t i0,
+                                                 uint32_t i1, const double (&p0)[4], const double (&p1)[4], bool second,
+                                                 const sphb_consts &k, SphbForceAcc &a)
+{
+    SphbPairTerms t0, t1;
+    sphb_force_geom(recB, i0, p0, true, a, t0);
+    sphb_force_geom(recB, i1, p1, second, a, t1);
+    const bool v0 = t0.ok && t0.vdr < 0.0, v1 = t1.ok && t1.vdr < 0.0;
+    double ph0 = 0.0, ph1 = 0.0;
+    if (v0 || v1) {
+        double rho0 = 1.0, cs0 = 0.0, rho1 = 1.0, cs1 = 0.0, u0, u1;
+        if (v0) sphb_load4(recC, i0, rho0, cs0, u0, u1);
+        if (v1) sphb_load4(recC, i1, rho1, cs1, u0, u1);
+        const double pi0 = sphb_force_pi(k, a, t0, rho0, cs0);
+        const double pi1 = sphb_force_pi(k, a, t1, rho1, cs1);
+        if ((v0 && pi0 < 0.0) || (v1 && pi1 < 0.0)) a.negpi = 1;
+        ph0 = v0 ? 0.5 * pi0 : 0.0;
+        ph1 = v1 ? 0.5 * pi1 : 0.0;
+    }
+    sphb_force_accumulate<GRAV>(bgrav, i0, ph0, t0, a);
+    sphb_force_accumulate<GRAV>(bgrav, i1, ph1, t1, a);
+}
+
+#ifndef SPHB_FORCE_ILP
+#define SPHB_FORCE_ILP 1
+#endif
+
+// drain the lane's list (SPHB_FORCE_ILP 1: two entries side by side, the next two position records in flight;
+// 2: two side by side without look-ahead; 0: one at a time with one record of look-ahead)
 template <bool GRAV>
 __device__ __forceinline__ void sphb_force_flush(const double *posh, const double *recB, const double *recC,
                                                  const double *bgrav, const SphbWarpShared &ws, int lane, int cnt,
                                                  const sphb_consts &k, SphbForceAcc &a)
 {
+#if SPHB_FORCE_ILP == 1
+    double A[4], B[4], C[4], D[4];
+    uint32_t ia = 0, ib = 0, ic = 0, id = 0;
+    A[0] = A[1] = A[2] = B[0] = B[1] = B[2] = 0.0;
+    A[3] = B[3] = 1.0;
+    if (cnt > 0) {
+        ia = sphb_list_get(ws, lane, 0);
+        sphb_load4(posh, ia, A[0], A[1], A[2], A[3]);
+    }
+    if (cnt > 1) {
+        ib = sphb_list_get(ws, lane, 1);
+        sphb_load4(posh, ib, B[0], B[1], B[2], B[3]);
+    }
+    int n_ = 0;
+    while (n_ < cnt) {
+        C[0] = C[1] = C[2] = D[0] = D[1] = D[2] = 0.0;
+        C[3] = D[3] = 1.0;
+        if (n_ + 2 < cnt) {
+            ic = sphb_list_get(ws, lane, n_ + 2);
+            sphb_load4(posh, ic, C[0], C[1], C[2], C[3]);
+        }
+        if (n_ + 3 < cnt) {
+            id = sphb_list_get(ws, lane, n_ + 3);
+            sphb_load4(posh, id, D[0], D[1], D[2], D[3]);
+        }
+        sphb_force_pair2<GRAV>(recB, recC, bgrav, ia, ib, A, B, n_ + 1 < cnt, k, a);
+        n_ += 2;
+        if (n_ >= cnt) break;
+        A[0] = A[1] = A[2] = B[0] = B[1] = B[2] = 0.0;
+        A[3] = B[3] = 1.0;
+        if (n_ + 2 < cnt) {
+            ia = sphb_list_get(ws, lane, n_ + 2);
+            sphb_load4(posh, ia, A[0], A[1], A[2], A[3]);
+        }
+        if (n_ + 3 < cnt) {
+            ib = sphb_list_get(ws, lane, n_ + 3);
+            sphb_load4(posh, ib, B[0], B[1], B[2], B[3]);
+        }
+        sphb_force_pair2<GRAV>(recB, recC, bgrav, ic, id, C, D, n_ + 1 < cnt, k, a);
+        n_ += 2;
+    }
+#elif SPHB_FORCE_ILP == 2
+    for (int n_ = 0; n_ < cnt; n_ += 2) {
+        double A[4], B[4];
+        B[0] = B[1] = B[2] = 0.0;
+        B[3] = 1.0;
+        const uint32_t ia = sphb_list_get(ws, lane, n_);
+        uint32_t ib = ia;
+        sphb_load4(posh, ia, A[0], A[1], A[2], A[3]);
+        if (n_ + 1 < cnt) {
+            ib = sphb_list_get(ws, lane, n_ + 1);
+            sphb_load4(posh, ib, B[0], B[1], B[2], B[3]);
+        }
+        sphb_force_pair2<GRAV>(recB, recC, bgrav, ia, ib, A, B, n_ + 1 < cnt, k, a);
+    }
+#else
     double ax, ay, az, ah, bx, by, bz, bh;
     uint32_t ia = 0, ib = 0;
     if (cnt > 0) {
@@ -188,6 +334,7 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
         sphb_force_pair<GRAV>(recB, recC, bgrav, ib, bx, by, bz, bh, k, a);
         ++n_;
     }
+#endif
 }
 
 template <bool GRAV>

@@ -51,12 +51,80 @@ __device__ __forceinline__ void sphb_own_pair(double x, double y, double z, Sphb
     if (XI) a.sumX += sphb_grav_pX(q);
 }
 
-// drain the lane's list: the record of entry k+1 is in flight while entry k is evaluated (two register
-// buffers, loop unrolled by two so that no copies are needed)
+// the pair's terms without touching the accumulators: two of these are independent instruction streams
+template <bool XI = false>
+__device__ __forceinline__ void sphb_own_terms(double x, double y, double z, const SphbOwnAcc &a, double &f, double &g,
+                                               int &in, double &px)
+{
+    const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
+    const double d2 = sphb_d2(dx, dy, dz);
+    const double r = sphb_nonzero(d2) ? d2 * sphb_rsqrt(d2) : 0.0;
+    const double q = r * a.hinv;
+    double fp;
+    sphb_m4c(q, f, fp);
+    g = fma(q, fp, 3.0 * f);
+    in = (q < 2.0) ? 1 : 0;
+    px = XI ? sphb_grav_pX(q) : 0.0;
+}
+
+// entries k and k+1 evaluated side by side (the second only counted when it exists), accumulated in list order
+template <bool XI = false>
+__device__ __forceinline__ void sphb_own_pair2(const double (&p)[4], const double (&q)[4], bool second, SphbOwnAcc &a)
+{
+    double f0, g0, x0, f1, g1, x1;
+    int n0, n1;
+    sphb_own_terms<XI>(p[0], p[1], p[2], a, f0, g0, n0, x0);
+    sphb_own_terms<XI>(q[0], q[1], q[2], a, f1, g1, n1, x1);
+    a.sumF += f0;
+    a.sumG += g0;
+    a.nn += n0;
+    if (XI) a.sumX += x0;
+    if (second) {
+        a.sumF += f1;
+        a.sumG += g1;
+        a.nn += n1;
+        if (XI) a.sumX += x1;
+    }
+}
+
+#ifndef SPHB_OWN_ILP
+#define SPHB_OWN_ILP 1
+#endif
+
+// drain the lane's list, two entries at a time so that two independent FP64 chains are in flight per lane
+// (SPHB_OWN_ILP 1: the records of the next two entries are loaded while the current two are evaluated;
+//  2: no look-ahead, fewer registers; 0: one entry at a time with one record of look-ahead)
 template <bool XI = false>
 __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWarpShared &ws, int lane, int cnt,
                                                SphbOwnAcc &a)
 {
+#if SPHB_OWN_ILP == 1
+    double A[4], B[4], C[4], D[4];
+    A[0] = A[1] = A[2] = B[0] = B[1] = B[2] = 0.0;
+    if (cnt > 0) sphb_load_posh(posh, sphb_list_get(ws, lane, 0), A[0], A[1], A[2], A[3]);
+    if (cnt > 1) sphb_load_posh(posh, sphb_list_get(ws, lane, 1), B[0], B[1], B[2], B[3]);
+    int k = 0;
+    while (k < cnt) {
+        C[0] = C[1] = C[2] = D[0] = D[1] = D[2] = 0.0;
+        if (k + 2 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 2), C[0], C[1], C[2], C[3]);
+        if (k + 3 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 3), D[0], D[1], D[2], D[3]);
+        sphb_own_pair2<XI>(A, B, k + 1 < cnt, a);
+        k += 2;
+        if (k >= cnt) break;
+        if (k + 2 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 2), A[0], A[1], A[2], A[3]);
+        if (k + 3 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 3), B[0], B[1], B[2], B[3]);
+        sphb_own_pair2<XI>(C, D, k + 1 < cnt, a);
+        k += 2;
+    }
+#elif SPHB_OWN_ILP == 2
+    for (int k = 0; k < cnt; k += 2) {
+        double A[4], B[4];
+        B[0] = B[1] = B[2] = 0.0;
+        sphb_load_posh(posh, sphb_list_get(ws, lane, k), A[0], A[1], A[2], A[3]);
+        if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), B[0], B[1], B[2], B[3]);
+        sphb_own_pair2<XI>(A, B, k + 1 < cnt, a);
+    }
+#else
     double ax, ay, az, ah, bx, by, bz, bh;
     if (cnt > 0) sphb_load_posh(posh, sphb_list_get(ws, lane, 0), ax, ay, az, ah);
     int k = 0;
@@ -69,6 +137,7 @@ __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWar
         sphb_own_pair<XI>(bx, by, bz, a);
         ++k;
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
