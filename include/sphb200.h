@@ -121,6 +121,28 @@ int sphb_gather_f64(const double *src, const uint32_t *perm, int64_t n, int32_t 
 int sphb_scatter_f64(const double *src, const uint32_t *perm, int64_t n, int32_t ncomp, double *dst, void *stream);
 int sphb_gather_u32(const uint32_t *src, const uint32_t *perm, int64_t n, uint32_t *dst, void *stream);
 
+/* ---- neighbour lists kept between kernels (optional) -----------------------------------------------
+ * Every gather kernel first scans the cells around its 32 targets; within one step several kernels scan the SAME
+ * snapshot (pyfluid.py:502-507: omega_arr then energy_rate_arr/acceleration_arr at (pos0, h0); :516-522: the Newton
+ * solve then the same two at pos_mid).  With a sphb_lists the first of them (sphb_density_omega or sphb_newton_h, the
+ * PRODUCER) scans with the symmetric support max(h_j, h_i) and parks every warp's lists in `store`; sphb_force (the
+ * CONSUMER) drains them instead of scanning again.  Sums are unchanged: the lists are supersets in the same slot order
+ * and membership is still decided pair by pair in fp64.
+ *   store        sphb_lists_bytes(n) bytes of device memory
+ *   broken       device flag, zeroed by the caller before the producer runs; the Newton producer sets it when some
+ *                h ends above cover * (h the cell list holds), i.e. when the parked lists may be incomplete for the new
+ *                h -- the consumer then scans for itself.  A warp whose lists overflowed also scans for itself.
+ *   hmax_global  device float: max h of the snapshot (sphb_hmax), bounds the symmetric search of the producer
+ *   cover        >= 1: how much every h may grow between producer and consumer (1 when h does not change)
+ * The producer and the consumer must be called with the same `target` flags.  NULL = every kernel scans. */
+typedef struct sphb_lists {
+    void *store;
+    int32_t *broken;
+    const float *hmax_global;
+    double cover;
+} sphb_lists;
+size_t sphb_lists_bytes(int64_t n);
+
 /* ---- K2: M4 density summation + grad-h sums ----------------------------------------------------
  * replaces density/density_arr (pyfluid.py:218-232) and omega_j/omega_arr (pyfluid.py:91-105).
  * For every slot j whose `target` flag is set (NULL = all slots):
@@ -134,7 +156,7 @@ int sphb_gather_u32(const uint32_t *src, const uint32_t *perm, int64_t n, uint32
  * h_j is cells->posh[j][3] unless h_target != NULL.  ngb_count (optional) = #{i : q < 2}. */
 int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *h_target,
                        const double *rho_in, double *rho_sum, double *dwdh_sum, double *omega, double *xi,
-                       int32_t *ngb_count, void *stream);
+                       int32_t *ngb_count, const sphb_lists *lists, void *stream);
 
 /* ---- K3: Newton-Raphson smoothing-length solve ---------------------------------------------------
  * replaces newton_smoothlength_iteration/_while/_arr (pyfluid.py:155-179, 203-211) and
@@ -145,7 +167,7 @@ int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint
  * computes next (pyfluid.py:517-518); it comes from one more pass over the converged iteration's neighbour list. */
 int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *h_guess,
                   double *h_out, double *omega_out, int32_t *iters, int32_t *code, uint32_t *fail_list,
-                  sphb_status *status, void *stream);
+                  sphb_status *status, const sphb_lists *lists, void *stream);
 /* bisection for an explicit list of target slots (also used for bisection_h(j, pos) itself);
  * n_list < 0: take the list length from status->nfail (device side).  oob (optional, per list entry) */
 int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, const uint32_t *list, int64_t n_list,
@@ -177,7 +199,7 @@ int sphb_eos(const double *posh, const double *vel, const double *u, const doubl
  * acc (n,3) and dudt (n) for target slots. */
 int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *recB,
                const double *recC, const double *bgrav, const float *hmax_global, double *acc, double *dudt,
-               sphb_status *status, void *stream);
+               sphb_status *status, const sphb_lists *lists, void *stream);
 /* Softened self-gravity, the long-range part (smoothed_gravity_acceleration_comp, pyfluid.py:420-432): exact all-pairs
  * fp64 sum, acc (n,3) (+)= sum_i -G/2 m (grav_force(d,h_j) + grav_force(d,h_i)) (r_j - r_i)/d.  O(n^2).  posh in any
  * order; acc in the same order. */

@@ -50,6 +50,11 @@ class Cells(C.Structure):
                 ("pad_", C.c_float)]
 
 
+class Lists(C.Structure):
+    """sphb_lists: neighbour lists parked between two kernels on one snapshot"""
+    _fields_ = [("store", C.c_void_p), ("broken", C.c_void_p), ("hmax_global", C.c_void_p), ("cover", C.c_double)]
+
+
 P = C.c_void_p
 I64 = C.c_int64
 I32 = C.c_int32
@@ -68,12 +73,13 @@ SIGNATURES = {
     "sphb_gather_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_scatter_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_gather_u32": (C.c_int, [P, P, I64, P, P]),
-    "sphb_density_omega": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
-    "sphb_newton_h": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
+    "sphb_lists_bytes": (C.c_size_t, [I64]),
+    "sphb_density_omega": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),
+    "sphb_newton_h": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),
     "sphb_bisect_h": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, I64, P, P, P, P, I32, P, P]),
     "sphb_neighbours": (C.c_int, [C.POINTER(Cells), P, I64, I32, P, P, I64, P, P]),
     "sphb_eos": (C.c_int, [P, P, P, P, P, P, P, I64, C.POINTER(Consts), P, P, P, P, P, P, P]),
-    "sphb_force": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
+    "sphb_force": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),
     "sphb_gravity_direct": (C.c_int, [P, I64, C.POINTER(Consts), I32, P, P]),
     "sphb_grav_eval": (C.c_int, [P, P, I64, P, P, P, P]),
     "sphb_pair_terms": (C.c_int, [P, P, P, P, I64, C.POINTER(Consts), P, P, P, P, P, P, P]),

@@ -341,7 +341,8 @@ template <bool GRAV>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     k_force(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ recB,
             const double *__restrict__ recC, const double *__restrict__ bgrav, const float *__restrict__ hmax_global,
-            double *__restrict__ acc, double *__restrict__ dudt, sphb_status *__restrict__ status)
+            double *__restrict__ acc, double *__restrict__ dudt, sphb_status *__restrict__ status,
+            const SphbWarpSaved *__restrict__ saved, const int32_t *__restrict__ broken)
 {
     __shared__ SphbWarpShared sh[SPHB_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -378,8 +379,16 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     SphbList L;
     L.init(ws, lane);
     auto flush = [&](int n_) { sphb_force_flush<GRAV>(c.posh, recB, recC, bgrav, ws, lane, n_, k, a); };
-    sphb_warp_scan<true, SPHB_FORCE_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush);
-    flush(L.count());
+    // lists parked by the producer kernel of this snapshot (sphb_lists): drain them, no scan
+    int parked = -1;
+    if (saved != nullptr && __ldg(broken) == 0)
+        parked = sphb_lists_load(ws, lane, saved + ((long long)blockIdx.x * SPHB_WARPS + warp));
+    if (parked >= 0) {
+        flush(tgt ? parked : 0);
+    } else {
+        sphb_warp_scan<true, SPHB_FORCE_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush);
+        flush(L.count());
+    }
     if (tgt) {
         const double m = k.particle_mass;
         acc[3 * j] = m * a.ax;
@@ -876,20 +885,23 @@ extern "C" int sphb_eos(const double *posh, const double *vel, const double *u, 
 
 extern "C" int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target, const double *recB,
                           const double *recC, const double *bgrav, const float *hmax_global, double *acc, double *dudt,
-                          sphb_status *status, void *stream)
+                          sphb_status *status, const sphb_lists *lists, void *stream)
 {
     if (!cells || !k || !recB || !recC || !hmax_global || !acc || !dudt || !status) return SPHB_E_ARG;
+    if (lists && (!lists->store || !lists->broken)) return SPHB_E_ARG;
     if (cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh || !cells->frec)
         return SPHB_E_ARG;
     if (k->G != 0.0 && !bgrav) return SPHB_E_ARG;   // with gravity on, the grad-h correction factors are required
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
+    const SphbWarpSaved *saved = lists ? reinterpret_cast<const SphbWarpSaved *>(lists->store) : nullptr;
+    const int32_t *broken = lists ? lists->broken : nullptr;
     if (bgrav)
         k_force<true><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, bgrav,
-                                                                                  hmax_global, acc, dudt, status);
+                                                                                  hmax_global, acc, dudt, status, saved, broken);
     else
         k_force<false><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, bgrav,
-                                                                                   hmax_global, acc, dudt, status);
+                                                                                   hmax_global, acc, dudt, status, saved, broken);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

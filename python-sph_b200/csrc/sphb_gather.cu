@@ -143,11 +143,13 @@ __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWar
 // ------------------------------------------------------------------------------------------------
 // K2
 // ------------------------------------------------------------------------------------------------
-template <bool XI>
+// PRODUCE: scan with the symmetric support and park the lists for sphb_force (sphb_lists, include/sphb200.h)
+template <bool XI, bool PRODUCE>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_density_omega(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_target,
                     const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
-                    double *__restrict__ omega, double *__restrict__ xi_out, int32_t *__restrict__ ngb_count)
+                    double *__restrict__ omega, double *__restrict__ xi_out, int32_t *__restrict__ ngb_count,
+                    sphb_lists lists)
 {
     __shared__ SphbWarpShared sh[SPHB_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,9 +178,21 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     SphbWarpShared &ws = sh[warp];
     SphbList L;
     L.init(ws, lane);
-    auto flush = [&](int n_) { sphb_own_flush<XI>(c.posh, ws, lane, n_, a); };
-    sphb_warp_scan<false, SPHB_OWN_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
-    flush(L.count());
+    bool flushed = false;   // warp-uniform
+    auto flush = [&](int n_) {
+        flushed = true;
+        sphb_own_flush<XI>(c.posh, ws, lane, n_, a);
+    };
+    if (PRODUCE) {
+        const float cov = (float)lists.cover * 1.000001f;
+        const float RH = sphb_radius_of_h((double)lists.hmax_global[0] * (double)cov, g.delta);
+        const int nseg = sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+        sphb_lists_save(ws, lane, L.count(), nseg, !flushed,
+                        reinterpret_cast<SphbWarpSaved *>(lists.store) + ((long long)blockIdx.x * SPHB_WARPS + warp));
+    } else {
+        sphb_warp_scan<false, SPHB_OWN_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
+    }
+    sphb_own_flush<XI>(c.posh, ws, lane, L.count(), a);
     if (tgt) {
         const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
         const double rs = pref * a.sumF;
@@ -216,11 +230,12 @@ __device__ __forceinline__ double sphb_omega_from_sumG(const sphb_consts &k, dou
     return 1.0 + h / (3.0 * sphb_var_density(k, h)) * ds;       // pyfluid.py:97 with rho = m (eta/h)^3
 }
 
-template <bool FUSED>
+template <bool FUSED, bool PRODUCE>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_newton_h(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_guess,
                double *__restrict__ h_out, double *__restrict__ omega_out, int32_t *__restrict__ iters,
-               int32_t *__restrict__ code, uint32_t *__restrict__ fail_list, sphb_status *__restrict__ status)
+               int32_t *__restrict__ code, uint32_t *__restrict__ fail_list, sphb_status *__restrict__ status,
+               sphb_lists lists)
 {
     __shared__ SphbWarpShared sh[SPHB_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,7 +246,8 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     const bool tgt = valid && (target == nullptr || target[j] != 0);
     const SphbScanCtx g = sphb_make_ctx(c);
     SphbWarpShared &ws = sh[warp];
-    const double rmargin = 1.0 + SPHB_NEWTON_MARGIN;
+    const double rmargin = PRODUCE ? lists.cover : 1.0 + SPHB_NEWTON_MARGIN;
+    bool first_scan = true;   // PRODUCE: the lists of the first scan (every target at its guess) are the ones parked
 
     SphbOwnAcc a;
     a.xj = a.yj = a.zj = 0.0;
@@ -250,6 +266,9 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     double h_cover = 0.0;    // the lane's list holds every neighbour of any h <= h_cover
     bool have_lists = false; // warp-uniform: the lists of the last scan are intact (no overflow flush)
     int cnt = 0, it = 0;
+    if (PRODUCE && !__any_sync(SPHB_FULL, tgt))   // a warp without targets never scans: park empty lists
+        sphb_lists_save(ws, lane, 0, 0, true,
+                        reinterpret_cast<SphbWarpSaved *>(lists.store) + ((long long)blockIdx.x * SPHB_WARPS + warp));
 #ifdef SPHB_NEWTON_TRACE
     const long long trace_t0 = clock64();
     int trace_scans = 0, trace_rounds = 0;
@@ -274,7 +293,17 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                 flushed = true;
                 sphb_own_flush(c.posh, ws, lane, n_, a);
             };
-            sphb_warp_scan<false>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
+            if (PRODUCE && first_scan) {
+                // symmetric support, every h taken at its cover: complete for sphb_force at any h below the cover
+                const float cov = (float)lists.cover * 1.000001f;
+                const float RH = sphb_radius_of_h((double)lists.hmax_global[0] * (double)cov, g.delta);
+                const int nseg = sphb_warp_scan<true>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+                sphb_lists_save(ws, lane, L.count(), nseg, !flushed,
+                                reinterpret_cast<SphbWarpSaved *>(lists.store) + ((long long)blockIdx.x * SPHB_WARPS + warp));
+                first_scan = false;
+            } else {
+                sphb_warp_scan<false>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
+            }
             cnt = L.count();   // 0 for lanes that were not scanned for
             have_lists = !flushed;
             h_cover = pend ? hs : 0.0;
@@ -296,6 +325,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                 if (iters) iters[j] = it;
                 if (code) code[j] = 0;
                 want = FUSED ? 2 : 0;
+                if (PRODUCE && !(h_new <= h_guess[j] * lists.cover)) atomicOr(lists.broken, 1);
             } else if (it >= k.newton_limit) {
                 // "WARNING: Failure to converge in newton_new_h." -> bisection_h(j, pos), pyfluid.py:178-179
                 atomicAdd(&status->newton_warn, 1);
@@ -306,6 +336,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                 if (iters) iters[j] = it;
                 if (code) code[j] = 1;
                 want = 0;
+                if (PRODUCE) atomicOr(lists.broken, 1);   // the bisection may return any h
             }
             h_cur = h_new;
         } else if (want == 2) {
@@ -507,21 +538,37 @@ static inline int sphb_cells_ok(const sphb_cells *c)
            c->grid.ny > 0 && c->grid.nz > 0 && c->grid.cell > 0.0;
 }
 
+static bool sphb_lists_ok(const sphb_lists *l)
+{
+    return !l || (l->store && l->broken && l->hmax_global && l->cover >= 1.0 && l->cover < 2.0);
+}
+
 extern "C" int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target,
                                   const double *h_target, const double *rho_in, double *rho_sum, double *dwdh_sum,
-                                  double *omega, double *xi_out, int32_t *ngb_count, void *stream)
+                                  double *omega, double *xi_out, int32_t *ngb_count, const sphb_lists *lists,
+                                  void *stream)
 {
-    if (!sphb_cells_ok(cells) || !k) return SPHB_E_ARG;
+    if (!sphb_cells_ok(cells) || !k || !sphb_lists_ok(lists)) return SPHB_E_ARG;
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
-    if (xi_out)
-        k_density_omega<true><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(
-            *cells, *k, target, h_target, rho_in, rho_sum, dwdh_sum, omega, xi_out, ngb_count);
-    else
-        k_density_omega<false><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(
-            *cells, *k, target, h_target, rho_in, rho_sum, dwdh_sum, omega, xi_out, ngb_count);
+    const sphb_lists ls = lists ? *lists : sphb_lists{nullptr, nullptr, nullptr, 1.0};
+#define SPHB_K2(XI_, PR_)                                                                         \
+    k_density_omega<XI_, PR_><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(        \
+        *cells, *k, target, h_target, rho_in, rho_sum, dwdh_sum, omega, xi_out, ngb_count, ls)
+    if (xi_out) {
+        if (lists) SPHB_K2(true, true); else SPHB_K2(true, false);
+    } else {
+        if (lists) SPHB_K2(false, true); else SPHB_K2(false, false);
+    }
+#undef SPHB_K2
     SPHB_LAUNCHED();
     return SPHB_OK;
+}
+
+extern "C" size_t sphb_lists_bytes(int64_t n)
+{
+    const long long warps = (n + 31) / 32;
+    return (size_t)(warps > 0 ? warps : 1) * sizeof(SphbWarpSaved);
 }
 
 extern "C" int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, const uint32_t *list, int64_t n_list,
@@ -540,18 +587,23 @@ extern "C" int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, cons
 
 extern "C" int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, const uint8_t *target,
                              const double *h_guess, double *h_out, double *omega_out, int32_t *iters, int32_t *code,
-                             uint32_t *fail_list, sphb_status *status, void *stream)
+                             uint32_t *fail_list, sphb_status *status, const sphb_lists *lists, void *stream)
 {
-    if (!sphb_cells_ok(cells) || !k || !h_guess || !h_out || !fail_list || !status) return SPHB_E_ARG;
+    if (!sphb_cells_ok(cells) || !k || !h_guess || !h_out || !fail_list || !status || !sphb_lists_ok(lists))
+        return SPHB_E_ARG;
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
     SPHB_CUDA(cudaMemsetAsync(&status->nfail, 0, sizeof(int32_t), sphb_stream(stream)));
-    if (omega_out)
-        k_newton_h<true><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out,
-                                                                                     omega_out, iters, code, fail_list, status);
-    else
-        k_newton_h<false><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out,
-                                                                                      omega_out, iters, code, fail_list, status);
+    const sphb_lists ls = lists ? *lists : sphb_lists{nullptr, nullptr, nullptr, 1.0};
+#define SPHB_K3(FU_, PR_)                                                                                   \
+    k_newton_h<FU_, PR_><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out, \
+                                                                                     omega_out, iters, code, fail_list, status, ls)
+    if (omega_out) {
+        if (lists) SPHB_K3(true, true); else SPHB_K3(true, false);
+    } else {
+        if (lists) SPHB_K3(false, true); else SPHB_K3(false, false);
+    }
+#undef SPHB_K3
     SPHB_LAUNCHED();
     // the fallback reads its list length from status->nfail on the device: no host round trip
     return sphb_bisect_h(cells, k, fail_list, -1, h_out, omega_out, code, nullptr, 1, status, stream);

@@ -38,6 +38,50 @@ struct SphbWarpShared {
     uint16_t list[SPHB_LIST * 32];
 };
 
+// One warp's lists parked in global memory between two kernels that work on the same snapshot (sphb_lists,
+// include/sphb200.h): the producer scans once with the symmetric support, the consumer drains without scanning.
+struct SphbWarpSaved {
+    uint32_t nrows;   // rows of `list` in use = largest per-lane count; SPHB_SAVED_NONE: this warp must scan
+    uint32_t nseg;
+    uint32_t pad[2];
+    uint16_t count[32];
+    uint32_t segbase[SPHB_NSEG];
+    uint16_t list[SPHB_LIST * 32];
+};
+#define SPHB_SAVED_NONE 0xffffffffu
+
+__device__ __forceinline__ void sphb_lists_save(const SphbWarpShared &ws, int lane, int cnt, int nseg, bool complete,
+                                                SphbWarpSaved *dst)
+{
+    __syncwarp();
+    const int rows = __reduce_max_sync(SPHB_FULL, cnt);
+    if (lane == 0) {
+        dst->nrows = complete ? (uint32_t)rows : SPHB_SAVED_NONE;
+        dst->nseg = (uint32_t)nseg;
+    }
+    if (!complete) return;
+    dst->count[lane] = (uint16_t)cnt;
+    for (int s = lane; s < nseg; s += 32) dst->segbase[s] = ws.segbase[s];
+    const uint4 *src = reinterpret_cast<const uint4 *>(ws.list);
+    uint4 *d = reinterpret_cast<uint4 *>(dst->list);
+    for (int c = lane; c < rows * 4; c += 32) d[c] = src[c];
+}
+
+// -> the lane's count, or -1 (warp-uniform) when the warp has no parked lists
+__device__ __forceinline__ int sphb_lists_load(SphbWarpShared &ws, int lane, const SphbWarpSaved *src)
+{
+    const uint32_t rows = __ldg(&src->nrows);
+    const int nseg = (int)__ldg(&src->nseg);
+    if (rows > (uint32_t)SPHB_LIST || nseg > SPHB_NSEG) return -1;   // SPHB_SAVED_NONE, or not a parked record
+    for (int s = lane; s < nseg; s += 32) ws.segbase[s] = __ldg(src->segbase + s);
+    const uint4 *g = reinterpret_cast<const uint4 *>(src->list);
+    uint4 *d = reinterpret_cast<uint4 *>(ws.list);
+    for (int c = lane; c < (int)rows * 4; c += 32) d[c] = __ldg(g + c);
+    const int cnt = (int)__ldg(src->count + lane);
+    __syncwarp();
+    return cnt;
+}
+
 struct SphbScanCtx {
     const uint32_t *cell_start;
     const float *cell_hmax;
@@ -132,10 +176,13 @@ __device__ __forceinline__ uint32_t sphb_list_get(const SphbWarpShared &ws, int 
 //   FLUSH_ROWS: 0 = drain only when a list fills up; n > 0 = also after every n rows of cells; -1 = after every z layer
 //              of rows.  Early drains keep the lanes of the warp inside the same few rows while they gather their
 //              neighbours' records (shorter reuse distance in L1, fewer distinct lines per gather).
+//   symscale : SYM only, >= 1: the candidates' supports are taken as symscale times what the grid stores (lists
+//              that have to stay complete while every h may still grow by that factor)
+// Returns the number of live segments (what sphb_lists_save needs).
 template <bool SYM, int FLUSH_ROWS = 0, class Flush>
-__device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpShared &ws, int lane, bool tgt, float fx,
-                                               float fy, float fz, float Rj, float thr, uint32_t cid, float RH,
-                                               SphbList &L, Flush &&flush)
+__device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShared &ws, int lane, bool tgt, float fx,
+                                              float fy, float fz, float Rj, float thr, uint32_t cid, float RH,
+                                              SphbList &L, Flush &&flush, float symscale = 1.f)
 {
     int nseg = 0;   // live entries of ws.segbase (warp-uniform)
     unsigned remaining = __ballot_sync(SPHB_FULL, tgt);
@@ -205,7 +252,7 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                     const int wh = sphb_cell_hi(xmax + hxw, g.inv_cellx, g.nx);
                     // extend the tight range outwards to the farthest cell whose h_max reaches the group
                     for (int cx = wl; cx < lo && cx <= wh; ++cx) {
-                        const double hm = (double)g.cell_hmax[rowbase + cx];
+                        const double hm = (double)g.cell_hmax[rowbase + cx] * (double)symscale;
                         const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
                         const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cellx);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
@@ -215,7 +262,7 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                         }
                     }
                     for (int cx = wh; cx > hi && cx >= wl; --cx) {
-                        const double hm = (double)g.cell_hmax[rowbase + cx];
+                        const double hm = (double)g.cell_hmax[rowbase + cx] * (double)symscale;
                         const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
                         const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cellx);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
@@ -273,7 +320,7 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
                         float th = thrp;
                         if (SYM) {
                             const float ttile = __int_as_float(__reduce_max_sync(SPHB_FULL, __float_as_int(wthr)));
-                            th = fmaxf(thrp, ttile + offp);
+                            th = fmaxf(thrp, __fmul_ru(ttile, symscale * symscale) + offp);
                         }
                         __syncwarp();
                         const int nt = (int)((t1 - t) < 32u ? (t1 - t) : 32u);
@@ -301,4 +348,5 @@ __device__ __forceinline__ void sphb_warp_scan(const SphbScanCtx &g, SphbWarpSha
             }
         }
     }
+    return nseg;
 }

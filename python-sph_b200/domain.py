@@ -23,6 +23,7 @@ gloo tests on CPU exercise; `SlabRunner` drives the CUDA kernels through engine.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -113,6 +114,7 @@ class SlabRunner:
             raise NotImplementedError("SlabRunner: the all-pairs gravity sum is single-GPU only; run with G = 0")
         self.e, self.consts, self.world, self.rank, self.margin = eng, consts, world, rank, margin
         self.balance = balance
+        self.park = os.environ.get("SPHB_NO_PARK") is None   # share neighbour lists between kernels of one snapshot
         self.calib_left = calib_steps if balance else 0   # optional: time the first steps per rank and re-balance
         self.dev = eng.device
         self.statuses = []
@@ -199,22 +201,26 @@ class SlabRunner:
         return torch.cat([owned_vals, snap["hx"].exchange([owned_vals])[0]])
 
     # ---- physics stages -----------------------------------------------------------------------------------
-    def _stage(self, snap, status_ptr, om_own=None):
-        """the six calls of pyfluid.py:502-507 for the owned particles -> acc, dudt (owned order)"""
+    def _stage(self, snap, status_ptr, om_own=None, lists=None):
+        """the six calls of pyfluid.py:502-507 for the owned particles -> acc, dudt (owned order)
+        lists: neighbour lists parked by the Newton kernel of this snapshot (else the Omega pass parks its own)"""
         e, dg = self.e, snap["dg"]
         if om_own is None:
-            _, _, om_S, _ = e.density_omega(dg, self.consts, target=snap["target"], want_rho=False, want_omega=True)
+            lists = e.park_lists(dg) if self.park else None
+            _, _, om_S, _ = e.density_omega(dg, self.consts, target=snap["target"], want_rho=False, want_omega=True,
+                                            lists=lists)
             om_own = self._owned_from_grid(snap, om_S, 1)
         om_L = self._fill_ghosts(snap, om_own)
         vel_S = self._to_grid(snap, snap["vel"], 3)
         u_S = self._to_grid(snap, snap["u"], 1)
         _, _, rB, rC = e.eos(dg.posh, vel_S, u_S, self._to_grid(snap, om_L, 1), self.consts, status_ptr)
-        acc_S, dudt_S = e.force(dg, self.consts, rB, rC, e.hmax(dg.posh), status_ptr, target=snap["target"])
+        acc_S, dudt_S = e.force(dg, self.consts, rB, rC, e.hmax(dg.posh), status_ptr, target=snap["target"], lists=lists)
         return self._owned_from_grid(snap, acc_S, 3), self._owned_from_grid(snap, dudt_S, 1)
 
-    def _newton(self, snap, status_ptr, want_omega=False):
+    def _newton(self, snap, status_ptr, want_omega=False, lists=None):
         e, dg = self.e, snap["dg"]
-        r = e.newton(dg, self.consts, dg.posh[:, 3].contiguous(), status_ptr, target=snap["target"], want_omega=want_omega)
+        r = e.newton(dg, self.consts, dg.posh[:, 3].contiguous(), status_ptr, target=snap["target"], want_omega=want_omega,
+                     lists=lists)
         h_own = self._owned_from_grid(snap, r[0] if want_omega else r, 1)
         e.check_neg_h(h_own, status_ptr)
         return (h_own, self._owned_from_grid(snap, r[1], 1)) if want_omega else h_own
@@ -330,11 +336,16 @@ class SlabRunner:
             wfac = torch.ones_like(st["h"])
         # h_mid
         s1 = self._snapshot(mid, ["pos", "h", "vel", "u"])
-        h_mid, om_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID), want_omega=True)
+        # the Newton kernel parks symmetric-support lists that stay complete while no h (own or ghost, hence the
+        # all-reduce of the flag) grows by more than PARK_COVER; the mid-stage force kernel drains them
+        l1 = e.park_lists(s1["dg"], cover=E.PARK_COVER) if self.park else None
+        h_mid, om_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID), want_omega=True, lists=l1)
+        if l1 is not None:
+            dist.all_reduce(l1.broken, op=dist.ReduceOp.MAX)
         self._note_plan_use(mid["pos"], h_mid)
         h_mid_L = self._fill_ghosts(s1, h_mid)
         e.set_h(s1["dg"], self._to_grid(s1, h_mid_L, 1))
-        acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID), om_own=om_mid)
+        acc1, dudt1 = self._stage(s1, stt.ptr(E.S_STAGE_MID), om_own=om_mid, lists=l1)
         # corrector (owned only, t0 state is still in owned order)
         posh_1, vel_1, u_1 = e.correct(posh0, st["vel"], st["u"], acc1, dudt1, dt, stt.ptr(E.S_CORR))
         new = dict(gid=st["gid"], pos=posh_1[:, :3].contiguous(), h=h_mid, vel=vel_1, u=u_1, wfac=wfac)

@@ -31,6 +31,18 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class ParkedLists:
+    """sphb_lists: one producer kernel's neighbour lists, kept for the force kernel of the same snapshot"""
+
+    def __init__(self, store, broken, hmax, cover):
+        self.store, self.broken, self.hmax = store, broken, hmax   # keep the tensors alive
+        self.c = N.Lists(store.data_ptr(), broken.data_ptr(), hmax.data_ptr(), float(cover))
+
+
+def _lists(pl):
+    return C.byref(pl.c) if pl is not None else None
+
+
 def require_cuda():
     lib = N.load()
     if not torch.cuda.is_available():
@@ -219,10 +231,22 @@ class Engine:
         self._run("gather_u32", self.lib.sphb_gather_u32, _ptr(src), _ptr(perm), perm.shape[0], _ptr(dst), _stream())
         return dst
 
+    # -- neighbour lists parked between kernels (sphb_lists) ------------------------------------
+    def park_lists(self, dg, cover=1.0):
+        """-> ParkedLists for this cell list: pass it to ONE producer (density_omega or newton) and then to force.
+        cover: how much any h may grow between the two (1 when h does not change).  The store lives in `dg`."""
+        need = int(self.lib.sphb_lists_bytes(dg.n))
+        if getattr(dg, "_lists_store", None) is None or dg._lists_store.numel() < need:
+            dg._lists_store = torch.empty(need, dtype=torch.uint8, device=self.device)
+            dg._lists_broken = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dg._lists_broken.zero_()
+        return ParkedLists(dg._lists_store, dg._lists_broken, self.hmax(dg.posh), cover)
+
     # -- K2 ------------------------------------------------------------------------------------
     def density_omega(self, dg, consts, target=None, h_target=None, rho_in=None, want_rho=True, want_dwdh=False,
-                      want_omega=False, want_ngb=False, want_xi=False):
-        """-> rho_sum, dwdh_sum, omega, ngb_count (, xi when want_xi); entries not asked for are None"""
+                      want_omega=False, want_ngb=False, want_xi=False, lists=None):
+        """-> rho_sum, dwdh_sum, omega, ngb_count (, xi when want_xi); entries not asked for are None
+        lists: a ParkedLists to fill for the force call on the same cell list"""
         n = dg.n
         xi = torch.empty(n, dtype=F64, device=self.device) if want_xi else None
         rho = torch.empty(n, dtype=F64, device=self.device) if want_rho else None
@@ -230,12 +254,13 @@ class Engine:
         om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
         ng = torch.empty(n, dtype=torch.int32, device=self.device) if want_ngb else None
         self._run("density_omega", self.lib.sphb_density_omega, dg.cells(), C.byref(consts), _ptr(target), _ptr(h_target), _ptr(rho_in), _ptr(rho),
-                                            _ptr(dw), _ptr(om), _ptr(xi), _ptr(ng), _stream())
+                                            _ptr(dw), _ptr(om), _ptr(xi), _ptr(ng), _lists(lists), _stream())
         return (rho, dw, om, ng, xi) if want_xi else (rho, dw, om, ng)
 
     # -- K3 ------------------------------------------------------------------------------------
-    def newton(self, dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False):
-        """-> h (, iters, code) (, omega at the returned h when want_omega)"""
+    def newton(self, dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False, lists=None):
+        """-> h (, iters, code) (, omega at the returned h when want_omega)
+        lists: a ParkedLists to fill for the force call on the same cell list (after set_h with the result)"""
         n = dg.n
         om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
         h = torch.full((n,), float("nan"), dtype=F64, device=self.device) if target is not None else \
@@ -244,7 +269,7 @@ class Engine:
         code = torch.zeros(n, dtype=torch.int32, device=self.device) if details else None
         fail = torch.empty(n, dtype=torch.int32, device=self.device)
         self._run("newton_h", self.lib.sphb_newton_h, dg.cells(), C.byref(consts), _ptr(target), _ptr(h_guess), _ptr(h), _ptr(om), _ptr(it), _ptr(code),
-                                       _ptr(fail), status_ptr, _stream())
+                                       _ptr(fail), status_ptr, _lists(lists), _stream())
         out = (h, it, code) if details else (h,)
         if want_omega:
             out = out + (om,)
@@ -301,14 +326,15 @@ class Engine:
         self._run("grav_eval", self.lib.sphb_grav_eval, _ptr(dist), _ptr(h), n, _ptr(phi), _ptr(f), _ptr(dp), _stream())
         return phi, f, dp
 
-    def force(self, dg, consts, recB, recC, hmax, status_ptr, target=None, bgrav=None):
+    def force(self, dg, consts, recB, recC, hmax, status_ptr, target=None, bgrav=None, lists=None):
+        """lists: the ParkedLists a producer filled on this cell list (drained instead of scanning)"""
         n = dg.n
         acc = torch.zeros((n, 3), dtype=F64, device=self.device) if target is not None else \
             torch.empty((n, 3), dtype=F64, device=self.device)
         dudt = torch.zeros(n, dtype=F64, device=self.device) if target is not None else \
             torch.empty(n, dtype=F64, device=self.device)
         self._run("force", self.lib.sphb_force, dg.cells(), C.byref(consts), _ptr(target), _ptr(recB), _ptr(recC), _ptr(bgrav), _ptr(hmax), _ptr(acc),
-                                    _ptr(dudt), status_ptr, _stream())
+                                    _ptr(dudt), status_ptr, _lists(lists), _stream())
         return acc, dudt
 
     def pair_terms(self, posh, recB, recC, pairs, consts, status_ptr, bgrav=None, want_grav=False):
@@ -395,6 +421,9 @@ def raise_for_status(st, printer=print):
         hard(int(row[0]))
 
 
+PARK_COVER = float(os.environ.get("SPHB_PARK_COVER", "1.016"))
+
+
 class Stepper:
     """var_smoothlength_leapfrog on device tensors (pyfluid.py:498-532), G = 0.
 
@@ -422,11 +451,14 @@ class Stepper:
         # multi-GPU runner does the same with global ids: k-rank results equal 1-rank results bit for bit).
         grav = consts.G != 0.0
 
-        def stage(dg, vel_c, u_c, sidx, om=None):
+        park = os.environ.get("SPHB_NO_PARK") is None
+
+        def stage(dg, vel_c, u_c, sidx, om=None, lists=None):
             """the six calls at pyfluid.py:502-507 / :517-522 -> acc, dudt in caller order
-            (om: Omega already produced by the Newton kernel for this snapshot)"""
+            (om: Omega already produced by the Newton kernel for this snapshot; lists: its parked neighbour lists)"""
             if not grav and om is None:
-                _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True)
+                lists = e.park_lists(dg) if park else None   # the Omega pass scans once for itself and for the force
+                _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True, lists=lists)
             if hooks is not None and sidx == S_STAGE0:
                 hooks.before_vel_u()          # velocities and energies are first needed here
             vel_s, u_s = e.gather(vel_c, dg.perm, 3), e.gather(u_c, dg.perm, 1)
@@ -439,12 +471,12 @@ class Stepper:
                 e.gravity_direct(dg.posh, consts, acc=acc)
             else:
                 _, _, rB, rC = e.eos(dg.posh, vel_s, u_s, om, consts, st.ptr(sidx))
-                acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx))
+                acc, dudt = e.force(dg, consts, rB, rC, e.hmax(dg.posh), st.ptr(sidx), lists=lists)
             return e.scatter(acc, dg.perm, 3), e.scatter(dudt, dg.perm, 1)
 
-        def solve_h(dg, sidx, want_omega=False):
+        def solve_h(dg, sidx, want_omega=False, lists=None):
             """newton_smoothlength_arr(pos, guess = the h carried in the snapshot), grid order"""
-            r = e.newton(dg, consts, dg.posh[:, 3].contiguous(), st.ptr(sidx), want_omega=want_omega)
+            r = e.newton(dg, consts, dg.posh[:, 3].contiguous(), st.ptr(sidx), want_omega=want_omega, lists=lists)
             e.check_neg_h(r[0] if want_omega else r, st.ptr(sidx))
             return r
 
@@ -456,9 +488,12 @@ class Stepper:
         posh_m, vel_m, u_m = e.predict(posh0, vel0, u0, acc0, dudt0, dt, st.ptr(S_PRED))
         # ---- h_mid = newton(pos_mid, h0), stage mid: pyfluid.py:516-522 -------------------------------
         g1 = pool[1] = e.build(posh_m, grid, delta, out=pool[1])
-        h_mid_s, om_mid = solve_h(g1, S_NEWTON_MID, want_omega=True)
+        # the mid-step Newton kernel scans with the symmetric support and a cover of PARK_COVER on every h: its lists
+        # serve the force kernel at h_mid as long as no h grew by more than that (else the force kernel scans itself)
+        l1 = e.park_lists(g1, cover=PARK_COVER) if (park and not grav) else None
+        h_mid_s, om_mid = solve_h(g1, S_NEWTON_MID, want_omega=True, lists=l1)
         e.set_h(g1, h_mid_s)
-        acc1, dudt1 = stage(g1, vel_m, u_m, S_STAGE_MID, om=om_mid)
+        acc1, dudt1 = stage(g1, vel_m, u_m, S_STAGE_MID, om=om_mid, lists=l1)
         h_mid = e.scatter(h_mid_s, g1.perm, 1)
         # ---- corrector: pyfluid.py:524-528 ---------------------------------------------------------------
         posh_1, vel1, u1 = e.correct(posh0, vel0, u0, acc1, dudt1, dt, st.ptr(S_CORR))

@@ -22,8 +22,8 @@ _newton = eng.newton
 rec = []
 
 
-def spy(dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False):
-    r = _newton(dg, consts, h_guess, status_ptr, target=target, details=True, want_omega=want_omega)
+def spy(dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False, lists=None):
+    r = _newton(dg, consts, h_guess, status_ptr, target=target, details=True, want_omega=want_omega, lists=lists)
     it = r[1]
     if os.environ.get("TRACE"):
         n32 = it.numel() // 32 * 32

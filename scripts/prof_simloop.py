@@ -49,8 +49,8 @@ _newton = eng.newton
 _its = []
 
 
-def newton_spy(dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False):
-    r = _newton(dg, consts, h_guess, status_ptr, target=target, details=True, want_omega=want_omega)
+def newton_spy(dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False, lists=None):
+    r = _newton(dg, consts, h_guess, status_ptr, target=target, details=True, want_omega=want_omega, lists=lists)
     _its.append(r[1])
     M = 1 << 21
     print("      ptrs MB (off KB):", {k: (v.data_ptr() >> 20, (v.data_ptr() % M) >> 10) for k, v in
@@ -59,9 +59,9 @@ def newton_spy(dg, consts, h_guess, status_ptr, target=None, details=False, want
     return (r[0], r[3]) if want_omega else r[0]
 
 
-def newton_twice(dg, consts, h_guess, status_ptr, target=None, details=False, want_omega=False):
-    _newton(dg, consts, h_guess, status_ptr, target=target, details=details, want_omega=want_omega)
-    return _newton(dg, consts, h_guess, status_ptr, target=target, details=details, want_omega=want_omega)
+def newton_twice(dg, consts, h_guess, status_ptr, **kw):
+    _newton(dg, consts, h_guess, status_ptr, **kw)
+    return _newton(dg, consts, h_guess, status_ptr, **kw)
 
 
 plain = lambda s: stp.step(s[0], s[1], s[2], s[3], w["dt"], c, defer_status=True)

@@ -34,6 +34,7 @@ def test_struct_sizes_match_header(native):
     assert C.sizeof(native.Grid) == 8 * 4 + 4 * 4
     assert C.sizeof(native.Status) == 32
     assert C.sizeof(native.Cells) == 48 + 8 + 5 * 8 + 8
+    assert C.sizeof(native.Lists) == 3 * 8 + 8
 
 
 def test_no_compute_entry_points_without_gpu(native):
@@ -45,7 +46,7 @@ def test_no_compute_entry_points_without_gpu(native):
     assert lib.sphb_grid_workspace_bytes(1000, C.byref(g)) > 0
     # argument validation happens before any CUDA call
     assert lib.sphb_grid_build(None, None, -1, C.byref(g), 0.0, None, None, None, None, None, None, None, 0, None) == -1
-    assert lib.sphb_force(None, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.sphb_force(None, None, None, None, None, None, None, None, None, None, None, None) == -1
 
 
 def test_product_fails_loudly_without_gpu():
