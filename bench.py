@@ -68,7 +68,7 @@ class ClockSampler:
         self.lines = []
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -76,11 +76,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        """the timed region begins now (the sampler itself was started before the warm-up, so that nvidia-smi's
+        start-up -- NVML initialisation takes driver locks -- does not fall into the timed steps)"""
+        self.t0 = time.time()
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -88,7 +94,9 @@ class ClockSampler:
             self.p.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.25]
+        for ln in (inside or [ln for _, ln in self.lines[-1:]]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -223,6 +231,7 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         state = step(state)
         if runner is None:
@@ -230,7 +239,8 @@ def run_ours(a):
     barrier()
     lib = eng.lib
     launches0 = lib.sphb_launch_count()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.mark_start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
@@ -251,26 +261,6 @@ def run_ours(a):
             E.raise_for_status(st.read(), printer=lambda *_: None)
     clk = clocks.stop() if clocks else None
     value = n_total * a.steps / (ms * 1e-3)
-
-    # ---- time loop variant: Omega(pos1, h1) leaves step t's last Newton kernel and enters step t+1 (what
-    # var_smoothlength_sim does); same results, one cell scan fewer per step.  Reported beside `value`, not as it.
-    sim_loop = None
-    if runner is None:
-        s5 = stepper.step(state[0], state[1], state[2], state[3], dt, consts, defer_status=True, want_omega1=True)
-        for _ in range(2):   # warm-up of this variant's own allocation pattern
-            s5 = stepper.step(s5[0], s5[1], s5[2], s5[3], dt, consts, defer_status=True, omega0=s5[4], want_omega1=True)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.steps):
-            s5 = stepper.step(s5[0], s5[1], s5[2], s5[3], dt, consts, defer_status=True, omega0=s5[4], want_omega1=True)
-        e1.record()
-        torch.cuda.synchronize()
-        E.raise_for_status(stepper.last_status.read(), printer=lambda *_: None)
-        sms = e0.elapsed_time(e1) / a.steps
-        sim_loop = {"value": n_total / (sms * 1e-3), "unit": "particle-steps/s", "ms_per_step": sms,
-                    "note": "Omega carried from the previous step's last Newton kernel (var_smoothlength_sim loop)"}
-        del s5
 
     # ---- e2e: public API semantics on pinned host buffers (H2D + step + D2H each step) ----------------
     e2e = None
@@ -387,7 +377,7 @@ def run_ours(a):
             "config": {"workload": w["name"], "n_particles": n_total, "dt": dt, "l2": "inputs_larger_than_L2 (state ~1 GB vs 126 MB L2)",
                        "parallelism": f"slab{world}" if world > 1 else "single"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-            "sim_loop": sim_loop, "kernels": per_kernel}
+            "kernels": per_kernel}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

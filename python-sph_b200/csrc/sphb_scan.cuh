@@ -32,6 +32,34 @@
 #define SPHB_SEG_LEN (1u << SPHB_SEG_BITS)
 #define SPHB_NSEG (1 << (16 - SPHB_SEG_BITS)) /* live segments a 16-bit code can address */
 
+#ifndef SPHB_FILTER_MASK
+#define SPHB_FILTER_MASK 0 /* pre-filter results collected in a register mask, entries written once per tile: measured slower, off */
+#endif
+#ifndef SPHB_FILTER_X2
+#define SPHB_FILTER_X2 0 /* fp32 pre-filter two candidates per instruction (FFMA2): measured no faster, off */
+#endif
+
+#if SPHB_FILTER_MASK && SPHB_FILTER_X2
+#error "SPHB_FILTER_X2 uses its own tile layout: build it with -DSPHB_FILTER_MASK=0"
+#endif
+
+__device__ __forceinline__ unsigned long long sphb_pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void sphb_unpack2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sphb_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 struct SphbWarpShared {
     float4 tile[32];      // x', y', z', |c'|^2 of the staged candidates (NaN-padded)
     uint32_t segbase[SPHB_NSEG]; // first sorted slot of each live segment
@@ -221,6 +249,9 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShar
         const float dmax = 0.5f * (hdx + hdy + hdz) + (float)Rw + 1.8f * (float)g.cell;   // >= |c'| of anything in range
         const float err = 4e-6f * dmax * dmax;
         const float m2x = -2.f * tx, m2y = -2.f * ty, m2z = -2.f * tz;
+#if SPHB_FILTER_X2
+        const unsigned long long m2x2 = sphb_pack2(m2x, m2x), m2y2 = sphb_pack2(m2y, m2y), m2z2 = sphb_pack2(m2z, m2z);
+#endif
         // pass  <=>  |c'|^2 - 2 c'.t' <= thr - |t'|^2 + err ; lanes outside the group never pass
         const float thrp = ing ? (thr - tt + err) : -inf;
         const float offp = ing ? (err - tt) : -inf;   // SYM: candidate threshold + offp
@@ -313,7 +344,19 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShar
                             rec.w = fmaf(rec.z, rec.z, fmaf(rec.y, rec.y, rec.x * rec.x));
                             wthr = f.w;
                         }
+#if SPHB_FILTER_X2
+                        {
+                            // pair layout for the packed filter: tile[2p] = (x_a, x_b, y_a, y_b), tile[2p+1] =
+                            // (z_a, z_b, w_a, w_b) for candidates a = 2p, b = 2p+1; the even lane takes its partner's
+                            // x, y, the odd lane its partner's z, w -- two shuffles, one conflict-free STS.128 each
+                            const bool odd = lane & 1;
+                            const float r1 = __shfl_xor_sync(SPHB_FULL, odd ? rec.x : rec.z, 1);
+                            const float r2 = __shfl_xor_sync(SPHB_FULL, odd ? rec.y : rec.w, 1);
+                            ws.tile[lane] = odd ? make_float4(r1, rec.z, r2, rec.w) : make_float4(rec.x, r1, rec.y, r2);
+                        }
+#else
                         ws.tile[lane] = rec;
+#endif
                         // SYM: the candidates' own supports enter through the largest threshold of the tile (one
                         // warp reduction per 32 candidates instead of a load + max per candidate; thresholds are
                         // non-negative floats, so their bit patterns order like integers)
@@ -324,11 +367,59 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShar
                         }
                         __syncwarp();
                         const int nt = (int)((t1 - t) < 32u ? (t1 - t) : 32u);
+#if SPHB_FILTER_MASK
+                        // the tests only set bits of a per-lane mask (no shared-memory traffic); the mask becomes
+                        // list entries once per tile, in ascending order
+                        uint32_t hit = 0;
+                        for (int c0 = 0; c0 < nt; c0 += SPHB_SUB) {
+                            float4 f[SPHB_SUB];
+#pragma unroll
+                            for (int c = 0; c < SPHB_SUB; ++c) f[c] = ws.tile[c0 + c];
+                            float sv[SPHB_SUB];
+#pragma unroll
+                            for (int c = 0; c < SPHB_SUB; ++c)
+                                sv[c] = fmaf(f[c].x, m2x, fmaf(f[c].y, m2y, fmaf(f[c].z, m2z, f[c].w)));
+                            uint32_t m = 0;
+#pragma unroll
+                            for (int c = 0; c < SPHB_SUB; ++c) m |= (sv[c] <= th) ? (1u << c) : 0u;
+                            hit |= m << c0;
+                        }
+                        if (__any_sync(SPHB_FULL, L.count() + __popc(hit) > SPHB_LIST)) {
+                            flush(L.count());
+                            L.reset();
+                        }
+                        while (hit) {
+                            L.push(code + (uint32_t)(__ffs(hit) - 1));
+                            hit &= hit - 1;
+                        }
+                        code += 32;
+#else
                         for (int c0 = 0; c0 < nt; c0 += SPHB_SUB) {
                             if (__any_sync(SPHB_FULL, L.count() > SPHB_LIST - SPHB_SUB)) {
                                 flush(L.count());
                                 L.reset();
                             }
+#if SPHB_FILTER_X2
+                            // two candidates per FFMA2 (fma.rn.f32x2, sm_100): same roundings as the scalar form
+                            const ulonglong2 *t2 = reinterpret_cast<const ulonglong2 *>(ws.tile) + c0;
+                            ulonglong2 xy[SPHB_SUB / 2], zw[SPHB_SUB / 2];
+#pragma unroll
+                            for (int q = 0; q < SPHB_SUB / 2; ++q) {
+                                xy[q] = t2[2 * q];
+                                zw[q] = t2[2 * q + 1];
+                            }
+                            unsigned long long sv2[SPHB_SUB / 2];
+#pragma unroll
+                            for (int q = 0; q < SPHB_SUB / 2; ++q)
+                                sv2[q] = sphb_fma2(xy[q].x, m2x2, sphb_fma2(xy[q].y, m2y2, sphb_fma2(zw[q].x, m2z2, zw[q].y)));
+#pragma unroll
+                            for (int q = 0; q < SPHB_SUB / 2; ++q) {
+                                float sa, sb;
+                                sphb_unpack2(sv2[q], sa, sb);
+                                if (sa <= th) L.push(code + 2 * q);
+                                if (sb <= th) L.push(code + 2 * q + 1);
+                            }
+#else
                             // all loads of the sub-tile first (independent LDS.128), then the tests
                             float4 f[SPHB_SUB];
 #pragma unroll
@@ -340,8 +431,10 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShar
 #pragma unroll
                             for (int c = 0; c < SPHB_SUB; ++c)
                                 if (sv[c] <= th) L.push(code + c);
+#endif
                             code += SPHB_SUB;
                         }
+#endif
                         __syncwarp();
                     }
                 }

@@ -591,8 +591,9 @@ def static_smoothlength_sim(time, positions_with_time, velocities_with_time, ene
 
 def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlength_approx):
     """pyfluid.py:535-602: returns (Nt,N,3), (Nt,N,3), (Nt,N), (Nt,N) histories (numpy in -> numpy out).
-    Inside the loop Omega at (pos[t+1], h[t+1]) comes out of step t's last Newton kernel and is handed to step
-    t+1, which would otherwise recompute exactly that sum (pyfluid.py:503); the results are unchanged."""
+    (Stepper.step can also take Omega(pos[t], h[t]) from step t-1's last Newton kernel -- omega0 / want_omega1 -- but
+    since the Omega pass parks its neighbour lists for the force kernel that follows it, recomputing Omega is the
+    faster loop; see DESIGN.md.)"""
     global _stepper
     io = _IO(positions0, velocities0, energies0, smoothlength_approx)
     dt = float(time_arr[1] - time_arr[0])
@@ -615,10 +616,9 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
         put(arr, 0, x)
     if _stepper is None:
         _stepper = _E.Stepper(_eng())
-    om = None
     for t in range(Nt - 1):
         print("time step:", t, "of", Nt)
-        pos, vel, u, h, om = _stepper.step(pos, vel, u, h, dt, _consts(), omega0=om, want_omega1=True)
+        pos, vel, u, h = _stepper.step(pos, vel, u, h, dt, _consts())
         for arr, x in ((P, pos), (V, vel), (E, u), (H, h)):
             put(arr, t + 1, x)
     return P, V, E, H
