@@ -270,17 +270,20 @@ def run_ours(a):
         sph.G = 0.0
         sph.PARTICLE_MASS = w["m"]
         hin = [t.cpu().pin_memory() for t in state]
+        hout = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in hin]   # two pinned sets used in turn
         nb = sum(t.numel() * 8 for t in hin)
         ke = max(1, min(a.steps, 3))
-        for _ in range(2):   # warm-up (pinned and device allocations, streams)
-            hin = list(sph.var_smoothlength_leapfrog(hin[0], hin[1], hin[2], hin[3], dt))
+        for _ in range(2):   # warm-up (device allocations, streams)
+            sph.var_smoothlength_leapfrog(hin[0], hin[1], hin[2], hin[3], dt, out=hout)
+            hin, hout = hout, hin
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(ke):
-            hin = list(sph.var_smoothlength_leapfrog(hin[0], hin[1], hin[2], hin[3], dt))
+            sph.var_smoothlength_leapfrog(hin[0], hin[1], hin[2], hin[3], dt, out=hout)
+            hin, hout = hout, hin
         el = time.perf_counter() - t0
         e2e = {"value": n_total * ke / el, "unit": "particle-steps/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
-               "steps": ke, "api": "pyfluid.var_smoothlength_leapfrog on pinned host tensors (transfers overlapped with kernels)"}
+               "steps": ke, "api": "pyfluid.var_smoothlength_leapfrog(pos, vel, u, h, dt, out=...) on pinned host tensors, two sets used in turn (transfers overlapped with kernels)"}
     elif runner is not None and not a.no_e2e:
         e2e = runner.e2e(state, dt, max(1, min(a.steps, 3)))
 
@@ -317,8 +320,9 @@ def run_ours(a):
         ach = flops_force / (f_ms * 1e-3) / 1e12
         bytes_force = 104.0 * n_total
         # DRAM bytes per launch: dram__bytes_read+write of k_force from the committed ncu --set full capture
-        # (profiles/r01_ncu_final_summary.txt: 292.1 MB for 1 990 656 particles), scaled per particle
-        traffic_force = 292.089e6 / 1990656 * n_total
+        # (profiles/r01_ncu_final_summary.txt: 570.9 MB read + 73.4 MB written for 1 990 656 particles; the parked
+        # neighbour lists are most of the reads), scaled per particle
+        traffic_force = 644.308e6 / 1990656 * n_total
         roof = {"kernel": "k_force", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                 "traffic": traffic_force, "traffic_source": "ncu capture at 1 990 656 particles scaled per particle (profiles/)", "peak_source": "DFMA microbenchmark in this run (sphb_fp64_peak); not in MEASURED_PEAKS.json",
                 "launch_ms": f_ms, "share_of_step": prof["force"][1] / step_ms,

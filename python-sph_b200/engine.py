@@ -545,7 +545,9 @@ def step_pinned(stepper, pos_h, vel_h, u_h, h_h, dt, consts, out=None, printer=p
     e = stepper.e
     dev = e.device
     main = torch.cuda.current_stream()
-    cs = torch.cuda.Stream(device=dev)
+    cs = getattr(stepper, "_copy_stream", None)
+    if cs is None:
+        cs = stepper._copy_stream = torch.cuda.Stream(device=dev)
     if out is None:
         out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (pos_h, vel_h, u_h, h_h)]
     pos_d = pos_h.to(dev, non_blocking=True)

@@ -538,9 +538,11 @@ def acceleration_arr(position_arr, density_arr, velocity_arr, pressure_arr, smoo
 _stepper = None
 
 
-def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt):
+def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt, out=None):
     """pyfluid.py:498-532: one midpoint predictor-corrector step (Cossins 3.152-3.155), G = 0.
-    Returns fresh (pos1, vel1, energy1, h1); inputs are not modified."""
+    Returns fresh (pos1, vel1, energy1, h1); inputs are not modified.
+    out (extension, pinned host tensors only): four pinned tensors to receive the results instead of newly pinned
+    memory -- pinning a gigabyte costs more than the step, so a time loop over host buffers hands in two sets in turn."""
     global _stepper
     io = _IO(pos0, vel0, energy0, h0)
     if _stepper is None:
@@ -549,7 +551,7 @@ def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt):
     if len(host) == 4 and all(t.is_pinned() and t.dtype == torch.float64 and t.is_contiguous() for t in host):
         # pinned host tensors in -> pinned host tensors out, transfers overlapped with the kernels
         return tuple(_E.step_pinned(_stepper, pos0.reshape(-1, 3), vel0.reshape(-1, 3), energy0.reshape(-1), h0.reshape(-1),
-                                    float(dt), _consts()))
+                                    float(dt), _consts(), out=list(out) if out is not None else None))
     p, v, u, h = _stepper.step(io.dev64(pos0, (-1, 3)), io.dev64(vel0, (-1, 3)), io.dev64(energy0, (-1,)),
                                io.dev64(h0, (-1,)), float(dt), _consts())
     return io.out(p), io.out(v), io.out(u), io.out(h)

@@ -542,3 +542,8 @@ def test_pinned_host_tensors_overlapped_path(sph, golden):
     out = sph.var_smoothlength_leapfrog(*host, 1e-3)
     for a, b in zip(ref, out):
         assert (not b.is_cuda) and b.is_pinned() and torch.equal(a.cpu(), b)
+    # caller-provided pinned result buffers (the time-loop form: two sets used in turn)
+    mine = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in host]
+    got = sph.var_smoothlength_leapfrog(*host, 1e-3, out=mine)
+    for a, b, m in zip(ref, got, mine):
+        assert b.data_ptr() == m.data_ptr() and torch.equal(a.cpu(), b)
