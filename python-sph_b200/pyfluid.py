@@ -591,8 +591,51 @@ def static_smoothlength_sim(time, positions_with_time, velocities_with_time, ene
                                                                       np.ascontiguousarray(energies_with_time[:, t]), dt)
 
 
-def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlength_approx):
+class _HistoryWriter:
+    """Snapshots to host memory while the next step runs (the authors' TODO at pyfluid.py:585-588): each snapshot
+    goes device -> one of two pinned staging sets on a copy stream, and is copied into the numpy histories when that
+    set comes round again (or at the end), so neither the (Nt,N,.) history nor a blocking read sits on the GPU."""
+
+    def __init__(self, hist, like):
+        self.hist = hist                                  # [P, V, E, H] numpy histories
+        self.stream = torch.cuda.Stream(device=like[0].device)
+        self.slots = [[torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in like] for _ in range(2)]
+        self.pending = [None, None]                       # (event, history index) per staging set
+        self.count = 0
+
+    def _drain(self, k):
+        if self.pending[k] is not None:
+            ev, idx = self.pending[k]
+            ev.synchronize()
+            for arr, t in zip(self.hist, self.slots[k]):
+                arr[idx] = t.numpy()
+            self.pending[k] = None
+
+    def put(self, idx, fields):
+        k = self.count % 2
+        self.count += 1
+        self._drain(k)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for dst, src in zip(self.slots[k], fields):
+                dst.copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        for src in fields:
+            src.record_stream(self.stream)
+        self.pending[k] = (done, idx)
+
+    def finish(self):
+        self._drain(0)
+        self._drain(1)
+
+
+def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlength_approx, stride=1):
     """pyfluid.py:535-602: returns (Nt,N,3), (Nt,N,3), (Nt,N), (Nt,N) histories (numpy in -> numpy out).
+    stride (extension): keep every stride-th snapshot only -- the histories then have
+    1 + (Nt-1)//stride entries (snapshot k is time_arr[k*stride]); 1 = the reference's behaviour.
     (Stepper.step can also take Omega(pos[t], h[t]) from step t-1's last Newton kernel -- omega0 / want_omega1 -- but
     since the Omega pass parks its neighbour lists for the force kernel that follows it, recomputing Omega is the
     faster loop; see DESIGN.md.)"""
@@ -600,27 +643,35 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
     io = _IO(positions0, velocities0, energies0, smoothlength_approx)
     dt = float(time_arr[1] - time_arr[0])
     Nt = len(time_arr)
+    stride = max(1, int(stride))
+    Ns = 1 + (Nt - 1) // stride
     pos = io.dev64(positions0, (-1, 3))
     vel = io.dev64(velocities0, (-1, 3))
     u = io.dev64(energies0, (-1,))
     N = u.shape[0]
-    if io.torch_out:
-        mk = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=pos.device)
-        put = lambda arr, t, x: arr.__setitem__(t, x)
-    else:
-        # numpy callers get numpy histories: each snapshot goes to host memory as it is produced, so the (Nt,N,.)
-        # history never has to fit in HBM (the reference's own TODO at pyfluid.py:585-588)
-        mk = lambda *shape: np.zeros(shape)
-        put = lambda arr, t, x: arr.__setitem__(t, x.cpu().numpy())
-    P, V, E, H = mk(Nt, N, 3), mk(Nt, N, 3), mk(Nt, N), mk(Nt, N)
     h = newton_smoothlength_arr(pos, io.dev64(smoothlength_approx, (-1,)))
-    for arr, x in ((P, pos), (V, vel), (E, u), (H, h)):
-        put(arr, 0, x)
+    if io.torch_out:
+        P, V, E, H = (torch.zeros(shape, dtype=torch.float64, device=pos.device)
+                      for shape in ((Ns, N, 3), (Ns, N, 3), (Ns, N), (Ns, N)))
+
+        def put(idx, fields):
+            for arr, x in zip((P, V, E, H), fields):
+                arr[idx] = x
+
+        finish = lambda: None
+    else:
+        # numpy callers get numpy histories, written through pinned staging buffers as the steps run, so the
+        # (Nt,N,.) history never has to fit in HBM
+        P, V, E, H = np.zeros((Ns, N, 3)), np.zeros((Ns, N, 3)), np.zeros((Ns, N)), np.zeros((Ns, N))
+        writer = _HistoryWriter([P, V, E, H], (pos, vel, u, h))
+        put, finish = writer.put, writer.finish
+    put(0, (pos, vel, u, h))
     if _stepper is None:
         _stepper = _E.Stepper(_eng())
     for t in range(Nt - 1):
         print("time step:", t, "of", Nt)
         pos, vel, u, h = _stepper.step(pos, vel, u, h, dt, _consts())
-        for arr, x in ((P, pos), (V, vel), (E, u), (H, h)):
-            put(arr, t + 1, x)
+        if (t + 1) % stride == 0:
+            put((t + 1) // stride, (pos, vel, u, h))
+    finish()
     return P, V, E, H
