@@ -247,6 +247,41 @@ class Oracle:
             P[t + 1], V[t + 1], E[t + 1], H[t + 1] = self.var_smoothlength_leapfrog(P[t], V[t], E[t], H[t], dt)
         return P, V, E, H
 
+    # -- static-h path, REPAIRED: small-N numpy restatement over the C primitives --------
+    def energy_evolve_arr(self, pos, vel, e, P, rho, h, dt):
+        """pyfluid.py:292-314: e_j + P_j/rho_j^2 * sum_i m (v_j - v_i).dellM4(r_j, r_i, h_j) * dt, index-order sum,
+        dellM4 = M4_d1(distance) * direction_i_j (:50-54, :81-82; zero for coincident positions)"""
+        pos, vel, e, P, rho, h = map(_f64, (pos, vel, e, P, rho, h)); n = len(pos)
+        m = float(self.k["PARTICLE_MASS"])
+        out = np.empty(n)
+        for j in range(n):
+            change = 0.0
+            for i in range(n):
+                if np.array_equal(pos[j], pos[i]):
+                    grad = np.zeros(3)
+                else:
+                    d = self.distance(pos[j], pos[i])
+                    grad = self.M4_d1(d, h[j]) * ((pos[j] - pos[i]) / d)
+                change += m * np.dot(vel[j] - vel[i], grad)
+            out[j] = e[j] + P[j] / rho[j] ** 2 * change * dt
+        return out
+
+    def static_smoothlength_leapfrog(self, pos0, vel0, e0, dt, h_static=2.0):
+        """pyfluid.py:607-621 with the minimal repair of the two broken calls (acceleration_arr with Omega = 1, xi = 0;
+        energy_evolve_arr with its unused 7th argument); h_static = DEFAULT_SMOOTHLENGTH (:6)"""
+        pos0, vel0, e0 = map(_f64, (pos0, vel0, e0)); n = len(pos0)
+        hs, one, zero = np.full(n, float(h_static)), np.ones(n), np.zeros(n)
+        den0 = self.density_arr(pos0, hs)
+        press0 = self.pressure_arr(e0, den0)
+        acc0 = self.acceleration_arr(pos0, den0, vel0, press0, hs, one, zero)
+        pos1 = pos0 + vel0 * dt + 0.5 * acc0 * dt ** 2
+        e1 = self.energy_evolve_arr(pos0, vel0, e0, press0, den0, hs, dt)
+        den1 = self.density_arr(pos1, hs)
+        press1 = self.pressure_arr(e1, den1)
+        acc1 = self.acceleration_arr(pos1, den1, vel0, press1, hs, one, zero)
+        vel1 = vel0 + 0.5 * (acc0 + acc1) * dt
+        return pos1, vel1, e1
+
     def step_work_sample(self, pos, vel, e, h, jlist):
         """Per-particle share of one step for the sampled j (bench.py cpu_baseline)."""
         pos, vel, e, h = map(_f64, (pos, vel, e, h)); jl = self._jl(jlist, len(pos)); sink = np.empty(len(jl))

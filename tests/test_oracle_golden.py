@@ -161,6 +161,19 @@ def test_case_G_coincident_particles(golden, oracle_mod):
     vclose(o.acceleration_arr(pos, rho, vel, P, h, om, np.zeros(64)), g["G_acc_G0"], 1e-12)
 
 
+def test_case_S_static_path_repaired(golden, oracle_mod):
+    """BASELINE config 1 through the documented repair (SURVEY 8(f) #3), with and without gravity: three steps"""
+    g = golden
+    for tag, G in (("G0", 0.0), ("G", None)):
+        o = oracle_mod.Oracle(G=0.0) if G == 0.0 else oracle_mod.Oracle()
+        p, v, e = g["S_%s_pos" % tag][0], g["S_%s_vel" % tag][0], g["S_%s_e" % tag][0]
+        for t in range(1, 4):
+            p, v, e = o.static_smoothlength_leapfrog(p, v, e, 0.1)
+            close(p, g["S_%s_pos" % tag][t], 1e-12, atol=1e-12)
+            np.testing.assert_allclose(v, g["S_%s_vel" % tag][t], rtol=1e-11, atol=1e-12)
+            close(e, g["S_%s_e" % tag][t], 1e-12)
+
+
 def test_negative_energy_raises(golden, oracle_mod):
     g = golden
     o = oracle_mod.Oracle(G=0.0)
