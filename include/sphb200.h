@@ -134,7 +134,8 @@ int sphb_gather_u32(const uint32_t *src, const uint32_t *perm, int64_t n, uint32
  *                h -- the consumer then scans for itself.  A warp whose lists overflowed also scans for itself.
  *   hmax_global  device float: max h of the snapshot (sphb_hmax), bounds the symmetric search of the producer
  *   cover        >= 1: how much every h may grow between producer and consumer (1 when h does not change)
- * The producer and the consumer must be called with the same `target` flags.  NULL = every kernel scans. */
+ * The producer and the consumer must be called with the same `target` flags, and a Newton producer with h_guess = the
+ * h the cell list holds (the cover is relative to it).  NULL = every kernel scans. */
 typedef struct sphb_lists {
     void *store;
     int32_t *broken;
