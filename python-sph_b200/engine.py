@@ -425,7 +425,8 @@ PARK_COVER = float(os.environ.get("SPHB_PARK_COVER", "1.016"))
 
 
 class Stepper:
-    """var_smoothlength_leapfrog on device tensors (pyfluid.py:498-532), G = 0.
+    """var_smoothlength_leapfrog on device tensors (pyfluid.py:498-532); with consts.G != 0 the softened self-gravity
+    terms (:420-437, :481-483) are included (single GPU, all-pairs long-range sum).
 
     step(pos0 (n,3), vel0 (n,3), u0 (n), h0 (n), dt) -> pos1, vel1, u1, h1 in caller order; inputs are
     not modified.  `defer_status=True` skips the end-of-step status read (bench loops read it once)."""
