@@ -144,6 +144,55 @@ typedef struct sphb_lists {
 } sphb_lists;
 size_t sphb_lists_bytes(int64_t n);
 
+/* ---- neighbour lists kept across kernels AND steps (no reference counterpart: the reference sums over all N) ----------
+ * sphb_nlist_build scans the cell list ONCE -- symmetric support 2 max(h_j, h_i), every h widened by cover_h + skin --
+ * and stores each warp's candidates (32 consecutive sorted slots = one warp) as rows of slot indices in `pool`.  The
+ * sphb_nlist_* gather kernels only drain those rows: they read the CURRENT sorted records (positions and h rewritten in
+ * place, slot order frozen) and decide membership pair by pair in fp64, exactly like the scanning kernels; entries
+ * outside the current support add exact zeros and rows are in ascending slot order, so the sums are the same bits.  The
+ * lists stay complete while, for every record, h_now <= cover_h * h_build and |x_now - x_build| <= skin * h_build;
+ * sphb_nlist_check and sphb_nlist_newton_h set SPHB_NL_BROKEN in *flags otherwise (SPHB_NL_AGING at half of a bound),
+ * and the caller rebuilds (and redoes the step that saw BROKEN). */
+#define SPHB_NL_NONE 0xffffffffu /* padding entry of a row */
+#define SPHB_NL_POOL 1       /* pool too small for this build: enlarge (sphb_nlist_pool_rows is always enough) and rebuild */
+#define SPHB_NL_BROKEN 2     /* a record left what the lists cover, or a Newton solve needs the bisection fallback */
+#define SPHB_NL_AGING 4      /* half of a bound is used up: rebuild before the next step */
+#define SPHB_NL_UNLISTABLE 8 /* some target has more candidates than a warp's reserve holds (unbounded h): scanning path only */
+typedef struct sphb_nlist {
+    int64_t n;                 /* sorted slots covered (targets + ghosts) */
+    uint32_t *warp_off;        /* [ceil(n/32)] first pool row of each warp's lists */
+    uint32_t *warp_rows;       /* [ceil(n/32)] rows in use: row k holds entry k of each of the 32 lanes */
+    uint32_t *pool;            /* [pool_rows][32] sorted-slot indices, SPHB_NL_NONE where a lane has fewer entries */
+    int64_t pool_rows;
+    unsigned long long *cursor; /* device: rows handed out by the build */
+    int32_t *flags;            /* device: OR of SPHB_NL_* */
+    const double *posh_build;  /* [n][4] the sorted records the lists were built from (must stay alive and unchanged) */
+    double cover_h;            /* >= 1 */
+    double skin;               /* >= 0, in units of each record's h at build time */
+} sphb_nlist;
+int64_t sphb_nlist_pool_rows(int64_t n);
+/* cells->posh must be nl->posh_build.  Zeroes *cursor and *flags first. */
+int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global, const sphb_nlist *nl,
+                     void *stream);
+int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, void *stream);
+/* sphb_density_omega on kept lists (h_j = posh[j][3]) */
+int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
+                             const double *rho_in, double *rho_sum, double *dwdh_sum, double *omega, int32_t *ngb_count,
+                             void *stream);
+/* sphb_newton_h on kept lists, guess = h_guess[j] (NULL: posh[j][3]).  posh_out (optional, != posh): the records with the solved h.
+ * Non-convergence within the limit is NOT bisected here: h_out = NaN and SPHB_NL_BROKEN (redo on the scanning path). */
+int sphb_nlist_newton_h(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
+                        const double *h_guess, double *h_out, double *omega_out, double *posh_out, int32_t *iters, sphb_status *status,
+                        void *stream);
+/* sphb_force on kept lists (G must be 0); posh carries the current h, recB / recC come from sphb_eos */
+int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
+                     const double *recB, const double *recC, double *acc, double *dudt, sphb_status *status, void *stream);
+/* caller order <-> slot order for the whole state in one pass (any pointer group may be NULL) */
+int sphb_gather_state(const double *pos, const double *h, const double *vel, const double *u, const uint32_t *perm,
+                      int64_t n, double *posh_s, double *vel_s, double *u_s, void *stream);
+int sphb_scatter_state(const double *posh_s, const double *vel_s, const double *u_s, const uint32_t *perm, int64_t n,
+                       double *pos, double *h, double *vel, double *u, void *stream);
+
 /* ---- K2: M4 density summation + grad-h sums ----------------------------------------------------
  * replaces density/density_arr (pyfluid.py:218-232) and omega_j/omega_arr (pyfluid.py:91-105).
  * For every slot j whose `target` flag is set (NULL = all slots):

@@ -55,6 +55,16 @@ class Lists(C.Structure):
     _fields_ = [("store", C.c_void_p), ("broken", C.c_void_p), ("hmax_global", C.c_void_p), ("cover", C.c_double)]
 
 
+class NList(C.Structure):
+    """sphb_nlist: neighbour lists kept across kernels and steps"""
+    _fields_ = [("n", C.c_int64), ("warp_off", C.c_void_p), ("warp_rows", C.c_void_p), ("pool", C.c_void_p),
+                ("pool_rows", C.c_int64), ("cursor", C.c_void_p), ("flags", C.c_void_p), ("posh_build", C.c_void_p),
+                ("cover_h", C.c_double), ("skin", C.c_double)]
+
+
+NL_NONE = 0xFFFFFFFF
+NL_POOL, NL_BROKEN, NL_AGING, NL_UNLISTABLE = 1, 2, 4, 8
+
 P = C.c_void_p
 I64 = C.c_int64
 I32 = C.c_int32
@@ -74,6 +84,14 @@ SIGNATURES = {
     "sphb_scatter_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_gather_u32": (C.c_int, [P, P, I64, P, P]),
     "sphb_lists_bytes": (C.c_size_t, [I64]),
+    "sphb_nlist_pool_rows": (I64, [I64]),
+    "sphb_nlist_build": (C.c_int, [C.POINTER(Cells), P, P, C.POINTER(NList), P]),
+    "sphb_nlist_check": (C.c_int, [C.POINTER(NList), P, P]),
+    "sphb_nlist_density_omega": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
+    "sphb_nlist_newton_h": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
+    "sphb_nlist_force": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
+    "sphb_gather_state": (C.c_int, [P, P, P, P, P, I64, P, P, P, P]),
+    "sphb_scatter_state": (C.c_int, [P, P, P, P, I64, P, P, P, P, P]),
     "sphb_density_omega": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),
     "sphb_newton_h": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),
     "sphb_bisect_h": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, I64, P, P, P, P, I32, P, P]),

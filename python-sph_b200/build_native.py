@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsphb200.so")
-SOURCES = ["sphb_grid.cu", "sphb_gather.cu", "sphb_force.cu"]
-HEADERS = ["sphb_common.cuh", "sphb_scan.cuh", os.path.join("..", "..", "include", "sphb200.h")]
+SOURCES = ["sphb_grid.cu", "sphb_gather.cu", "sphb_force.cu", "sphb_nlist.cu"]
+HEADERS = ["sphb_common.cuh", "sphb_scan.cuh", "sphb_pair.cuh", os.path.join("..", "..", "include", "sphb200.h")]
 # -fmad=false: only the fma() calls written in the sources are fused.  Implicit contraction would let two inlined
 # copies of the same pair function (list drained inside the scan / after it, even / odd unrolled slot) round
 # differently, and per-particle sums would then depend on how targets are chunked into warps and ranks.

@@ -3,6 +3,7 @@
 #include <stdio.h>
 
 #include "sphb_scan.cuh"
+#include "sphb_pair.cuh"
 
 #define SPHB_WARPS 4
 #ifndef SPHB_MINB_FORCE
@@ -12,11 +13,6 @@
 #ifndef SPHB_FORCE_FLUSH_ROWS
 #define SPHB_FORCE_FLUSH_ROWS 0
 #endif
-
-__device__ __forceinline__ void sphb_load4(const double *rec, size_t i, double &a, double &b, double &c, double &d)
-{
-    sphb_ld4(rec, i, a, b, c, d);
-}
 
 // ------------------------------------------------------------------------------------------------
 // EOS prologue: var_density (pyfluid.py:237-245), pressure (:248-259), plus the per-particle factors
@@ -50,199 +46,6 @@ __global__ void k_eos(const double *__restrict__ posh, const double *__restrict_
     double2 *c = reinterpret_cast<double2 *>(recC) + 2 * i;
     c[0] = make_double2(rho, cs);
     c[1] = make_double2(1.0 / h, 1.0 / (SPHB_PI * (h2 * h2)));
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4 pair sums.  For target j over i with q_j < 2 or q_i < 2 (pair terms vanish otherwise) and
-// r_ji != 0 (coincident particles contribute exactly 0: pyfluid.py:51-52,461):
-//   gradW(h) = W'(r,h) (r_j - r_i)/r = s (r_j - r_i),  s = fp(q)/(pi h^4)/r
-//   dens  += s_j (v_ji . r_ji)                                        :327-331
-//   Pi_ji  per :261-285 (convergent pairs only)
-//   acc   -= (A_j s_j + A_i s_i + Pi/2 (s_j + s_i)) r_ji              :464-474
-//   visc  += Pi (1/2 (s_j + s_i)) (v_ji . r_ji)                       :333-343
-// m, and the final 1/2 of :346, are applied once per target.
-// ------------------------------------------------------------------------------------------------
-struct SphbForceAcc {
-    double xj, yj, zj, hj;
-    double vxj, vyj, vzj, Aj;
-    double rhoj, csj, hinvj, gj;
-    double ax, ay, az, dens, visc;
-    double Bj;   // GRAV: (G/2) xi_j / Omega_j
-    int negpi;
-#ifdef SPHB_DEBUG_FORCE
-    long long jslot;
-#endif
-};
-
-#ifdef SPHB_DEBUG_FORCE
-// debug aid (not built by default): record the contributing candidates of one target slot, in evaluation order
-__device__ long long g_dbg_target = -1;
-__device__ int g_dbg_count = 0;
-__device__ uint32_t g_dbg_list[4096];
-__device__ double g_dbg_val[4096];
-extern "C" int sphb_debug_force_set(long long t)
-{
-    int z = 0;
-    cudaMemcpyToSymbol(g_dbg_target, &t, sizeof(t));
-    cudaMemcpyToSymbol(g_dbg_count, &z, sizeof(z));
-    return 0;
-}
-extern "C" int sphb_debug_force_get(uint32_t *list_host, double *val_host)
-{
-    int n = 0;
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(&n, g_dbg_count, sizeof(n));
-    cudaMemcpyFromSymbol(list_host, g_dbg_list, sizeof(uint32_t) * 4096);
-    cudaMemcpyFromSymbol(val_host, g_dbg_val, sizeof(double) * 4096);
-    return n;
-}
-#define SPHB_DBG(jslot, islot, v)                                   \
-    if ((long long)(jslot) == g_dbg_target) {                       \
-        const int p_ = atomicAdd(&g_dbg_count, 1);                  \
-        if (p_ < 4096) {                                            \
-            g_dbg_list[p_] = (islot);                               \
-            g_dbg_val[p_] = (v);                                    \
-        }                                                           \
-    }
-#else
-#define SPHB_DBG(jslot, islot, v)
-#endif
-
-// one pair, given the candidate's position record; the other two records are only fetched for real pairs.
-// GRAV: the compact grad-h correction of the softened gravity (smoothed_gravity_correction_comp, pyfluid.py:434-437)
-// has the same shape as the pressure term, -m (B_j gradW(h_j) + B_i gradW(h_i)) with B = (G/2) xi/Omega, and rides
-// in the acceleration coefficient only (du/dt keeps the pure A_j).
-template <bool GRAV>
-__device__ __forceinline__ void sphb_force_pair(const double *recB, const double *recC, const double *bgrav, uint32_t i,
-                                                double x, double y, double z, double hi, const sphb_consts &k,
-                                                SphbForceAcc &a)
-{
-    const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
-    const double d2 = sphb_d2(dx, dy, dz);
-    if (!sphb_nonzero(d2)) return;   // coincident positions contribute exactly 0 (pyfluid.py:51-52,461)
-    // 1/h_i and 1/(pi h_i^4) are recomputed (7 FP64 instructions) rather than gathered: the third record is then
-    // only needed by the viscous branch, i.e. for about half of the pairs
-    const double hinvi = sphb_rcp(hi);
-    const double hi2 = hinvi * hinvi;
-    const double gi = (hi2 * hi2) * 0.3183098861837907;   // 1/pi
-    const double rinv = sphb_rsqrt(d2);
-    const double r = d2 * rinv;
-    const double qj = r * a.hinvj, qi = r * hinvi;
-    if (!(qj < 2.0) && !(qi < 2.0)) return;   // prefilter false positive
-    double vxi, vyi, vzi, Ai;
-    sphb_load4(recB, i, vxi, vyi, vzi, Ai);
-    const double sj = sphb_m4c_fp(qj) * a.gj * rinv;
-    const double si = sphb_m4c_fp(qi) * gi * rinv;
-    const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
-    const double vdr = sphb_dot3(dx, dy, dz, dvx, dvy, dvz);
-    a.dens = fma(sj, vdr, a.dens);
-    const double sm = sj + si;
-    double pi_half = 0.0;
-    if (vdr < 0.0) {
-        double rhoi, csi, hinv_unused, g_unused;
-        sphb_load4(recC, i, rhoi, csi, hinv_unused, g_unused);
-        const double mean_h = 0.5 * (a.hj + hi);
-        const double den = fma(k.epsilon * mean_h, mean_h, d2);
-        const double mean_rho = 0.5 * (a.rhoj + rhoi);
-        const double inv = sphb_rcp(den * mean_rho);
-        const double mu = (mean_h * vdr) * (inv * mean_rho);
-        const double cs = 0.5 * (csi + a.csj);
-        const double pi = (mu * fma(k.beta, mu, -k.alpha * cs)) * (inv * den);
-        if (pi < 0.0) a.negpi = 1;
-        pi_half = 0.5 * pi;
-    }
-    double coef = fma(a.Aj, sj, fma(Ai, si, pi_half * sm));
-    if (GRAV) coef = fma(a.Bj, sj, fma(__ldg(bgrav + i), si, coef));
-    SPHB_DBG(a.jslot, i, coef * dx);
-    a.ax = fma(-coef, dx, a.ax);
-    a.ay = fma(-coef, dy, a.ay);
-    a.az = fma(-coef, dz, a.az);
-    a.visc = fma(pi_half * sm, vdr, a.visc);
-}
-
-// ---- two list entries side by side ---------------------------------------------------------------------
-// The same operations per pair as sphb_force_pair, arranged as straight-line code for two candidates so that two
-// independent FP64 dependency chains are in flight per lane; the accumulators are then updated in list order, which
-// keeps every sum bit-identical to the one-at-a-time loop.  `ok` replaces the early returns.
-struct SphbPairTerms {
-    double dx, dy, dz, d2, hi, sj, si, vdr, Ai, pism, coef;
-    bool ok;
-};
-
-__device__ __forceinline__ void sphb_force_geom(const double *recB, uint32_t i, const double (&p)[4], bool present,
-                                                const SphbForceAcc &a, SphbPairTerms &t)
-{
-    t.dx = a.xj - p[0];
-    t.dy = a.yj - p[1];
-    t.dz = a.zj - p[2];
-    t.hi = p[3];
-    t.d2 = sphb_d2(t.dx, t.dy, t.dz);
-    const double hinvi = sphb_rcp(t.hi);
-    const double hi2 = hinvi * hinvi;
-    const double gi = (hi2 * hi2) * 0.3183098861837907;   // 1/pi
-    const double rinv = sphb_rsqrt(t.d2);
-    const double r = t.d2 * rinv;
-    const double qj = r * a.hinvj, qi = r * hinvi;
-    t.ok = present && sphb_nonzero(t.d2) && ((qj < 2.0) || (qi < 2.0));
-    double vxi = 0.0, vyi = 0.0, vzi = 0.0;
-    t.Ai = 0.0;
-    if (t.ok) sphb_load4(recB, i, vxi, vyi, vzi, t.Ai);
-    t.sj = sphb_m4c_fp(qj) * a.gj * rinv;
-    t.si = sphb_m4c_fp(qi) * gi * rinv;
-    const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
-    t.vdr = sphb_dot3(t.dx, t.dy, t.dz, dvx, dvy, dvz);
-}
-
-__device__ __forceinline__ double sphb_force_pi(const sphb_consts &k, const SphbForceAcc &a, const SphbPairTerms &t,
-                                                double rhoi, double csi)
-{
-    const double mean_h = 0.5 * (a.hj + t.hi);
-    const double den = fma(k.epsilon * mean_h, mean_h, t.d2);
-    const double mean_rho = 0.5 * (a.rhoj + rhoi);
-    const double inv = sphb_rcp(den * mean_rho);
-    const double mu = (mean_h * t.vdr) * (inv * mean_rho);
-    const double cs = 0.5 * (csi + a.csj);
-    return (mu * fma(k.beta, mu, -k.alpha * cs)) * (inv * den);
-}
-
-template <bool GRAV>
-__device__ __forceinline__ void sphb_force_accumulate(const double *bgrav, uint32_t i, double pi_half,
-                                                      const SphbPairTerms &t, SphbForceAcc &a)
-{
-    if (!t.ok) return;
-    a.dens = fma(t.sj, t.vdr, a.dens);
-    const double sm = t.sj + t.si;
-    double coef = fma(a.Aj, t.sj, fma(t.Ai, t.si, pi_half * sm));
-    if (GRAV) coef = fma(a.Bj, t.sj, fma(__ldg(bgrav + i), t.si, coef));
-    SPHB_DBG(a.jslot, i, coef * t.dx);
-    a.ax = fma(-coef, t.dx, a.ax);
-    a.ay = fma(-coef, t.dy, a.ay);
-    a.az = fma(-coef, t.dz, a.az);
-    a.visc = fma(pi_half * sm, t.vdr, a.visc);
-}
-
-template <bool GRAV>
-__device__ __forceinline__ void sphb_force_pair2(const double *recB, const double *recC, const double *bgrav, uint32_t i0,
-                                                 uint32_t i1, const double (&p0)[4], const double (&p1)[4], bool second,
-                                                 const sphb_consts &k, SphbForceAcc &a)
-{
-    SphbPairTerms t0, t1;
-    sphb_force_geom(recB, i0, p0, true, a, t0);
-    sphb_force_geom(recB, i1, p1, second, a, t1);
-    const bool v0 = t0.ok && t0.vdr < 0.0, v1 = t1.ok && t1.vdr < 0.0;
-    double ph0 = 0.0, ph1 = 0.0;
-    if (v0 || v1) {
-        double rho0 = 1.0, cs0 = 0.0, rho1 = 1.0, cs1 = 0.0, u0, u1;
-        if (v0) sphb_load4(recC, i0, rho0, cs0, u0, u1);
-        if (v1) sphb_load4(recC, i1, rho1, cs1, u0, u1);
-        const double pi0 = sphb_force_pi(k, a, t0, rho0, cs0);
-        const double pi1 = sphb_force_pi(k, a, t1, rho1, cs1);
-        if ((v0 && pi0 < 0.0) || (v1 && pi1 < 0.0)) a.negpi = 1;
-        ph0 = v0 ? 0.5 * pi0 : 0.0;
-        ph1 = v1 ? 0.5 * pi1 : 0.0;
-    }
-    sphb_force_accumulate<GRAV>(bgrav, i0, ph0, t0, a);
-    sphb_force_accumulate<GRAV>(bgrav, i1, ph1, t1, a);
 }
 
 #ifndef SPHB_FORCE_ILP

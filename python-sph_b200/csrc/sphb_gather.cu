@@ -3,6 +3,7 @@
 #include <stdio.h>
 
 #include "sphb_scan.cuh"
+#include "sphb_pair.cuh"
 
 #define SPHB_WARPS 4
 #ifndef SPHB_MINB_OWN
@@ -12,80 +13,6 @@
 #ifndef SPHB_OWN_FLUSH_ROWS
 #define SPHB_OWN_FLUSH_ROWS 0
 #endif
-
-__device__ __forceinline__ void sphb_load_posh(const double *posh, size_t i, double &x, double &y, double &z, double &h)
-{
-    sphb_ld4(posh, i, x, y, z, h);
-}
-
-// One evaluation of sumF = sum f(q), sumG = sum (q f'(q) + 3 f(q)) over the lane's list.
-// rho_sum = m sumF/(pi h^3) (pyfluid.py:218-224), sum m dW/dh = -m sumG/(pi h^4) (pyfluid.py:85-87,91-97).
-struct SphbOwnAcc {
-    double xj, yj, zj, hinv;
-    double sumF, sumG, sumX;
-    int nn;
-};
-
-// -h^2 dphi/dh of the softened potential, dimensionless: grav_potential_smoothlength_derivative(dist, h) =
-// -(1/h^2) pX(x), x = dist/h (pyfluid.py:391-399); np.piecewise order [x < 1, 1 <= x < 2, x >= 2], NaN -> 0
-__device__ __forceinline__ double sphb_grav_pX(double x)
-{
-    const double x2 = x * x, x3 = x2 * x;
-    const double in = fma(0.6, x2 * x3, fma(-1.2, x3, fma(2.0, x2, -1.4)));
-    const double mid = fma(-0.2, x2 * x3, fma(1.5, x2 * x2, fma(-4.0, x3, fma(4.0, x2, -1.6))));
-    return (x < 1.0) ? in : ((x >= 1.0 && x < 2.0) ? mid : 0.0);
-}
-
-template <bool XI = false>
-__device__ __forceinline__ void sphb_own_pair(double x, double y, double z, SphbOwnAcc &a)
-{
-    const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
-    const double d2 = sphb_d2(dx, dy, dz);
-    const double r = sphb_nonzero(d2) ? d2 * sphb_rsqrt(d2) : 0.0;
-    const double q = r * a.hinv;
-    double f, fp;
-    sphb_m4c(q, f, fp);
-    a.sumF += f;
-    a.sumG += fma(q, fp, 3.0 * f);
-    a.nn += (q < 2.0) ? 1 : 0;
-    if (XI) a.sumX += sphb_grav_pX(q);
-}
-
-// the pair's terms without touching the accumulators: two of these are independent instruction streams
-template <bool XI = false>
-__device__ __forceinline__ void sphb_own_terms(double x, double y, double z, const SphbOwnAcc &a, double &f, double &g,
-                                               int &in, double &px)
-{
-    const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
-    const double d2 = sphb_d2(dx, dy, dz);
-    const double r = sphb_nonzero(d2) ? d2 * sphb_rsqrt(d2) : 0.0;
-    const double q = r * a.hinv;
-    double fp;
-    sphb_m4c(q, f, fp);
-    g = fma(q, fp, 3.0 * f);
-    in = (q < 2.0) ? 1 : 0;
-    px = XI ? sphb_grav_pX(q) : 0.0;
-}
-
-// entries k and k+1 evaluated side by side (the second only counted when it exists), accumulated in list order
-template <bool XI = false>
-__device__ __forceinline__ void sphb_own_pair2(const double (&p)[4], const double (&q)[4], bool second, SphbOwnAcc &a)
-{
-    double f0, g0, x0, f1, g1, x1;
-    int n0, n1;
-    sphb_own_terms<XI>(p[0], p[1], p[2], a, f0, g0, n0, x0);
-    sphb_own_terms<XI>(q[0], q[1], q[2], a, f1, g1, n1, x1);
-    a.sumF += f0;
-    a.sumG += g0;
-    a.nn += n0;
-    if (XI) a.sumX += x0;
-    if (second) {
-        a.sumF += f1;
-        a.sumG += g1;
-        a.nn += n1;
-        if (XI) a.sumX += x1;
-    }
-}
 
 #ifndef SPHB_OWN_ILP
 #define SPHB_OWN_ILP 1
@@ -222,13 +149,6 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
 #ifndef SPHB_NEWTON_MARGIN
 #define SPHB_NEWTON_MARGIN 4e-3
 #endif
-
-__device__ __forceinline__ double sphb_omega_from_sumG(const sphb_consts &k, double h, double sumG)
-{
-    const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
-    const double ds = -(pref / h) * sumG;                       // sum_i m dW/dh
-    return 1.0 + h / (3.0 * sphb_var_density(k, h)) * ds;       // pyfluid.py:97 with rho = m (eta/h)^3
-}
 
 template <bool FUSED, bool PRODUCE>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)

@@ -1,0 +1,522 @@
+// sphb_nlist.cu -- neighbour lists that outlive a kernel AND a step, and the gather kernels that only drain them.
+//
+// The scanning kernels (sphb_gather.cu, sphb_force.cu) find every target's candidates again in each launch; one
+// var_smoothlength_leapfrog step (pyfluid.py:498-532) launches five of them on three snapshots that differ by
+// v dt -- a small fraction of h.  Here the candidates are found ONCE (sphb_nlist_build: the same warp scan, with the
+// symmetric support 2 max(h_j, h_i) widened by cover_h + skin) and stored as rows of sorted-slot indices; the gather
+// kernels below (density / Omega, Newton h solve, momentum + energy) are pure drains: no cell list, no scan code, no
+// shared-memory lists, far fewer registers.  The particle state stays in the build's slot order, positions and h are
+// rewritten in place, and the lists stay complete while
+//       h_now <= cover_h * h_build      and      |x_now - x_build| <= skin * h_build        for every record
+// (sphb_nlist_check and the Newton drain set SPHB_NL_BROKEN otherwise; the caller then rebuilds and redoes the step).
+// Entries outside the current support add exact zeros (membership is still decided pair by pair in FP64 with the
+// reference's q < 2 rule), and rows are in ascending slot order, so every sum has the same bits as the scanning
+// kernels give on the same cell list.
+#include <stdio.h>
+
+#include "sphb_scan.cuh"
+#include "sphb_pair.cuh"
+
+#define NL_WARPS 4
+#define NL_THREADS (NL_WARPS * 32)
+#ifndef SPHB_NL_HEAVY_ROWS
+#define SPHB_NL_HEAVY_ROWS 4096 /* rows reserved for a warp whose lists outgrow the shared-memory staging area */
+#endif
+#ifndef SPHB_MINB_NL_BUILD
+#define SPHB_MINB_NL_BUILD 4
+#endif
+#ifndef SPHB_MINB_NL_OWN
+#define SPHB_MINB_NL_OWN 8
+#endif
+#ifndef SPHB_MINB_NL_FORCE
+#define SPHB_MINB_NL_FORCE 4
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// build: one warp = 32 consecutive slots; its lists become `rows` rows of 32 slot indices (row k = entry k of every
+// lane, SPHB_NL_NONE where a lane has fewer), handed out from the pool by one atomicAdd per warp.  A warp whose lists
+// do not fit the shared-memory staging area (128 entries per lane) takes a fixed reserve of SPHB_NL_HEAVY_ROWS rows
+// and appends one padded chunk per overflow.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
+    k_nl_build(sphb_cells c, const uint8_t *__restrict__ target, const float *__restrict__ hmax_global, sphb_nlist nl)
+{
+    __shared__ SphbWarpShared sh[NL_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * NL_WARPS + warp;
+    const long long base = w * 32;
+    if (base >= c.n) return;
+    const long long j = base + lane;
+    const bool valid = j < c.n;
+    const bool tgt = valid && (target == nullptr || target[j] != 0);
+    const SphbScanCtx g = sphb_make_ctx(c);
+    SphbWarpShared &ws = sh[warp];
+
+    double x, y, z, h = 1.0;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t cid = 0xffffffffu;
+    if (valid) {
+        sphb_load_posh(c.posh, (size_t)j, x, y, z, h);
+        f = __ldg(g.frec + j);
+        cid = c.cell_id[j];
+    }
+    // complete for any later state with h <= cover_h h_build and |dx| <= skin h_build on both sides of a pair:
+    // |r_build| <= |r_now| + |dx_j| + |dx_i| < 2 max(h_now) + skin (h_j + h_i) <= 2 max(h_build) (cover_h + skin)
+    const double kappa = nl.cover_h + nl.skin;
+    const double hs = h * kappa;
+    const float Rj = sphb_radius_of_h(hs, g.delta), thr = sphb_thr_of_h(hs, g.delta);
+    const float cov = (float)kappa * 1.000001f;
+    const float RH = sphb_radius_of_h((double)hmax_global[0] * (double)cov, g.delta);
+
+    uint32_t row0 = 0, used = 0, cap = 0;   // warp-uniform
+    bool heavy = false, over = false;       // warp-uniform
+    auto emit = [&](int cnt, bool final) {
+        __syncwarp();
+        const uint32_t rows = (uint32_t)__reduce_max_sync(SPHB_FULL, cnt);
+        if (!heavy && !over) {
+            cap = final ? rows : (uint32_t)SPHB_NL_HEAVY_ROWS;
+            unsigned long long r0 = 0;
+            if (lane == 0 && cap) r0 = atomicAdd(nl.cursor, (unsigned long long)cap);
+            r0 = __shfl_sync(SPHB_FULL, r0, 0);
+            if (r0 + cap > (unsigned long long)nl.pool_rows) {
+                over = true;
+                if (lane == 0) atomicOr(nl.flags, SPHB_NL_POOL);
+            }
+            row0 = (uint32_t)r0;
+            heavy = !final;
+        }
+        if (!over && used + rows > cap) {
+            over = true;
+            if (lane == 0) atomicOr(nl.flags, SPHB_NL_UNLISTABLE);
+        }
+        if (!over) {
+            uint32_t *dst = nl.pool + ((size_t)row0 + used) * 32 + lane;
+            for (uint32_t r = 0; r < rows; ++r)
+                dst[(size_t)r * 32] = ((int)r < cnt) ? sphb_list_get(ws, lane, (int)r) : SPHB_NL_NONE;
+            used += rows;
+        }
+        __syncwarp();
+    };
+    SphbList L;
+    L.init(ws, lane);
+    auto flush = [&](int n_) { emit(n_, false); };
+    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+    emit(L.count(), true);
+    if (lane == 0) {
+        nl.warp_off[w] = row0;
+        nl.warp_rows[w] = over ? 0u : used;
+    }
+}
+
+// did any record leave what the lists were built to cover?  (half of a bound used up: SPHB_NL_AGING)
+__global__ void k_nl_check(const double *__restrict__ posh_build, const double *__restrict__ posh_now, long long n,
+                           double skin, double cover_h, int32_t *__restrict__ flags)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false, old = false;
+    if (i < n) {
+        double x0, y0, z0, h0, x1, y1, z1, h1;
+        sphb_load_posh(posh_build, (size_t)i, x0, y0, z0, h0);
+        sphb_load_posh(posh_now, (size_t)i, x1, y1, z1, h1);
+        const double dx = x1 - x0, dy = y1 - y0, dz = z1 - z0;
+        const double d2 = dx * dx + dy * dy + dz * dz, lim = skin * h0;
+        bad = !(d2 <= lim * lim) || !(h1 <= cover_h * h0);
+        old = !(d2 <= 0.25 * (lim * lim)) || !(h1 <= (1.0 + 0.5 * (cover_h - 1.0)) * h0);
+    }
+    const bool anybad = __any_sync(SPHB_FULL, bad), anyold = __any_sync(SPHB_FULL, old);
+    if ((threadIdx.x & 31) == 0 && (anybad || anyold))
+        atomicOr(flags, (anybad ? SPHB_NL_BROKEN : 0) | (anyold ? SPHB_NL_AGING : 0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// drains
+// ------------------------------------------------------------------------------------------------
+// one list row for this lane: the neighbour's record, or (padding) a record so far away that every kernel term
+// is an exact zero
+__device__ __forceinline__ void nl_fetch(const double *__restrict__ posh, uint32_t s, uint32_t self, double (&p)[4])
+{
+    const bool real = s != SPHB_NL_NONE;
+    sphb_load_posh(posh, (size_t)(real ? s : self), p[0], p[1], p[2], p[3]);
+    if (!real) p[0] = 1e150;
+}
+
+__device__ __forceinline__ uint32_t nl_row(const uint32_t *__restrict__ p, int k, int nrows)
+{
+    return (k < nrows) ? __ldg(p + (size_t)k * 32) : SPHB_NL_NONE;
+}
+
+// sumF, sumG (, nn) over the lane's rows: two entries side by side (two independent FP64 chains), the records of the
+// next two rows and the indices of the two after them in flight
+__device__ __forceinline__ void nl_own_drain(const double *__restrict__ posh, const uint32_t *__restrict__ rows, int nrows,
+                                             int lane, uint32_t self, SphbOwnAcc &a)
+{
+    const uint32_t *p = rows + lane;
+    uint32_t i0 = nl_row(p, 0, nrows), i1 = nl_row(p, 1, nrows), i2 = nl_row(p, 2, nrows), i3 = nl_row(p, 3, nrows);
+    double A[4], B[4], C[4], D[4];
+    nl_fetch(posh, i0, self, A);
+    nl_fetch(posh, i1, self, B);
+    int k = 0;
+    while (k < nrows) {
+        nl_fetch(posh, i2, self, C);
+        nl_fetch(posh, i3, self, D);
+        i0 = nl_row(p, k + 4, nrows);
+        i1 = nl_row(p, k + 5, nrows);
+        sphb_own_pair2<false>(A, B, true, a);
+        k += 2;
+        if (k >= nrows) break;
+        nl_fetch(posh, i0, self, A);
+        nl_fetch(posh, i1, self, B);
+        i2 = nl_row(p, k + 4, nrows);
+        i3 = nl_row(p, k + 5, nrows);
+        sphb_own_pair2<false>(C, D, true, a);
+        k += 2;
+    }
+}
+
+// K2 on kept lists: density / density_arr (pyfluid.py:218-232), omega_j / omega_arr (:91-105)
+__global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
+    k_nl_density_omega(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
+                       const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
+                       double *__restrict__ omega, int32_t *__restrict__ ngb_count)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * NL_WARPS + warp;
+    const long long base = w * 32;
+    if (base >= nl.n) return;
+    const long long j = base + lane;
+    const bool valid = j < nl.n;
+    const bool tgt = valid && (target == nullptr || target[j] != 0);
+    SphbOwnAcc a;
+    double h = 1.0;
+    a.xj = a.yj = a.zj = 0.0;
+    if (valid) sphb_load_posh(posh, (size_t)j, a.xj, a.yj, a.zj, h);
+    a.hinv = 1.0 / h;
+    a.sumF = a.sumG = a.sumX = 0.0;
+    a.nn = 0;
+    const int nrows = (int)nl.warp_rows[w];
+    const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
+    nl_own_drain(posh, rows, nrows, lane, valid ? (uint32_t)j : 0u, a);
+    if (tgt) {
+        const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
+        const double rs = pref * a.sumF;
+        const double ds = -(pref / h) * a.sumG;
+        if (rho_sum) rho_sum[j] = rs;
+        if (dwdh_sum) dwdh_sum[j] = ds;
+        const double rho = rho_in ? rho_in[j] : sphb_var_density(k, h);
+        if (omega) omega[j] = 1.0 + h / (3.0 * rho) * ds;   // pyfluid.py:97
+        if (ngb_count) ngb_count[j] = a.nn;
+    }
+}
+
+// K3 on kept lists: newton_smoothlength_iteration / _while / _arr (pyfluid.py:155-179, 203-211), guess = h_guess, or
+// the h the records carry.  Same sequence of iterates and the same stop rule as sphb_newton_h; every evaluation is one more
+// pass over the rows.  What the lists cannot serve -- an iterate outside (0, cover_h h_build], or no convergence
+// within the limit (the reference then bisects over all particles, :178-179) -- sets SPHB_NL_BROKEN: the caller
+// redoes the step with the scanning kernels, which replay the reference to the letter.
+template <bool FUSED>
+__global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
+    k_nl_newton_h(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
+                  const double *__restrict__ h_guess, double *__restrict__ h_out, double *__restrict__ omega_out, double *__restrict__ posh_out,
+                  int32_t *__restrict__ iters, sphb_status *__restrict__ status)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * NL_WARPS + warp;
+    const long long base = w * 32;
+    if (base >= nl.n) return;
+    const long long j = base + lane;
+    const bool valid = j < nl.n;
+    const bool tgt = valid && (target == nullptr || target[j] != 0);
+    SphbOwnAcc a;
+    a.xj = a.yj = a.zj = 0.0;
+    double h_cur = 1.0, hb = 1.0;
+    if (valid) {
+        sphb_load_posh(posh, (size_t)j, a.xj, a.yj, a.zj, h_cur);
+        if (h_guess) h_cur = h_guess[j];
+        hb = nl.posh_build[4 * j + 3];
+    }
+    const double h_in = h_cur;
+    const double h_cover = hb * nl.cover_h, h_old = hb * (1.0 + 0.5 * (nl.cover_h - 1.0));
+    const int nrows = (int)nl.warp_rows[w];
+    const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
+    const uint32_t self = valid ? (uint32_t)j : 0u;
+    // what the lane needs next: 1 = the sums of a Newton iterate at h_cur, 2 = sum m dW/dh at the converged h_cur
+    // (FUSED: Omega at the solved h, pyfluid.py:518), 0 = nothing
+    int want = tgt ? 1 : 0, it = 0, fl = 0;
+    double h_res = h_in;
+    while (__any_sync(SPHB_FULL, want != 0)) {
+        if (want != 0 && !(h_cur > 0.0 && h_cur <= h_cover)) fl |= SPHB_NL_BROKEN;
+        a.hinv = 1.0 / h_cur;
+        a.sumF = a.sumG = a.sumX = 0.0;
+        a.nn = 0;
+        nl_own_drain(posh, rows, nrows, lane, self, a);
+        if (want == 1) {
+            // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
+            const double pref = k.particle_mass / (SPHB_PI * (h_cur * h_cur * h_cur));
+            const double rho = pref * a.sumF;
+            const double sdh = -(pref / h_cur) * a.sumG;
+            const double vd = sphb_var_density(k, h_cur);
+            const double zeta = vd - rho;
+            const double zetap = -sdh - 3.0 * vd / h_cur;
+            const double h_new = h_cur - zeta / zetap;
+            ++it;
+            // smoothlength_variation(old, new) = |old - new| / |new|, pyfluid.py:119-120,172
+            if (fabs(h_cur - h_new) / fabs(h_new) < k.h_tol && h_new > 0.0) {
+                h_res = h_new;
+                want = FUSED ? 2 : 0;
+                if (!(h_new <= h_cover)) fl |= SPHB_NL_BROKEN;
+                if (!(h_new <= h_old)) fl |= SPHB_NL_AGING;
+            } else if (it >= k.newton_limit) {
+                h_res = CUDART_NAN;
+                if (FUSED) omega_out[j] = CUDART_NAN;
+                want = 0;
+                fl |= SPHB_NL_BROKEN;   // the bisection (pyfluid.py:178-179) needs all particles: scanning path
+            }
+            h_cur = h_new;
+        } else if (want == 2) {
+            omega_out[j] = sphb_omega_from_sumG(k, h_cur, a.sumG);
+            want = 0;
+        }
+        __syncwarp();
+    }
+    if (tgt) {
+        h_out[j] = h_res;
+        if (iters) iters[j] = it;
+        if (h_res < 0.0) fl |= 0x10000;   // pyfluid.py:209-210
+    }
+    if (valid && posh_out) {
+        double2 *o = reinterpret_cast<double2 *>(posh_out) + 2 * j;
+        o[0] = make_double2(a.xj, a.yj);
+        o[1] = make_double2(a.zj, tgt ? h_res : h_in);
+    }
+    const int any = __reduce_or_sync(SPHB_FULL, fl);
+    if (lane == 0 && any) {
+        if (any & 0xffff) atomicOr(nl.flags, any & 0xffff);
+        if (any & 0x10000) atomicOr(&status->flags, SPHB_ST_NEG_H);
+    }
+}
+
+// K4 on kept lists: energy_rate / _arr (pyfluid.py:316-361), Pi (:261-285), fluid_accel_viscosity_comp (:459-474),
+// acceleration / _arr (:477-493) with G = 0.  posh carries the CURRENT h; recB / recC are sphb_eos's records.
+__global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
+    k_nl_force(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
+               const double *__restrict__ recB, const double *__restrict__ recC, double *__restrict__ acc,
+               double *__restrict__ dudt, sphb_status *__restrict__ status)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * NL_WARPS + warp;
+    const long long base = w * 32;
+    if (base >= nl.n) return;
+    const long long j = base + lane;
+    const bool valid = j < nl.n;
+    const bool tgt = valid && (target == nullptr || target[j] != 0);
+    SphbForceAcc a;
+    a.xj = a.yj = a.zj = 0.0;
+    a.hj = 1.0;
+    a.vxj = a.vyj = a.vzj = a.Aj = 0.0;
+    a.rhoj = a.csj = a.hinvj = a.gj = 0.0;
+    if (valid) {
+        sphb_load4(posh, (size_t)j, a.xj, a.yj, a.zj, a.hj);
+        sphb_load4(recB, (size_t)j, a.vxj, a.vyj, a.vzj, a.Aj);
+        sphb_load4(recC, (size_t)j, a.rhoj, a.csj, a.hinvj, a.gj);
+    }
+    a.ax = a.ay = a.az = a.dens = a.visc = 0.0;
+    a.negpi = 0;
+    a.Bj = 0.0;
+    const int nrows = (int)nl.warp_rows[w];
+    const uint32_t *p = nl.pool + (size_t)nl.warp_off[w] * 32 + lane;
+    const uint32_t self = valid ? (uint32_t)j : 0u;
+    {
+        uint32_t i0 = nl_row(p, 0, nrows), i1 = nl_row(p, 1, nrows), i2 = nl_row(p, 2, nrows), i3 = nl_row(p, 3, nrows);
+        double A[4], B[4], C[4], D[4];
+        nl_fetch(posh, i0, self, A);
+        nl_fetch(posh, i1, self, B);
+        int kk = 0;
+        while (kk < nrows) {
+            nl_fetch(posh, i2, self, C);
+            nl_fetch(posh, i3, self, D);
+            uint32_t n0 = nl_row(p, kk + 4, nrows), n1 = nl_row(p, kk + 5, nrows);
+            sphb_force_pair2<false>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a, i0 != SPHB_NL_NONE);
+            kk += 2;
+            if (kk >= nrows) break;
+            i0 = n0;
+            i1 = n1;
+            nl_fetch(posh, i0, self, A);
+            nl_fetch(posh, i1, self, B);
+            n0 = nl_row(p, kk + 4, nrows);
+            n1 = nl_row(p, kk + 5, nrows);
+            sphb_force_pair2<false>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a, i2 != SPHB_NL_NONE);
+            i2 = n0;
+            i3 = n1;
+            kk += 2;
+        }
+    }
+    if (tgt) {
+        const double m = k.particle_mass;
+        acc[3 * j] = m * a.ax;
+        acc[3 * j + 1] = m * a.ay;
+        acc[3 * j + 2] = m * a.az;
+        const double visc = 0.5 * (m * a.visc);                 // viscosity_sum *= 0.5, pyfluid.py:346
+        dudt[j] = fma(a.Aj, m * a.dens, visc);                  // P_j/(rho_j^2 omega_j) * density_change + viscosity_sum
+        int fl = 0;
+        if (a.negpi) fl |= SPHB_ST_NEG_PI;
+        if (visc < 0.0) fl |= SPHB_ST_NEG_VISC;
+        if (fl) atomicOr(&status->flags, fl);
+    }
+}
+
+// caller order -> slot order in one pass: posh (n,4) from pos (n,3) + h (n), vel (n,3), u (n) through perm
+__global__ void k_nl_gather_state(const double *__restrict__ pos, const double *__restrict__ h,
+                                  const double *__restrict__ vel, const double *__restrict__ u,
+                                  const uint32_t *__restrict__ perm, long long n, double *__restrict__ posh_s,
+                                  double *__restrict__ vel_s, double *__restrict__ u_s)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const size_t i = perm[s];
+    if (posh_s) {
+        double2 *o = reinterpret_cast<double2 *>(posh_s) + 2 * s;
+        o[0] = make_double2(pos[3 * i], pos[3 * i + 1]);
+        o[1] = make_double2(pos[3 * i + 2], h[i]);
+    }
+    if (vel_s) {
+        vel_s[3 * s] = vel[3 * i];
+        vel_s[3 * s + 1] = vel[3 * i + 1];
+        vel_s[3 * s + 2] = vel[3 * i + 2];
+    }
+    if (u_s) u_s[s] = u[i];
+}
+
+// slot order -> caller order: pos (n,3), h (n) from posh_s, vel, u through perm
+__global__ void k_nl_scatter_state(const double *__restrict__ posh_s, const double *__restrict__ vel_s,
+                                   const double *__restrict__ u_s, const uint32_t *__restrict__ perm, long long n,
+                                   double *__restrict__ pos, double *__restrict__ h, double *__restrict__ vel,
+                                   double *__restrict__ u)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const size_t i = perm[s];
+    if (posh_s) {
+        const double2 a = reinterpret_cast<const double2 *>(posh_s)[2 * s];
+        const double2 b = reinterpret_cast<const double2 *>(posh_s)[2 * s + 1];
+        if (pos) {
+            pos[3 * i] = a.x;
+            pos[3 * i + 1] = a.y;
+            pos[3 * i + 2] = b.x;
+        }
+        if (h) h[i] = b.y;
+    }
+    if (vel_s && vel) {
+        vel[3 * i] = vel_s[3 * s];
+        vel[3 * i + 1] = vel_s[3 * s + 1];
+        vel[3 * i + 2] = vel_s[3 * s + 2];
+    }
+    if (u_s && u) u[i] = u_s[s];
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+static inline bool nl_ok(const sphb_nlist *nl)
+{
+    return nl && nl->n >= 0 && nl->warp_off && nl->warp_rows && nl->pool && nl->pool_rows > 0 &&
+           nl->pool_rows < (int64_t)0xffffffffll && nl->cursor && nl->flags && nl->posh_build && nl->cover_h >= 1.0 &&
+           nl->skin >= 0.0 && nl->cover_h + nl->skin < 4.0;
+}
+
+static inline unsigned nl_blocks(int64_t n) { return (unsigned)((n + NL_THREADS - 1) / NL_THREADS); }
+
+extern "C" int64_t sphb_nlist_pool_rows(int64_t n)
+{
+    // every warp that fits the staging area needs at most SPHB_LIST rows; plus room for 1/64 of the warps to be heavy
+    const int64_t warps = (n + 31) / 32;
+    return warps * SPHB_LIST + (warps / 64 + 16) * SPHB_NL_HEAVY_ROWS;
+}
+
+extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global,
+                                const sphb_nlist *nl, void *stream)
+{
+    if (!cells || cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh ||
+        !cells->frec || !hmax_global || !nl_ok(nl) || nl->n != cells->n || nl->posh_build != cells->posh)
+        return SPHB_E_ARG;
+    cudaStream_t st = sphb_stream(stream);
+    SPHB_CUDA(cudaMemsetAsync(nl->cursor, 0, sizeof(unsigned long long), st));
+    SPHB_CUDA(cudaMemsetAsync(nl->flags, 0, sizeof(int32_t), st));
+    if (cells->n == 0) return SPHB_OK;
+    k_nl_build<<<nl_blocks(cells->n), NL_THREADS, 0, st>>>(*cells, target, hmax_global, *nl);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, void *stream)
+{
+    if (!nl_ok(nl) || !posh_now) return SPHB_E_ARG;
+    if (nl->n == 0) return SPHB_OK;
+    k_nl_check<<<(unsigned)((nl->n + 255) / 256), 256, 0, sphb_stream(stream)>>>(nl->posh_build, posh_now, (long long)nl->n,
+                                                                               nl->skin, nl->cover_h, nl->flags);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target,
+                                        const double *posh, const double *rho_in, double *rho_sum, double *dwdh_sum,
+                                        double *omega, int32_t *ngb_count, void *stream)
+{
+    if (!nl_ok(nl) || !k || !posh) return SPHB_E_ARG;
+    if (nl->n == 0) return SPHB_OK;
+    k_nl_density_omega<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, rho_in, rho_sum,
+                                                                                 dwdh_sum, omega, ngb_count);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_nlist_newton_h(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
+                                   const double *h_guess, double *h_out, double *omega_out, double *posh_out, int32_t *iters,
+                                   sphb_status *status, void *stream)
+{
+    if (!nl_ok(nl) || !k || !posh || !h_out || !status || posh_out == posh) return SPHB_E_ARG;
+    if (nl->n == 0) return SPHB_OK;
+    if (omega_out)
+        k_nl_newton_h<true><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, h_guess, h_out,
+                                                                                      omega_out, posh_out, iters, status);
+    else
+        k_nl_newton_h<false><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, h_guess, h_out,
+                                                                                       omega_out, posh_out, iters, status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
+                                const double *recB, const double *recC, double *acc, double *dudt, sphb_status *status,
+                                void *stream)
+{
+    if (!nl_ok(nl) || !k || !posh || !recB || !recC || !acc || !dudt || !status) return SPHB_E_ARG;
+    if (k->G != 0.0) return SPHB_E_ARG;   // the softened-gravity terms ride in the scanning kernels only
+    if (nl->n == 0) return SPHB_OK;
+    k_nl_force<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recC, acc, dudt,
+                                                                         status);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_gather_state(const double *pos, const double *h, const double *vel, const double *u,
+                                 const uint32_t *perm, int64_t n, double *posh_s, double *vel_s, double *u_s, void *stream)
+{
+    if (n < 0 || (n > 0 && !perm)) return SPHB_E_ARG;
+    if (n > 0 && ((posh_s && (!pos || !h)) || (vel_s && !vel) || (u_s && !u))) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_nl_gather_state<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(pos, h, vel, u, perm, (long long)n, posh_s,
+                                                                                  vel_s, u_s);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_scatter_state(const double *posh_s, const double *vel_s, const double *u_s, const uint32_t *perm,
+                                  int64_t n, double *pos, double *h, double *vel, double *u, void *stream)
+{
+    if (n < 0 || (n > 0 && !perm)) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_nl_scatter_state<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh_s, vel_s, u_s, perm, (long long)n, pos,
+                                                                                   h, vel, u);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}

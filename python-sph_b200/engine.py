@@ -43,6 +43,38 @@ def _lists(pl):
     return C.byref(pl.c) if pl is not None else None
 
 
+class KeptLists:
+    """sphb_nlist: neighbour lists that outlive kernels and steps, with the buffers they point to.
+    Built from ONE cell list (dg); the drain kernels then only need the current sorted records."""
+
+    def __init__(self, engine, dg, cover_h, skin, pool_rows=None):
+        lib, dev = engine.lib, engine.device
+        n = dg.n
+        nw = max(1, (n + 31) // 32)
+        self.n = n
+        self.dg = dg                      # keeps posh_build (dg.posh) and perm alive
+        self.cover_h, self.skin = float(cover_h), float(skin)
+        rows = int(pool_rows if pool_rows is not None else lib.sphb_nlist_pool_rows(n))
+        self.pool_rows = rows
+        self.warp_off = torch.empty(nw, dtype=torch.int32, device=dev)
+        self.warp_rows = torch.zeros(nw, dtype=torch.int32, device=dev)
+        self.pool = torch.empty((rows, 32), dtype=torch.int32, device=dev)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.c = N.NList(n, self.warp_off.data_ptr(), self.warp_rows.data_ptr(), self.pool.data_ptr(), rows,
+                         self.cursor.data_ptr(), self.flags.data_ptr(), dg.posh.data_ptr(), self.cover_h, self.skin)
+
+    def ref(self):
+        return C.byref(self.c)
+
+    def read_flags(self):
+        """one 4-byte D2H read (synchronises the stream)"""
+        return int(self.flags.item())
+
+    def rows_used(self):
+        return int(self.cursor.item())
+
+
 def require_cuda():
     lib = N.load()
     if not torch.cuda.is_available():
@@ -298,6 +330,71 @@ class Engine:
                                          _ptr(cnt), _stream())
         return out, cnt
 
+    # -- kept neighbour lists (sphb_nlist) -------------------------------------------------------
+    def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None) -> KeptLists:
+        nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows)
+        hm = hmax if hmax is not None else self.hmax(dg.posh)
+        nl._hmax = hm
+        self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(), _stream())
+        return nl
+
+    def nl_check(self, nl, posh):
+        self._run("nl_check", self.lib.sphb_nlist_check, nl.ref(), _ptr(posh), _stream())
+
+    def nl_density_omega(self, nl, consts, posh, target=None, rho_in=None, want_rho=False, want_dwdh=False, want_omega=True,
+                         want_ngb=False):
+        n = nl.n
+        rho = torch.empty(n, dtype=F64, device=self.device) if want_rho else None
+        dw = torch.empty(n, dtype=F64, device=self.device) if want_dwdh else None
+        om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
+        ng = torch.empty(n, dtype=torch.int32, device=self.device) if want_ngb else None
+        self._run("nl_density_omega", self.lib.sphb_nlist_density_omega, nl.ref(), C.byref(consts), _ptr(target), _ptr(posh),
+                  _ptr(rho_in), _ptr(rho), _ptr(dw), _ptr(om), _ptr(ng), _stream())
+        return rho, dw, om, ng
+
+    def nl_newton(self, nl, consts, posh, status_ptr, target=None, h_guess=None, want_omega=False, want_posh=True,
+                  want_iters=False):
+        """-> h, omega (or None), posh_out (or None), iters (or None)"""
+        n = nl.n
+        h = torch.empty(n, dtype=F64, device=self.device)
+        om = torch.empty(n, dtype=F64, device=self.device) if want_omega else None
+        po = torch.empty((n, 4), dtype=F64, device=self.device) if want_posh else None
+        it = torch.zeros(n, dtype=torch.int32, device=self.device) if want_iters else None
+        self._run("nl_newton_h", self.lib.sphb_nlist_newton_h, nl.ref(), C.byref(consts), _ptr(target), _ptr(posh),
+                  _ptr(h_guess), _ptr(h), _ptr(om), _ptr(po), _ptr(it), status_ptr, _stream())
+        return h, om, po, it
+
+    def nl_force(self, nl, consts, posh, recB, recC, status_ptr, target=None):
+        n = nl.n
+        acc = torch.zeros((n, 3), dtype=F64, device=self.device) if target is not None else \
+            torch.empty((n, 3), dtype=F64, device=self.device)
+        dudt = torch.zeros(n, dtype=F64, device=self.device) if target is not None else \
+            torch.empty(n, dtype=F64, device=self.device)
+        self._run("nl_force", self.lib.sphb_nlist_force, nl.ref(), C.byref(consts), _ptr(target), _ptr(posh), _ptr(recB),
+                  _ptr(recC), _ptr(acc), _ptr(dudt), status_ptr, _stream())
+        return acc, dudt
+
+    def gather_state(self, perm, pos=None, h=None, vel=None, u=None):
+        """caller order -> slot order: posh (n,4), vel (n,3), u (n) (None for what was not given)"""
+        n = perm.shape[0]
+        po = torch.empty((n, 4), dtype=F64, device=self.device) if pos is not None else None
+        ve = torch.empty((n, 3), dtype=F64, device=self.device) if vel is not None else None
+        uu = torch.empty(n, dtype=F64, device=self.device) if u is not None else None
+        self._run("gather_state", self.lib.sphb_gather_state, _ptr(pos), _ptr(h), _ptr(vel), _ptr(u), _ptr(perm), n, _ptr(po),
+                  _ptr(ve), _ptr(uu), _stream())
+        return po, ve, uu
+
+    def scatter_state(self, perm, posh=None, vel=None, u=None):
+        """slot order -> caller order: pos (n,3), h (n), vel (n,3), u (n)"""
+        n = perm.shape[0]
+        pos = torch.empty((n, 3), dtype=F64, device=self.device) if posh is not None else None
+        h = torch.empty(n, dtype=F64, device=self.device) if posh is not None else None
+        ve = torch.empty((n, 3), dtype=F64, device=self.device) if vel is not None else None
+        uu = torch.empty(n, dtype=F64, device=self.device) if u is not None else None
+        self._run("scatter_state", self.lib.sphb_scatter_state, _ptr(posh), _ptr(vel), _ptr(u), _ptr(perm), n, _ptr(pos), _ptr(h),
+                  _ptr(ve), _ptr(uu), _stream())
+        return pos, h, ve, uu
+
     # -- K4 ------------------------------------------------------------------------------------
     def eos(self, posh, vel, u, omega, consts, status_ptr, rho_in=None, P_in=None, records=True, want_rho_P=False, xi=None,
             want_bgrav=False):
@@ -514,6 +611,240 @@ class Stepper:
         return pos1, vel1, u1, h1
 
 
+NL_COVER_H = float(os.environ.get("SPHB_NL_COVER_H", "1.03"))
+NL_SKIN = float(os.environ.get("SPHB_NL_SKIN", "0.03"))
+
+
+class FastStepper:
+    """var_smoothlength_leapfrog (pyfluid.py:498-532, G = 0) on neighbour lists that are kept across kernels and steps.
+
+    One cell-list build + one scan (sphb_nlist_build) serve every gather kernel of every step until a device-side check
+    says the lists no longer cover the state (h grew past cover_h x, or a particle moved more than skin x, its h at build
+    time).  Between builds the state lives in the build's slot order; the five gather kernels of a step are pure drains.
+    A step runs speculatively: if it ends with SPHB_NL_BROKEN it is redone after a rebuild from its (unmodified) input,
+    and if that fails too -- or the input cannot be listed at all -- by the scanning Stepper, which replays the
+    reference to the letter (bisection fallback, unbounded h).  Sums are formed in (cell, caller index) order like the
+    scanning path: on the same grid geometry the results are the same bits.
+
+    Two ways to drive it:
+      * step(pos0, vel0, u0, h0, dt, consts) -> pos1, vel1, u1, h1   pure function on caller-order device tensors, same
+        contract as Stepper.step; the lists of the previous call are reused when the new input passes the check;
+      * load(pos, vel, u, h) / advance(dt, consts) / state()          the state stays resident in slot order (time loops).
+    """
+
+    def __init__(self, engine, cover_h=None, skin=None):
+        self.e = engine
+        self.cover_h = NL_COVER_H if cover_h is None else float(cover_h)
+        self.skin = NL_SKIN if skin is None else float(skin)
+        self.safe = Stepper(engine)
+        self.geom = None          # (grid, delta) pinned by the caller; None: from the bounding box at every build
+        self.nl = None
+        self.perm = None          # int32 (n): caller index of slot s
+        self.ids = None           # int64 copy of perm (tie keys of the next build)
+        self.P = self.V = self.U = None
+        self.stale = True
+        self.last_status = None
+        self.hold = 0             # steps left on the scanning path after the lists failed twice on one step
+        self.caller_state = None  # resident state in caller order while on hold
+        self.stats = dict(steps=0, builds=0, redos=0, safe_steps=0, reuse_rejected=0)
+
+    # ---- builds ------------------------------------------------------------------------------------
+    def _rebuild_from(self, posh_in, vel_in, u_in, ids_in):
+        """sort records (any order; ids_in = caller index of each input row, None = identity) into a fresh cell list,
+        scan it once, and take the state along in the new slot order"""
+        e = self.e
+        if self.geom is not None:
+            grid, delta = self.geom
+            self.safe.geom = self.geom
+        else:
+            grid, delta = e.grid_for(posh_in)
+        self.nl = None                       # drop the old pool before the new one is allocated
+        dg = e.build(posh_in, grid, delta, tie_key=ids_in)
+        perm_l = dg.perm.long()
+        self.V = vel_in.index_select(0, perm_l) if vel_in is not None else None
+        self.U = u_in.index_select(0, perm_l) if u_in is not None else None
+        if ids_in is None:
+            self.perm = dg.perm
+            self.ids = perm_l
+        else:
+            self.ids = ids_in.index_select(0, perm_l)
+            self.perm = self.ids.to(torch.int32)
+        self.P = dg.posh                     # never written in place: every kernel below returns fresh arrays
+        self.nl = e.nl_build(dg, self.cover_h, self.skin)
+        self.stats["builds"] += 1
+        self.stale = False
+
+    # ---- one step in slot order ---------------------------------------------------------------------
+    def _slots_step(self, P0, V0, U0, dt, consts, st, hooks=None):
+        """pyfluid.py:502-530 on the kept lists -> P1 (x, y, z, h1), V1, U1 in slot order; inputs untouched"""
+        e, nl = self.e, self.nl
+        _, _, om0, _ = e.nl_density_omega(nl, consts, P0)                               # :503
+        if hooks is not None:
+            V0, U0 = hooks.vel_u()
+        _, _, rB, rC = e.eos(P0, V0, U0, om0, consts, st.ptr(S_STAGE0))                 # :502,:505
+        acc0, dudt0 = e.nl_force(nl, consts, P0, rB, rC, st.ptr(S_STAGE0))              # :506-507
+        Pm, Vm, Um = e.predict(P0, V0, U0, acc0, dudt0, dt, st.ptr(S_PRED))             # :511-515
+        e.nl_check(nl, Pm)
+        hm, omm, Pm2, _ = e.nl_newton(nl, consts, Pm, st.ptr(S_NEWTON_MID), want_omega=True)   # :516-518
+        _, _, rB, rC = e.eos(Pm2, Vm, Um, omm, consts, st.ptr(S_STAGE_MID))             # :517,:520
+        acc1, dudt1 = e.nl_force(nl, consts, Pm2, rB, rC, st.ptr(S_STAGE_MID))          # :521-522
+        P1, V1, U1 = e.correct(P0, V0, U0, acc1, dudt1, dt, st.ptr(S_CORR))             # :524-528
+        if hooks is not None:
+            hooks.after_corrector(P1, V1, U1)
+        e.nl_check(nl, P1)
+        _, _, P1b, _ = e.nl_newton(nl, consts, P1, st.ptr(S_NEWTON_1), h_guess=hm)      # :530
+        return P1b, V1, U1
+
+    _BAD = N.NL_BROKEN | N.NL_POOL | N.NL_UNLISTABLE
+
+    def _try(self, dt, consts, hooks=None):
+        """run one step on the current lists; -> (ok, P1, V1, U1, status)"""
+        st = Status(S_COUNT, self.e.device)
+        P1, V1, U1 = self._slots_step(self.P, self.V, self.U, dt, consts, st, hooks)
+        fl = self.nl.read_flags()
+        if fl & N.NL_AGING:
+            self.stale = True
+        return (fl & self._BAD) == 0, P1, V1, U1, st
+
+    # ---- resident-state API ---------------------------------------------------------------------------
+    SAFE_HOLD = 8
+
+    def load(self, pos, vel, u, h):
+        self.caller_state = None
+        self._rebuild_from(self.e.pack_posh(pos, h), vel, u, None)
+
+    def state(self):
+        """-> pos, vel, u, h in caller order"""
+        if self.caller_state is not None:
+            return self.caller_state
+        pos, h, vel, u = self.e.scatter_state(self.perm, self.P, self.V, self.U)
+        return pos, vel, u, h
+
+    def _safe_advance(self, dt, consts, defer_status, printer):
+        self.stats["safe_steps"] += 1
+        pos, vel, u, h = self.caller_state
+        self.caller_state = self.safe.step(pos, vel, u, h, dt, consts, defer_status=defer_status, printer=printer)
+        self.last_status = self.safe.last_status
+        self.hold -= 1
+        if self.hold <= 0:
+            self.load(*self.caller_state)
+
+    def advance(self, dt, consts, defer_status=True, printer=print):
+        if consts.G != 0.0:
+            raise ValueError("FastStepper runs the G = 0 path; use Stepper for the softened-gravity terms")
+        self.stats["steps"] += 1
+        if self.hold > 0:
+            return self._safe_advance(dt, consts, defer_status, printer)
+        for attempt in (0, 1):
+            if self.stale or attempt == 1:
+                self._rebuild_from(self.P, self.V, self.U, self.ids)
+            ok, P1, V1, U1, st = self._try(dt, consts)
+            if ok:
+                self.P, self.V, self.U = P1, V1, U1
+                self.last_status = st
+                if not defer_status:
+                    raise_for_status(st.read(), printer)
+                return
+            self.stats["redos"] += 1
+        # the lists cannot serve this step (bisection fallback, unbounded h ...): scanning path for a while
+        self.caller_state = self.state()
+        self.nl = None
+        self.hold = self.SAFE_HOLD
+        self._safe_advance(dt, consts, defer_status, printer)
+
+    # ---- pure-function API (same contract as Stepper.step) -----------------------------------------------
+    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, hooks=None):
+        if consts.G != 0.0:
+            r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks)
+            self.last_status = self.safe.last_status
+            return r
+        e = self.e
+        n = pos0.shape[0]
+        self.stats["steps"] += 1
+        if self.hold > 0:
+            self.hold -= 1
+            self.stats["safe_steps"] += 1
+            r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks)
+            self.last_status = self.safe.last_status
+            return r
+        fh = _FastHooks(self, hooks, vel0, u0) if hooks is not None else None
+        reuse = self.nl is not None and not self.stale and self.nl.n == n
+        if reuse:
+            # the new input in the old slot order; does it pass the lists' own validity check?
+            self.P, _, _ = e.gather_state(self.perm, pos=pos0, h=h0)
+            e.nl_check(self.nl, self.P)
+            if self.nl.read_flags() != 0:
+                reuse = False
+                self.stats["reuse_rejected"] += 1
+            elif fh is None:
+                _, self.V, self.U = e.gather_state(self.perm, vel=vel0, u=u0)
+        for attempt in (0, 1):
+            if not reuse:
+                if fh is not None:
+                    fh.wait_inputs()
+                self._rebuild_from(e.pack_posh(pos0, h0), vel0, u0, None)
+                if fh is not None:
+                    fh.have_state()
+            ok, P1, V1, U1, st = self._try(dt, consts, fh)
+            if ok:
+                self.last_status = st
+                if fh is not None:
+                    out = fh.finish(P1)
+                else:
+                    pos1, h1, vel1, u1 = e.scatter_state(self.perm, P1, V1, U1)
+                    out = (pos1, vel1, u1, h1)
+                self.P, self.V, self.U = P1, V1, U1
+                if not defer_status:
+                    raise_for_status(st.read(), printer)
+                return out
+            self.stats["redos"] += 1
+            reuse = False
+        self.stats["safe_steps"] += 1
+        self.nl = None
+        self.stale = True
+        self.hold = self.SAFE_HOLD
+        r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks)
+        self.last_status = self.safe.last_status
+        return r
+
+
+class _FastHooks:
+    """adapts the pinned-transfer hooks (before_vel_u / after_corrector take caller-order tensors) to the slot-order step"""
+
+    def __init__(self, fs, hooks, vel0, u0):
+        self.fs, self.hooks, self.vel0, self.u0 = fs, hooks, vel0, u0
+        self.waited = False
+        self.state_ready = False
+
+    def wait_inputs(self):
+        if not self.waited:
+            self.hooks.before_vel_u()
+            self.waited = True
+
+    def have_state(self):
+        self.state_ready = True   # _rebuild_from gathered V, U
+
+    def vel_u(self):
+        fs = self.fs
+        if not self.state_ready:
+            self.wait_inputs()
+            _, fs.V, fs.U = fs.e.gather_state(fs.perm, vel=self.vel0, u=self.u0)
+            self.state_ready = True
+        return fs.V, fs.U
+
+    def after_corrector(self, P1, V1, U1):
+        # pos1, vel1, u1 are final: back to caller order, their copy-out can start while the last Newton solve runs
+        e = self.fs.e
+        pos1, _, vel1, u1 = e.scatter_state(self.fs.perm, P1, V1, U1)
+        self.pos1, self.vel1, self.u1 = pos1, vel1, u1
+        self.hooks.after_corrector_caller(pos1, vel1, u1)
+
+    def finish(self, P1b):
+        e = self.fs.e
+        _, h1, _, _ = e.scatter_state(self.fs.perm, P1b)
+        return self.pos1, self.vel1, self.u1, h1
+
+
 class _PinnedHooks:
     """stream choreography of Stepper.step_pinned"""
 
@@ -525,17 +856,19 @@ class _PinnedHooks:
         torch.cuda.current_stream().wait_event(self.ev)
 
     def after_corrector(self, posh_1, vel1, u1):
+        self.after_corrector_caller(posh_1[:, :3], vel1, u1)
+
+    def after_corrector_caller(self, pos1, vel1, u1):
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
-        pos1 = posh_1[:, :3]
         with torch.cuda.stream(self.cs):
             self.cs.wait_event(ev)
             self.out[0].copy_(pos1, non_blocking=True)
             self.out[1].copy_(vel1, non_blocking=True)
             self.out[2].copy_(u1, non_blocking=True)
             self.ev_out.record(self.cs)
-        for t in (posh_1, vel1, u1):
+        for t in (pos1, vel1, u1):
             t.record_stream(self.cs)
 
 

@@ -538,15 +538,24 @@ def acceleration_arr(position_arr, density_arr, velocity_arr, pressure_arr, smoo
 _stepper = None
 
 
+def _get_stepper():
+    """the step driver: kept neighbour lists (engine.FastStepper) for G = 0, the scanning Stepper for the
+    softened-gravity terms (FastStepper hands those calls on); SPHB_NO_NLIST=1 forces the scanning path"""
+    global _stepper
+    if _stepper is None:
+        import os
+        _stepper = _E.Stepper(_eng()) if os.environ.get("SPHB_NO_NLIST") else _E.FastStepper(_eng())
+    return _stepper
+
+
 def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt, out=None):
-    """pyfluid.py:498-532: one midpoint predictor-corrector step (Cossins 3.152-3.155), G = 0.
+    """pyfluid.py:498-532: one midpoint predictor-corrector step (Cossins 3.152-3.155) with the module's constants
+    (G included: the default 39.4227 adds the softened self-gravity terms, :481-483; set G = 0 for the hydro path).
     Returns fresh (pos1, vel1, energy1, h1); inputs are not modified.
     out (extension, pinned host tensors only): four pinned tensors to receive the results instead of newly pinned
     memory -- pinning a gigabyte costs more than the step, so a time loop over host buffers hands in two sets in turn."""
-    global _stepper
     io = _IO(pos0, vel0, energy0, h0)
-    if _stepper is None:
-        _stepper = _E.Stepper(_eng())
+    _stepper = _get_stepper()
     host = [t for t in (pos0, vel0, energy0, h0) if isinstance(t, torch.Tensor) and not t.is_cuda]
     if len(host) == 4 and all(t.is_pinned() and t.dtype == torch.float64 and t.is_contiguous() for t in host):
         # pinned host tensors in -> pinned host tensors out, transfers overlapped with the kernels
@@ -639,7 +648,6 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
     (Stepper.step can also take Omega(pos[t], h[t]) from step t-1's last Newton kernel -- omega0 / want_omega1 -- but
     since the Omega pass parks its neighbour lists for the force kernel that follows it, recomputing Omega is the
     faster loop; see DESIGN.md.)"""
-    global _stepper
     io = _IO(positions0, velocities0, energies0, smoothlength_approx)
     dt = float(time_arr[1] - time_arr[0])
     Nt = len(time_arr)
@@ -666,12 +674,22 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
         writer = _HistoryWriter([P, V, E, H], (pos, vel, u, h))
         put, finish = writer.put, writer.finish
     put(0, (pos, vel, u, h))
-    if _stepper is None:
-        _stepper = _E.Stepper(_eng())
-    for t in range(Nt - 1):
-        print("time step:", t, "of", Nt)
-        pos, vel, u, h = _stepper.step(pos, vel, u, h, dt, _consts())
-        if (t + 1) % stride == 0:
-            put((t + 1) // stride, (pos, vel, u, h))
+    stepper = _get_stepper()
+    consts = _consts()
+    if isinstance(stepper, _E.FastStepper) and consts.G == 0.0:
+        # the state stays resident in the neighbour lists' slot order; it is brought back to caller order only
+        # for the snapshots that are kept
+        stepper.load(pos, vel, u, h)
+        for t in range(Nt - 1):
+            print("time step:", t, "of", Nt)
+            stepper.advance(dt, _consts(), defer_status=False)
+            if (t + 1) % stride == 0:
+                put((t + 1) // stride, stepper.state())
+    else:
+        for t in range(Nt - 1):
+            print("time step:", t, "of", Nt)
+            pos, vel, u, h = stepper.step(pos, vel, u, h, dt, _consts())
+            if (t + 1) % stride == 0:
+                put((t + 1) // stride, (pos, vel, u, h))
     finish()
     return P, V, E, H
