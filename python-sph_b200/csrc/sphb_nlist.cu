@@ -19,8 +19,8 @@
 
 #define NL_WARPS 4
 #define NL_THREADS (NL_WARPS * 32)
-#ifndef SPHB_NL_HEAVY_ROWS
-#define SPHB_NL_HEAVY_ROWS 4096 /* rows reserved for a warp whose lists outgrow the shared-memory staging area */
+#ifndef SPHB_NL_MAX_ROWS
+#define SPHB_NL_MAX_ROWS (1 << 18) /* rows one warp may take (32 MiB): beyond that the input is "unlistable" */
 #endif
 #ifndef SPHB_MINB_NL_BUILD
 #define SPHB_MINB_NL_BUILD 4
@@ -35,8 +35,7 @@
 // ------------------------------------------------------------------------------------------------
 // build: one warp = 32 consecutive slots; its lists become `rows` rows of 32 slot indices (row k = entry k of every
 // lane, SPHB_NL_NONE where a lane has fewer), handed out from the pool by one atomicAdd per warp.  A warp whose lists
-// do not fit the shared-memory staging area (128 entries per lane) takes a fixed reserve of SPHB_NL_HEAVY_ROWS rows
-// and appends one padded chunk per overflow.
+// do not fit the shared-memory staging area (128 entries per lane) counts its rows first and scans twice.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     k_nl_build(sphb_cells c, const uint8_t *__restrict__ target, const float *__restrict__ hmax_global, sphb_nlist nl)
@@ -68,27 +67,37 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     const float cov = (float)kappa * 1.000001f;
     const float RH = sphb_radius_of_h((double)hmax_global[0] * (double)cov, g.delta);
 
-    uint32_t row0 = 0, used = 0, cap = 0;   // warp-uniform
-    bool heavy = false, over = false;       // warp-uniform
+    // mode 0: the lists are expected to fit the staging area: one exact allocation at the end, one store.
+    // A warp that has to flush before the end of its scan (heavy: a sparse target next to a dense region) only COUNTS
+    // the rows of every chunk for the rest of that scan (mode 1), allocates exactly that, and scans once more to store
+    // (mode 2; the scan is deterministic, the chunks come out the same).  Rows of a chunk are padded to its longest lane.
+    uint32_t row0 = 0, used = 0, total = 0;   // warp-uniform
+    int mode = 0;                             // warp-uniform
+    bool over = false;                        // warp-uniform
+    auto alloc = [&](uint32_t rows) {
+        unsigned long long r0 = 0;
+        if (lane == 0 && rows) r0 = atomicAdd(nl.cursor, (unsigned long long)rows);
+        r0 = __shfl_sync(SPHB_FULL, r0, 0);
+        if (r0 + rows > (unsigned long long)nl.pool_rows) {
+            over = true;
+            if (lane == 0) atomicOr(nl.flags, SPHB_NL_POOL);
+        }
+        row0 = (uint32_t)r0;
+        used = 0;
+    };
     auto emit = [&](int cnt, bool final) {
         __syncwarp();
         const uint32_t rows = (uint32_t)__reduce_max_sync(SPHB_FULL, cnt);
-        if (!heavy && !over) {
-            cap = final ? rows : (uint32_t)SPHB_NL_HEAVY_ROWS;
-            unsigned long long r0 = 0;
-            if (lane == 0 && cap) r0 = atomicAdd(nl.cursor, (unsigned long long)cap);
-            r0 = __shfl_sync(SPHB_FULL, r0, 0);
-            if (r0 + cap > (unsigned long long)nl.pool_rows) {
+        if (mode == 0 && !final) mode = 1;
+        if (mode == 1) {
+            total += rows;
+            if (total > (uint32_t)SPHB_NL_MAX_ROWS && !over) {
                 over = true;
-                if (lane == 0) atomicOr(nl.flags, SPHB_NL_POOL);
+                if (lane == 0) atomicOr(nl.flags, SPHB_NL_UNLISTABLE);
             }
-            row0 = (uint32_t)r0;
-            heavy = !final;
+            return;
         }
-        if (!over && used + rows > cap) {
-            over = true;
-            if (lane == 0) atomicOr(nl.flags, SPHB_NL_UNLISTABLE);
-        }
+        if (mode == 0) alloc(rows);
         if (!over) {
             uint32_t *dst = nl.pool + ((size_t)row0 + used) * 32 + lane;
             for (uint32_t r = 0; r < rows; ++r)
@@ -97,11 +106,17 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
         }
         __syncwarp();
     };
-    SphbList L;
-    L.init(ws, lane);
     auto flush = [&](int n_) { emit(n_, false); };
-    sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
-    emit(L.count(), true);
+    for (int pass = 0; pass < 2; ++pass) {
+        SphbList L;
+        L.init(ws, lane);
+        sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+        emit(L.count(), true);
+        if (mode != 1 || over) break;
+        alloc(total);
+        mode = 2;
+        __syncwarp();
+    }
     if (lane == 0) {
         nl.warp_off[w] = row0;
         nl.warp_rows[w] = over ? 0u : used;
@@ -427,9 +442,10 @@ static inline unsigned nl_blocks(int64_t n) { return (unsigned)((n + NL_THREADS 
 
 extern "C" int64_t sphb_nlist_pool_rows(int64_t n)
 {
-    // every warp that fits the staging area needs at most SPHB_LIST rows; plus room for 1/64 of the warps to be heavy
+    // a warp that fits the staging area takes at most SPHB_LIST rows (typically ~2/3 of that: the slack is what the
+    // heavy warps use); an input that needs more sets SPHB_NL_POOL and is rebuilt with a larger pool by the caller
     const int64_t warps = (n + 31) / 32;
-    return warps * SPHB_LIST + (warps / 64 + 16) * SPHB_NL_HEAVY_ROWS;
+    return warps * SPHB_LIST + 16384;
 }
 
 extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global,

@@ -644,7 +644,11 @@ class FastStepper:
         self.P = self.V = self.U = None
         self.stale = True
         self.last_status = None
-        self.hold = 0             # steps left on the scanning path after the lists failed twice on one step
+        self.pool_rows = None     # rows of the list pool (None: sphb_nlist_pool_rows)
+        self.fresh = False
+        self.fresh_failed = False
+        self.last_flags = 0
+        self.hold = 0             # steps left on the scanning path after the lists failed on one step
         self.caller_state = None  # resident state in caller order while on hold
         self.stats = dict(steps=0, builds=0, redos=0, safe_steps=0, reuse_rejected=0)
 
@@ -670,9 +674,32 @@ class FastStepper:
             self.ids = ids_in.index_select(0, perm_l)
             self.perm = self.ids.to(torch.int32)
         self.P = dg.posh                     # never written in place: every kernel below returns fresh arrays
-        self.nl = e.nl_build(dg, self.cover_h, self.skin)
+        self.nl = e.nl_build(dg, self.cover_h, self.skin, pool_rows=self.pool_rows)
         self.stats["builds"] += 1
         self.stale = False
+        self.fresh = True                    # no step has run on these lists yet
+
+    MAX_SKIN = 0.25
+
+    def _adapt(self, flags):
+        """a step failed on its lists (flags = SPHB_NL_*): what to change before the rebuild.  -> False: give up"""
+        if flags & N.NL_UNLISTABLE:
+            return False
+        if flags & N.NL_POOL:
+            cur = self.nl.pool_rows if self.nl is not None else int(self.e.lib.sphb_nlist_pool_rows(self.P.shape[0]))
+            if cur * 128 * 2 > 64 * 2 ** 30:
+                return False
+            self.pool_rows = 2 * cur
+            return True
+        if self.fresh_failed:
+            # even lists built for this very state broke within the step: particles move (or h grows) by more than the
+            # margins per step -- widen them, then give up
+            if self.skin >= self.MAX_SKIN:
+                return False
+            self.skin = min(self.MAX_SKIN, max(2.0 * self.skin, 0.02))
+            self.cover_h = 1.0 + min(0.25, max(2.0 * (self.cover_h - 1.0), 0.02))
+            self.stats["widened"] = self.stats.get("widened", 0) + 1
+        return True
 
     # ---- one step in slot order ---------------------------------------------------------------------
     def _slots_step(self, P0, V0, U0, dt, consts, st, hooks=None):
@@ -697,14 +724,19 @@ class FastStepper:
 
     _BAD = N.NL_BROKEN | N.NL_POOL | N.NL_UNLISTABLE
 
+    MAX_ATTEMPTS = 4
+
     def _try(self, dt, consts, hooks=None):
-        """run one step on the current lists; -> (ok, P1, V1, U1, status)"""
+        """run one step on the current lists; -> (ok, P1, V1, U1, status); self.last_flags = the lists' flags"""
         st = Status(S_COUNT, self.e.device)
         P1, V1, U1 = self._slots_step(self.P, self.V, self.U, dt, consts, st, hooks)
-        fl = self.nl.read_flags()
+        fl = self.last_flags = self.nl.read_flags()
+        ok = (fl & self._BAD) == 0
+        self.fresh_failed = self.fresh and not ok
+        self.fresh = False
         if fl & N.NL_AGING:
             self.stale = True
-        return (fl & self._BAD) == 0, P1, V1, U1, st
+        return ok, P1, V1, U1, st
 
     # ---- resident-state API ---------------------------------------------------------------------------
     SAFE_HOLD = 8
@@ -735,8 +767,8 @@ class FastStepper:
         self.stats["steps"] += 1
         if self.hold > 0:
             return self._safe_advance(dt, consts, defer_status, printer)
-        for attempt in (0, 1):
-            if self.stale or attempt == 1:
+        for attempt in range(self.MAX_ATTEMPTS):
+            if self.stale or attempt > 0:
                 self._rebuild_from(self.P, self.V, self.U, self.ids)
             ok, P1, V1, U1, st = self._try(dt, consts)
             if ok:
@@ -746,6 +778,8 @@ class FastStepper:
                     raise_for_status(st.read(), printer)
                 return
             self.stats["redos"] += 1
+            if not self._adapt(self.last_flags):
+                break
         # the lists cannot serve this step (bisection fallback, unbounded h ...): scanning path for a while
         self.caller_state = self.state()
         self.nl = None
@@ -778,7 +812,7 @@ class FastStepper:
                 self.stats["reuse_rejected"] += 1
             elif fh is None:
                 _, self.V, self.U = e.gather_state(self.perm, vel=vel0, u=u0)
-        for attempt in (0, 1):
+        for attempt in range(self.MAX_ATTEMPTS):
             if not reuse:
                 if fh is not None:
                     fh.wait_inputs()
@@ -799,6 +833,8 @@ class FastStepper:
                 return out
             self.stats["redos"] += 1
             reuse = False
+            if not self._adapt(self.last_flags):
+                break
         self.stats["safe_steps"] += 1
         self.nl = None
         self.stale = True

@@ -209,8 +209,9 @@ def test_fast_stepper_vs_oracle_two_steps(sph, oracle_mod):
 
 
 def test_broken_lists_redo_and_fallback(sph, capsys):
-    """(1) a step that moves particles by more than the skin is redone after a rebuild and still equals the scanning
-    path; (2) a step whose Newton solve needs the bisection is handed to the scanning Stepper (same prints)"""
+    """(1) a step that moves particles by more than the skin is redone on lists with wider margins and still equals the
+    scanning path; (2) a step with absurd h guesses (lists far beyond the pool, Newton solves that may need the
+    bisection) ends up wherever it must -- larger pool, or the scanning Stepper -- with the same prints and results"""
     import engine as E
     eng = sph._eng()
     pos, vel, e, L = cloud(6000, 63, vscale=1.0)
@@ -220,7 +221,8 @@ def test_broken_lists_redo_and_fallback(sph, capsys):
     fast, safe = E.FastStepper(eng, cover_h=1.004, skin=0.0005), E.Stepper(eng)
     a = fast.step(*s0, 2e-3, c)          # 0.5 * 2e-3 * |v| ~ 5e-4 >> skin * h
     b = safe.step(*s0, 2e-3, c)
-    assert fast.stats["redos"] >= 1 and fast.stats["safe_steps"] == 1, fast.stats
+    assert fast.stats["redos"] >= 1 and fast.stats.get("widened", 0) >= 1 and fast.stats["safe_steps"] == 0, fast.stats
+    assert fast.skin >= 0.02
     for x, y in zip(a, b):
         assert rel(x.cpu().numpy(), y.cpu().numpy()) < 1e-12
     # bad guesses: 2.5x too large -> Newton fails for some particles -> WARNING + bisection on the scanning path
@@ -231,7 +233,7 @@ def test_broken_lists_redo_and_fallback(sph, capsys):
     out_fast = capsys.readouterr().out
     b = safe.step(*s1, 1e-4, c)
     out_safe = capsys.readouterr().out
-    assert fast2.stats["safe_steps"] == 1
+    assert fast2.stats["redos"] >= 1, fast2.stats
     assert out_fast == out_safe
     for x, y in zip(a, b):
         assert rel(x.cpu().numpy(), y.cpu().numpy()) < 1e-12
