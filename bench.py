@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--nx", type=int, default=384, help="sod: left-half lattice points along x (384 -> 15.9 M)")
     ap.add_argument("--side", type=int, default=100, help="lattice: cube side")
     ap.add_argument("--n", type=int, default=262144, help="planar: particle count")
+    ap.add_argument("--path", default="lists", choices=["lists", "scan"],
+                    help="lists: neighbour lists kept across kernels and steps (default); scan: the scanning kernels only")
+    ap.add_argument("--warm-state-steps", type=int, default=0, help="untimed steps at setup so that the timed steps see a developed flow")
+    ap.add_argument("--dt-scale", type=float, default=1.0, help="multiply the workload's dt (sod: 0.05 a; 6 is a CFL-sized step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -117,6 +121,7 @@ def cpu_sample(w, h, seconds, consts_over):
     import oracle
     oracle.build()
     o = oracle.Oracle(**consts_over)
+    o.set_num_threads(os.cpu_count() or 1)
     o.set_wide(True)
     n = len(w["pos"])
     rng = np.random.default_rng(123)
@@ -145,6 +150,7 @@ def run_reference(a):
     w = make_workload(a)
     n = len(w["pos"])
     o = oracle.Oracle(G=0.0, PARTICLE_MASS=w["m"])
+    o.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: take the box's cores at every N
     o.set_wide(True)
     h = w["h_guess"] * (1.3012 / 1.2) if a.workload == "sod" else w["h_guess"]
     rng = np.random.default_rng(7)
@@ -173,6 +179,30 @@ def run_reference(a):
     print(json.dumps(line))
 
 
+def bit_checksum(tensors):
+    """order-independent exact fingerprint of a particle state: the sum (mod 2^64) of the IEEE bit patterns of every
+    value -- it does not depend on how particles are ordered or split over ranks, and any flipped bit changes it"""
+    import torch
+    tot = torch.zeros((), dtype=torch.int64, device=tensors[0].device)
+    for t in tensors:
+        tot = tot + t.contiguous().view(torch.int64).sum()
+    return tot
+
+
+def interactions(eng, E, consts, pos, h, n_total, dev):
+    """mean interaction counts of a state: own support (q_j < 2, incl. self) and symmetric support"""
+    import torch
+    posh = eng.pack_posh(pos, h)
+    grid, delta = eng.grid_for(posh)
+    dg = eng.build(posh, grid, delta)
+    _, _, _, ng = eng.density_omega(dg, consts, want_rho=False, want_ngb=True)
+    n_own = float(ng.double().sum().item())
+    q = torch.arange(0, n_total, max(1, n_total // 200000), dtype=torch.int32, device=dev)
+    _, cs = eng.neighbours(dg, q, 1, symmetric=True)
+    n_sym = float(cs.double().mean().item()) * n_total
+    return n_own, n_sym
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -193,17 +223,19 @@ def run_ours(a):
              BISECTION_ITERATION_LIMIT=100, ALPHA_SPH=1.0, BETA_SPH=2.0, EPSILON=0.01, BISECTION_TOLERANCE=1e-10,
              INITIAL_BISECTION_SMOOTHLENGTH_A=1e3, INITIAL_BISECTION_SMOOTHLENGTH_B=1e-3, G=0.0, ADIABATIC_INDEX=5 / 3)
     consts = E.make_consts(k)
-    dt = w["dt"]
+    dt = w["dt"] * a.dt_scale
+    use_lists = a.path == "lists"
 
     if world > 1:
         import domain
-        runner = domain.SlabRunner(eng, consts, world, rank)
+        runner = domain.make_runner(eng, consts, world, rank, lists=use_lists)
         state = runner.scatter_initial(w)
     else:
         runner = None
 
-    # ---- setup (untimed): state to HBM, cold h solve ------------------------------------------------
+    # ---- setup (untimed): state to HBM, cold h solve, warm-state steps ------------------------------
     host = {key: torch.from_numpy(np.ascontiguousarray(w[key])).pin_memory() for key in ("pos", "vel", "u", "h_guess")}
+    fs = None
     if runner is None:
         pos = host["pos"].to(dev, non_blocking=True)
         vel = host["vel"].to(dev, non_blocking=True)
@@ -217,13 +249,28 @@ def run_ours(a):
         h = eng.scatter(h_s, dg.perm, 1)
         E.raise_for_status(st0.read(), printer=lambda *_: None)
         del dg, posh, h_s
-        stepper = E.Stepper(eng)
-        step = lambda s: stepper.step(s[0], s[1], s[2], s[3], dt, consts, defer_status=True)
-        state = (pos, vel, u, h)
         statuses = []
+        if use_lists:
+            fs = E.FastStepper(eng)
+            fs.load(pos, vel, u, h)
+
+            def step(s):
+                fs.advance(dt, consts, defer_status=True)
+                statuses.append(fs.last_status)
+                return s
+            get_state = fs.state
+        else:
+            stepper = E.Stepper(eng)
+
+            def step(s):
+                r = stepper.step(s[0], s[1], s[2], s[3], dt, consts, defer_status=True)
+                statuses.append(stepper.last_status)
+                return r
+            get_state = None
+        state = (pos, vel, u, h)
     else:
         state = runner.cold_solve(state)
-        state = runner.calibrate(state, dt)   # setup: two throw-away steps to balance the cut planes by measured time
+        state = runner.calibrate(state, dt)   # setup: throw-away steps to balance the cut planes by measured time
         step = lambda s: runner.step(s, dt)
 
     def barrier():
@@ -231,36 +278,58 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def flush_status():
+        if world > 1:
+            runner.check_status()
+        else:
+            for st in statuses:
+                if st is not None:
+                    E.raise_for_status(st.read(), printer=lambda *_: None)
+            statuses.clear()
+
+    for _ in range(a.warm_state_steps):       # untimed: let the flow develop before anything is measured
+        state = step(state)
+    flush_status()
     clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         state = step(state)
-        if runner is None:
-            statuses.append(stepper.last_status)
     barrier()
     lib = eng.lib
     launches0 = lib.sphb_launch_count()
+    stats0 = dict(fs.stats) if fs is not None else (dict(runner.stats) if runner is not None and hasattr(runner, "stats") else {})
     if clocks:
         clocks.mark_start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.steps):
         state = step(state)
-        if runner is None:
-            statuses.append(stepper.last_status)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = lib.sphb_launch_count() - launches0
+    stats1 = dict(fs.stats) if fs is not None else (dict(runner.stats) if runner is not None and hasattr(runner, "stats") else {})
+    list_stats = {kk: stats1[kk] - stats0.get(kk, 0) for kk in stats1}
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        runner.check_status()
-    else:
-        for st in statuses:
-            E.raise_for_status(st.read(), printer=lambda *_: None)
+    flush_status()
     clk = clocks.stop() if clocks else None
     value = n_total * a.steps / (ms * 1e-3)
+
+    # ---- state fingerprint after warm-state + warm-up + timed steps (the same at every N when the runs agree bit for bit)
+    if runner is None:
+        cur = get_state() if get_state is not None else state
+        csum = bit_checksum([cur[0], cur[1], cur[2], cur[3]])
+        sums = [float(cur[3].sum()), float(cur[2].sum()), float(cur[1].norm(dim=1).sum()), float(cur[0].norm(dim=1).sum())]
+    else:
+        csum = bit_checksum([state["pos"], state["vel"], state["u"], state["h"]])
+        dist.all_reduce(csum, op=dist.ReduceOp.SUM)
+        sv = torch.stack([state["h"].sum(), state["u"].sum(), state["vel"].norm(dim=1).sum(), state["pos"].norm(dim=1).sum()])
+        dist.all_reduce(sv, op=dist.ReduceOp.SUM)
+        sums = sv.tolist()
+    checksum = {"bits_mod_2_64": int(csum.item()) & 0xFFFFFFFFFFFFFFFF, "sum_h": sums[0], "sum_u": sums[1], "sum_speed": sums[2],
+                "sum_radius": sums[3], "steps_taken": a.warm_state_steps + a.warmup + a.steps}
 
     # ---- e2e: public API semantics on pinned host buffers (H2D + step + D2H each step) ----------------
     e2e = None
@@ -269,11 +338,17 @@ def run_ours(a):
         import pyfluid as sph
         sph.G = 0.0
         sph.PARTICLE_MASS = w["m"]
-        hin = [t.cpu().pin_memory() for t in state]
+        if not use_lists:
+            os.environ["SPHB_NO_NLIST"] = "1"
+        cur = get_state() if get_state is not None else state
+        hin = [t.cpu().pin_memory() for t in cur]
         hout = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in hin]   # two pinned sets used in turn
         nb = sum(t.numel() * 8 for t in hin)
-        ke = max(1, min(a.steps, 3))
-        for _ in range(2):   # warm-up (device allocations, streams)
+        ke = max(1, min(a.steps, 10))
+        if fs is not None:
+            fs.nl = None          # the public module keeps its own lists: free these (8 GB) first
+            torch.cuda.empty_cache()
+        for _ in range(2):   # warm-up (device allocations, streams, the module's own neighbour lists)
             sph.var_smoothlength_leapfrog(hin[0], hin[1], hin[2], hin[3], dt, out=hout)
             hin, hout = hout, hin
         torch.cuda.synchronize()
@@ -284,10 +359,16 @@ def run_ours(a):
         el = time.perf_counter() - t0
         e2e = {"value": n_total * ke / el, "unit": "particle-steps/s", "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
                "steps": ke, "api": "pyfluid.var_smoothlength_leapfrog(pos, vel, u, h, dt, out=...) on pinned host tensors, two sets used in turn (transfers overlapped with kernels)"}
+        pst = sph._get_stepper()
+        if hasattr(pst, "stats"):
+            e2e["list_stats"] = dict(pst.stats)
+            pst.nl = None
+            pst.stale = True
+            torch.cuda.empty_cache()
     elif runner is not None and not a.no_e2e:
         e2e = runner.e2e(state, dt, max(1, min(a.steps, 3)))
 
-    # ---- per-kernel profile of one more step + roofline -------------------------------------------------
+    # ---- per-kernel profile + roofline ---------------------------------------------------------------------
     roof, per_kernel = None, None
     if runner is None:
         fp64_peak = max(eng.fp64_peak() for _ in range(3))
@@ -298,67 +379,99 @@ def run_ours(a):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        if fs is not None and fs.nl is None and fs.hold == 0:
+            fs.stale = True
+        # the same number of steps again with CUDA events around every C-ABI call (includes the rebuilds they need)
+        b0 = fs.stats["builds"] if fs is not None else 0
         eng.prof_start()
-        state2 = step(state)
+        for _ in range(a.steps):
+            state = step(state)
         prof = eng.prof_stop()
-        # interaction counts of the current state (own support and symmetric support)
-        posh = eng.pack_posh(state[0], state[3])
-        grid, delta = eng.grid_for(posh)
-        dg = eng.build(posh, grid, delta)
-        _, _, _, ng = eng.density_omega(dg, consts, want_rho=False, want_ngb=True)
-        n_own = float(ng.double().sum().item())
-        q = torch.arange(0, n_total, max(1, n_total // 200000), dtype=torch.int32, device=dev)
-        _, cs = eng.neighbours(dg, q, 1, symmetric=True)
-        n_sym = float(cs.double().mean().item()) * n_total
-        del dg, posh, state2
+        flush_status()
+        prof_builds = (fs.stats["builds"] - b0) if fs is not None else 3 * a.steps
+        cur = get_state() if get_state is not None else state
+        n_own, n_sym = interactions(eng, E, consts, cur[0], cur[3], n_total, dev)
+        # Newton evaluations per particle (iterations, + 1 for the fused Omega of the mid-step solve)
+        if fs is not None and fs.nl is not None and fs.hold == 0:
+            stx = E.Status(1, dev)
+            _, _, _, its = eng.nl_newton(fs.nl, consts, fs.P, stx.ptr(0), want_posh=False, want_iters=True)
+            newton_its = float(its.double().mean().item())
+        else:
+            newton_its = 1.0
+        step_ms = sum(v[1] for v in prof.values()) / a.steps
         per_kernel = {}
         for name, (calls, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-            per_kernel[name] = {"calls": calls, "ms": round(tms, 4)}
-        step_ms = sum(v[1] for v in prof.values())
-        f_ms = prof["force"][1] / prof["force"][0]
-        flops_force = FLOP_FORCE * n_sym
-        ach = flops_force / (f_ms * 1e-3) / 1e12
-        bytes_force = 104.0 * n_total
-        # DRAM bytes per launch: dram__bytes_read+write of k_force from the committed ncu --set full capture
-        # (profiles/r01_ncu_final_summary.txt: 570.9 MB read + 73.4 MB written for 1 990 656 particles; the parked
-        # neighbour lists are most of the reads), scaled per particle
-        traffic_force = 644.308e6 / 1990656 * n_total
-        roof = {"kernel": "k_force", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                "traffic": traffic_force, "traffic_source": "ncu capture at 1 990 656 particles scaled per particle (profiles/)", "peak_source": "DFMA microbenchmark in this run (sphb_fp64_peak); not in MEASURED_PEAKS.json",
-                "launch_ms": f_ms, "share_of_step": prof["force"][1] / step_ms,
-                "hbm": {"achieved": bytes_force / (f_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": bytes_force / (f_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+            per_kernel[name] = {"calls_per_step": calls / a.steps, "ms_per_step": round(tms / a.steps, 4), "ms_per_call": round(tms / calls, 4)}
+
+        def fp64_line(name, flops_per_call):
+            if name in prof:
+                ms1 = prof[name][1] / prof[name][0]
+                tf = flops_per_call / (ms1 * 1e-3) / 1e12
+                per_kernel[name].update({"tflops": tf, "frac_fp64": tf / fp64_peak})
+
+        def hbm_line(name, bytes_per_call):
+            if name in prof:
+                ms1 = prof[name][1] / prof[name][0]
+                gbs = bytes_per_call / (ms1 * 1e-3) / 1e9
+                per_kernel[name].update({"gbs": gbs, "frac_hbm": gbs / hbm_peak})
+
+        evals_newton = 0.5 * ((newton_its + 1.0) + newton_its)       # mean over the two launches of a step
+        fp64_line("nl_force", FLOP_FORCE * n_sym)
+        fp64_line("force", FLOP_FORCE * n_sym)
+        fp64_line("nl_density_omega", FLOP_OWN * n_own)
+        fp64_line("density_omega", FLOP_OWN * n_own)
+        fp64_line("nl_newton_h", FLOP_OWN * n_own * evals_newton)
+        fp64_line("newton_h", FLOP_OWN * n_own * evals_newton)
+        hbm_line("grid_build", 188.0 * n_total)
+        hbm_line("predict", 144.0 * n_total)
+        hbm_line("correct", 144.0 * n_total)
+        hbm_line("eos", (32.0 + 24.0 + 8.0 + 8.0 + 64.0) * n_total)
+        hbm_line("nl_check", 64.0 * n_total)
+        if fs is not None and fs.nl is not None:
+            rows = fs.nl.rows_used()
+            hbm_line("nl_build", 128.0 * rows + 56.0 * n_total)   # list rows written + fp32 records / cell ids read
+            per_kernel.get("nl_build", {}).update({"list_rows": rows, "list_bytes": 128 * rows})
+        top = max(prof.items(), key=lambda kv: kv[1][1])[0]
+        topk = per_kernel[top]
+        # step fraction = (F / peak_fp64 + B_K1K5 / peak_hbm) / t_step per particle
+        F = FLOP_OWN * (n_own / n_total) * (2.0 * newton_its + 2.0) + FLOP_FORCE * (n_sym / n_total) * 2.0
+        builds_per_step = prof_builds / a.steps
+        B15 = 288.0 + 188.0 * builds_per_step
+        lower_ms = (F / (fp64_peak * 1e12) + B15 / (hbm_peak * 1e9)) * n_total * 1e3
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tr.get("k_" + top) or tr.get(top)
+            if ent:
+                traffic = ent["dram_bytes"] / ent["n_particles"] * n_total
+                traffic_src = f"{ent['source']}: {ent['dram_bytes']:.4g} B at {ent['n_particles']} particles, scaled per particle"
+        except (OSError, ValueError, KeyError):
+            pass
+        roof = {"kernel": "k_" + top, "bound": "fp64" if "tflops" in topk else "hbm",
+                "achieved": topk.get("tflops", topk.get("gbs")), "peak": fp64_peak if "tflops" in topk else hbm_peak,
+                "unit": "TFLOP/s" if "tflops" in topk else "GB/s", "frac": topk.get("frac_fp64", topk.get("frac_hbm")),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "DFMA microbenchmark in this run (sphb_fp64_peak); MEASURED_PEAKS.json has no fp64 entry; HBM: " + hbm_src,
+                "launch_ms": topk["ms_per_call"], "share_of_step": prof[top][1] / a.steps / step_ms,
+                "step_frac": lower_ms / (ms / a.steps), "step_lower_bound_ms": lower_ms,
+                "step_flops_per_particle": F, "step_hbm_bytes_per_particle": B15,
+                "hbm_peak": hbm_peak, "newton_iterations_per_solve": newton_its, "builds_per_step": builds_per_step,
                 "interactions_per_particle": {"own": n_own / n_total, "symmetric": n_sym / n_total}}
-        own_ms = prof["density_omega"][1] / prof["density_omega"][0]
-        per_kernel["density_omega"]["tflops"] = FLOP_OWN * n_own / (own_ms * 1e-3) / 1e12
-        per_kernel["density_omega"]["frac_fp64"] = per_kernel["density_omega"]["tflops"] / fp64_peak
-        nw_ms = prof["newton_h"][1] / prof["newton_h"][0]
-        per_kernel["newton_h"]["tflops"] = FLOP_OWN * n_own / (nw_ms * 1e-3) / 1e12
-        per_kernel["newton_h"]["frac_fp64"] = per_kernel["newton_h"]["tflops"] / fp64_peak
-        per_kernel["force"]["tflops"] = ach
-        per_kernel["force"]["frac_fp64"] = ach / fp64_peak
-        gb_ms = prof["grid_build"][1] / prof["grid_build"][0]
-        per_kernel["grid_build"]["gbs"] = 188.0 * n_total / (gb_ms * 1e-3) / 1e9
-        per_kernel["grid_build"]["frac_hbm"] = per_kernel["grid_build"]["gbs"] / hbm_peak
-        for nm in ("predict", "correct"):
-            pm = prof[nm][1] / prof[nm][0]
-            per_kernel[nm]["gbs"] = 144.0 * n_total / (pm * 1e-3) / 1e9
-            per_kernel[nm]["frac_hbm"] = per_kernel[nm]["gbs"] / hbm_peak
 
     if runner is not None:
-        # rank-0 view of the dominant kernel in the decomposed run: its own particles, its own launch time.
-        # Interactions per particle are the single-GPU measurement of this workload (80.37 symmetric pairs).
+        # rank-0 view of the dominant kernel in the decomposed run: its own particles, its own launch time
         eng.prof_start()
         state = step(state)
         prof = eng.prof_stop()
         runner.statuses.clear()
         if rank == 0:
             fp64_peak = max(eng.fp64_peak() for _ in range(3))
-            n_own = int(state["gid"].numel())
-            f_ms = prof["force"][1] / prof["force"][0]
-            ach = FLOP_FORCE * 80.37 * n_own / (f_ms * 1e-3) / 1e12
-            roof = {"kernel": "k_force", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": ach / fp64_peak, "traffic": None, "scope": f"rank 0 of {world}: {n_own} owned particles",
+            n_own_r = int(state["gid"].numel())
+            fname = "nl_force" if "nl_force" in prof else "force"
+            f_ms = prof[fname][1] / prof[fname][0]
+            ach = FLOP_FORCE * 80.37 * n_own_r / (f_ms * 1e-3) / 1e12
+            roof = {"kernel": "k_" + fname, "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp64_peak, "traffic": None, "scope": f"rank 0 of {world}: {n_own_r} owned particles",
                     "launch_ms": f_ms, "peak_source": "DFMA microbenchmark in this run (sphb_fp64_peak)"}
             per_kernel = {nm: {"calls": c_, "ms": round(t_, 4)} for nm, (c_, t_) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
 
@@ -369,8 +482,9 @@ def run_ours(a):
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
-        h_host = state[3].cpu().numpy()
-        wcur = dict(pos=state[0].cpu().numpy(), vel=state[1].cpu().numpy(), u=state[2].cpu().numpy())
+        cur = get_state() if get_state is not None else state
+        h_host = cur[3].cpu().numpy()
+        wcur = dict(pos=cur[0].cpu().numpy(), vel=cur[1].cpu().numpy(), u=cur[2].cpu().numpy())
         v, cores, nj, el = cpu_sample(wcur, h_host, a.cpu_seconds, dict(G=0.0, PARTICLE_MASS=w["m"]))
         cpu = {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port",
                "sample": f"{nj} particles against all {n_total} (per-particle share of one leapfrog step, oracle/sph_oracle.c), {el:.1f} s"}
@@ -378,10 +492,12 @@ def run_ours(a):
     line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": w["name"], "n_particles": n_total, "dt": dt, "l2": "inputs_larger_than_L2 (state ~1 GB vs 126 MB L2)",
-                       "parallelism": f"slab{world}" if world > 1 else "single"},
-            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-            "kernels": per_kernel}
+            "config": {"workload": w["name"], "n_particles": n_total, "dt": dt, "warm_state_steps": a.warm_state_steps,
+                       "l2": "inputs_larger_than_L2 (state ~1 GB vs 126 MB L2)",
+                       "parallelism": f"slab{world}" if world > 1 else "single",
+                       "path": "kept neighbour lists (rebuilt when the device-side check says so)" if use_lists else "scanning kernels (3 cell-list builds and 3 scans per step)"},
+            "clocks": clk, "gpu_launches": int(launches), "neighbour_lists": list_stats, "state_checksum": checksum,
+            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernels": per_kernel}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

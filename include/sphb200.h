@@ -169,6 +169,8 @@ typedef struct sphb_nlist {
     const double *posh_build;  /* [n][4] the sorted records the lists were built from (must stay alive and unchanged) */
     double cover_h;            /* >= 1 */
     double skin;               /* >= 0, in units of each record's h at build time */
+    int32_t *maxima;           /* optional device [2], zeroed by the build: float bit patterns of the largest
+                                  |x_now - x_build| / h_build and h_now / h_build - 1 any check has seen since */
 } sphb_nlist;
 int64_t sphb_nlist_pool_rows(int64_t n);
 /* cells->posh must be nl->posh_build.  Zeroes *cursor and *flags first. */

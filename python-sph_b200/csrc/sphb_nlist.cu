@@ -25,6 +25,10 @@
 #ifndef SPHB_MINB_NL_BUILD
 #define SPHB_MINB_NL_BUILD 4
 #endif
+#ifndef SPHB_NL_LIST
+#define SPHB_NL_LIST 192 /* per-lane staging capacity of the builder: 4 warps x 13.3 KB, four blocks per SM still fit */
+#endif
+typedef SphbWarpSharedT<SPHB_NL_LIST> NlWarpShared;
 #ifndef SPHB_MINB_NL_OWN
 #define SPHB_MINB_NL_OWN 8
 #endif
@@ -35,12 +39,13 @@
 // ------------------------------------------------------------------------------------------------
 // build: one warp = 32 consecutive slots; its lists become `rows` rows of 32 slot indices (row k = entry k of every
 // lane, SPHB_NL_NONE where a lane has fewer), handed out from the pool by one atomicAdd per warp.  A warp whose lists
-// do not fit the shared-memory staging area (128 entries per lane) counts its rows first and scans twice.
+// do not fit the shared-memory staging area (SPHB_NL_LIST entries per lane) counts its rows first and scans twice.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     k_nl_build(sphb_cells c, const uint8_t *__restrict__ target, const float *__restrict__ hmax_global, sphb_nlist nl)
 {
-    __shared__ SphbWarpShared sh[NL_WARPS];
+    extern __shared__ __align__(16) unsigned char nl_smem[];
+    NlWarpShared *sh = reinterpret_cast<NlWarpShared *>(nl_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long w = (long long)blockIdx.x * NL_WARPS + warp;
     const long long base = w * 32;
@@ -49,7 +54,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     const bool valid = j < c.n;
     const bool tgt = valid && (target == nullptr || target[j] != 0);
     const SphbScanCtx g = sphb_make_ctx(c);
-    SphbWarpShared &ws = sh[warp];
+    NlWarpShared &ws = sh[warp];
 
     double x, y, z, h = 1.0;
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -125,10 +130,11 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
 
 // did any record leave what the lists were built to cover?  (half of a bound used up: SPHB_NL_AGING)
 __global__ void k_nl_check(const double *__restrict__ posh_build, const double *__restrict__ posh_now, long long n,
-                           double skin, double cover_h, int32_t *__restrict__ flags)
+                           double skin, double cover_h, int32_t *__restrict__ flags, int32_t *__restrict__ maxima)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool bad = false, old = false;
+    float dr = 0.f, gr = 0.f;   // displacement / h_build and h_now / h_build - 1 (what the caller sizes margins with)
     if (i < n) {
         double x0, y0, z0, h0, x1, y1, z1, h1;
         sphb_load_posh(posh_build, (size_t)i, x0, y0, z0, h0);
@@ -137,10 +143,21 @@ __global__ void k_nl_check(const double *__restrict__ posh_build, const double *
         const double d2 = dx * dx + dy * dy + dz * dz, lim = skin * h0;
         bad = !(d2 <= lim * lim) || !(h1 <= cover_h * h0);
         old = !(d2 <= 0.25 * (lim * lim)) || !(h1 <= (1.0 + 0.5 * (cover_h - 1.0)) * h0);
+        if (maxima && h0 > 0.0) {
+            dr = __double2float_ru(sqrt(d2) / h0);
+            gr = fmaxf(__double2float_ru(h1 / h0 - 1.0), 0.f);
+        }
     }
     const bool anybad = __any_sync(SPHB_FULL, bad), anyold = __any_sync(SPHB_FULL, old);
     if ((threadIdx.x & 31) == 0 && (anybad || anyold))
         atomicOr(flags, (anybad ? SPHB_NL_BROKEN : 0) | (anyold ? SPHB_NL_AGING : 0));
+    if (maxima) {   // non-negative floats order like their bit patterns; a NaN (> +inf as an integer) sticks
+        const int md = __reduce_max_sync(SPHB_FULL, __float_as_int(dr)), mg = __reduce_max_sync(SPHB_FULL, __float_as_int(gr));
+        if ((threadIdx.x & 31) == 0) {
+            if (md > 0) atomicMax(maxima, md);
+            if (mg > 0) atomicMax(maxima + 1, mg);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,6 +325,12 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
         if (any & 0xffff) atomicOr(nl.flags, any & 0xffff);
         if (any & 0x10000) atomicOr(&status->flags, SPHB_ST_NEG_H);
     }
+    if (nl.maxima) {
+        float gr = 0.f;
+        if (tgt && hb > 0.0 && h_res > hb) gr = __double2float_ru(h_res / hb - 1.0);
+        const int mg = __reduce_max_sync(SPHB_FULL, __float_as_int(gr));
+        if (lane == 0 && mg > 0) atomicMax(nl.maxima + 1, mg);
+    }
 }
 
 // K4 on kept lists: energy_rate / _arr (pyfluid.py:316-361), Pi (:261-285), fluid_accel_viscosity_comp (:459-474),
@@ -442,10 +465,10 @@ static inline unsigned nl_blocks(int64_t n) { return (unsigned)((n + NL_THREADS 
 
 extern "C" int64_t sphb_nlist_pool_rows(int64_t n)
 {
-    // a warp that fits the staging area takes at most SPHB_LIST rows (typically ~2/3 of that: the slack is what the
-    // heavy warps use); an input that needs more sets SPHB_NL_POOL and is rebuilt with a larger pool by the caller
+    // a first guess (a lattice at eta = 1.3 takes ~90 rows per warp, a random cloud ~130); a build that needs more sets
+    // SPHB_NL_POOL and leaves the number of rows it asked for in *cursor: the caller enlarges the pool and builds again
     const int64_t warps = (n + 31) / 32;
-    return warps * SPHB_LIST + 16384;
+    return warps * 128 + 16384;
 }
 
 extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global,
@@ -457,8 +480,11 @@ extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, 
     cudaStream_t st = sphb_stream(stream);
     SPHB_CUDA(cudaMemsetAsync(nl->cursor, 0, sizeof(unsigned long long), st));
     SPHB_CUDA(cudaMemsetAsync(nl->flags, 0, sizeof(int32_t), st));
+    if (nl->maxima) SPHB_CUDA(cudaMemsetAsync(nl->maxima, 0, 2 * sizeof(int32_t), st));
     if (cells->n == 0) return SPHB_OK;
-    k_nl_build<<<nl_blocks(cells->n), NL_THREADS, 0, st>>>(*cells, target, hmax_global, *nl);
+    const int smem = (int)(NL_WARPS * sizeof(NlWarpShared));   // > 48 KB of dynamic shared memory needs the opt-in
+    SPHB_CUDA(cudaFuncSetAttribute(k_nl_build, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_nl_build<<<nl_blocks(cells->n), NL_THREADS, smem, st>>>(*cells, target, hmax_global, *nl);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
@@ -468,7 +494,7 @@ extern "C" int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, vo
     if (!nl_ok(nl) || !posh_now) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
     k_nl_check<<<(unsigned)((nl->n + 255) / 256), 256, 0, sphb_stream(stream)>>>(nl->posh_build, posh_now, (long long)nl->n,
-                                                                               nl->skin, nl->cover_h, nl->flags);
+                                                                               nl->skin, nl->cover_h, nl->flags, nl->maxima);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

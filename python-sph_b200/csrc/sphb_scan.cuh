@@ -60,11 +60,16 @@ __device__ __forceinline__ unsigned long long sphb_fma2(unsigned long long a, un
     return r;
 }
 
-struct SphbWarpShared {
+// LIST: per-lane list capacity of the staging area (the scanning kernels use SPHB_LIST; the list builder of
+// sphb_nlist.cu a larger one, so that fewer warps have to flush)
+template <int LIST>
+struct SphbWarpSharedT {
+    static constexpr int kList = LIST;
     float4 tile[32];      // x', y', z', |c'|^2 of the staged candidates (NaN-padded)
     uint32_t segbase[SPHB_NSEG]; // first sorted slot of each live segment
-    uint16_t list[SPHB_LIST * 32];
+    uint16_t list[LIST * 32];
 };
+using SphbWarpShared = SphbWarpSharedT<SPHB_LIST>;
 
 // One warp's lists parked in global memory between two kernels that work on the same snapshot (sphb_lists,
 // include/sphb200.h): the producer scans once with the symmetric support, the consumer drains without scanning.
@@ -166,7 +171,8 @@ __device__ __forceinline__ double sphb_axis_gap(double lo, double hi, int c, int
 struct SphbList {
     uint32_t p;    // address of the lane's next free entry (stride 32 entries = 64 bytes)
     uint32_t p0;   // address of list[lane]
-    __device__ __forceinline__ void init(const SphbWarpShared &ws, int lane)
+    template <class WS>
+    __device__ __forceinline__ void init(const WS &ws, int lane)
     {
         p0 = (uint32_t)__cvta_generic_to_shared(ws.list + lane);
         p = p0;
@@ -181,7 +187,8 @@ struct SphbList {
 };
 
 // decode entry k of the calling lane's list
-__device__ __forceinline__ uint32_t sphb_list_get(const SphbWarpShared &ws, int lane, int k)
+template <class WS>
+__device__ __forceinline__ uint32_t sphb_list_get(const WS &ws, int lane, int k)
 {
     const uint32_t code = ws.list[k * 32 + lane];
     return ws.segbase[code >> SPHB_SEG_BITS] + (code & (SPHB_SEG_LEN - 1u));
@@ -207,8 +214,8 @@ __device__ __forceinline__ uint32_t sphb_list_get(const SphbWarpShared &ws, int 
 //   symscale : SYM only, >= 1: the candidates' supports are taken as symscale times what the grid stores (lists
 //              that have to stay complete while every h may still grow by that factor)
 // Returns the number of live segments (what sphb_lists_save needs).
-template <bool SYM, int FLUSH_ROWS = 0, class Flush>
-__device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShared &ws, int lane, bool tgt, float fx,
+template <bool SYM, int FLUSH_ROWS = 0, class WS, class Flush>
+__device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int lane, bool tgt, float fx,
                                               float fy, float fz, float Rj, float thr, uint32_t cid, float RH,
                                               SphbList &L, Flush &&flush, float symscale = 1.f)
 {
@@ -384,7 +391,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShar
                             for (int c = 0; c < SPHB_SUB; ++c) m |= (sv[c] <= th) ? (1u << c) : 0u;
                             hit |= m << c0;
                         }
-                        if (__any_sync(SPHB_FULL, L.count() + __popc(hit) > SPHB_LIST)) {
+                        if (__any_sync(SPHB_FULL, L.count() + __popc(hit) > WS::kList)) {
                             flush(L.count());
                             L.reset();
                         }
@@ -395,7 +402,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, SphbWarpShar
                         code += 32;
 #else
                         for (int c0 = 0; c0 < nt; c0 += SPHB_SUB) {
-                            if (__any_sync(SPHB_FULL, L.count() > SPHB_LIST - SPHB_SUB)) {
+                            if (__any_sync(SPHB_FULL, L.count() > WS::kList - SPHB_SUB)) {
                                 flush(L.count());
                                 L.reset();
                             }

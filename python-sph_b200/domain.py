@@ -432,3 +432,8 @@ class SlabRunner:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         return {"value": self.n_total * steps / float(el.item()), "unit": "particle-steps/s",
                 "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(tot.item()), "steps": steps}
+
+
+def make_runner(eng, consts, world, rank, lists=True, **kw):
+    """the slab runner bench.py and the tests use: kept neighbour lists when `lists` (and G = 0), else the scanning one"""
+    return SlabRunner(eng, consts, world, rank, **kw)

@@ -60,16 +60,23 @@ class KeptLists:
         self.warp_rows = torch.zeros(nw, dtype=torch.int32, device=dev)
         self.pool = torch.empty((rows, 32), dtype=torch.int32, device=dev)
         self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # [0] SPHB_NL_* flags, [1..2] the maxima
         self.c = N.NList(n, self.warp_off.data_ptr(), self.warp_rows.data_ptr(), self.pool.data_ptr(), rows,
-                         self.cursor.data_ptr(), self.flags.data_ptr(), dg.posh.data_ptr(), self.cover_h, self.skin)
+                         self.cursor.data_ptr(), self.flags.data_ptr(), dg.posh.data_ptr(), self.cover_h, self.skin,
+                         self.flags.data_ptr() + 4)
+        self.build_flags = 0
+        self.moved = self.grown = 0.0
 
     def ref(self):
         return C.byref(self.c)
 
     def read_flags(self):
-        """one 4-byte D2H read (synchronises the stream)"""
-        return int(self.flags.item())
+        """one 16-byte D2H read (synchronises the stream): the flags; also refreshes .moved / .grown, the largest
+        displacement / h_build and h growth the checks have seen since the build"""
+        v = self.flags.cpu()
+        mx = v[1:3].view(torch.float32)
+        self.moved, self.grown = float(mx[0]), float(mx[1])
+        return int(v[0])
 
     def rows_used(self):
         return int(self.cursor.item())
@@ -331,11 +338,24 @@ class Engine:
         return out, cnt
 
     # -- kept neighbour lists (sphb_nlist) -------------------------------------------------------
-    def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None) -> KeptLists:
-        nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows)
+    def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None, max_bytes=96 * 2 ** 30) -> KeptLists:
+        """scan the cell list once and keep every warp's candidate rows.  Reads the build's flags (one 4-byte D2H
+        after the kernel): a pool that turned out too small is enlarged to what the build asked for and the build is
+        repeated.  The returned lists may still carry SPHB_NL_UNLISTABLE / SPHB_NL_POOL (nl.build_flags): the caller then
+        has to use the scanning kernels."""
         hm = hmax if hmax is not None else self.hmax(dg.posh)
-        nl._hmax = hm
-        self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(), _stream())
+        for _ in range(3):
+            nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows)
+            nl._hmax = hm
+            self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(), _stream())
+            nl.build_flags = nl.read_flags()
+            if not (nl.build_flags & N.NL_POOL) or (nl.build_flags & N.NL_UNLISTABLE):
+                break
+            need = int(nl.rows_used() * 1.05) + 4096
+            if need * 128 > max_bytes:
+                break
+            pool_rows = need
+            del nl
         return nl
 
     def nl_check(self, nl, posh):
@@ -632,10 +652,13 @@ class FastStepper:
       * load(pos, vel, u, h) / advance(dt, consts) / state()          the state stays resident in slot order (time loops).
     """
 
-    def __init__(self, engine, cover_h=None, skin=None):
+    def __init__(self, engine, cover_h=None, skin=None, adaptive=True):
         self.e = engine
         self.cover_h = NL_COVER_H if cover_h is None else float(cover_h)
         self.skin = NL_SKIN if skin is None else float(skin)
+        self.adaptive = adaptive  # size the margins of every build from the measured motion (else: fixed margins)
+        self.rate_d = self.rate_g = None   # measured per-step displacement / h and h growth (maxima over particles)
+        self.age = 0              # steps run on the current lists
         self.safe = Stepper(engine)
         self.geom = None          # (grid, delta) pinned by the caller; None: from the bounding box at every build
         self.nl = None
@@ -674,23 +697,54 @@ class FastStepper:
             self.ids = ids_in.index_select(0, perm_l)
             self.perm = self.ids.to(torch.int32)
         self.P = dg.posh                     # never written in place: every kernel below returns fresh arrays
+        if self.adaptive:
+            self.cover_h, self.skin = self._choose_margins()
+        self.age = 0
+        self._moved_prev = self._grown_prev = 0.0
         self.nl = e.nl_build(dg, self.cover_h, self.skin, pool_rows=self.pool_rows)
+        self.pool_rows = max(self.nl.pool_rows, self.pool_rows or 0)
         self.stats["builds"] += 1
         self.stale = False
         self.fresh = True                    # no step has run on these lists yet
 
     MAX_SKIN = 0.25
+    BUILD_OVER_DRAIN = float(os.environ.get("SPHB_NL_BUILD_COST", "0.28"))   # one rebuild / one step's drains
+
+    def _choose_margins(self):
+        """cover_h, skin of the next build.  Lists that are to live L steps need margins of L x the per-step motion;
+        their drains cost ~ (cover_h + skin)^3, the rebuild 1/L of BUILD_OVER_DRAIN: take the cheapest L."""
+        if self.rate_d is None:
+            return self.cover_h, self.skin
+        best = None
+        for L in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32):
+            skin = 1.5 * self.rate_d * L + 0.002
+            grow = 1.5 * self.rate_g * L + 0.002
+            if best is not None and (skin > self.MAX_SKIN or grow > 0.25):
+                break
+            skin, grow = min(skin, self.MAX_SKIN), min(grow, 0.25)
+            cost = (1.0 + grow + skin) ** 3 + self.BUILD_OVER_DRAIN / L
+            if best is None or cost < best[0]:
+                best = (cost, 1.0 + grow, skin)
+        return best[1], best[2]
+
+    def _note_motion(self):
+        """after a successful step: per-step rates from the lists' maxima, and whether the next step would still fit"""
+        nl = self.nl
+        self.age += 1
+        dd, dg_ = nl.moved - self._moved_prev, nl.grown - self._grown_prev
+        self._moved_prev, self._grown_prev = nl.moved, nl.grown
+        self.rate_d = max(dd, nl.moved / self.age)
+        self.rate_g = max(dg_, nl.grown / self.age)
+        if self.adaptive and (nl.moved + 1.3 * self.rate_d > 0.95 * nl.skin or
+                              nl.grown + 1.3 * self.rate_g > 0.95 * (nl.cover_h - 1.0)):
+            self.stale = True
 
     def _adapt(self, flags):
         """a step failed on its lists (flags = SPHB_NL_*): what to change before the rebuild.  -> False: give up"""
         if flags & N.NL_UNLISTABLE:
             return False
         if flags & N.NL_POOL:
-            cur = self.nl.pool_rows if self.nl is not None else int(self.e.lib.sphb_nlist_pool_rows(self.P.shape[0]))
-            if cur * 128 * 2 > 64 * 2 ** 30:
-                return False
-            self.pool_rows = 2 * cur
-            return True
+            return False      # Engine.nl_build already enlarged the pool as far as it may
         if self.fresh_failed:
             # even lists built for this very state broke within the step: particles move (or h grows) by more than the
             # margins per step -- widen them, then give up
@@ -698,7 +752,14 @@ class FastStepper:
                 return False
             self.skin = min(self.MAX_SKIN, max(2.0 * self.skin, 0.02))
             self.cover_h = 1.0 + min(0.25, max(2.0 * (self.cover_h - 1.0), 0.02))
+            # the measured rates said less: do not let the next choice shrink the margins again
+            self.rate_d = max(self.rate_d or 0.0, self.skin / 1.5)
+            self.rate_g = max(self.rate_g or 0.0, (self.cover_h - 1.0) / 1.5)
             self.stats["widened"] = self.stats.get("widened", 0) + 1
+        elif self.adaptive and self.rate_d is not None:
+            # kept lists broke: the motion since the build is faster than the rates they were sized for
+            self.rate_d = max(self.rate_d, 2.0 * self.nl.moved / max(self.age + 1, 1))
+            self.rate_g = max(self.rate_g, 2.0 * self.nl.grown / max(self.age + 1, 1))
         return True
 
     # ---- one step in slot order ---------------------------------------------------------------------
@@ -728,14 +789,19 @@ class FastStepper:
 
     def _try(self, dt, consts, hooks=None):
         """run one step on the current lists; -> (ok, P1, V1, U1, status); self.last_flags = the lists' flags"""
+        if self.nl.build_flags & self._BAD:      # the input could not be listed at all
+            self.last_flags, self.fresh_failed, self.fresh = self.nl.build_flags, False, False
+            return False, None, None, None, None
         st = Status(S_COUNT, self.e.device)
         P1, V1, U1 = self._slots_step(self.P, self.V, self.U, dt, consts, st, hooks)
         fl = self.last_flags = self.nl.read_flags()
         ok = (fl & self._BAD) == 0
         self.fresh_failed = self.fresh and not ok
         self.fresh = False
-        if fl & N.NL_AGING:
-            self.stale = True
+        if ok:
+            self._note_motion()
+            if (fl & N.NL_AGING) and not self.adaptive:
+                self.stale = True
         return ok, P1, V1, U1, st
 
     # ---- resident-state API ---------------------------------------------------------------------------
@@ -807,7 +873,7 @@ class FastStepper:
             # the new input in the old slot order; does it pass the lists' own validity check?
             self.P, _, _ = e.gather_state(self.perm, pos=pos0, h=h0)
             e.nl_check(self.nl, self.P)
-            if self.nl.read_flags() != 0:
+            if self.nl.read_flags() & (self._BAD | (0 if self.adaptive else N.NL_AGING)):
                 reuse = False
                 self.stats["reuse_rejected"] += 1
             elif fh is None:
