@@ -186,9 +186,14 @@ int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts *k, const u
 int sphb_nlist_newton_h(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
                         const double *h_guess, double *h_out, double *omega_out, double *posh_out, int32_t *iters, sphb_status *status,
                         void *stream);
-/* sphb_force on kept lists (G must be 0); posh carries the current h, recB / recC come from sphb_eos */
+/* sphb_force on kept lists (G must be 0); posh carries the current h.  Records: recB + recC from sphb_eos (recD NULL),
+ * or recB + recD from sphb_nlist_eos (recC NULL): recD is a dense [n][2] array of {rho, cs} -- what the viscosity
+ * branch gathers per neighbour -- so that a gathered entry shares its cache line with seven others; same bits. */
+int sphb_nlist_eos(const double *posh, const double *vel, const double *u, const double *omega, int64_t n,
+                   const sphb_consts *k, double *recB, double *recD, sphb_status *status, void *stream);
 int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
-                     const double *recB, const double *recC, double *acc, double *dudt, sphb_status *status, void *stream);
+                     const double *recB, const double *recC, const double *recD, double *acc, double *dudt,
+                     sphb_status *status, void *stream);
 /* caller order <-> slot order for the whole state in one pass (any pointer group may be NULL) */
 int sphb_gather_state(const double *pos, const double *h, const double *vel, const double *u, const uint32_t *perm,
                       int64_t n, double *posh_s, double *vel_s, double *u_s, void *stream);

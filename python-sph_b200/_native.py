@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsphb200.so")
+# SPHB_LIB: a variant library built by `build_native.py --out ... -D...` (tuning sweeps); never set in tests or bench
+LIB_PATH = os.environ.get("SPHB_LIB") or os.path.join(_HERE, "libsphb200.so")
 
 # status bits (include/sphb200.h SPHB_ST_*)
 ST_NEG_H, ST_NEG_P, ST_NEG_PI, ST_NEG_VISC, ST_NEG_E, ST_BISECT_NONE = 1, 2, 4, 8, 16, 32
@@ -89,7 +90,8 @@ SIGNATURES = {
     "sphb_nlist_check": (C.c_int, [C.POINTER(NList), P, P]),
     "sphb_nlist_density_omega": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
     "sphb_nlist_newton_h": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
-    "sphb_nlist_force": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
+    "sphb_nlist_eos": (C.c_int, [P, P, P, P, I64, C.POINTER(Consts), P, P, P, P]),
+    "sphb_nlist_force": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
     "sphb_gather_state": (C.c_int, [P, P, P, P, P, I64, P, P, P, P]),
     "sphb_scatter_state": (C.c_int, [P, P, P, P, I64, P, P, P, P, P]),
     "sphb_density_omega": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),

@@ -22,19 +22,25 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None, extra=()):
+    """out / extra: tuning sweeps build VARIANTS (e.g. extra=["-DSPHB_MINB_NL_FORCE=6"]) into their own file, selected at
+    run time with SPHB_LIB=<path>; the default library is only ever built with the default flags."""
+    if out is None and not force and not stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    extra = os.environ.get("SPHB_NVCC_EXTRA", "").split()   # tuning sweeps only (e.g. -DSPHB_LIST=96)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, f) for f in SOURCES]
+    out = out or OUT
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         print(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python build_native.py [--force] [-v] [--out variant.so -DNAME=VALUE ...]
+    args = sys.argv[1:]
+    out = args[args.index("--out") + 1] if "--out" in args else None
+    extra = [x for x in args if x.startswith("-D") or x.startswith("-maxrregcount")]
+    print(build(force="--force" in args, verbose="-v" in args, out=out, extra=extra))

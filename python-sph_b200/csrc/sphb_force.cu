@@ -23,7 +23,8 @@ __global__ void k_eos(const double *__restrict__ posh, const double *__restrict_
                       const double *__restrict__ omega, const double *__restrict__ rho_in,
                       const double *__restrict__ P_in, const double *__restrict__ xi, long long n, sphb_consts k,
                       double *__restrict__ rho_out, double *__restrict__ P_out, double *__restrict__ recB,
-                      double *__restrict__ recC, double *__restrict__ bgrav, sphb_status *__restrict__ status)
+                      double *__restrict__ recC, double *__restrict__ bgrav, sphb_status *__restrict__ status,
+                      double *__restrict__ recD)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -35,13 +36,15 @@ __global__ void k_eos(const double *__restrict__ posh, const double *__restrict_
     if (rho_out) rho_out[i] = rho;
     if (P_out) P_out[i] = P;
     if (bgrav) bgrav[i] = xi ? (k.G / 2.0) * (xi[i] / omega[i]) : 0.0;   // (G/2) xi/Omega, pyfluid.py:436
-    if (!recB || !recC) return;
+    if (!recB || (!recC && !recD)) return;
     const double om = omega[i];
     const double A = P / (om * (rho * rho));
     const double cs = sqrt(k.gamma * P / rho);
     double2 *b = reinterpret_cast<double2 *>(recB) + 2 * i;
     b[0] = make_double2(vel[3 * i], vel[3 * i + 1]);
     b[1] = make_double2(vel[3 * i + 2], A);
+    if (recD) reinterpret_cast<double2 *>(recD)[i] = make_double2(rho, cs);
+    if (!recC) return;
     const double h2 = h * h;
     double2 *c = reinterpret_cast<double2 *>(recC) + 2 * i;
     c[0] = make_double2(rho, cs);
@@ -681,7 +684,21 @@ extern "C" int sphb_eos(const double *posh, const double *vel, const double *u, 
     if (n == 0) return SPHB_OK;
     if (bgrav && !omega) return SPHB_E_ARG;
     k_eos<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh, vel, u, omega, rho_in, P_in, xi, n, *k, rho,
-                                                                        P, recB, recC, bgrav, status);
+                                                                        P, recB, recC, bgrav, status, nullptr);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+// the force records of the list-draining kernel (sphb_nlist_force): recB = {vx, vy, vz, A} as above, recD = dense
+// {rho, cs} (the kernel takes 1/h and 1/(pi h^4) of its own target from h, with the same two divisions)
+extern "C" int sphb_nlist_eos(const double *posh, const double *vel, const double *u, const double *omega, int64_t n,
+                              const sphb_consts *k, double *recB, double *recD, sphb_status *status, void *stream)
+{
+    if (n < 0 || !k || !status) return SPHB_E_ARG;
+    if (n > 0 && (!posh || !vel || !u || !omega || !recB || !recD)) return SPHB_E_ARG;
+    if (n == 0) return SPHB_OK;
+    k_eos<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh, vel, u, omega, nullptr, nullptr, nullptr, n, *k,
+                                                                        nullptr, nullptr, recB, nullptr, nullptr, status, recD);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

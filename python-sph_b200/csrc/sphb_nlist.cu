@@ -334,7 +334,9 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
 }
 
 // K4 on kept lists: energy_rate / _arr (pyfluid.py:316-361), Pi (:261-285), fluid_accel_viscosity_comp (:459-474),
-// acceleration / _arr (:477-493) with G = 0.  posh carries the CURRENT h; recB / recC are sphb_eos's records.
+// acceleration / _arr (:477-493) with G = 0.  posh carries the CURRENT h; recB / recC are sphb_eos's records, or
+// (DENSE) recB and sphb_nlist_eos's dense {rho, cs}.
+template <bool DENSE>
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
     k_nl_force(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
                const double *__restrict__ recB, const double *__restrict__ recC, double *__restrict__ acc,
@@ -355,7 +357,16 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
     if (valid) {
         sphb_load4(posh, (size_t)j, a.xj, a.yj, a.zj, a.hj);
         sphb_load4(recB, (size_t)j, a.vxj, a.vyj, a.vzj, a.Aj);
-        sphb_load4(recC, (size_t)j, a.rhoj, a.csj, a.hinvj, a.gj);
+        if (DENSE) {
+            const double2 d = reinterpret_cast<const double2 *>(recC)[j];
+            a.rhoj = d.x;
+            a.csj = d.y;
+            const double h2 = a.hj * a.hj;
+            a.hinvj = 1.0 / a.hj;                       // the same two divisions as k_eos: same bits
+            a.gj = 1.0 / (SPHB_PI * (h2 * h2));
+        } else {
+            sphb_load4(recC, (size_t)j, a.rhoj, a.csj, a.hinvj, a.gj);
+        }
     }
     a.ax = a.ay = a.az = a.dens = a.visc = 0.0;
     a.negpi = 0;
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
             nl_fetch(posh, i2, self, C);
             nl_fetch(posh, i3, self, D);
             uint32_t n0 = nl_row(p, kk + 4, nrows), n1 = nl_row(p, kk + 5, nrows);
-            sphb_force_pair2<false>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a, i0 != SPHB_NL_NONE);
+            sphb_force_pair2<false, DENSE>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a, i0 != SPHB_NL_NONE);
             kk += 2;
             if (kk >= nrows) break;
             i0 = n0;
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
             nl_fetch(posh, i1, self, B);
             n0 = nl_row(p, kk + 4, nrows);
             n1 = nl_row(p, kk + 5, nrows);
-            sphb_force_pair2<false>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a, i2 != SPHB_NL_NONE);
+            sphb_force_pair2<false, DENSE>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a, i2 != SPHB_NL_NONE);
             i2 = n0;
             i3 = n1;
             kk += 2;
@@ -528,14 +539,18 @@ extern "C" int sphb_nlist_newton_h(const sphb_nlist *nl, const sphb_consts *k, c
 }
 
 extern "C" int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
-                                const double *recB, const double *recC, double *acc, double *dudt, sphb_status *status,
-                                void *stream)
+                                const double *recB, const double *recC, const double *recD, double *acc, double *dudt,
+                                sphb_status *status, void *stream)
 {
-    if (!nl_ok(nl) || !k || !posh || !recB || !recC || !acc || !dudt || !status) return SPHB_E_ARG;
+    if (!nl_ok(nl) || !k || !posh || !recB || (!recC == !recD) || !acc || !dudt || !status) return SPHB_E_ARG;
     if (k->G != 0.0) return SPHB_E_ARG;   // the softened-gravity terms ride in the scanning kernels only
     if (nl->n == 0) return SPHB_OK;
-    k_nl_force<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recC, acc, dudt,
-                                                                         status);
+    if (recD)
+        k_nl_force<true><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recD, acc,
+                                                                                   dudt, status);
+    else
+        k_nl_force<false><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recC, acc,
+                                                                                    dudt, status);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -263,7 +263,9 @@ __device__ __forceinline__ void sphb_force_accumulate(const double *bgrav, uint3
     a.visc = fma(pi_half * sm, t.vdr, a.visc);
 }
 
-template <bool GRAV>
+// DENSE: recC is a dense [n][2] array of (rho, cs) instead of the 32-byte record (a gathered 16-byte entry shares its
+// cache line with seven neighbours instead of three)
+template <bool GRAV, bool DENSE = false>
 __device__ __forceinline__ void sphb_force_pair2(const double *recB, const double *recC, const double *bgrav, uint32_t i0,
                                                  uint32_t i1, const double (&p0)[4], const double (&p1)[4], bool second,
                                                  const sphb_consts &k, SphbForceAcc &a, bool first = true)
@@ -275,8 +277,21 @@ __device__ __forceinline__ void sphb_force_pair2(const double *recB, const doubl
     double ph0 = 0.0, ph1 = 0.0;
     if (v0 || v1) {
         double rho0 = 1.0, cs0 = 0.0, rho1 = 1.0, cs1 = 0.0, u0, u1;
-        if (v0) sphb_load4(recC, i0, rho0, cs0, u0, u1);
-        if (v1) sphb_load4(recC, i1, rho1, cs1, u0, u1);
+        if (DENSE) {
+            if (v0) {
+                const double2 d = __ldg(reinterpret_cast<const double2 *>(recC) + i0);
+                rho0 = d.x;
+                cs0 = d.y;
+            }
+            if (v1) {
+                const double2 d = __ldg(reinterpret_cast<const double2 *>(recC) + i1);
+                rho1 = d.x;
+                cs1 = d.y;
+            }
+        } else {
+            if (v0) sphb_load4(recC, i0, rho0, cs0, u0, u1);
+            if (v1) sphb_load4(recC, i1, rho1, cs1, u0, u1);
+        }
         const double pi0 = sphb_force_pi(k, a, t0, rho0, cs0);
         const double pi1 = sphb_force_pi(k, a, t1, rho1, cs1);
         if ((v0 && pi0 < 0.0) || (v1 && pi1 < 0.0)) a.negpi = 1;

@@ -384,14 +384,23 @@ class Engine:
                   _ptr(h_guess), _ptr(h), _ptr(om), _ptr(po), _ptr(it), status_ptr, _stream())
         return h, om, po, it
 
-    def nl_force(self, nl, consts, posh, recB, recC, status_ptr, target=None):
+    def nl_eos(self, posh, vel, u, omega, consts, status_ptr):
+        """-> recB (n,4) = vx, vy, vz, A and recD (n,2) = rho, cs for nl_force(..., recD=)"""
+        n = posh.shape[0]
+        recB = torch.empty((n, 4), dtype=F64, device=self.device)
+        recD = torch.empty((n, 2), dtype=F64, device=self.device)
+        self._run("eos", self.lib.sphb_nlist_eos, _ptr(posh), _ptr(vel), _ptr(u), _ptr(omega), n, C.byref(consts), _ptr(recB),
+                  _ptr(recD), status_ptr, _stream())
+        return recB, recD
+
+    def nl_force(self, nl, consts, posh, recB, recC, status_ptr, target=None, recD=None):
         n = nl.n
         acc = torch.zeros((n, 3), dtype=F64, device=self.device) if target is not None else \
             torch.empty((n, 3), dtype=F64, device=self.device)
         dudt = torch.zeros(n, dtype=F64, device=self.device) if target is not None else \
             torch.empty(n, dtype=F64, device=self.device)
         self._run("nl_force", self.lib.sphb_nlist_force, nl.ref(), C.byref(consts), _ptr(target), _ptr(posh), _ptr(recB),
-                  _ptr(recC), _ptr(acc), _ptr(dudt), status_ptr, _stream())
+                  _ptr(recC), _ptr(recD), _ptr(acc), _ptr(dudt), status_ptr, _stream())
         return acc, dudt
 
     def gather_state(self, perm, pos=None, h=None, vel=None, u=None):
@@ -769,13 +778,13 @@ class FastStepper:
         _, _, om0, _ = e.nl_density_omega(nl, consts, P0)                               # :503
         if hooks is not None:
             V0, U0 = hooks.vel_u()
-        _, _, rB, rC = e.eos(P0, V0, U0, om0, consts, st.ptr(S_STAGE0))                 # :502,:505
-        acc0, dudt0 = e.nl_force(nl, consts, P0, rB, rC, st.ptr(S_STAGE0))              # :506-507
+        rB, rD = e.nl_eos(P0, V0, U0, om0, consts, st.ptr(S_STAGE0))                    # :502,:505
+        acc0, dudt0 = e.nl_force(nl, consts, P0, rB, None, st.ptr(S_STAGE0), recD=rD)   # :506-507
         Pm, Vm, Um = e.predict(P0, V0, U0, acc0, dudt0, dt, st.ptr(S_PRED))             # :511-515
         e.nl_check(nl, Pm)
         hm, omm, Pm2, _ = e.nl_newton(nl, consts, Pm, st.ptr(S_NEWTON_MID), want_omega=True)   # :516-518
-        _, _, rB, rC = e.eos(Pm2, Vm, Um, omm, consts, st.ptr(S_STAGE_MID))             # :517,:520
-        acc1, dudt1 = e.nl_force(nl, consts, Pm2, rB, rC, st.ptr(S_STAGE_MID))          # :521-522
+        rB, rD = e.nl_eos(Pm2, Vm, Um, omm, consts, st.ptr(S_STAGE_MID))                # :517,:520
+        acc1, dudt1 = e.nl_force(nl, consts, Pm2, rB, None, st.ptr(S_STAGE_MID), recD=rD)   # :521-522
         P1, V1, U1 = e.correct(P0, V0, U0, acc1, dudt1, dt, st.ptr(S_CORR))             # :524-528
         if hooks is not None:
             hooks.after_corrector(P1, V1, U1)
@@ -808,7 +817,9 @@ class FastStepper:
     SAFE_HOLD = 8
 
     def load(self, pos, vel, u, h):
+        """take a caller-order state (device tensors); it stays resident, in slot order, until state() is asked for"""
         self.caller_state = None
+        self.hold = 0
         self._rebuild_from(self.e.pack_posh(pos, h), vel, u, None)
 
     def state(self):

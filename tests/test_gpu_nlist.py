@@ -115,6 +115,9 @@ def test_drains_equal_scanning_kernels_bit_for_bit(sph, case, cover_h, skin):
         acc_a, du_a = eng.force(dg, c, rB, rC, eng.hmax(dg.posh), st.ptr(0))
         acc_b, du_b = eng.nl_force(nl, c, dg.posh, rB, rC, st.ptr(1))
         assert torch.equal(acc_a, acc_b) and torch.equal(du_a, du_b)
+        rB2, rD = eng.nl_eos(dg.posh, vel_s, u_s, om_a, c, st.ptr(1))          # dense {rho, cs} records
+        acc_c, du_c = eng.nl_force(nl, c, dg.posh, rB2, None, st.ptr(1), recD=rD)
+        assert torch.equal(rB, rB2) and torch.equal(acc_a, acc_c) and torch.equal(du_a, du_c)
         # K3 from a slightly wrong guess that stays inside the cover (Omega fused)
         if cover_h > 1.0:
             g = dg.posh[:, 3].contiguous() * 0.995
