@@ -171,27 +171,11 @@ typedef struct sphb_nlist {
     double skin;               /* >= 0, in units of each record's h at build time */
     int32_t *maxima;           /* optional device [2], zeroed by the build: float bit patterns of the largest
                                   |x_now - x_build| / h_build and h_now / h_build - 1 any check has seen since */
-    /* staging (sphb_nlist_compact; all NULL / 0: not staged).  A block of the drain kernels = 8 warps = 256 consecutive
-     * slots; the distinct neighbour slots of such a block (its "stage list", ~3000 on a lattice at eta = 1.3) are what
-     * the block copies into shared memory once per launch, and its rows are rewritten as 16-bit indices into that copy
-     * (first 64 bytes of each 128-byte row).  Blocks whose stage list exceeds stage_cap keep 32-bit slot rows. */
-    uint32_t *blk_off;         /* [ceil(n/256)] first entry of the block's stage list in stage_pool */
-    uint32_t *blk_nstage;      /* [ceil(n/256)] its length; 0: the block is not staged */
-    uint32_t *stage_pool;      /* [stage_pool_len] sorted-slot indices */
-    int64_t stage_pool_len;
-    int32_t stage_cap;         /* per-block limit, <= SPHB_NL_STAGE_MAX */
-    int32_t pad_;
-    uint32_t *stage_stats;     /* device [4]: entries handed out, staged blocks, largest stage list, blocks left unstaged */
 } sphb_nlist;
-#define SPHB_NL_STAGE_MAX 4000
-#define SPHB_NL_BLOCK 256      /* slots per block of the list-draining kernels */
 int64_t sphb_nlist_pool_rows(int64_t n);
-int64_t sphb_sizeof_nlist(void); /* sizeof(sphb_nlist), for bindings to check their own layout against */
 /* cells->posh must be nl->posh_build.  Zeroes *cursor and *flags first. */
 int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global, const sphb_nlist *nl,
                      void *stream);
-/* after sphb_nlist_build: per block of 256 slots, the distinct neighbour slots -> stage_pool, rows -> 16-bit indices */
-int sphb_nlist_compact(const sphb_nlist *nl, void *stream);
 int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, void *stream);
 /* sphb_density_omega on kept lists (h_j = posh[j][3]) */
 int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,

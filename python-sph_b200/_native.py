@@ -60,12 +60,9 @@ class NList(C.Structure):
     """sphb_nlist: neighbour lists kept across kernels and steps"""
     _fields_ = [("n", C.c_int64), ("warp_off", C.c_void_p), ("warp_rows", C.c_void_p), ("pool", C.c_void_p),
                 ("pool_rows", C.c_int64), ("cursor", C.c_void_p), ("flags", C.c_void_p), ("posh_build", C.c_void_p),
-                ("cover_h", C.c_double), ("skin", C.c_double), ("maxima", C.c_void_p),
-                ("blk_off", C.c_void_p), ("blk_nstage", C.c_void_p), ("stage_pool", C.c_void_p),
-                ("stage_pool_len", C.c_int64), ("stage_cap", C.c_int32), ("pad_", C.c_int32), ("stage_stats", C.c_void_p)]
+                ("cover_h", C.c_double), ("skin", C.c_double), ("maxima", C.c_void_p)]
 
 
-NL_BLOCK = 256   # SPHB_NL_BLOCK
 NL_NONE = 0xFFFFFFFF
 NL_POOL, NL_BROKEN, NL_AGING, NL_UNLISTABLE = 1, 2, 4, 8
 
@@ -89,9 +86,7 @@ SIGNATURES = {
     "sphb_gather_u32": (C.c_int, [P, P, I64, P, P]),
     "sphb_lists_bytes": (C.c_size_t, [I64]),
     "sphb_nlist_pool_rows": (I64, [I64]),
-    "sphb_sizeof_nlist": (I64, []),
     "sphb_nlist_build": (C.c_int, [C.POINTER(Cells), P, P, C.POINTER(NList), P]),
-    "sphb_nlist_compact": (C.c_int, [C.POINTER(NList), P]),
     "sphb_nlist_check": (C.c_int, [C.POINTER(NList), P, P]),
     "sphb_nlist_density_omega": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
     "sphb_nlist_newton_h": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),

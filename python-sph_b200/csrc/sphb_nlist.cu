@@ -30,10 +30,10 @@
 #endif
 typedef SphbWarpSharedT<SPHB_NL_LIST> NlWarpShared;
 #ifndef SPHB_MINB_NL_OWN
-#define SPHB_MINB_NL_OWN 4 /* blocks of 256 threads per SM the density / Newton drains are compiled for (64 registers) */
+#define SPHB_MINB_NL_OWN 8
 #endif
 #ifndef SPHB_MINB_NL_FORCE
-#define SPHB_MINB_NL_FORCE 2 /* ... the force drain (128 registers) */
+#define SPHB_MINB_NL_FORCE 4
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -161,128 +161,6 @@ __global__ void k_nl_check(const double *__restrict__ posh_build, const double *
 }
 
 // ------------------------------------------------------------------------------------------------
-// compaction: the distinct neighbour slots of a block of 8 warps, and its rows as 16-bit indices into that set
-// ------------------------------------------------------------------------------------------------
-#define NLB_WARPS 8
-#define NLB_THREADS (NLB_WARPS * 32)
-#define NL_HASH 8192          /* hash table of the compaction kernel: 256 columns of 32 */
-#define NL_EMPTY 0xffffffffu
-#if SPHB_NL_BLOCK != NLB_THREADS
-#error "SPHB_NL_BLOCK (include/sphb200.h) must equal the block size of the drain kernels"
-#endif
-
-// Slots s with the same s >> 5 live in one 32-entry column of the table, at lane s & 31 (other columns on a
-// collision): the stage list then keeps neighbouring slots next to each other, and the lanes of a warp -- whose k-th
-// neighbours are mostly neighbouring slots -- read neighbouring shared-memory banks.
-__device__ __forceinline__ uint32_t nl_hash_col(uint32_t s) { return ((s >> 5) * 2654435761u) >> 24; }
-
-__device__ __forceinline__ uint32_t nl_hash_find(const uint32_t *keys, uint32_t s)
-{
-    uint32_t pos = (nl_hash_col(s) << 5) | (s & 31u);
-    while (keys[pos] != s) pos = (pos + 32u) & (NL_HASH - 1u);
-    return pos;
-}
-
-__global__ void __launch_bounds__(NLB_THREADS) k_nl_compact(sphb_nlist nl)
-{
-    extern __shared__ __align__(16) unsigned char nl_csm[];   // keys[NL_HASH] u32 | cidx[NL_HASH] u16
-    uint32_t *keys = reinterpret_cast<uint32_t *>(nl_csm);
-    uint16_t *cidx = reinterpret_cast<uint16_t *>(nl_csm + NL_HASH * sizeof(uint32_t));
-    __shared__ uint32_t s_count, s_base, s_ok;
-    __shared__ uint32_t wsum[NLB_WARPS];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long b = blockIdx.x;
-    const long long w = b * NLB_WARPS + warp;
-    const long long nw = (nl.n + 31) / 32;
-    for (int i = tid; i < NL_HASH; i += NLB_THREADS) keys[i] = NL_EMPTY;
-    if (tid == 0) {
-        s_count = 0;
-        s_ok = 1;
-    }
-    __syncthreads();
-    const bool have = w < nw;
-    const uint32_t nrows = have ? nl.warp_rows[w] : 0u;
-    uint32_t *rowbase = have ? nl.pool + (size_t)nl.warp_off[w] * 32 : nullptr;
-    const uint32_t cap = (uint32_t)nl.stage_cap;
-    // pass 1: the set of distinct slots
-    for (uint32_t r = 0; r < nrows; ++r) {
-        const uint32_t s = rowbase[(size_t)r * 32 + lane];
-        if (s != SPHB_NL_NONE) {
-            uint32_t pos = (nl_hash_col(s) << 5) | (s & 31u);
-            while (true) {
-                const uint32_t old = atomicCAS(&keys[pos], NL_EMPTY, s);
-                if (old == NL_EMPTY) {
-                    atomicAdd(&s_count, 1u);
-                    break;
-                }
-                if (old == s) break;
-                pos = (pos + 32u) & (NL_HASH - 1u);
-            }
-        }
-        // too many for one stage (and the table must never fill up): the block keeps its 32-bit rows
-        if (*(volatile uint32_t *)&s_count > cap) break;
-    }
-    __syncthreads();
-    const uint32_t nst = s_count;
-    if (nst > cap || nst == 0) {
-        if (tid == 0) {
-            nl.blk_nstage[b] = 0;
-            nl.blk_off[b] = 0;
-            if (nst) atomicAdd(nl.stage_stats + 3, 1u);
-        }
-        return;
-    }
-    // pass 2: compact indices in table order (column by column, lanes ascending)
-    uint32_t mine = 0;
-    for (int c = warp * 32; c < warp * 32 + 32; ++c) mine += __popc(__ballot_sync(SPHB_FULL, keys[c * 32 + lane] != NL_EMPTY));
-    if (lane == 0) wsum[warp] = mine;
-    __syncthreads();
-    uint32_t run = 0;
-    for (int q = 0; q < warp; ++q) run += wsum[q];
-    if (tid == 0) {
-        const unsigned long long at = atomicAdd(nl.cursor + 1, (unsigned long long)nst);
-        uint32_t ok = (at + nst <= (unsigned long long)nl.stage_pool_len) ? 1u : 0u;
-        s_base = (uint32_t)at;
-        s_ok = ok;
-    }
-    __syncthreads();
-    if (!s_ok) {   // stage pool exhausted: not staged (the caller sized it from the build's own row count: rare)
-        if (tid == 0) {
-            nl.blk_nstage[b] = 0;
-            nl.blk_off[b] = 0;
-            atomicAdd(nl.stage_stats + 3, 1u);
-        }
-        return;
-    }
-    uint32_t *stage = nl.stage_pool + s_base;
-    for (int c = warp * 32; c < warp * 32 + 32; ++c) {
-        const uint32_t key = keys[c * 32 + lane];
-        const unsigned m = __ballot_sync(SPHB_FULL, key != NL_EMPTY);
-        if (key != NL_EMPTY) {
-            const uint32_t ci = run + __popc(m & ((1u << lane) - 1u));
-            cidx[c * 32 + lane] = (uint16_t)ci;
-            stage[ci] = key;
-        }
-        run += __popc(m);
-    }
-    __syncthreads();
-    // pass 3: rows -> 16-bit stage indices, in place (first 64 bytes of each 128-byte row); padding -> index nst, where
-    // the drain kernels keep a far-away dummy record
-    for (uint32_t r = 0; r < nrows; ++r) {
-        const uint32_t s = rowbase[(size_t)r * 32 + lane];
-        const uint16_t code = (s == SPHB_NL_NONE) ? (uint16_t)nst : cidx[nl_hash_find(keys, s)];
-        __syncwarp();
-        reinterpret_cast<uint16_t *>(rowbase + (size_t)r * 32)[lane] = code;
-    }
-    if (tid == 0) {
-        nl.blk_nstage[b] = nst;
-        nl.blk_off[b] = s_base;
-        atomicAdd(nl.stage_stats + 1, 1u);
-        atomicMax(nl.stage_stats + 2, nst);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // drains
 // ------------------------------------------------------------------------------------------------
 // one list row for this lane: the neighbour's record, or (padding) a record so far away that every kernel term
@@ -294,165 +172,48 @@ __device__ __forceinline__ void nl_fetch(const double *__restrict__ posh, uint32
     if (!real) p[0] = 1e150;
 }
 
-// Where a warp's rows and its neighbours' records come from.
-// NlGlobal: 32-bit slot rows, records gathered from global memory (through L1).
-struct NlGlobal {
-    const double *posh;
-    const uint32_t *p;   // the lane's column of the warp's rows
-    int nrows;
-    uint32_t self;
-    __device__ __forceinline__ uint32_t row(int k) const { return (k < nrows) ? __ldg(p + (size_t)k * 32) : SPHB_NL_NONE; }
-    __device__ __forceinline__ void fetch(uint32_t e, double (&q)[4]) const { nl_fetch(posh, e, self, q); }
-    __device__ __forceinline__ bool real(uint32_t e) const { return e != SPHB_NL_NONE; }
-    __device__ __forceinline__ uint32_t slot(uint32_t e) const { return e != SPHB_NL_NONE ? e : self; }
-};
-// NlStaged: 16-bit rows indexing the block's stage list, whose records sit in shared memory (x, y, z [, h, slot] as
-// separate arrays: a lane reads 8 bytes per array, neighbouring entries are neighbouring banks)
-template <bool FULL>
-struct NlStaged {
-    const double *sx, *sy, *sz, *sh;
-    const uint32_t *sslot;
-    const uint16_t *p;
-    int nrows;
-    uint32_t dummy;
-    __device__ __forceinline__ uint32_t row(int k) const { return (k < nrows) ? (uint32_t)__ldg(p + (size_t)k * 64) : dummy; }
-    __device__ __forceinline__ void fetch(uint32_t e, double (&q)[4]) const
-    {
-        q[0] = sx[e];
-        q[1] = sy[e];
-        q[2] = sz[e];
-        q[3] = FULL ? sh[e] : 1.0;
-    }
-    __device__ __forceinline__ bool real(uint32_t e) const { return e != dummy; }
-    __device__ __forceinline__ uint32_t slot(uint32_t e) const { return sslot[e]; }
-};
-
-// the block copies its stage list's records into shared memory (every distinct neighbour once per launch instead of
-// once per lane that lists it); entry nst is the dummy record of padded rows
-template <bool FULL>
-__device__ __forceinline__ void nl_stage_in(const sphb_nlist &nl, const double *__restrict__ posh, uint32_t nst, uint32_t off,
-                                            int cap, unsigned char *smem, NlStaged<FULL> &S, uint32_t self_any)
+__device__ __forceinline__ uint32_t nl_row(const uint32_t *__restrict__ p, int k, int nrows)
 {
-    double *sx = reinterpret_cast<double *>(smem);
-    double *sy = sx + (cap + 1), *sz = sy + (cap + 1), *sh = sz + (cap + 1);
-    uint32_t *ss = reinterpret_cast<uint32_t *>(FULL ? sh + (cap + 1) : sh);
-    const uint32_t *stage = nl.stage_pool + off;
-    for (uint32_t i = threadIdx.x; i < nst; i += NLB_THREADS) {
-        const uint32_t s = __ldg(stage + i);
-        double x, y, z, h;
-        sphb_load_posh(posh, (size_t)s, x, y, z, h);
-        sx[i] = x;
-        sy[i] = y;
-        sz[i] = z;
-        if (FULL) {
-            sh[i] = h;
-            ss[i] = s;
-        }
-    }
-    if (threadIdx.x == 0) {
-        sx[nst] = 1e150;
-        sy[nst] = 0.0;
-        sz[nst] = 0.0;
-        if (FULL) {
-            sh[nst] = 1.0;
-            ss[nst] = self_any;
-        }
-    }
-    S.sx = sx;
-    S.sy = sy;
-    S.sz = sz;
-    S.sh = sh;
-    S.sslot = ss;
-    S.dummy = nst;
+    return (k < nrows) ? __ldg(p + (size_t)k * 32) : SPHB_NL_NONE;
 }
 
 // sumF, sumG (, nn) over the lane's rows: two entries side by side (two independent FP64 chains), the records of the
 // next two rows and the indices of the two after them in flight
-template <class Src>
-__device__ __forceinline__ void nl_own_drain(const Src &S, SphbOwnAcc &a)
+__device__ __forceinline__ void nl_own_drain(const double *__restrict__ posh, const uint32_t *__restrict__ rows, int nrows,
+                                             int lane, uint32_t self, SphbOwnAcc &a)
 {
-    const int nrows = S.nrows;
-    uint32_t i0 = S.row(0), i1 = S.row(1), i2 = S.row(2), i3 = S.row(3);
+    const uint32_t *p = rows + lane;
+    uint32_t i0 = nl_row(p, 0, nrows), i1 = nl_row(p, 1, nrows), i2 = nl_row(p, 2, nrows), i3 = nl_row(p, 3, nrows);
     double A[4], B[4], C[4], D[4];
-    S.fetch(i0, A);
-    S.fetch(i1, B);
+    nl_fetch(posh, i0, self, A);
+    nl_fetch(posh, i1, self, B);
     int k = 0;
     while (k < nrows) {
-        S.fetch(i2, C);
-        S.fetch(i3, D);
-        i0 = S.row(k + 4);
-        i1 = S.row(k + 5);
+        nl_fetch(posh, i2, self, C);
+        nl_fetch(posh, i3, self, D);
+        i0 = nl_row(p, k + 4, nrows);
+        i1 = nl_row(p, k + 5, nrows);
         sphb_own_pair2<false>(A, B, true, a);
         k += 2;
         if (k >= nrows) break;
-        S.fetch(i0, A);
-        S.fetch(i1, B);
-        i2 = S.row(k + 4);
-        i3 = S.row(k + 5);
+        nl_fetch(posh, i0, self, A);
+        nl_fetch(posh, i1, self, B);
+        i2 = nl_row(p, k + 4, nrows);
+        i3 = nl_row(p, k + 5, nrows);
         sphb_own_pair2<false>(C, D, true, a);
         k += 2;
     }
 }
 
-#ifndef SPHB_NL_EARLY_B
-#define SPHB_NL_EARLY_B 1 /* force drain: the {v, A} records of the next two rows are loaded with their positions */
-#endif
-
-template <bool DENSE, class Src>
-__device__ __forceinline__ void nl_force_drain(const Src &S, const double *__restrict__ recB, const double *__restrict__ recC,
-                                               const sphb_consts &k, SphbForceAcc &a)
-{
-    const int nrows = S.nrows;
-    uint32_t i0 = S.row(0), i1 = S.row(1), i2 = S.row(2), i3 = S.row(3);
-    double A[4], B[4], C[4], D[4];
-    S.fetch(i0, A);
-    S.fetch(i1, B);
-    int kk = 0;
-    while (kk < nrows) {
-        S.fetch(i2, C);
-        S.fetch(i3, D);
-        uint32_t n0 = S.row(kk + 4), n1 = S.row(kk + 5);
-        sphb_force_pair2<false, DENSE>(recB, recC, nullptr, S.slot(i0), S.slot(i1), A, B, S.real(i1), k, a, S.real(i0));
-        kk += 2;
-        if (kk >= nrows) break;
-        i0 = n0;
-        i1 = n1;
-        S.fetch(i0, A);
-        S.fetch(i1, B);
-        n0 = S.row(kk + 4);
-        n1 = S.row(kk + 5);
-        sphb_force_pair2<false, DENSE>(recB, recC, nullptr, S.slot(i2), S.slot(i3), C, D, S.real(i3), k, a, S.real(i2));
-        i2 = n0;
-        i3 = n1;
-        kk += 2;
-    }
-}
-
-// the calling block's stage (0 entries: not staged) -- block-uniform
-__device__ __forceinline__ uint32_t nl_block_stage(const sphb_nlist &nl, uint32_t &off)
-{
-    if (nl.blk_nstage == nullptr) return 0;
-    off = nl.blk_off[blockIdx.x];
-    return nl.blk_nstage[blockIdx.x];
-}
-
 // K2 on kept lists: density / density_arr (pyfluid.py:218-232), omega_j / omega_arr (:91-105)
-__global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_OWN)
+__global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
     k_nl_density_omega(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
                        const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
-                       double *__restrict__ omega, int32_t *__restrict__ ngb_count, int cap)
+                       double *__restrict__ omega, int32_t *__restrict__ ngb_count)
 {
-    extern __shared__ __align__(16) unsigned char nl_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long w = (long long)blockIdx.x * NLB_WARPS + warp;
+    const long long w = (long long)blockIdx.x * NL_WARPS + warp;
     const long long base = w * 32;
-    uint32_t off = 0;
-    const uint32_t nst = nl_block_stage(nl, off);
-    NlStaged<false> SS;
-    if (nst) {
-        nl_stage_in<false>(nl, posh, nst, off, cap, nl_dyn, SS, 0u);
-        __syncthreads();
-    }
     if (base >= nl.n) return;
     const long long j = base + lane;
     const bool valid = j < nl.n;
@@ -466,14 +227,7 @@ __global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_OWN)
     a.nn = 0;
     const int nrows = (int)nl.warp_rows[w];
     const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
-    if (nst) {
-        SS.p = reinterpret_cast<const uint16_t *>(rows) + lane;
-        SS.nrows = nrows;
-        nl_own_drain(SS, a);
-    } else {
-        const NlGlobal SG{posh, rows + lane, nrows, valid ? (uint32_t)j : 0u};
-        nl_own_drain(SG, a);
-    }
+    nl_own_drain(posh, rows, nrows, lane, valid ? (uint32_t)j : 0u, a);
     if (tgt) {
         const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
         const double rs = pref * a.sumF;
@@ -492,22 +246,14 @@ __global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_OWN)
 // within the limit (the reference then bisects over all particles, :178-179) -- sets SPHB_NL_BROKEN: the caller
 // redoes the step with the scanning kernels, which replay the reference to the letter.
 template <bool FUSED>
-__global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_OWN)
+__global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
     k_nl_newton_h(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
                   const double *__restrict__ h_guess, double *__restrict__ h_out, double *__restrict__ omega_out, double *__restrict__ posh_out,
-                  int32_t *__restrict__ iters, sphb_status *__restrict__ status, int cap)
+                  int32_t *__restrict__ iters, sphb_status *__restrict__ status)
 {
-    extern __shared__ __align__(16) unsigned char nl_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long w = (long long)blockIdx.x * NLB_WARPS + warp;
+    const long long w = (long long)blockIdx.x * NL_WARPS + warp;
     const long long base = w * 32;
-    uint32_t off = 0;
-    const uint32_t nst = nl_block_stage(nl, off);
-    NlStaged<false> SS;
-    if (nst) {
-        nl_stage_in<false>(nl, posh, nst, off, cap, nl_dyn, SS, 0u);
-        __syncthreads();
-    }
     if (base >= nl.n) return;
     const long long j = base + lane;
     const bool valid = j < nl.n;
@@ -524,9 +270,7 @@ __global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_OWN)
     const double h_cover = hb * nl.cover_h, h_old = hb * (1.0 + 0.5 * (nl.cover_h - 1.0));
     const int nrows = (int)nl.warp_rows[w];
     const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
-    SS.p = reinterpret_cast<const uint16_t *>(rows) + lane;
-    SS.nrows = nrows;
-    const NlGlobal SG{posh, rows + lane, nrows, valid ? (uint32_t)j : 0u};
+    const uint32_t self = valid ? (uint32_t)j : 0u;
     // what the lane needs next: 1 = the sums of a Newton iterate at h_cur, 2 = sum m dW/dh at the converged h_cur
     // (FUSED: Omega at the solved h, pyfluid.py:518), 0 = nothing
     int want = tgt ? 1 : 0, it = 0, fl = 0;
@@ -536,10 +280,7 @@ __global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_OWN)
         a.hinv = 1.0 / h_cur;
         a.sumF = a.sumG = a.sumX = 0.0;
         a.nn = 0;
-        if (nst)
-            nl_own_drain(SS, a);
-        else
-            nl_own_drain(SG, a);
+        nl_own_drain(posh, rows, nrows, lane, self, a);
         if (want == 1) {
             // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
             const double pref = k.particle_mass / (SPHB_PI * (h_cur * h_cur * h_cur));
@@ -596,23 +337,14 @@ __global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_OWN)
 // acceleration / _arr (:477-493) with G = 0.  posh carries the CURRENT h; recB / recC are sphb_eos's records, or
 // (DENSE) recB and sphb_nlist_eos's dense {rho, cs}.
 template <bool DENSE>
-__global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_FORCE)
+__global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
     k_nl_force(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
                const double *__restrict__ recB, const double *__restrict__ recC, double *__restrict__ acc,
-               double *__restrict__ dudt, sphb_status *__restrict__ status, int cap)
+               double *__restrict__ dudt, sphb_status *__restrict__ status)
 {
-    extern __shared__ __align__(16) unsigned char nl_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long w = (long long)blockIdx.x * NLB_WARPS + warp;
+    const long long w = (long long)blockIdx.x * NL_WARPS + warp;
     const long long base = w * 32;
-    uint32_t off = 0;
-    const uint32_t nst = nl_block_stage(nl, off);
-    NlStaged<true> SS;
-    if (nst) {
-        const long long b0 = (long long)blockIdx.x * NLB_THREADS;
-        nl_stage_in<true>(nl, posh, nst, off, cap, nl_dyn, SS, (uint32_t)(b0 < nl.n ? b0 : 0));
-        __syncthreads();
-    }
     if (base >= nl.n) return;
     const long long j = base + lane;
     const bool valid = j < nl.n;
@@ -640,14 +372,32 @@ __global__ void __launch_bounds__(NLB_THREADS, SPHB_MINB_NL_FORCE)
     a.negpi = 0;
     a.Bj = 0.0;
     const int nrows = (int)nl.warp_rows[w];
-    const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
-    if (nst) {
-        SS.p = reinterpret_cast<const uint16_t *>(rows) + lane;
-        SS.nrows = nrows;
-        nl_force_drain<DENSE>(SS, recB, recC, k, a);
-    } else {
-        const NlGlobal SG{posh, rows + lane, nrows, valid ? (uint32_t)j : 0u};
-        nl_force_drain<DENSE>(SG, recB, recC, k, a);
+    const uint32_t *p = nl.pool + (size_t)nl.warp_off[w] * 32 + lane;
+    const uint32_t self = valid ? (uint32_t)j : 0u;
+    {
+        uint32_t i0 = nl_row(p, 0, nrows), i1 = nl_row(p, 1, nrows), i2 = nl_row(p, 2, nrows), i3 = nl_row(p, 3, nrows);
+        double A[4], B[4], C[4], D[4];
+        nl_fetch(posh, i0, self, A);
+        nl_fetch(posh, i1, self, B);
+        int kk = 0;
+        while (kk < nrows) {
+            nl_fetch(posh, i2, self, C);
+            nl_fetch(posh, i3, self, D);
+            uint32_t n0 = nl_row(p, kk + 4, nrows), n1 = nl_row(p, kk + 5, nrows);
+            sphb_force_pair2<false, DENSE>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a, i0 != SPHB_NL_NONE);
+            kk += 2;
+            if (kk >= nrows) break;
+            i0 = n0;
+            i1 = n1;
+            nl_fetch(posh, i0, self, A);
+            nl_fetch(posh, i1, self, B);
+            n0 = nl_row(p, kk + 4, nrows);
+            n1 = nl_row(p, kk + 5, nrows);
+            sphb_force_pair2<false, DENSE>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a, i2 != SPHB_NL_NONE);
+            i2 = n0;
+            i3 = n1;
+            kk += 2;
+        }
     }
     if (tgt) {
         const double m = k.particle_mass;
@@ -717,43 +467,12 @@ __global__ void k_nl_scatter_state(const double *__restrict__ posh_s, const doub
 // ------------------------------------------------------------------------------------------------
 static inline bool nl_ok(const sphb_nlist *nl)
 {
-    if (!(nl && nl->n >= 0 && nl->warp_off && nl->warp_rows && nl->pool && nl->pool_rows > 0 &&
-          nl->pool_rows < (int64_t)0xffffffffll && nl->cursor && nl->flags && nl->posh_build && nl->cover_h >= 1.0 &&
-          nl->skin >= 0.0 && nl->cover_h + nl->skin < 4.0))
-        return false;
-    if (nl->blk_nstage &&
-        !(nl->blk_off && nl->stage_pool && nl->stage_stats && nl->stage_pool_len > 0 && nl->stage_cap > 0 &&
-          nl->stage_cap <= SPHB_NL_STAGE_MAX))
-        return false;
-    return true;
+    return nl && nl->n >= 0 && nl->warp_off && nl->warp_rows && nl->pool && nl->pool_rows > 0 &&
+           nl->pool_rows < (int64_t)0xffffffffll && nl->cursor && nl->flags && nl->posh_build && nl->cover_h >= 1.0 &&
+           nl->skin >= 0.0 && nl->cover_h + nl->skin < 4.0;
 }
 
-static inline unsigned nl_blocks(int64_t n) { return (unsigned)((n + NL_THREADS - 1) / NL_THREADS); }     // builder
-static inline unsigned nlb_blocks(int64_t n) { return (unsigned)((n + NLB_THREADS - 1) / NLB_THREADS); }  // drains
-
-// dynamic shared memory of a drain launch: the stage of one block ((cap + 1) records; 0 when the lists are not staged)
-static inline int nl_stage_bytes(const sphb_nlist *nl, bool full)
-{
-    if (!nl->blk_nstage) return 0;
-    const int per = full ? 4 * 8 + 4 : 3 * 8;
-    return (nl->stage_cap + 1) * per + 16;
-}
-
-extern "C" int64_t sphb_sizeof_nlist(void) { return (int64_t)sizeof(sphb_nlist); }
-
-extern "C" int sphb_nlist_compact(const sphb_nlist *nl, void *stream)
-{
-    if (!nl_ok(nl) || !nl->blk_nstage) return SPHB_E_ARG;
-    cudaStream_t st = sphb_stream(stream);
-    SPHB_CUDA(cudaMemsetAsync(nl->cursor + 1, 0, sizeof(unsigned long long), st));
-    SPHB_CUDA(cudaMemsetAsync(nl->stage_stats, 0, 4 * sizeof(uint32_t), st));
-    if (nl->n == 0) return SPHB_OK;
-    const int smem = NL_HASH * (int)(sizeof(uint32_t) + sizeof(uint16_t));
-    SPHB_CUDA(cudaFuncSetAttribute(k_nl_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_nl_compact<<<nlb_blocks(nl->n), NLB_THREADS, smem, st>>>(*nl);
-    SPHB_LAUNCHED();
-    return SPHB_OK;
-}
+static inline unsigned nl_blocks(int64_t n) { return (unsigned)((n + NL_THREADS - 1) / NL_THREADS); }
 
 extern "C" int64_t sphb_nlist_pool_rows(int64_t n)
 {
@@ -797,10 +516,8 @@ extern "C" int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts 
 {
     if (!nl_ok(nl) || !k || !posh) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
-    const int smem = nl_stage_bytes(nl, false);
-    if (smem > 48 * 1024) SPHB_CUDA(cudaFuncSetAttribute(k_nl_density_omega, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_nl_density_omega<<<nlb_blocks(nl->n), NLB_THREADS, smem, sphb_stream(stream)>>>(*nl, *k, target, posh, rho_in, rho_sum,
-                                                                                      dwdh_sum, omega, ngb_count, nl->stage_cap);
+    k_nl_density_omega<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, rho_in, rho_sum,
+                                                                                 dwdh_sum, omega, ngb_count);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
@@ -811,16 +528,12 @@ extern "C" int sphb_nlist_newton_h(const sphb_nlist *nl, const sphb_consts *k, c
 {
     if (!nl_ok(nl) || !k || !posh || !h_out || !status || posh_out == posh) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
-    const int smem = nl_stage_bytes(nl, false);
-    if (omega_out) {
-        if (smem > 48 * 1024) SPHB_CUDA(cudaFuncSetAttribute(k_nl_newton_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_nl_newton_h<true><<<nlb_blocks(nl->n), NLB_THREADS, smem, sphb_stream(stream)>>>(
-            *nl, *k, target, posh, h_guess, h_out, omega_out, posh_out, iters, status, nl->stage_cap);
-    } else {
-        if (smem > 48 * 1024) SPHB_CUDA(cudaFuncSetAttribute(k_nl_newton_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_nl_newton_h<false><<<nlb_blocks(nl->n), NLB_THREADS, smem, sphb_stream(stream)>>>(
-            *nl, *k, target, posh, h_guess, h_out, omega_out, posh_out, iters, status, nl->stage_cap);
-    }
+    if (omega_out)
+        k_nl_newton_h<true><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, h_guess, h_out,
+                                                                                      omega_out, posh_out, iters, status);
+    else
+        k_nl_newton_h<false><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, h_guess, h_out,
+                                                                                       omega_out, posh_out, iters, status);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
@@ -832,16 +545,12 @@ extern "C" int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, cons
     if (!nl_ok(nl) || !k || !posh || !recB || (!recC == !recD) || !acc || !dudt || !status) return SPHB_E_ARG;
     if (k->G != 0.0) return SPHB_E_ARG;   // the softened-gravity terms ride in the scanning kernels only
     if (nl->n == 0) return SPHB_OK;
-    const int smem = nl_stage_bytes(nl, true);
-    if (recD) {
-        if (smem > 48 * 1024) SPHB_CUDA(cudaFuncSetAttribute(k_nl_force<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_nl_force<true><<<nlb_blocks(nl->n), NLB_THREADS, smem, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recD, acc,
-                                                                                        dudt, status, nl->stage_cap);
-    } else {
-        if (smem > 48 * 1024) SPHB_CUDA(cudaFuncSetAttribute(k_nl_force<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_nl_force<false><<<nlb_blocks(nl->n), NLB_THREADS, smem, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recC, acc,
-                                                                                         dudt, status, nl->stage_cap);
-    }
+    if (recD)
+        k_nl_force<true><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recD, acc,
+                                                                                   dudt, status);
+    else
+        k_nl_force<false><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recC, acc,
+                                                                                    dudt, status);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

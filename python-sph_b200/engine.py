@@ -47,8 +47,7 @@ class KeptLists:
     """sphb_nlist: neighbour lists that outlive kernels and steps, with the buffers they point to.
     Built from ONE cell list (dg); the drain kernels then only need the current sorted records."""
 
-    def __init__(self, engine, dg, cover_h, skin, pool_rows=None, stage_cap=None):
-        """stage_cap: per-block limit of the shared-memory stage (0: lists are not staged; None: NL_STAGE_CAP)"""
+    def __init__(self, engine, dg, cover_h, skin, pool_rows=None):
         lib, dev = engine.lib, engine.device
         n = dg.n
         nw = max(1, (n + 31) // 32)
@@ -60,27 +59,13 @@ class KeptLists:
         self.warp_off = torch.empty(nw, dtype=torch.int32, device=dev)
         self.warp_rows = torch.zeros(nw, dtype=torch.int32, device=dev)
         self.pool = torch.empty((rows, 32), dtype=torch.int32, device=dev)
-        self.cursor = torch.zeros(2, dtype=torch.int64, device=dev)  # rows handed out, stage entries handed out
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # [0] SPHB_NL_* flags, [1..2] the maxima
-        cap = NL_STAGE_CAP if stage_cap is None else int(stage_cap)
-        self.stage_cap = cap
-        if cap > 0:
-            nb = max(1, (n + N.NL_BLOCK - 1) // N.NL_BLOCK)
-            self.blk_off = torch.zeros(nb, dtype=torch.int32, device=dev)
-            self.blk_nstage = torch.zeros(nb, dtype=torch.int32, device=dev)
-            self.stage_len = nb * cap
-            self.stage_pool = torch.empty(self.stage_len, dtype=torch.int32, device=dev)
-            self.stage_stats = torch.zeros(4, dtype=torch.int32, device=dev)
-            st = (self.blk_off.data_ptr(), self.blk_nstage.data_ptr(), self.stage_pool.data_ptr(), self.stage_len, cap, 0,
-                  self.stage_stats.data_ptr())
-        else:
-            st = (None, None, None, 0, 0, 0, None)
         self.c = N.NList(n, self.warp_off.data_ptr(), self.warp_rows.data_ptr(), self.pool.data_ptr(), rows,
                          self.cursor.data_ptr(), self.flags.data_ptr(), dg.posh.data_ptr(), self.cover_h, self.skin,
-                         self.flags.data_ptr() + 4, *st)
+                         self.flags.data_ptr() + 4)
         self.build_flags = 0
         self.moved = self.grown = 0.0
-        self.staged = None    # after compaction: dict(blocks, staged, largest, unstaged, entries)
 
     def ref(self):
         return C.byref(self.c)
@@ -94,14 +79,7 @@ class KeptLists:
         return int(v[0])
 
     def rows_used(self):
-        return int(self.cursor[0].item())
-
-    def read_stage_stats(self):
-        v = self.stage_stats.cpu().tolist()
-        nb = self.blk_off.numel()
-        self.staged = dict(blocks=nb, entries=v[0] if v[0] else int(self.cursor[1].item()), staged=v[1], largest=v[2],
-                           unstaged=v[3], cap=self.stage_cap)
-        return self.staged
+        return int(self.cursor.item())
 
 
 def require_cuda():
@@ -360,15 +338,14 @@ class Engine:
         return out, cnt
 
     # -- kept neighbour lists (sphb_nlist) -------------------------------------------------------
-    def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None, max_bytes=96 * 2 ** 30,
-                 stage_cap=None) -> KeptLists:
+    def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None, max_bytes=96 * 2 ** 30) -> KeptLists:
         """scan the cell list once and keep every warp's candidate rows.  Reads the build's flags (one 4-byte D2H
         after the kernel): a pool that turned out too small is enlarged to what the build asked for and the build is
         repeated.  The returned lists may still carry SPHB_NL_UNLISTABLE / SPHB_NL_POOL (nl.build_flags): the caller then
         has to use the scanning kernels."""
         hm = hmax if hmax is not None else self.hmax(dg.posh)
         for _ in range(3):
-            nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows, stage_cap=stage_cap)
+            nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows)
             nl._hmax = hm
             self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(), _stream())
             nl.build_flags = nl.read_flags()
@@ -379,10 +356,6 @@ class Engine:
                 break
             pool_rows = need
             del nl
-        if nl.stage_cap > 0 and not (nl.build_flags & (N.NL_POOL | N.NL_UNLISTABLE)):
-            # per block of 256 slots: the distinct neighbour slots (what the drains copy to shared memory once per
-            # launch) and the rows as 16-bit indices into them
-            self._run("nl_compact", self.lib.sphb_nlist_compact, nl.ref(), _stream())
         return nl
 
     def nl_check(self, nl, posh):
@@ -667,7 +640,6 @@ class Stepper:
         return pos1, vel1, u1, h1
 
 
-NL_STAGE_CAP = int(os.environ.get("SPHB_NL_STAGE_CAP", "3072"))
 NL_COVER_H = float(os.environ.get("SPHB_NL_COVER_H", "1.03"))
 NL_SKIN = float(os.environ.get("SPHB_NL_SKIN", "0.03"))
 

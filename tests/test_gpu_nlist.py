@@ -69,10 +69,7 @@ def _to(a):
 
 @pytest.mark.parametrize("case", ["cloud", "two_density"])
 @pytest.mark.parametrize("cover_h,skin", [(1.0, 0.0), (1.03, 0.03)])
-@pytest.mark.parametrize("stage_cap", [0, 3072, 1500])
-def test_drains_equal_scanning_kernels_bit_for_bit(sph, case, cover_h, skin, stage_cap):
-    """stage_cap 0: 32-bit slot rows, records gathered from global memory; 3072: every block copies its distinct
-    neighbours to shared memory and walks 16-bit rows; 1500: a mix (blocks with a larger stage keep their 32-bit rows)"""
+def test_drains_equal_scanning_kernels_bit_for_bit(sph, case, cover_h, skin):
     import torch
     import engine as E
     eng = sph._eng()
@@ -89,43 +86,23 @@ def test_drains_equal_scanning_kernels_bit_for_bit(sph, case, cover_h, skin, sta
         grid, delta = eng.grid_for(posh)
         dg = eng.build(posh, grid, delta)
         st = E.Status(2, eng.device)
-        nl = eng.nl_build(dg, cover_h, skin, stage_cap=stage_cap)
+        nl = eng.nl_build(dg, cover_h, skin)
         fl = nl.read_flags()
         assert fl == 0, fl
         rows = nl.warp_rows.cpu().numpy()
         if case == "two_density":
-            assert rows.max() > 192, "the interface warps were meant to overflow the builder's staging area"
-        off = nl.warp_off.cpu().numpy().astype(np.int64)
+            assert rows.max() > 128, "the interface warps were meant to overflow the staging area"
+        # exact symmetric neighbour sets are subsets of the rows
         q = torch.arange(0, dg.n, 97, dtype=torch.int32, device="cuda")
         out, cnt = eng.neighbours(dg, q, 1024, symmetric=True)
         out, cnt, qq = out.cpu().numpy(), cnt.cpu().numpy(), q.cpu().numpy()
-        if stage_cap == 0:
-            # exact symmetric neighbour sets are subsets of the rows
-            for k, s in enumerate(qq):
-                w, lane = s // 32, s % 32
-                mine = nl.pool[off[w]:off[w] + rows[w], lane].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-                mine = mine[mine != 0xFFFFFFFF]
-                assert (np.diff(mine) > 0).all(), "rows must be in ascending slot order"
-                assert set(out[k, :cnt[k]].tolist()) <= set(mine.tolist())
-        else:
-            stg = nl.read_stage_stats()
-            assert stg["staged"] + stg["unstaged"] <= stg["blocks"] and stg["largest"] <= stage_cap
-            if stage_cap == 3072 and case == "cloud":
-                assert stg["staged"] > 0
-            # staged blocks: 16-bit rows index the block's stage list; decoded, they are the same ascending slot sets
-            nst = nl.blk_nstage.cpu().numpy().astype(np.int64)
-            boff = nl.blk_off.cpu().numpy().astype(np.int64)
-            stage = nl.stage_pool.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-            pool16 = nl.pool.view(torch.int16)
-            for k, s in enumerate(qq):
-                w, lane, b = s // 32, s % 32, s // 256
-                if nst[b] == 0:
-                    continue
-                codes = pool16[off[w]:off[w] + rows[w], lane].cpu().numpy().astype(np.int64) & 0xFFFF
-                assert codes.max() <= nst[b]
-                mine = stage[boff[b] + codes[codes < nst[b]]]
-                assert (np.diff(mine) > 0).all()
-                assert set(out[k, :cnt[k]].tolist()) <= set(mine.tolist())
+        off = nl.warp_off.cpu().numpy().astype(np.int64)
+        for k, s in enumerate(qq):
+            w, lane = s // 32, s % 32
+            mine = nl.pool[off[w]:off[w] + rows[w], lane].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            mine = mine[mine != 0xFFFFFFFF]
+            assert (np.diff(mine) > 0).all(), "rows must be in ascending slot order"
+            assert set(out[k, :cnt[k]].tolist()) <= set(mine.tolist())
         # K2
         rho_a, dw_a, om_a, ng_a = eng.density_omega(dg, c, want_rho=True, want_dwdh=True, want_omega=True, want_ngb=True)
         rho_b, dw_b, om_b, ng_b = eng.nl_density_omega(nl, c, dg.posh, want_rho=True, want_dwdh=True, want_omega=True,
