@@ -173,6 +173,7 @@ typedef struct sphb_nlist {
                                   |x_now - x_build| / h_build and h_now / h_build - 1 any check has seen since */
 } sphb_nlist;
 int64_t sphb_nlist_pool_rows(int64_t n);
+int64_t sphb_sizeof_nlist(void); /* sizeof(sphb_nlist), for bindings to check their own layout against */
 /* cells->posh must be nl->posh_build.  Zeroes *cursor and *flags first. */
 int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global, const sphb_nlist *nl,
                      void *stream);

@@ -86,6 +86,7 @@ SIGNATURES = {
     "sphb_gather_u32": (C.c_int, [P, P, I64, P, P]),
     "sphb_lists_bytes": (C.c_size_t, [I64]),
     "sphb_nlist_pool_rows": (I64, [I64]),
+    "sphb_sizeof_nlist": (I64, []),
     "sphb_nlist_build": (C.c_int, [C.POINTER(Cells), P, P, C.POINTER(NList), P]),
     "sphb_nlist_check": (C.c_int, [C.POINTER(NList), P, P]),
     "sphb_nlist_density_omega": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),

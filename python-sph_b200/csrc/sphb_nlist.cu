@@ -474,6 +474,8 @@ static inline bool nl_ok(const sphb_nlist *nl)
 
 static inline unsigned nl_blocks(int64_t n) { return (unsigned)((n + NL_THREADS - 1) / NL_THREADS); }
 
+extern "C" int64_t sphb_sizeof_nlist(void) { return (int64_t)sizeof(sphb_nlist); }
+
 extern "C" int64_t sphb_nlist_pool_rows(int64_t n)
 {
     // a first guess (a lattice at eta = 1.3 takes ~90 rows per warp, a random cloud ~130); a build that needs more sets

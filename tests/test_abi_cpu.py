@@ -35,6 +35,7 @@ def test_struct_sizes_match_header(native):
     assert C.sizeof(native.Status) == 32
     assert C.sizeof(native.Cells) == 48 + 8 + 5 * 8 + 8
     assert C.sizeof(native.Lists) == 3 * 8 + 8
+    assert C.sizeof(native.NList) == native.load().sphb_sizeof_nlist()
 
 
 def test_no_compute_entry_points_without_gpu(native):
