@@ -174,9 +174,11 @@ typedef struct sphb_nlist {
 } sphb_nlist;
 int64_t sphb_nlist_pool_rows(int64_t n);
 int64_t sphb_sizeof_nlist(void); /* sizeof(sphb_nlist), for bindings to check their own layout against */
-/* cells->posh must be nl->posh_build.  Zeroes *cursor and *flags first. */
+/* cells->posh must be nl->posh_build.  Zeroes *cursor and *flags first.
+ * omega (optional, needs k): Omega_j = 1 + h_j/(3 rho_j) sum_i m dW/dh with rho_j = m (eta/h_j)^3 at the build-time records
+ * (what sphb_nlist_density_omega would return for them), formed while the lists are still in the staging area. */
 int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global, const sphb_nlist *nl,
-                     void *stream);
+                     const sphb_consts *k, double *omega, void *stream);
 int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, void *stream);
 /* sphb_density_omega on kept lists (h_j = posh[j][3]) */
 int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,

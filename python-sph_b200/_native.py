@@ -87,7 +87,7 @@ SIGNATURES = {
     "sphb_lists_bytes": (C.c_size_t, [I64]),
     "sphb_nlist_pool_rows": (I64, [I64]),
     "sphb_sizeof_nlist": (I64, []),
-    "sphb_nlist_build": (C.c_int, [C.POINTER(Cells), P, P, C.POINTER(NList), P]),
+    "sphb_nlist_build": (C.c_int, [C.POINTER(Cells), P, P, C.POINTER(NList), C.POINTER(Consts), P, P]),
     "sphb_nlist_check": (C.c_int, [C.POINTER(NList), P, P]),
     "sphb_nlist_density_omega": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
     "sphb_nlist_newton_h": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),

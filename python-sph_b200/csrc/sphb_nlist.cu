@@ -19,6 +19,9 @@
 
 #define NL_WARPS 4
 #define NL_THREADS (NL_WARPS * 32)
+#ifndef SPHB_NL_RESERVE
+#define SPHB_NL_RESERVE 768 /* rows a warp reserves when its lists outgrow the staging area (4 chunks) */
+#endif
 #ifndef SPHB_NL_MAX_ROWS
 #define SPHB_NL_MAX_ROWS (1 << 18) /* rows one warp may take (32 MiB): beyond that the input is "unlistable" */
 #endif
@@ -41,8 +44,37 @@ typedef SphbWarpSharedT<SPHB_NL_LIST> NlWarpShared;
 // lane, SPHB_NL_NONE where a lane has fewer), handed out from the pool by one atomicAdd per warp.  A warp whose lists
 // do not fit the shared-memory staging area (SPHB_NL_LIST entries per lane) counts its rows first and scans twice.
 // ------------------------------------------------------------------------------------------------
+// the density / grad-h sums of a chunk of staged lists (what sphb_own_flush does in the scanning kernels): two entries
+// side by side, the records of the next two in flight
+template <class WS>
+__device__ __forceinline__ void nl_flush_own(const double *__restrict__ posh, const WS &ws, int lane, int cnt, SphbOwnAcc &a)
+{
+    double A[4], B[4], C[4], D[4];
+    A[0] = A[1] = A[2] = B[0] = B[1] = B[2] = 0.0;
+    if (cnt > 0) sphb_load_posh(posh, sphb_list_get(ws, lane, 0), A[0], A[1], A[2], A[3]);
+    if (cnt > 1) sphb_load_posh(posh, sphb_list_get(ws, lane, 1), B[0], B[1], B[2], B[3]);
+    int k = 0;
+    while (k < cnt) {
+        C[0] = C[1] = C[2] = D[0] = D[1] = D[2] = 0.0;
+        if (k + 2 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 2), C[0], C[1], C[2], C[3]);
+        if (k + 3 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 3), D[0], D[1], D[2], D[3]);
+        sphb_own_pair2<false>(A, B, k + 1 < cnt, a);
+        k += 2;
+        if (k >= cnt) break;
+        if (k + 2 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 2), A[0], A[1], A[2], A[3]);
+        if (k + 3 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 3), B[0], B[1], B[2], B[3]);
+        sphb_own_pair2<false>(C, D, k + 1 < cnt, a);
+        k += 2;
+    }
+}
+
+// OMEGA: also return Omega(pos, h) of the build-time records (pyfluid.py:91-105 with the algebraic density, :503):
+// every chunk is drained once more from the staging area while it is stored -- the first gather pass of the step that
+// follows a rebuild comes for the price of its arithmetic, without reading a single row back.
+template <bool OMEGA>
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
-    k_nl_build(sphb_cells c, const uint8_t *__restrict__ target, const float *__restrict__ hmax_global, sphb_nlist nl)
+    k_nl_build(sphb_cells c, const uint8_t *__restrict__ target, const float *__restrict__ hmax_global, sphb_nlist nl,
+               sphb_consts kc, double *__restrict__ omega)
 {
     extern __shared__ __align__(16) unsigned char nl_smem[];
     NlWarpShared *sh = reinterpret_cast<NlWarpShared *>(nl_smem);
@@ -73,9 +105,17 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     const float RH = sphb_radius_of_h((double)hmax_global[0] * (double)cov, g.delta);
 
     // mode 0: the lists are expected to fit the staging area: one exact allocation at the end, one store.
-    // A warp that has to flush before the end of its scan (heavy: a sparse target next to a dense region) only COUNTS
-    // the rows of every chunk for the rest of that scan (mode 1), allocates exactly that, and scans once more to store
-    // (mode 2; the scan is deterministic, the chunks come out the same).  Rows of a chunk are padded to its longest lane.
+    // A warp that has to flush before the end of its scan (heavy: a sparse target next to a dense region) takes a
+    // reserve of SPHB_NL_RESERVE rows and appends its chunks there (mode 3).  If even that is outgrown it only COUNTS the
+    // rows of every further chunk (mode 1), allocates exactly the total, and scans once more to store (mode 2; the scan
+    // is deterministic, the chunks come out the same).  Rows of a chunk are padded to its longest lane.
+    SphbOwnAcc oa;
+    oa.xj = x;
+    oa.yj = y;
+    oa.zj = z;
+    oa.hinv = 1.0 / h;
+    oa.sumF = oa.sumG = oa.sumX = 0.0;
+    oa.nn = 0;
     uint32_t row0 = 0, used = 0, total = 0;   // warp-uniform
     int mode = 0;                             // warp-uniform
     bool over = false;                        // warp-uniform
@@ -93,7 +133,14 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     auto emit = [&](int cnt, bool final) {
         __syncwarp();
         const uint32_t rows = (uint32_t)__reduce_max_sync(SPHB_FULL, cnt);
-        if (mode == 0 && !final) mode = 1;
+        if (mode == 0 && !final) {   // first overflow: an optimistic reserve, so that most heavy warps still scan once
+            alloc((uint32_t)SPHB_NL_RESERVE);
+            mode = 3;
+        }
+        if (mode == 3 && used + rows > (uint32_t)SPHB_NL_RESERVE) {   // outgrown: count the rest, then scan again
+            mode = 1;
+            total = used;
+        }
         if (mode == 1) {
             total += rows;
             if (total > (uint32_t)SPHB_NL_MAX_ROWS && !over) {
@@ -108,6 +155,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
             for (uint32_t r = 0; r < rows; ++r)
                 dst[(size_t)r * 32] = ((int)r < cnt) ? sphb_list_get(ws, lane, (int)r) : SPHB_NL_NONE;
             used += rows;
+            if (OMEGA) nl_flush_own(c.posh, ws, lane, cnt, oa);
         }
         __syncwarp();
     };
@@ -120,12 +168,15 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
         if (mode != 1 || over) break;
         alloc(total);
         mode = 2;
+        oa.sumF = oa.sumG = 0.0;   // the chunks drained so far are drained again by the second scan
+        oa.nn = 0;
         __syncwarp();
     }
     if (lane == 0) {
         nl.warp_off[w] = row0;
         nl.warp_rows[w] = over ? 0u : used;
     }
+    if (OMEGA && tgt) omega[j] = over ? CUDART_NAN : sphb_omega_from_sumG(kc, h, oa.sumG);
 }
 
 // did any record leave what the lists were built to cover?  (half of a bound used up: SPHB_NL_AGING)
@@ -485,8 +536,9 @@ extern "C" int64_t sphb_nlist_pool_rows(int64_t n)
 }
 
 extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global,
-                                const sphb_nlist *nl, void *stream)
+                                const sphb_nlist *nl, const sphb_consts *k, double *omega, void *stream)
 {
+    if (omega && !k) return SPHB_E_ARG;
     if (!cells || cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh ||
         !cells->frec || !hmax_global || !nl_ok(nl) || nl->n != cells->n || nl->posh_build != cells->posh)
         return SPHB_E_ARG;
@@ -496,8 +548,13 @@ extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, 
     if (nl->maxima) SPHB_CUDA(cudaMemsetAsync(nl->maxima, 0, 2 * sizeof(int32_t), st));
     if (cells->n == 0) return SPHB_OK;
     const int smem = (int)(NL_WARPS * sizeof(NlWarpShared));   // > 48 KB of dynamic shared memory needs the opt-in
-    SPHB_CUDA(cudaFuncSetAttribute(k_nl_build, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_nl_build<<<nl_blocks(cells->n), NL_THREADS, smem, st>>>(*cells, target, hmax_global, *nl);
+    if (omega) {
+        SPHB_CUDA(cudaFuncSetAttribute(k_nl_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_nl_build<true><<<nl_blocks(cells->n), NL_THREADS, smem, st>>>(*cells, target, hmax_global, *nl, *k, omega);
+    } else {
+        SPHB_CUDA(cudaFuncSetAttribute(k_nl_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_nl_build<false><<<nl_blocks(cells->n), NL_THREADS, smem, st>>>(*cells, target, hmax_global, *nl, sphb_consts{}, nullptr);
+    }
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

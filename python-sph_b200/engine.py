@@ -338,16 +338,21 @@ class Engine:
         return out, cnt
 
     # -- kept neighbour lists (sphb_nlist) -------------------------------------------------------
-    def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None, max_bytes=96 * 2 ** 30) -> KeptLists:
+    def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None, max_bytes=96 * 2 ** 30,
+                 consts=None) -> KeptLists:
         """scan the cell list once and keep every warp's candidate rows.  Reads the build's flags (one 4-byte D2H
         after the kernel): a pool that turned out too small is enlarged to what the build asked for and the build is
         repeated.  The returned lists may still carry SPHB_NL_UNLISTABLE / SPHB_NL_POOL (nl.build_flags): the caller then
-        has to use the scanning kernels."""
+        has to use the scanning kernels.
+        consts: also form Omega of the build-time records while the lists are in the staging area -> nl.omega0"""
         hm = hmax if hmax is not None else self.hmax(dg.posh)
+        om = torch.empty(dg.n, dtype=F64, device=self.device) if consts is not None else None
         for _ in range(3):
             nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows)
             nl._hmax = hm
-            self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(), _stream())
+            nl.omega0 = om
+            self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(),
+                      C.byref(consts) if consts is not None else None, _ptr(om), _stream())
             nl.build_flags = nl.read_flags()
             if not (nl.build_flags & N.NL_POOL) or (nl.build_flags & N.NL_UNLISTABLE):
                 break
@@ -683,6 +688,7 @@ class FastStepper:
         self.hold = 0             # steps left on the scanning path after the lists failed on one step
         self.caller_state = None  # resident state in caller order while on hold
         self.stats = dict(steps=0, builds=0, redos=0, safe_steps=0, reuse_rejected=0)
+        self._consts = None       # the constants of the current call (the build forms Omega with them)
 
     # ---- builds ------------------------------------------------------------------------------------
     def _rebuild_from(self, posh_in, vel_in, u_in, ids_in):
@@ -710,7 +716,8 @@ class FastStepper:
             self.cover_h, self.skin = self._choose_margins()
         self.age = 0
         self._moved_prev = self._grown_prev = 0.0
-        self.nl = e.nl_build(dg, self.cover_h, self.skin, pool_rows=self.pool_rows)
+        # Omega(pos0, h0) of the step that follows comes out of the build itself (the lists are in the staging area)
+        self.nl = e.nl_build(dg, self.cover_h, self.skin, pool_rows=self.pool_rows, consts=self._consts)
         self.pool_rows = max(self.nl.pool_rows, self.pool_rows or 0)
         self.stats["builds"] += 1
         self.stale = False
@@ -775,7 +782,10 @@ class FastStepper:
     def _slots_step(self, P0, V0, U0, dt, consts, st, hooks=None):
         """pyfluid.py:502-530 on the kept lists -> P1 (x, y, z, h1), V1, U1 in slot order; inputs untouched"""
         e, nl = self.e, self.nl
-        _, _, om0, _ = e.nl_density_omega(nl, consts, P0)                               # :503
+        if self.fresh and nl.omega0 is not None and P0 is nl.dg.posh:
+            om0 = nl.omega0                                                             # :503, formed by the build
+        else:
+            _, _, om0, _ = e.nl_density_omega(nl, consts, P0)                           # :503
         if hooks is not None:
             V0, U0 = hooks.vel_u()
         rB, rD = e.nl_eos(P0, V0, U0, om0, consts, st.ptr(S_STAGE0))                    # :502,:505
@@ -816,10 +826,12 @@ class FastStepper:
     # ---- resident-state API ---------------------------------------------------------------------------
     SAFE_HOLD = 8
 
-    def load(self, pos, vel, u, h):
+    def load(self, pos, vel, u, h, consts=None):
         """take a caller-order state (device tensors); it stays resident, in slot order, until state() is asked for"""
         self.caller_state = None
         self.hold = 0
+        if consts is not None:
+            self._consts = consts
         self._rebuild_from(self.e.pack_posh(pos, h), vel, u, None)
 
     def state(self):
@@ -841,6 +853,7 @@ class FastStepper:
     def advance(self, dt, consts, defer_status=True, printer=print):
         if consts.G != 0.0:
             raise ValueError("FastStepper runs the G = 0 path; use Stepper for the softened-gravity terms")
+        self._consts = consts
         self.stats["steps"] += 1
         if self.hold > 0:
             return self._safe_advance(dt, consts, defer_status, printer)
@@ -871,6 +884,7 @@ class FastStepper:
             return r
         e = self.e
         n = pos0.shape[0]
+        self._consts = consts
         self.stats["steps"] += 1
         if self.hold > 0:
             self.hold -= 1

@@ -109,6 +109,10 @@ def test_drains_equal_scanning_kernels_bit_for_bit(sph, case, cover_h, skin):
                                                        want_ngb=True)
         for a, b in ((rho_a, rho_b), (dw_a, dw_b), (om_a, om_b), (ng_a, ng_b)):
             assert torch.equal(a, b)
+        nl2 = eng.nl_build(dg, cover_h, skin, consts=c)      # Omega formed by the build itself
+        assert nl2.read_flags() == 0 and torch.equal(nl2.omega0, om_a)
+        assert torch.equal(nl2.warp_rows, nl.warp_rows)
+        del nl2
         # K4
         vel_s, u_s = eng.gather(_to(vel), dg.perm, 3), eng.gather(_to(e), dg.perm, 1)
         _, _, rB, rC = eng.eos(dg.posh, vel_s, u_s, om_a, c, st.ptr(0))
