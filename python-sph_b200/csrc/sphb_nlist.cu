@@ -35,6 +35,9 @@ typedef SphbWarpSharedT<SPHB_NL_LIST> NlWarpShared;
 #ifndef SPHB_MINB_NL_OWN
 #define SPHB_MINB_NL_OWN 8
 #endif
+#ifndef SPHB_NL_EARLY_B
+#define SPHB_NL_EARLY_B 0 /* force drain: load the {v, A} records with the positions, two rows ahead */
+#endif
 #ifndef SPHB_MINB_NL_FORCE
 #define SPHB_MINB_NL_FORCE 4
 #endif
@@ -180,33 +183,49 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
 }
 
 // did any record leave what the lists were built to cover?  (half of a bound used up: SPHB_NL_AGING)
-__global__ void k_nl_check(const double *__restrict__ posh_build, const double *__restrict__ posh_now, long long n,
-                           double skin, double cover_h, int32_t *__restrict__ flags, int32_t *__restrict__ maxima)
+// Grid-stride, one atomic per block and quantity: half a million warps updating two addresses would serialise.
+#define NL_CHECK_THREADS 256
+#define NL_CHECK_BLOCKS 1184
+__global__ void __launch_bounds__(NL_CHECK_THREADS)
+    k_nl_check(const double *__restrict__ posh_build, const double *__restrict__ posh_now, long long n, double skin,
+               double cover_h, int32_t *__restrict__ flags, int32_t *__restrict__ maxima)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool bad = false, old = false;
+    __shared__ int sh[3][NL_CHECK_THREADS / 32];
+    int fl = 0;
     float dr = 0.f, gr = 0.f;   // displacement / h_build and h_now / h_build - 1 (what the caller sizes margins with)
-    if (i < n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double x0, y0, z0, h0, x1, y1, z1, h1;
         sphb_load_posh(posh_build, (size_t)i, x0, y0, z0, h0);
         sphb_load_posh(posh_now, (size_t)i, x1, y1, z1, h1);
         const double dx = x1 - x0, dy = y1 - y0, dz = z1 - z0;
         const double d2 = dx * dx + dy * dy + dz * dz, lim = skin * h0;
-        bad = !(d2 <= lim * lim) || !(h1 <= cover_h * h0);
-        old = !(d2 <= 0.25 * (lim * lim)) || !(h1 <= (1.0 + 0.5 * (cover_h - 1.0)) * h0);
-        if (maxima && h0 > 0.0) {
-            dr = __double2float_ru(sqrt(d2) / h0);
-            gr = fmaxf(__double2float_ru(h1 / h0 - 1.0), 0.f);
+        if (!(d2 <= lim * lim) || !(h1 <= cover_h * h0)) fl |= SPHB_NL_BROKEN;
+        if (!(d2 <= 0.25 * (lim * lim)) || !(h1 <= (1.0 + 0.5 * (cover_h - 1.0)) * h0)) fl |= SPHB_NL_AGING;
+        if (h0 > 0.0) {   // non-negative floats order like their bit patterns; a NaN (> +inf as an integer) sticks
+            dr = __int_as_float(max(__float_as_int(dr), __float_as_int(__double2float_ru(sqrt(d2) / h0))));
+            gr = __int_as_float(max(__float_as_int(gr), __float_as_int(fmaxf(__double2float_ru(h1 / h0 - 1.0), 0.f))));
         }
     }
-    const bool anybad = __any_sync(SPHB_FULL, bad), anyold = __any_sync(SPHB_FULL, old);
-    if ((threadIdx.x & 31) == 0 && (anybad || anyold))
-        atomicOr(flags, (anybad ? SPHB_NL_BROKEN : 0) | (anyold ? SPHB_NL_AGING : 0));
-    if (maxima) {   // non-negative floats order like their bit patterns; a NaN (> +inf as an integer) sticks
-        const int md = __reduce_max_sync(SPHB_FULL, __float_as_int(dr)), mg = __reduce_max_sync(SPHB_FULL, __float_as_int(gr));
-        if ((threadIdx.x & 31) == 0) {
-            if (md > 0) atomicMax(maxima, md);
-            if (mg > 0) atomicMax(maxima + 1, mg);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wf = __reduce_or_sync(SPHB_FULL, fl);
+    const int md = __reduce_max_sync(SPHB_FULL, __float_as_int(dr)), mg = __reduce_max_sync(SPHB_FULL, __float_as_int(gr));
+    if (lane == 0) {
+        sh[0][warp] = wf;
+        sh[1][warp] = md;
+        sh[2][warp] = mg;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int f = 0, d = 0, g = 0;
+        for (int q = 0; q < NL_CHECK_THREADS / 32; ++q) {
+            f |= sh[0][q];
+            d = max(d, sh[1][q]);
+            g = max(g, sh[2][q]);
+        }
+        if (f) atomicOr(flags, f);
+        if (maxima) {
+            if (d > 0) atomicMax(maxima, d);
+            if (g > 0) atomicMax(maxima + 1, g);
         }
     }
 }
@@ -380,7 +399,8 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
         float gr = 0.f;
         if (tgt && hb > 0.0 && h_res > hb) gr = __double2float_ru(h_res / hb - 1.0);
         const int mg = __reduce_max_sync(SPHB_FULL, __float_as_int(gr));
-        if (lane == 0 && mg > 0) atomicMax(nl.maxima + 1, mg);
+        // most warps do not raise the maximum: look before the atomic (half a million of them on one address serialise)
+        if (lane == 0 && mg > 0 && mg > __ldcg(nl.maxima + 1)) atomicMax(nl.maxima + 1, mg);
     }
 }
 
@@ -425,6 +445,42 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
     const int nrows = (int)nl.warp_rows[w];
     const uint32_t *p = nl.pool + (size_t)nl.warp_off[w] * 32 + lane;
     const uint32_t self = valid ? (uint32_t)j : 0u;
+#if SPHB_NL_EARLY_B
+    {
+        // the {v, A} records travel with the positions: both are in flight two rows ahead of the arithmetic
+        uint32_t i0 = nl_row(p, 0, nrows), i1 = nl_row(p, 1, nrows), i2 = nl_row(p, 2, nrows), i3 = nl_row(p, 3, nrows);
+        double A[4], B[4], C[4], D[4], VA[4], VB[4], VC[4], VD[4];
+        nl_fetch(posh, i0, self, A);
+        nl_fetch(posh, i1, self, B);
+        nl_fetch(recB, i0, self, VA);
+        nl_fetch(recB, i1, self, VB);
+        int kk = 0;
+        while (kk < nrows) {
+            nl_fetch(posh, i2, self, C);
+            nl_fetch(posh, i3, self, D);
+            nl_fetch(recB, i2, self, VC);
+            nl_fetch(recB, i3, self, VD);
+            uint32_t n0 = nl_row(p, kk + 4, nrows), n1 = nl_row(p, kk + 5, nrows);
+            sphb_force_pair2<false, DENSE, true>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a,
+                                                 i0 != SPHB_NL_NONE, VA, VB);
+            kk += 2;
+            if (kk >= nrows) break;
+            i0 = n0;
+            i1 = n1;
+            nl_fetch(posh, i0, self, A);
+            nl_fetch(posh, i1, self, B);
+            nl_fetch(recB, i0, self, VA);
+            nl_fetch(recB, i1, self, VB);
+            n0 = nl_row(p, kk + 4, nrows);
+            n1 = nl_row(p, kk + 5, nrows);
+            sphb_force_pair2<false, DENSE, true>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a,
+                                                 i2 != SPHB_NL_NONE, VC, VD);
+            i2 = n0;
+            i3 = n1;
+            kk += 2;
+        }
+    }
+#else
     {
         uint32_t i0 = nl_row(p, 0, nrows), i1 = nl_row(p, 1, nrows), i2 = nl_row(p, 2, nrows), i3 = nl_row(p, 3, nrows);
         double A[4], B[4], C[4], D[4];
@@ -450,6 +506,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
             kk += 2;
         }
     }
+#endif
     if (tgt) {
         const double m = k.particle_mass;
         acc[3 * j] = m * a.ax;
@@ -563,8 +620,10 @@ extern "C" int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, vo
 {
     if (!nl_ok(nl) || !posh_now) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
-    k_nl_check<<<(unsigned)((nl->n + 255) / 256), 256, 0, sphb_stream(stream)>>>(nl->posh_build, posh_now, (long long)nl->n,
-                                                                               nl->skin, nl->cover_h, nl->flags, nl->maxima);
+    long long nb = (nl->n + NL_CHECK_THREADS - 1) / NL_CHECK_THREADS;
+    if (nb > NL_CHECK_BLOCKS) nb = NL_CHECK_BLOCKS;
+    k_nl_check<<<(unsigned)nb, NL_CHECK_THREADS, 0, sphb_stream(stream)>>>(nl->posh_build, posh_now, (long long)nl->n, nl->skin,
+                                                                          nl->cover_h, nl->flags, nl->maxima);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -211,8 +211,11 @@ struct SphbPairTerms {
     bool ok;
 };
 
+// PRE: the candidate's {v, A} record was loaded ahead of time (vb) instead of after the membership test -- one
+// dependent load latency less per pair, a few wasted loads for the candidates that fail the test; same bits
+template <bool PRE = false>
 __device__ __forceinline__ void sphb_force_geom(const double *recB, uint32_t i, const double (&p)[4], bool present,
-                                                const SphbForceAcc &a, SphbPairTerms &t)
+                                                const SphbForceAcc &a, SphbPairTerms &t, const double *vb = nullptr)
 {
     t.dx = a.xj - p[0];
     t.dy = a.yj - p[1];
@@ -228,7 +231,14 @@ __device__ __forceinline__ void sphb_force_geom(const double *recB, uint32_t i, 
     t.ok = present && sphb_nonzero(t.d2) && ((qj < 2.0) || (qi < 2.0));
     double vxi = 0.0, vyi = 0.0, vzi = 0.0;
     t.Ai = 0.0;
-    if (t.ok) sphb_load4(recB, i, vxi, vyi, vzi, t.Ai);
+    if (PRE) {
+        vxi = vb[0];
+        vyi = vb[1];
+        vzi = vb[2];
+        t.Ai = vb[3];
+    } else if (t.ok) {
+        sphb_load4(recB, i, vxi, vyi, vzi, t.Ai);
+    }
     t.sj = sphb_m4c_fp(qj) * a.gj * rinv;
     t.si = sphb_m4c_fp(qi) * gi * rinv;
     const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
@@ -265,14 +275,15 @@ __device__ __forceinline__ void sphb_force_accumulate(const double *bgrav, uint3
 
 // DENSE: recC is a dense [n][2] array of (rho, cs) instead of the 32-byte record (a gathered 16-byte entry shares its
 // cache line with seven neighbours instead of three)
-template <bool GRAV, bool DENSE = false>
+template <bool GRAV, bool DENSE = false, bool PRE = false>
 __device__ __forceinline__ void sphb_force_pair2(const double *recB, const double *recC, const double *bgrav, uint32_t i0,
                                                  uint32_t i1, const double (&p0)[4], const double (&p1)[4], bool second,
-                                                 const sphb_consts &k, SphbForceAcc &a, bool first = true)
+                                                 const sphb_consts &k, SphbForceAcc &a, bool first = true,
+                                                 const double *vb0 = nullptr, const double *vb1 = nullptr)
 {
     SphbPairTerms t0, t1;
-    sphb_force_geom(recB, i0, p0, first, a, t0);
-    sphb_force_geom(recB, i1, p1, second, a, t1);
+    sphb_force_geom<PRE>(recB, i0, p0, first, a, t0, vb0);
+    sphb_force_geom<PRE>(recB, i1, p1, second, a, t1, vb1);
     const bool v0 = t0.ok && t0.vdr < 0.0, v1 = t1.ok && t1.vdr < 0.0;
     double ph0 = 0.0, ph1 = 0.0;
     if (v0 || v1) {

@@ -672,6 +672,7 @@ class FastStepper:
         self.skin = NL_SKIN if skin is None else float(skin)
         self.adaptive = adaptive  # size the margins of every build from the measured motion (else: fixed margins)
         self.rate_d = self.rate_g = None   # measured per-step displacement / h and h growth (maxima over particles)
+        self.slope_d = self.slope_g = 0.0  # and their change from one step to the next
         self.age = 0              # steps run on the current lists
         self.safe = Stepper(engine)
         self.geom = None          # (grid, delta) pinned by the caller; None: from the bounding box at every build
@@ -724,6 +725,7 @@ class FastStepper:
         self.fresh = True                    # no step has run on these lists yet
 
     MAX_SKIN = 0.25
+    SAFETY = float(os.environ.get("SPHB_NL_SAFETY", "1.25"))   # margin on the extrapolated motion
     BUILD_OVER_DRAIN = float(os.environ.get("SPHB_NL_BUILD_COST", "0.28"))   # one rebuild / one step's drains
 
     def _choose_margins(self):
@@ -732,9 +734,11 @@ class FastStepper:
         if self.rate_d is None:
             return self.cover_h, self.skin
         best = None
+        sd, sg = max(self.slope_d, 0.0), max(self.slope_g, 0.0)   # the per-step motion itself grows (accelerating flow)
         for L in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32):
-            skin = 1.5 * self.rate_d * L + 0.002
-            grow = 1.5 * self.rate_g * L + 0.002
+            f = self.SAFETY
+            skin = f * (self.rate_d * L + sd * L * (L + 1) / 2) + 0.001
+            grow = f * (self.rate_g * L + sg * L * (L + 1) / 2) + 0.001
             if best is not None and (skin > self.MAX_SKIN or grow > 0.25):
                 break
             skin, grow = min(skin, self.MAX_SKIN), min(grow, 0.25)
@@ -749,10 +753,13 @@ class FastStepper:
         self.age += 1
         dd, dg_ = nl.moved - self._moved_prev, nl.grown - self._grown_prev
         self._moved_prev, self._grown_prev = nl.moved, nl.grown
-        self.rate_d = max(dd, nl.moved / self.age)
-        self.rate_g = max(dg_, nl.grown / self.age)
-        if self.adaptive and (nl.moved + 1.3 * self.rate_d > 0.95 * nl.skin or
-                              nl.grown + 1.3 * self.rate_g > 0.95 * (nl.cover_h - 1.0)):
+        rd, rg = max(dd, nl.moved / self.age), max(dg_, nl.grown / self.age)
+        if self.rate_d is not None:
+            self.slope_d, self.slope_g = rd - self.rate_d, rg - self.rate_g
+        self.rate_d, self.rate_g = rd, rg
+        f = self.SAFETY
+        if self.adaptive and (nl.moved + f * (rd + max(self.slope_d, 0.0)) > nl.skin or
+                              nl.grown + f * (rg + max(self.slope_g, 0.0)) > nl.cover_h - 1.0):
             self.stale = True
 
     def _adapt(self, flags):
@@ -769,8 +776,8 @@ class FastStepper:
             self.skin = min(self.MAX_SKIN, max(2.0 * self.skin, 0.02))
             self.cover_h = 1.0 + min(0.25, max(2.0 * (self.cover_h - 1.0), 0.02))
             # the measured rates said less: do not let the next choice shrink the margins again
-            self.rate_d = max(self.rate_d or 0.0, self.skin / 1.5)
-            self.rate_g = max(self.rate_g or 0.0, (self.cover_h - 1.0) / 1.5)
+            self.rate_d = max(self.rate_d or 0.0, self.skin / self.SAFETY)
+            self.rate_g = max(self.rate_g or 0.0, (self.cover_h - 1.0) / self.SAFETY)
             self.stats["widened"] = self.stats.get("widened", 0) + 1
         elif self.adaptive and self.rate_d is not None:
             # kept lists broke: the motion since the build is faster than the rates they were sized for
