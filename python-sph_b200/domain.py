@@ -145,15 +145,17 @@ class SlabRunner:
         lo = pos.min(dim=0).values
         hi = pos.max(dim=0).values
         s = torch.stack([h.sum(), torch.tensor(float(h.numel()), dtype=F64, device=self.dev)])
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        if self.world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
         lo, hi, s = lo.tolist(), hi.tolist(), s.tolist()
         return E.choose_grid(lo, hi, s[0] / s[1], int(s[1]))
 
     def _hmax(self, h):
         t = h.max().reshape(1).clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def _make_plan(self, st, extra=1.0):
@@ -434,6 +436,324 @@ class SlabRunner:
                 "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(tot.item()), "steps": steps}
 
 
+
+class SlotExchanger:
+    """Ghost refresh in a FROZEN slot order (pure torch plumbing: any device, any backend).
+
+    Between two rebuilds of the neighbour lists the local arrays [owned..., ghosts...] keep their sorted slots; what
+    changes is the values.  `refresh` sends the owners' current values along the send lists of the halo plan and writes
+    what arrives straight into the ghosts' slots: one pack, one all_to_all_single, one unpack, for any number of arrays."""
+
+    def __init__(self, hx: HaloExchanger, slot_of_loc, n_own):
+        self.hx = hx
+        self.send_slots = slot_of_loc.index_select(0, hx.all_idx)          # destination-major, owned order within
+        self.ghost_slots = slot_of_loc[n_own:].contiguous()                # arrival order: source rank, sender's order
+        self.n_recv = hx.n_recv
+        self.calls = 0
+
+    def refresh(self, arrays):
+        """arrays: slot-order tensors (n_loc,) or (n_loc, k); the ghosts' rows are overwritten in place"""
+        cols = [a.reshape(a.shape[0], -1) for a in arrays]
+        widths = [c.shape[1] for c in cols]
+        K = sum(widths)
+        if self.hx.world == 1 or K == 0:
+            return
+        packed = torch.cat([c.index_select(0, self.send_slots) for c in cols], dim=1)
+        out = torch.empty((self.n_recv, K), dtype=packed.dtype, device=packed.device)
+        dist.all_to_all_single(out, packed, output_split_sizes=self.hx.recv_counts, input_split_sizes=self.hx.send_counts,
+                               group=self.hx.group)
+        self.calls += 1
+        o = 0
+        for c, wd in zip(cols, widths):
+            c.index_copy_(0, self.ghost_slots, out[:, o:o + wd])
+            o += wd
+
+
+class FastSlabRunner(SlabRunner):
+    """SlabRunner on neighbour lists that are kept across kernels and steps (engine.FastStepper's multi-GPU form).
+
+    At a rebuild (all ranks together, decided by the all-reduced list flags): migrate, refresh the grid geometry from
+    the global bounding box, fix the ghost set -- everything within 2 h_max (cover_h + skin) of the slab --, build ONE
+    cell list over [owned..., ghosts...] with ties broken by global id, and scan it once for the owned targets.  Until
+    the next rebuild the local arrays keep that slot order; a step is five list drains, the elementwise kernels, and
+    FOUR ghost refreshes (h + Omega, the predicted state, h_mid + Omega_mid, the corrected state) in the frozen order.
+    Sums are formed in (cell, global id) order on the same cells as a single-GPU FastStepper run: same bits."""
+
+    def __init__(self, eng: E.Engine, consts, world, rank, margin=0.0, balance=True, calib_steps=0, cover_h=None, skin=None,
+                 adaptive=True):
+        super().__init__(eng, consts, world, rank, margin=margin, balance=balance, calib_steps=calib_steps)
+        self.margins = E.ListMargins(cover_h, skin, adaptive)
+        self.nl = None
+        self.fast = None          # slot-order state between rebuilds: dict(P, V, U, gid_S, wfac_S, ...)
+        self.stale = True
+        self.hold = 0
+        self.stats = dict(steps=0, builds=0, redos=0, safe_steps=0, exchanges=0)
+
+    # ---- collectives on a few scalars ----------------------------------------------------------------------
+    def _allmax(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
+    # ---- rebuild ----------------------------------------------------------------------------------------------
+    def _to_owned(self):
+        """slot-order state -> the dict SlabRunner works with (owned particles only)"""
+        f = self.fast
+        own = f["own_slots"]
+        P = f["P"].index_select(0, own)
+        return dict(gid=f["gid_S"].index_select(0, own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
+                    vel=f["V"].index_select(0, own), u=f["U"].index_select(0, own), wfac=f["wfac_S"].index_select(0, own))
+
+    def _rebuild(self, st):
+        """st: owned-order dict.  Migrate, plan the halo for the lists' whole life, sort, scan."""
+        e = self.e
+        self.nl = None
+        self.fast = None
+        if self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None:
+            st = self._rebalance_rows(st)
+        else:
+            st = self._migrate(st) if self.world > 1 else st
+        self.geom = self._global_geom(st["pos"], st["h"])      # refreshed at every rebuild (cells follow the gas)
+        cover_h, skin = self.margins.choose()
+        self.margins.built()
+        hm = self._hmax(st["h"])
+        width = 2.0 * hm * (cover_h + skin) * (1.0 + 1e-6 + self.margin) + 4.0 * self.geom[1]
+        hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width) if self.world > 1 \
+            else None
+        n_own = st["gid"].numel()
+        if hx is not None:
+            g = hx.exchange([st["gid"].to(F64), st["pos"], st["h"], st["vel"], st["u"]])
+            gid_all = torch.cat([st["gid"], g[0].to(torch.int64)])
+            pos_L, h_L = torch.cat([st["pos"], g[1]]), torch.cat([st["h"], g[2]])
+            vel_L, u_L = torch.cat([st["vel"], g[3]]), torch.cat([st["u"], g[4]])
+        else:
+            gid_all, pos_L, h_L, vel_L, u_L = st["gid"], st["pos"], st["h"], st["vel"], st["u"]
+        dg = e.build(e.pack_posh(pos_L, h_L), *self.geom, tie_key=gid_all)
+        perm = dg.perm.long()                                   # slot -> local index
+        target = (perm < n_own).to(torch.uint8)
+        self.nl = e.nl_build(dg, cover_h, skin, target=target if self.world > 1 else None, consts=self.consts)
+        slot_of_loc = torch.empty_like(perm)
+        slot_of_loc[perm] = torch.arange(perm.numel(), device=perm.device)
+        wf = st.get("wfac")
+        if wf is None:
+            wf = torch.ones_like(st["h"])
+        wf_L = torch.cat([wf, torch.ones(perm.numel() - n_own, dtype=F64, device=self.dev)])
+        self.fast = dict(P=dg.posh, V=vel_L.index_select(0, perm), U=u_L.index_select(0, perm), gid_S=gid_all.index_select(0, perm),
+                         wfac_S=wf_L.index_select(0, perm), target=target if self.world > 1 else None,
+                         own_slots=slot_of_loc[:n_own].contiguous(), n_own=n_own,
+                         sx=SlotExchanger(hx, slot_of_loc, n_own) if hx is not None else None, fresh=True, ghost_h_stale=False)
+        self.stats["builds"] += 1
+        self.stale = False
+        # agree on the build's verdict (pool / unlistable) over all ranks
+        if self.world > 1:
+            bf = torch.tensor([self.nl.build_flags, 0, 0, 0], dtype=torch.int32, device=self.dev)
+            self._agree(bf)
+            self.nl.build_flags = int(bf[0].item())
+        self._note_rows()
+
+    def _agree(self, flags4):
+        """OR of the SPHB_NL_* flags and MAX of the two maxima over all ranks, in one all-reduce (bits as a MAX per bit;
+        non-negative float bit patterns order like integers)"""
+        if self.world == 1:
+            return
+        if not hasattr(self, "_bitpos"):
+            self._bitpos = torch.arange(8, dtype=torch.int32, device=self.dev)
+        v = torch.cat([(flags4[0:1] >> self._bitpos) & 1, flags4[1:3]])
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        flags4[0:1] = (v[:8] << self._bitpos).sum().to(torch.int32)
+        flags4[1:3] = v[8:10]
+
+    _rows_weight = None
+
+    def _rebalance_rows(self, st, nbins=16384):
+        """work-balanced cut planes from what the drains actually walk: the list rows of each particle's warp (measured
+        on the previous lists, travelling with the particle as `wfac`), one all-reduced weighted x-histogram"""
+        x = st["pos"][:, 0].contiguous()
+        wgt = st["wfac"]
+        ext = torch.stack([x.min(), -x.max()])
+        dist.all_reduce(ext, op=dist.ReduceOp.MIN)
+        xlo, xhi = float(ext[0].item()), float(-ext[1].item())
+        span = max(xhi - xlo, 1e-300)
+        b = ((x - xlo) * (nbins / span)).long().clamp_(0, nbins - 1)
+        hist = torch.bincount(b, weights=wgt, minlength=nbins)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        cum = torch.cumsum(hist, 0).cpu()
+        total = float(cum[-1])
+        cuts = [-math.inf]
+        for r in range(1, self.world):
+            k = int(torch.searchsorted(cum, torch.tensor(total * r / self.world, dtype=cum.dtype)).item())
+            cuts.append(xlo + (min(k, nbins - 1) + 1) * span / nbins)
+        cuts.append(math.inf)
+        self.cuts = cuts
+        return self._migrate(st)
+
+    def _note_rows(self):
+        """per-particle work weight for the next re-balance: rows of the particle's warp (+ a constant for the
+        elementwise kernels)"""
+        f, nl = self.fast, self.nl
+        rows = nl.warp_rows.to(F64).repeat_interleave(32)[:nl.n]
+        f["wfac_S"] = rows + 8.0
+        self._rows_weight = True
+
+    # ---- one step in slot order ------------------------------------------------------------------------------------
+    def _slots_step(self, dt, stt):
+        e, nl, f, c = self.e, self.nl, self.fast, self.consts
+        P0, V0, U0, tgt, sx = f["P"], f["V"], f["U"], f["target"], f["sx"]
+        if f["fresh"] and nl.omega0 is not None:
+            om0 = nl.omega0                                                             # pyfluid.py:503, formed by the build
+        else:
+            _, _, om0, _ = e.nl_density_omega(nl, c, P0, target=tgt)
+        if sx is not None:
+            if f["ghost_h_stale"]:
+                hcol = P0[:, 3].contiguous()
+                sx.refresh([hcol, om0])                                                 # ghosts' h1 (last step) and Omega
+                P0[:, 3] = hcol
+            else:
+                sx.refresh([om0])
+        rB, rD = e.nl_eos(P0, V0, U0, om0, c, stt.ptr(E.S_STAGE0))
+        acc0, dudt0 = e.nl_force(nl, c, P0, rB, None, stt.ptr(E.S_STAGE0), target=tgt, recD=rD)
+        Pm, Vm, Um = e.predict(P0, V0, U0, acc0, dudt0, dt, stt.ptr(E.S_PRED))
+        if sx is not None:
+            sx.refresh([Pm, Vm, Um])
+        e.nl_check(nl, Pm)
+        hm, omm, Pm2, _ = e.nl_newton(nl, c, Pm, stt.ptr(E.S_NEWTON_MID), target=tgt, want_omega=True)
+        if sx is not None:
+            sx.refresh([hm, omm])
+            Pm2[:, 3] = hm
+        rB, rD = e.nl_eos(Pm2, Vm, Um, omm, c, stt.ptr(E.S_STAGE_MID))
+        acc1, dudt1 = e.nl_force(nl, c, Pm2, rB, None, stt.ptr(E.S_STAGE_MID), target=tgt, recD=rD)
+        P1, V1, U1 = e.correct(P0, V0, U0, acc1, dudt1, dt, stt.ptr(E.S_CORR))
+        if sx is not None:
+            sx.refresh([P1, V1, U1])
+        e.nl_check(nl, P1)
+        _, _, P1b, _ = e.nl_newton(nl, c, P1, stt.ptr(E.S_NEWTON_1), target=tgt, h_guess=hm)
+        return P1b, V1, U1
+
+    _BAD = E.N.NL_BROKEN | E.N.NL_POOL | E.N.NL_UNLISTABLE
+
+    def _try(self, dt):
+        """one step on the current lists -> (ok, P1, V1, U1, status)"""
+        nl, f = self.nl, self.fast
+        if nl.build_flags & self._BAD:
+            self.last_flags, self.fresh_failed = nl.build_flags, False
+            return False, None, None, None, None
+        stt = E.Status(E.S_COUNT, self.dev)
+        P1, V1, U1 = self._slots_step(dt, stt)
+        self._agree(nl.flags)
+        flags = self.last_flags = nl.read_flags()
+        ok = (flags & self._BAD) == 0
+        self.fresh_failed = f["fresh"] and not ok
+        if ok and self.margins.note(nl.moved, nl.grown, flags & E.N.NL_AGING):
+            self.stale = True
+        return ok, P1, V1, U1, stt
+
+    MAX_ATTEMPTS = 4
+    SAFE_HOLD = 8
+
+    def _step(self, st, dt):
+        """st: an owned-order dict, or None when the state is resident in slot order (self.fast)"""
+        self.stats["steps"] += 1
+        if self.hold > 0:
+            self.hold -= 1
+            self.stats["safe_steps"] += 1
+            return SlabRunner._step(self, st, dt)
+        for attempt in range(self.MAX_ATTEMPTS):
+            if self.fast is None:
+                self._rebuild(st)
+            elif self.stale or attempt > 0:
+                self._rebuild(self._to_owned())
+            ok, P1, V1, U1, stt = self._try(dt)
+            if ok:
+                f = self.fast
+                f["P"], f["V"], f["U"], f["fresh"], f["ghost_h_stale"] = P1, V1, U1, False, f["sx"] is not None
+                self.statuses.append(stt)
+                if f["sx"] is not None:
+                    self.stats["exchanges"] += f["sx"].calls
+                    f["sx"].calls = 0
+                self._version += 1
+                return _LazyOwned(self, self._version)
+            self.stats["redos"] += 1
+            if self.last_flags & (E.N.NL_UNLISTABLE | E.N.NL_POOL):
+                break
+            if not self.margins.failed(self.fresh_failed, self.nl.moved, self.nl.grown):
+                break
+        # the lists cannot serve this step: scanning path for a while
+        st = self._to_owned()
+        self.nl = None
+        self.fast = None
+        self.plan = None
+        self.hold = self.SAFE_HOLD
+        self.stats["steps"] -= 1
+        return self._step(st, dt)
+
+    _version = 0
+
+    def step(self, st, dt):
+        """st: an owned-order dict (a new state), or what the previous step() returned"""
+        if isinstance(st, _LazyOwned):
+            if st.runner is self and st.version == self._version and self.fast is not None:
+                return self._step(None, dt)
+            st = dict(st.resolve())
+        self.fast = None
+        self.nl = None
+        return self._step(st, dt)
+
+    def calibrate(self, st, dt, rounds=2):
+        """the list rows ARE the measured work: one throw-away build + step is enough to balance the cuts"""
+        if not self.balance or self.world == 1:
+            return st
+        tok = self.step(st, dt)
+        self.statuses.pop()
+        out = dict(tok.resolve())           # the state BEFORE the throw-away step is `st`; keep it, take the weights
+        back = dict(st)
+        # weights by global id: the throw-away step did not migrate anybody (a rebuild migrates before it plans)
+        order = torch.argsort(out["gid"])
+        pos_in = torch.searchsorted(out["gid"][order], back["gid"])
+        back["wfac"] = out["wfac"][order][pos_in]
+        self.fast = None
+        self.nl = None
+        self.stale = True
+        self._rows_weight = True
+        self.margins = E.ListMargins(self.margins.cover_h, self.margins.skin, self.margins.adaptive)
+        return back
+
+
+class _LazyOwned(dict):
+    """The owned-order view of a FastSlabRunner's state, materialised only when somebody looks at it (bench checksums,
+    gather_state, tests): between rebuilds the state lives in the lists' slot order."""
+
+    def __init__(self, runner, version):
+        super().__init__()
+        self.runner, self.version = runner, version
+        self._done = False
+
+    def resolve(self):
+        if not self._done:
+            if self.version != self.runner._version or self.runner.fast is None:
+                raise RuntimeError("this state has been stepped past; keep what step() returned last")
+            super().update(self.runner._to_owned())
+            self._done = True
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self.resolve(), k)
+
+    def get(self, k, d=None):
+        return dict.get(self.resolve(), k, d)
+
+    def items(self):
+        return dict.items(self.resolve())
+
+    def keys(self):
+        return dict.keys(self.resolve())
+
+    def __iter__(self):
+        return dict.__iter__(self.resolve())
+
+
+
 def make_runner(eng, consts, world, rank, lists=True, **kw):
     """the slab runner bench.py and the tests use: kept neighbour lists when `lists` (and G = 0), else the scanning one"""
+    if lists and consts.G == 0.0:
+        return FastSlabRunner(eng, consts, world, rank, **kw)
     return SlabRunner(eng, consts, world, rank, **kw)

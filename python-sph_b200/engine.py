@@ -156,6 +156,11 @@ def choose_grid(lo, hi, h_mean, n, pad_cells=1.0, cell=None, xdiv=None):
     ext = [max(hi[k] - lo[k], 0.0) for k in range(3)]
     if cell is None:
         cell = 2.0 * h_mean * CELL_FACTOR
+        if cell > 0.0 and math.isfinite(cell):
+            # 12 significant bits: the mean h of a decomposed run (per-rank sums, then an all-reduce) differs from the
+            # single-GPU one in the last bits, and the two runs must still draw the very same cells
+            m, ex = math.frexp(cell)
+            cell = math.ldexp(round(m * 4096.0) / 4096.0, ex)
     if not (cell > 0.0) or not math.isfinite(cell):
         cell = max(max(ext), 1.0)
     cell = max(cell, max(ext) * 1e-4, 1e-300)   # at most 1e4 cells per axis (y,z)
@@ -649,6 +654,87 @@ NL_COVER_H = float(os.environ.get("SPHB_NL_COVER_H", "1.03"))
 NL_SKIN = float(os.environ.get("SPHB_NL_SKIN", "0.03"))
 
 
+class ListMargins:
+    """How wide the next neighbour lists are built (cover_h, skin) and when they are rebuilt.
+
+    Lists that are to live L steps need margins of L x the per-step motion; their drains cost ~ (cover_h + skin)^3,
+    the rebuild 1/L of BUILD_OVER_DRAIN: take the cheapest L.  The per-step motion (largest displacement / h and
+    largest relative h growth over all particles -- and over all ranks) is measured by the lists' own checks and
+    extrapolated linearly; a step that would leave the margins makes the lists stale BEFORE it runs.  Shared by the
+    single-GPU FastStepper and the slab runner: the same measurements give the same decisions on every rank."""
+    MAX_SKIN = 0.25
+    MAX_GROW = 0.25
+    SAFETY = float(os.environ.get("SPHB_NL_SAFETY", "1.25"))                  # margin on the extrapolated motion
+    BUILD_OVER_DRAIN = float(os.environ.get("SPHB_NL_BUILD_COST", "0.28"))    # one rebuild / one step's drains
+
+    def __init__(self, cover_h=None, skin=None, adaptive=True):
+        self.cover_h = NL_COVER_H if cover_h is None else float(cover_h)
+        self.skin = NL_SKIN if skin is None else float(skin)
+        self.adaptive = adaptive
+        self.rate_d = self.rate_g = None   # per-step displacement / h and h growth
+        self.slope_d = self.slope_g = 0.0  # their change from one step to the next
+        self.age = 0                       # steps run on the current lists
+        self._moved = self._grown = 0.0
+        self.widened = 0
+
+    def choose(self):
+        """-> cover_h, skin of the next build"""
+        if not self.adaptive or self.rate_d is None:
+            return self.cover_h, self.skin
+        best = None
+        sd, sg = max(self.slope_d, 0.0), max(self.slope_g, 0.0)   # the per-step motion itself grows (accelerating flow)
+        f = self.SAFETY
+        for L in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32):
+            skin = f * (self.rate_d * L + sd * L * (L + 1) / 2) + 0.001
+            grow = f * (self.rate_g * L + sg * L * (L + 1) / 2) + 0.001
+            if best is not None and (skin > self.MAX_SKIN or grow > self.MAX_GROW):
+                break
+            skin, grow = min(skin, self.MAX_SKIN), min(grow, self.MAX_GROW)
+            cost = (1.0 + grow + skin) ** 3 + self.BUILD_OVER_DRAIN / L
+            if best is None or cost < best[0]:
+                best = (cost, 1.0 + grow, skin)
+        self.cover_h, self.skin = best[1], best[2]
+        return self.cover_h, self.skin
+
+    def built(self):
+        self.age = 0
+        self._moved = self._grown = 0.0
+
+    def note(self, moved, grown, aging):
+        """after a successful step on lists with the current margins: moved / grown = the largest displacement / h
+        and h growth since their build.  -> True when the lists should be rebuilt before the next step"""
+        self.age += 1
+        dd, dg_ = moved - self._moved, grown - self._grown
+        self._moved, self._grown = moved, grown
+        rd, rg = max(dd, moved / self.age), max(dg_, grown / self.age)
+        if self.rate_d is not None:
+            self.slope_d, self.slope_g = rd - self.rate_d, rg - self.rate_g
+        self.rate_d, self.rate_g = rd, rg
+        if not self.adaptive:
+            return bool(aging)
+        f = self.SAFETY
+        return (moved + f * (rd + max(self.slope_d, 0.0)) > self.skin or
+                grown + f * (rg + max(self.slope_g, 0.0)) > self.cover_h - 1.0)
+
+    def failed(self, fresh, moved, grown):
+        """a step ended with SPHB_NL_BROKEN.  fresh: its lists had been built for that very step.  -> False: give up"""
+        if fresh:
+            # even lists built for this state broke within the step: the motion per step exceeds the margins -- widen
+            if self.skin >= self.MAX_SKIN:
+                return False
+            self.skin = min(self.MAX_SKIN, max(2.0 * self.skin, 0.02))
+            self.cover_h = 1.0 + min(self.MAX_GROW, max(2.0 * (self.cover_h - 1.0), 0.02))
+            # the measured rates said less: do not let the next choice shrink the margins again
+            self.rate_d = max(self.rate_d or 0.0, self.skin / self.SAFETY)
+            self.rate_g = max(self.rate_g or 0.0, (self.cover_h - 1.0) / self.SAFETY)
+            self.widened += 1
+        elif self.adaptive and self.rate_d is not None:
+            # kept lists broke: the motion since the build is faster than the rates they were sized for
+            self.rate_d = max(self.rate_d, 2.0 * moved / max(self.age + 1, 1))
+            self.rate_g = max(self.rate_g, 2.0 * grown / max(self.age + 1, 1))
+        return True
+
+
 class FastStepper:
     """var_smoothlength_leapfrog (pyfluid.py:498-532, G = 0) on neighbour lists that are kept across kernels and steps.
 
@@ -668,12 +754,7 @@ class FastStepper:
 
     def __init__(self, engine, cover_h=None, skin=None, adaptive=True):
         self.e = engine
-        self.cover_h = NL_COVER_H if cover_h is None else float(cover_h)
-        self.skin = NL_SKIN if skin is None else float(skin)
-        self.adaptive = adaptive  # size the margins of every build from the measured motion (else: fixed margins)
-        self.rate_d = self.rate_g = None   # measured per-step displacement / h and h growth (maxima over particles)
-        self.slope_d = self.slope_g = 0.0  # and their change from one step to the next
-        self.age = 0              # steps run on the current lists
+        self.margins = ListMargins(cover_h, skin, adaptive)   # how wide the lists are built, when they are rebuilt
         self.safe = Stepper(engine)
         self.geom = None          # (grid, delta) pinned by the caller; None: from the bounding box at every build
         self.nl = None
@@ -713,77 +794,34 @@ class FastStepper:
             self.ids = ids_in.index_select(0, perm_l)
             self.perm = self.ids.to(torch.int32)
         self.P = dg.posh                     # never written in place: every kernel below returns fresh arrays
-        if self.adaptive:
-            self.cover_h, self.skin = self._choose_margins()
-        self.age = 0
-        self._moved_prev = self._grown_prev = 0.0
+        cover_h, skin = self.margins.choose()
+        self.margins.built()
         # Omega(pos0, h0) of the step that follows comes out of the build itself (the lists are in the staging area)
-        self.nl = e.nl_build(dg, self.cover_h, self.skin, pool_rows=self.pool_rows, consts=self._consts)
+        self.nl = e.nl_build(dg, cover_h, skin, pool_rows=self.pool_rows, consts=self._consts)
         self.pool_rows = max(self.nl.pool_rows, self.pool_rows or 0)
         self.stats["builds"] += 1
         self.stale = False
         self.fresh = True                    # no step has run on these lists yet
 
-    MAX_SKIN = 0.25
-    SAFETY = float(os.environ.get("SPHB_NL_SAFETY", "1.25"))   # margin on the extrapolated motion
-    BUILD_OVER_DRAIN = float(os.environ.get("SPHB_NL_BUILD_COST", "0.28"))   # one rebuild / one step's drains
+    @property
+    def skin(self):
+        return self.margins.skin
 
-    def _choose_margins(self):
-        """cover_h, skin of the next build.  Lists that are to live L steps need margins of L x the per-step motion;
-        their drains cost ~ (cover_h + skin)^3, the rebuild 1/L of BUILD_OVER_DRAIN: take the cheapest L."""
-        if self.rate_d is None:
-            return self.cover_h, self.skin
-        best = None
-        sd, sg = max(self.slope_d, 0.0), max(self.slope_g, 0.0)   # the per-step motion itself grows (accelerating flow)
-        for L in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32):
-            f = self.SAFETY
-            skin = f * (self.rate_d * L + sd * L * (L + 1) / 2) + 0.001
-            grow = f * (self.rate_g * L + sg * L * (L + 1) / 2) + 0.001
-            if best is not None and (skin > self.MAX_SKIN or grow > 0.25):
-                break
-            skin, grow = min(skin, self.MAX_SKIN), min(grow, 0.25)
-            cost = (1.0 + grow + skin) ** 3 + self.BUILD_OVER_DRAIN / L
-            if best is None or cost < best[0]:
-                best = (cost, 1.0 + grow, skin)
-        return best[1], best[2]
+    @property
+    def cover_h(self):
+        return self.margins.cover_h
 
-    def _note_motion(self):
-        """after a successful step: per-step rates from the lists' maxima, and whether the next step would still fit"""
-        nl = self.nl
-        self.age += 1
-        dd, dg_ = nl.moved - self._moved_prev, nl.grown - self._grown_prev
-        self._moved_prev, self._grown_prev = nl.moved, nl.grown
-        rd, rg = max(dd, nl.moved / self.age), max(dg_, nl.grown / self.age)
-        if self.rate_d is not None:
-            self.slope_d, self.slope_g = rd - self.rate_d, rg - self.rate_g
-        self.rate_d, self.rate_g = rd, rg
-        f = self.SAFETY
-        if self.adaptive and (nl.moved + f * (rd + max(self.slope_d, 0.0)) > nl.skin or
-                              nl.grown + f * (rg + max(self.slope_g, 0.0)) > nl.cover_h - 1.0):
-            self.stale = True
+    @property
+    def age(self):
+        return self.margins.age
 
     def _adapt(self, flags):
         """a step failed on its lists (flags = SPHB_NL_*): what to change before the rebuild.  -> False: give up"""
-        if flags & N.NL_UNLISTABLE:
-            return False
-        if flags & N.NL_POOL:
+        if flags & (N.NL_UNLISTABLE | N.NL_POOL):
             return False      # Engine.nl_build already enlarged the pool as far as it may
-        if self.fresh_failed:
-            # even lists built for this very state broke within the step: particles move (or h grows) by more than the
-            # margins per step -- widen them, then give up
-            if self.skin >= self.MAX_SKIN:
-                return False
-            self.skin = min(self.MAX_SKIN, max(2.0 * self.skin, 0.02))
-            self.cover_h = 1.0 + min(0.25, max(2.0 * (self.cover_h - 1.0), 0.02))
-            # the measured rates said less: do not let the next choice shrink the margins again
-            self.rate_d = max(self.rate_d or 0.0, self.skin / self.SAFETY)
-            self.rate_g = max(self.rate_g or 0.0, (self.cover_h - 1.0) / self.SAFETY)
-            self.stats["widened"] = self.stats.get("widened", 0) + 1
-        elif self.adaptive and self.rate_d is not None:
-            # kept lists broke: the motion since the build is faster than the rates they were sized for
-            self.rate_d = max(self.rate_d, 2.0 * self.nl.moved / max(self.age + 1, 1))
-            self.rate_g = max(self.rate_g, 2.0 * self.nl.grown / max(self.age + 1, 1))
-        return True
+        ok = self.margins.failed(self.fresh_failed, self.nl.moved, self.nl.grown)
+        self.stats["widened"] = self.margins.widened
+        return ok
 
     # ---- one step in slot order ---------------------------------------------------------------------
     def _slots_step(self, P0, V0, U0, dt, consts, st, hooks=None):
@@ -824,10 +862,8 @@ class FastStepper:
         ok = (fl & self._BAD) == 0
         self.fresh_failed = self.fresh and not ok
         self.fresh = False
-        if ok:
-            self._note_motion()
-            if (fl & N.NL_AGING) and not self.adaptive:
-                self.stale = True
+        if ok and self.margins.note(self.nl.moved, self.nl.grown, fl & N.NL_AGING):
+            self.stale = True
         return ok, P1, V1, U1, st
 
     # ---- resident-state API ---------------------------------------------------------------------------
@@ -905,7 +941,7 @@ class FastStepper:
             # the new input in the old slot order; does it pass the lists' own validity check?
             self.P, _, _ = e.gather_state(self.perm, pos=pos0, h=h0)
             e.nl_check(self.nl, self.P)
-            if self.nl.read_flags() & (self._BAD | (0 if self.adaptive else N.NL_AGING)):
+            if self.nl.read_flags() & (self._BAD | (0 if self.margins.adaptive else N.NL_AGING)):
                 reuse = False
                 self.stats["reuse_rejected"] += 1
             elif fh is None:

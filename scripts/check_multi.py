@@ -24,14 +24,15 @@ def main():
     dev = torch.device("cuda", local)
     eng = E.Engine(dev)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
-    nsteps = 2
+    nsteps = int(os.environ.get("CHECK_STEPS", "2"))
+    lists = os.environ.get("CHECK_PATH", "lists") == "lists"
     w = workloads.sod_tube(int(sys.argv[2])) if len(sys.argv) > 2 else workloads.uniform_random(n, seed=3, vscale=0.5)
     k = dict(PARTICLE_MASS=w["m"], COUPLING_CONST=1.3, SMOOTHLENGTH_VARIATION_TOLERANCE=1e-3, NEWTON_ITERATION_LIMIT=20,
              BISECTION_ITERATION_LIMIT=100, ALPHA_SPH=1.0, BETA_SPH=2.0, EPSILON=0.01, BISECTION_TOLERANCE=1e-10,
              INITIAL_BISECTION_SMOOTHLENGTH_A=1e3, INITIAL_BISECTION_SMOOTHLENGTH_B=1e-3, G=0.0, ADIABATIC_INDEX=5 / 3)
     consts = E.make_consts(k)
     dt = w["dt"]
-    runner = domain.SlabRunner(eng, consts, world, rank)
+    runner = domain.make_runner(eng, consts, world, rank, lists=lists)
     st = runner.scatter_initial(w)
     geom0 = runner._global_geom(st["pos"], st["h"])
     st = runner.cold_solve(st)
@@ -47,15 +48,26 @@ def main():
         s0 = E.Status(1, dev)
         dg = eng.build(eng.pack_posh(pos, hg), *geom0)
         h = eng.scatter(eng.newton(dg, consts, dg.posh[:, 3].contiguous(), s0.ptr(0)), dg.perm, 1)
-        stp = E.Stepper(eng)
-        stp.geom = geom1
-        s = (pos, vel, u, h)
-        for _ in range(nsteps):
-            s = stp.step(s[0], s[1], s[2], s[3], dt, consts)
+        if lists:
+            # the single-GPU form of the same path: its builds take the geometry from the same (global) bounding box
+            stp = E.FastStepper(eng)
+            stp.load(pos, vel, u, h, consts)
+            for _ in range(nsteps):
+                stp.advance(dt, consts, defer_status=False)
+            s = stp.state()
+            res["_lists"] = {"ranks": dict(runner.stats), "single": dict(stp.stats)}
+        else:
+            stp = E.Stepper(eng)
+            stp.geom = geom1
+            s = (pos, vel, u, h)
+            for _ in range(nsteps):
+                s = stp.step(s[0], s[1], s[2], s[3], dt, consts)
         for name, a, b in (("pos", full["pos"], s[0]), ("vel", full["vel"], s[1]), ("u", full["u"], s[2]), ("h", full["h"], s[3])):
             res[name] = {"max_abs_diff": float((a - b).abs().max().item()), "bit_identical": bool(torch.equal(a, b)),
                          "scale": float(b.abs().max().item())}
-        print(json.dumps({"world": world, "n": int(pos.shape[0]), "steps": nsteps, "compare": res}))
+        stats = res.pop("_lists", None)
+        print(json.dumps({"world": world, "n": int(pos.shape[0]), "steps": nsteps, "path": "lists" if lists else "scan",
+                          "list_stats": stats, "compare": res}))
         ok = all(v["max_abs_diff"] <= 1e-12 * max(v["scale"], 1e-300) for v in res.values())
         if not ok:
             dist.destroy_process_group()

@@ -61,6 +61,58 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_slots(rank, world, port, q):
+    """SlotExchanger: ghost refresh in a frozen (shuffled) slot order"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import domain
+        rng = np.random.default_rng(1)
+        n = 3000
+        pos = rng.random((n, 3)) * np.array([10.0, 2.0, 2.0])
+        xs = torch.from_numpy(np.sort(pos[:, 0]))
+        cuts = domain.equal_count_cuts(xs, world)
+        own = np.nonzero((pos[:, 0] >= cuts[rank]) & (pos[:, 0] < cuts[rank + 1]))[0]
+        gid = torch.from_numpy(own.astype(np.int64))
+        p = torch.from_numpy(pos[own])
+        hx = domain.HaloExchanger(cuts, rank, world).plan(p[:, 0], 0.9)
+        g_gid = hx.exchange([gid.to(torch.float64)])[0].to(torch.int64)
+        gid_all = torch.cat([gid, g_gid])
+        n_own, n_loc = gid.numel(), gid_all.numel()
+        perm = torch.from_numpy(np.random.default_rng(5 + rank).permutation(n_loc))      # slot -> local index
+        slot_of_loc = torch.empty_like(perm)
+        slot_of_loc[perm] = torch.arange(n_loc)
+        sx = domain.SlotExchanger(hx, slot_of_loc, n_own)
+        gid_S = gid_all[perm]
+        owned_S = perm < n_own
+        ok = True
+        for round_ in range(3):
+            # "truth" values are functions of (global id, round); owners hold them, ghosts hold garbage before the refresh
+            f = lambda g, c: (g.to(torch.float64) + 1.0) * (c + 1) + 0.25 * round_
+            a = torch.where(owned_S, f(gid_S, 0), torch.full((n_loc,), -1.0, dtype=torch.float64))
+            b = torch.stack([torch.where(owned_S, f(gid_S, c), torch.full((n_loc,), -1.0, dtype=torch.float64)) for c in (1, 2, 3)], 1)
+            sx.refresh([a, b])
+            ok = ok and bool((a == f(gid_S, 0)).all()) and all(bool((b[:, c - 1] == f(gid_S, c)).all()) for c in (1, 2, 3))
+        ok = ok and sx.calls == 3
+        q.put((rank, bool(ok), int(n_loc - n_own)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slot_exchanger_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_slots, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(ng > 0 for _, _, ng in res)
+
+
 def test_halo_and_migration_two_ranks():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
