@@ -500,48 +500,55 @@ class FastSlabRunner(SlabRunner):
         """slot-order state -> the dict SlabRunner works with (owned particles only)"""
         f = self.fast
         own = f["own_slots"]
-        P = f["P"].index_select(0, own)
-        return dict(gid=f["gid_S"].index_select(0, own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
-                    vel=f["V"].index_select(0, own), u=f["U"].index_select(0, own), wfac=f["wfac_S"].index_select(0, own))
+        with self.e.section("host:to_owned"):
+            P = f["P"].index_select(0, own)
+            return dict(gid=f["gid_S"].index_select(0, own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
+                        vel=f["V"].index_select(0, own), u=f["U"].index_select(0, own), wfac=f["wfac_S"].index_select(0, own))
 
     def _rebuild(self, st):
         """st: owned-order dict.  Migrate, plan the halo for the lists' whole life, sort, scan."""
         e = self.e
         self.nl = None
         self.fast = None
-        if self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None:
-            st = self._rebalance_rows(st)
-        else:
-            st = self._migrate(st) if self.world > 1 else st
-        self.geom = self._global_geom(st["pos"], st["h"])      # refreshed at every rebuild (cells follow the gas)
-        cover_h, skin = self.margins.choose()
-        self.margins.built()
-        hm = self._hmax(st["h"])
+        with e.section("host:migrate"):
+            if self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None:
+                st = self._rebalance_rows(st)
+            else:
+                st = self._migrate(st) if self.world > 1 else st
+        with e.section("host:geometry"):
+            self.geom = self._global_geom(st["pos"], st["h"])      # refreshed at every rebuild (cells follow the gas)
+            cover_h, skin = self.margins.choose()
+            self.margins.built()
+            hm = self._hmax(st["h"])
         width = 2.0 * hm * (cover_h + skin) * (1.0 + 1e-6 + self.margin) + 4.0 * self.geom[1]
-        hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width) if self.world > 1 \
-            else None
+        with e.section("host:halo_plan"):
+            hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width) if self.world > 1 \
+                else None
         n_own = st["gid"].numel()
-        if hx is not None:
-            g = hx.exchange([st["gid"].to(F64), st["pos"], st["h"], st["vel"], st["u"]])
-            gid_all = torch.cat([st["gid"], g[0].to(torch.int64)])
-            pos_L, h_L = torch.cat([st["pos"], g[1]]), torch.cat([st["h"], g[2]])
-            vel_L, u_L = torch.cat([st["vel"], g[3]]), torch.cat([st["u"], g[4]])
-        else:
-            gid_all, pos_L, h_L, vel_L, u_L = st["gid"], st["pos"], st["h"], st["vel"], st["u"]
+        with e.section("host:halo_exchange"):
+            if hx is not None:
+                g = hx.exchange([st["gid"].to(F64), st["pos"], st["h"], st["vel"], st["u"]])
+                gid_all = torch.cat([st["gid"], g[0].to(torch.int64)])
+                pos_L, h_L = torch.cat([st["pos"], g[1]]), torch.cat([st["h"], g[2]])
+                vel_L, u_L = torch.cat([st["vel"], g[3]]), torch.cat([st["u"], g[4]])
+            else:
+                gid_all, pos_L, h_L, vel_L, u_L = st["gid"], st["pos"], st["h"], st["vel"], st["u"]
         dg = e.build(e.pack_posh(pos_L, h_L), *self.geom, tie_key=gid_all)
         perm = dg.perm.long()                                   # slot -> local index
         target = (perm < n_own).to(torch.uint8)
         self.nl = e.nl_build(dg, cover_h, skin, target=target if self.world > 1 else None, consts=self.consts)
-        slot_of_loc = torch.empty_like(perm)
-        slot_of_loc[perm] = torch.arange(perm.numel(), device=perm.device)
-        wf = st.get("wfac")
-        if wf is None:
-            wf = torch.ones_like(st["h"])
-        wf_L = torch.cat([wf, torch.ones(perm.numel() - n_own, dtype=F64, device=self.dev)])
-        self.fast = dict(P=dg.posh, V=vel_L.index_select(0, perm), U=u_L.index_select(0, perm), gid_S=gid_all.index_select(0, perm),
-                         wfac_S=wf_L.index_select(0, perm), target=target if self.world > 1 else None,
-                         own_slots=slot_of_loc[:n_own].contiguous(), n_own=n_own,
-                         sx=SlotExchanger(hx, slot_of_loc, n_own) if hx is not None else None, fresh=True, ghost_h_stale=False)
+        with e.section("host:slot_state"):
+            slot_of_loc = torch.empty_like(perm)
+            slot_of_loc[perm] = torch.arange(perm.numel(), device=perm.device)
+            wf = st.get("wfac")
+            if wf is None:
+                wf = torch.ones_like(st["h"])
+            wf_L = torch.cat([wf, torch.ones(perm.numel() - n_own, dtype=F64, device=self.dev)])
+            self.fast = dict(P=dg.posh, V=vel_L.index_select(0, perm), U=u_L.index_select(0, perm),
+                             gid_S=gid_all.index_select(0, perm), wfac_S=wf_L.index_select(0, perm),
+                             target=target if self.world > 1 else None, own_slots=slot_of_loc[:n_own].contiguous(),
+                             n_own=n_own, sx=SlotExchanger(hx, slot_of_loc, n_own) if hx is not None else None, fresh=True,
+                             ghost_h_stale=False)
         self.stats["builds"] += 1
         self.stale = False
         # agree on the build's verdict (pool / unlistable) over all ranks
@@ -598,7 +605,14 @@ class FastSlabRunner(SlabRunner):
     # ---- one step in slot order ------------------------------------------------------------------------------------
     def _slots_step(self, dt, stt):
         e, nl, f, c = self.e, self.nl, self.fast, self.consts
-        P0, V0, U0, tgt, sx = f["P"], f["V"], f["U"], f["target"], f["sx"]
+        P0, V0, U0, tgt, sx0 = f["P"], f["V"], f["U"], f["target"], f["sx"]
+
+        class _R:   # the ghost refresh, visible to the per-call profile
+            @staticmethod
+            def refresh(arrs):
+                with e.section("host:ghost_refresh"):
+                    sx0.refresh(arrs)
+        sx = _R if sx0 is not None else None
         if f["fresh"] and nl.omega0 is not None:
             om0 = nl.omega0                                                             # pyfluid.py:503, formed by the build
         else:

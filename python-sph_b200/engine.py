@@ -183,6 +183,23 @@ def choose_grid(lo, hi, h_mean, n, pad_cells=1.0, cell=None, xdiv=None):
     return g, delta
 
 
+class _Section:
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if self.eng.prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.eng.prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.eng.prof.append((self.name, self.e0, e1))
+        return False
+
+
 class Engine:
     """Stateless helpers around the C-ABI for one device."""
 
@@ -204,6 +221,11 @@ class Engine:
         N.check(fn(*args), name)
         e1.record()
         self.prof.append((name, e0, e1))
+
+    def section(self, name):
+        """with eng.section("host:plan"): ...  -- CUDA events around a stretch of host-side torch work while profiling
+        (sections may contain C-ABI calls, which are then counted in both)"""
+        return _Section(self, name)
 
     def prof_start(self):
         self.prof = []
