@@ -197,6 +197,10 @@ int sphb_nlist_eos(const double *posh, const double *vel, const double *u, const
 int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
                      const double *recB, const double *recC, const double *recD, double *acc, double *dudt,
                      sphb_status *status, void *stream);
+/* ghost refresh plumbing: rows idx[0..n_idx) of up to four fp64 arrays (row widths w0..w3; unused: NULL, 0) gathered into
+ * the packed buffer buf[n_idx][w0+w1+w2+w3] (unpack = 0), or scattered back from it (unpack != 0) */
+int sphb_rows_pack(double *s0, int32_t w0, double *s1, int32_t w1, double *s2, int32_t w2, double *s3, int32_t w3,
+                   const int64_t *idx, int64_t n_idx, double *buf, int32_t unpack, void *stream);
 /* caller order <-> slot order for the whole state in one pass (any pointer group may be NULL) */
 int sphb_gather_state(const double *pos, const double *h, const double *vel, const double *u, const uint32_t *perm,
                       int64_t n, double *posh_s, double *vel_s, double *u_s, void *stream);

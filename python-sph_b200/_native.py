@@ -93,6 +93,7 @@ SIGNATURES = {
     "sphb_nlist_newton_h": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
     "sphb_nlist_eos": (C.c_int, [P, P, P, P, I64, C.POINTER(Consts), P, P, P, P]),
     "sphb_nlist_force": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
+    "sphb_rows_pack": (C.c_int, [P, I32, P, I32, P, I32, P, I32, P, I64, P, I32, P]),
     "sphb_gather_state": (C.c_int, [P, P, P, P, P, I64, P, P, P, P]),
     "sphb_scatter_state": (C.c_int, [P, P, P, P, I64, P, P, P, P, P]),
     "sphb_density_omega": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),

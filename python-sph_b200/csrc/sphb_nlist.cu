@@ -570,6 +570,53 @@ __global__ void k_nl_scatter_state(const double *__restrict__ posh_s, const doub
     if (u_s && u) u[i] = u_s[s];
 }
 
+// rows of up to four fp64 arrays (widths w0..w3, K = their sum) gathered into / scattered from one packed buffer:
+// what a ghost refresh sends and receives.  One launch instead of a dozen tensor operations.
+struct NlRowSet {
+    double *p[4];
+    int w[4];
+};
+
+template <bool PACK>
+__global__ void k_nl_rows(NlRowSet rs, int K, const long long *__restrict__ idx, long long n_idx, double *__restrict__ buf)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_idx * K) return;
+    const long long r = t / K;
+    int c = (int)(t - r * K);
+    const long long row = idx[r];
+    int q = 0;
+    while (c >= rs.w[q]) {
+        c -= rs.w[q];
+        ++q;
+    }
+    double *e = rs.p[q] + row * rs.w[q] + c;
+    if (PACK)
+        buf[t] = *e;
+    else
+        *e = buf[t];
+}
+
+extern "C" int sphb_rows_pack(double *s0, int32_t w0, double *s1, int32_t w1, double *s2, int32_t w2, double *s3,
+                              int32_t w3, const int64_t *idx, int64_t n_idx, double *buf, int32_t unpack, void *stream)
+{
+    NlRowSet rs{{s0, s1, s2, s3}, {w0, w1, w2, w3}};
+    int K = 0;
+    for (int q = 0; q < 4; ++q) {
+        if (rs.w[q] < 0 || (rs.w[q] > 0 && !rs.p[q])) return SPHB_E_ARG;
+        K += rs.w[q];
+    }
+    if (n_idx < 0 || K <= 0 || (n_idx > 0 && (!idx || !buf))) return SPHB_E_ARG;
+    if (n_idx == 0) return SPHB_OK;
+    const long long tot = (long long)n_idx * K;
+    if (unpack)
+        k_nl_rows<false><<<(unsigned)((tot + 255) / 256), 256, 0, sphb_stream(stream)>>>(rs, K, (const long long *)idx, n_idx, buf);
+    else
+        k_nl_rows<true><<<(unsigned)((tot + 255) / 256), 256, 0, sphb_stream(stream)>>>(rs, K, (const long long *)idx, n_idx, buf);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------

@@ -66,12 +66,29 @@ class HaloExchanger:
         return self
 
     def plan_migration(self, x_owned):
+        """send lists of the particles that left the slab.  self.moved = how many do, over all ranks (0: nothing to do,
+        and then no index array is made at all)"""
         own = self.owner_of(x_owned)
-        q = torch.arange(self.world, device=x_owned.device)
-        m = own[None, :] == q[:, None]
-        self.stay = torch.nonzero(m[self.rank]).flatten()
-        m[self.rank] = False
-        self._from_mask(m)
+        leaving = own != self.rank
+        cnt = leaving.sum().reshape(1)
+        if self.world > 1:
+            dist.all_reduce(cnt, group=self.group)
+        self.moved = int(cnt.item())
+        if self.moved == 0:
+            self.stay = None
+            self.all_idx = torch.empty(0, dtype=torch.int64, device=x_owned.device)
+            self.send_counts = self.recv_counts = [0] * self.world
+            return self
+        idx = torch.nonzero(leaving).flatten()
+        dest = own.index_select(0, idx)
+        order = torch.argsort(dest, stable=True)              # destination-major, owned order within a destination
+        self.all_idx = idx.index_select(0, order)
+        self.stay = torch.nonzero(~leaving).flatten()
+        send = torch.bincount(dest, minlength=self.world)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        both = torch.stack([send, recv]).tolist()
+        self.send_counts, self.recv_counts = both[0], both[1]
         return self
 
     def _from_mask(self, m):
@@ -94,7 +111,7 @@ class HaloExchanger:
         cols = [a.reshape(a.shape[0], -1) for a in arrays]
         widths = [c.shape[1] for c in cols]
         K = sum(widths)
-        packed = torch.cat(cols, dim=1).index_select(0, self.all_idx).contiguous() if K else None
+        packed = torch.cat([c.index_select(0, self.all_idx) for c in cols], dim=1) if K else None
         out = torch.empty((self.n_recv, K), dtype=packed.dtype, device=packed.device)
         dist.all_to_all_single(out, packed, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
                                group=self.group)
@@ -360,6 +377,8 @@ class SlabRunner:
 
     def _migrate(self, st):
         hx = HaloExchanger(self.cuts, self.rank, self.world).plan_migration(st["pos"][:, 0].contiguous())
+        if hx.moved == 0:
+            return st
         names = ["pos", "h", "vel", "u", "wfac"]
         recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in names])
         out = dict(gid=torch.cat([st["gid"].index_select(0, hx.stay), recv[0].to(torch.int64)]))
@@ -444,8 +463,11 @@ class SlotExchanger:
     changes is the values.  `refresh` sends the owners' current values along the send lists of the halo plan and writes
     what arrives straight into the ghosts' slots: one pack, one all_to_all_single, one unpack, for any number of arrays."""
 
-    def __init__(self, hx: HaloExchanger, slot_of_loc, n_own):
+    def __init__(self, hx: HaloExchanger, slot_of_loc, n_own, engine=None):
+        """engine: an engine.Engine whose rows_pack kernel packs / unpacks in one launch each (CUDA tensors); without
+        it the same is done with torch indexing (any device: what the gloo tests run)"""
         self.hx = hx
+        self.engine = engine
         self.send_slots = slot_of_loc.index_select(0, hx.all_idx)          # destination-major, owned order within
         self.ghost_slots = slot_of_loc[n_own:].contiguous()                # arrival order: source rank, sender's order
         self.n_recv = hx.n_recv
@@ -458,11 +480,19 @@ class SlotExchanger:
         K = sum(widths)
         if self.hx.world == 1 or K == 0:
             return
-        packed = torch.cat([c.index_select(0, self.send_slots) for c in cols], dim=1)
+        fast = self.engine is not None and len(arrays) <= 4 and all(a.is_cuda and a.is_contiguous() and a.dtype == F64 for a in arrays)
+        if fast:
+            packed = torch.empty((self.send_slots.numel(), K), dtype=F64, device=arrays[0].device)
+            self.engine.rows_pack(arrays, self.send_slots, packed)
+        else:
+            packed = torch.cat([c.index_select(0, self.send_slots) for c in cols], dim=1)
         out = torch.empty((self.n_recv, K), dtype=packed.dtype, device=packed.device)
         dist.all_to_all_single(out, packed, output_split_sizes=self.hx.recv_counts, input_split_sizes=self.hx.send_counts,
                                group=self.hx.group)
         self.calls += 1
+        if fast:
+            self.engine.rows_pack(arrays, self.ghost_slots, out, unpack=True)
+            return
         o = 0
         for c, wd in zip(cols, widths):
             c.index_copy_(0, self.ghost_slots, out[:, o:o + wd])
@@ -499,7 +529,7 @@ class FastSlabRunner(SlabRunner):
     def _to_owned(self):
         """slot-order state -> the dict SlabRunner works with (owned particles only)"""
         f = self.fast
-        own = f["own_slots"]
+        own = f["own_sorted"]        # ascending slots: the copies below stream
         with self.e.section("host:to_owned"):
             P = f["P"].index_select(0, own)
             return dict(gid=f["gid_S"].index_select(0, own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
@@ -511,7 +541,8 @@ class FastSlabRunner(SlabRunner):
         self.nl = None
         self.fast = None
         with e.section("host:migrate"):
-            if self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None:
+            if self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None and \
+                    self.stats["builds"] % self.REBALANCE_EVERY == 1:
                 st = self._rebalance_rows(st)
             else:
                 st = self._migrate(st) if self.world > 1 else st
@@ -546,8 +577,9 @@ class FastSlabRunner(SlabRunner):
             wf_L = torch.cat([wf, torch.ones(perm.numel() - n_own, dtype=F64, device=self.dev)])
             self.fast = dict(P=dg.posh, V=vel_L.index_select(0, perm), U=u_L.index_select(0, perm),
                              gid_S=gid_all.index_select(0, perm), wfac_S=wf_L.index_select(0, perm),
-                             target=target if self.world > 1 else None, own_slots=slot_of_loc[:n_own].contiguous(),
-                             n_own=n_own, sx=SlotExchanger(hx, slot_of_loc, n_own) if hx is not None else None, fresh=True,
+                             target=target if self.world > 1 else None,
+                             own_sorted=torch.sort(slot_of_loc[:n_own]).values if self.world > 1 else slot_of_loc,
+                             n_own=n_own, sx=SlotExchanger(hx, slot_of_loc, n_own, engine=e) if hx is not None else None, fresh=True,
                              ghost_h_stale=False)
         self.stats["builds"] += 1
         self.stale = False
@@ -663,6 +695,7 @@ class FastSlabRunner(SlabRunner):
 
     MAX_ATTEMPTS = 4
     SAFE_HOLD = 8
+    REBALANCE_EVERY = 16      # builds between two re-cuts of the slabs (the first one right after the calibration step)
 
     def _step(self, st, dt):
         """st: an owned-order dict, or None when the state is resident in slot order (self.fast)"""

@@ -435,6 +435,12 @@ class Engine:
                   _ptr(recC), _ptr(recD), _ptr(acc), _ptr(dudt), status_ptr, _stream())
         return acc, dudt
 
+    def rows_pack(self, arrays, idx, buf, unpack=False):
+        """rows idx of up to four fp64 arrays <-> one packed (len(idx), K) buffer, in one launch (ghost refresh)"""
+        a = [(t, t.shape[1] if t.dim() > 1 else 1) for t in arrays] + [(None, 0)] * (4 - len(arrays))
+        self._run("rows_pack", self.lib.sphb_rows_pack, _ptr(a[0][0]), a[0][1], _ptr(a[1][0]), a[1][1], _ptr(a[2][0]), a[2][1],
+                  _ptr(a[3][0]), a[3][1], _ptr(idx), idx.shape[0], _ptr(buf), 1 if unpack else 0, _stream())
+
     def gather_state(self, perm, pos=None, h=None, vel=None, u=None):
         """caller order -> slot order: posh (n,4), vel (n,3), u (n) (None for what was not given)"""
         n = perm.shape[0]
