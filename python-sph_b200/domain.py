@@ -526,14 +526,21 @@ class FastSlabRunner(SlabRunner):
         return t
 
     # ---- rebuild ----------------------------------------------------------------------------------------------
+    def _rows(self, src, idx):
+        """src[idx] for an fp64 / int64 array of row width <= 4, in one launch of the library's row kernel"""
+        a = src.view(F64) if src.dtype == torch.int64 else src
+        out = torch.empty((idx.numel(),) + tuple(a.shape[1:]), dtype=F64, device=a.device)
+        self.e.rows_pack([a], idx, out)
+        return out.view(torch.int64) if src.dtype == torch.int64 else out
+
     def _to_owned(self):
-        """slot-order state -> the dict SlabRunner works with (owned particles only)"""
+        """slot-order state -> the dict SlabRunner works with (owned particles only, in ascending slot order)"""
         f = self.fast
-        own = f["own_sorted"]        # ascending slots: the copies below stream
+        own = f["own_sorted"]
         with self.e.section("host:to_owned"):
-            P = f["P"].index_select(0, own)
-            return dict(gid=f["gid_S"].index_select(0, own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
-                        vel=f["V"].index_select(0, own), u=f["U"].index_select(0, own), wfac=f["wfac_S"].index_select(0, own))
+            P = self._rows(f["P"], own)
+            return dict(gid=self._rows(f["gid_S"], own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
+                        vel=self._rows(f["V"], own), u=self._rows(f["U"], own), wfac=self._rows(f["wfac_S"], own))
 
     def _rebuild(self, st):
         """st: owned-order dict.  Migrate, plan the halo for the lists' whole life, sort, scan."""
@@ -575,8 +582,8 @@ class FastSlabRunner(SlabRunner):
             if wf is None:
                 wf = torch.ones_like(st["h"])
             wf_L = torch.cat([wf, torch.ones(perm.numel() - n_own, dtype=F64, device=self.dev)])
-            self.fast = dict(P=dg.posh, V=vel_L.index_select(0, perm), U=u_L.index_select(0, perm),
-                             gid_S=gid_all.index_select(0, perm), wfac_S=wf_L.index_select(0, perm),
+            self.fast = dict(P=dg.posh, V=e.gather(vel_L, dg.perm, 3), U=e.gather(u_L, dg.perm, 1),
+                             gid_S=e.gather(gid_all.view(F64), dg.perm, 1).view(torch.int64), wfac_S=e.gather(wf_L, dg.perm, 1),
                              target=target if self.world > 1 else None,
                              own_sorted=torch.sort(slot_of_loc[:n_own]).values if self.world > 1 else slot_of_loc,
                              n_own=n_own, sx=SlotExchanger(hx, slot_of_loc, n_own, engine=e) if hx is not None else None, fresh=True,

@@ -812,14 +812,13 @@ class FastStepper:
             grid, delta = e.grid_for(posh_in)
         self.nl = None                       # drop the old pool before the new one is allocated
         dg = e.build(posh_in, grid, delta, tie_key=ids_in)
-        perm_l = dg.perm.long()
-        self.V = vel_in.index_select(0, perm_l) if vel_in is not None else None
-        self.U = u_in.index_select(0, perm_l) if u_in is not None else None
+        self.V = e.gather(vel_in, dg.perm, 3) if vel_in is not None else None
+        self.U = e.gather(u_in, dg.perm, 1) if u_in is not None else None
         if ids_in is None:
             self.perm = dg.perm
-            self.ids = perm_l
+            self.ids = dg.perm.long()
         else:
-            self.ids = ids_in.index_select(0, perm_l)
+            self.ids = e.gather(ids_in.view(F64), dg.perm, 1).view(torch.int64)   # a bit-pattern copy
             self.perm = self.ids.to(torch.int32)
         self.P = dg.posh                     # never written in place: every kernel below returns fresh arrays
         cover_h, skin = self.margins.choose()
