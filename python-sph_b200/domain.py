@@ -585,7 +585,7 @@ class FastSlabRunner(SlabRunner):
             self.fast = dict(P=dg.posh, V=e.gather(vel_L, dg.perm, 3), U=e.gather(u_L, dg.perm, 1),
                              gid_S=e.gather(gid_all.view(F64), dg.perm, 1).view(torch.int64), wfac_S=e.gather(wf_L, dg.perm, 1),
                              target=target if self.world > 1 else None,
-                             own_sorted=torch.sort(slot_of_loc[:n_own]).values if self.world > 1 else slot_of_loc,
+                             own_sorted=torch.nonzero(target).flatten() if self.world > 1 else slot_of_loc,
                              n_own=n_own, sx=SlotExchanger(hx, slot_of_loc, n_own, engine=e) if hx is not None else None, fresh=True,
                              ghost_h_stale=False)
         self.stats["builds"] += 1
