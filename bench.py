@@ -471,6 +471,20 @@ def run_ours(a):
         state = step(state)
         prof = eng.prof_stop()
         runner.statuses.clear()
+        # per-rank time of the step that rebuilt: how well the cut planes balance the ranks
+        names = ["nl_build", "nl_force", "nl_newton_h", "nl_density_omega", "grid_build"]
+        pb = prof_build if prof_build is not None else prof
+        mine = [pb.get(nm, (0, 0.0))[1] for nm in names]
+        mine.append(sum(t_ for nm, (c_, t_) in pb.items() if not nm.startswith("host:")))
+        mine.append(sum(t_ for nm, (c_, t_) in pb.items() if nm.startswith("host:")))
+        mine.append(float(state["gid"].numel()))
+        mine.append(float(runner.nl.n - state["gid"].numel()) if getattr(runner, "nl", None) is not None else 0.0)
+        mine.append(float(runner.nl.warp_rows.double().mean().item()) if getattr(runner, "nl", None) is not None else 0.0)
+        tv = torch.tensor(mine, dtype=torch.float64, device=dev)
+        allv = [torch.empty_like(tv) for _ in range(world)]
+        dist.all_gather(allv, tv)
+        rank_table = {"columns": names + ["kernels_ms", "host_sections_ms", "owned", "ghosts", "rows_per_warp"],
+                      "rows": [[round(x, 3) for x in v.tolist()] for v in allv]}
         if rank == 0:
             fp64_peak = max(eng.fp64_peak() for _ in range(3))
             n_own_r = int(state["gid"].numel())
@@ -509,6 +523,8 @@ def run_ours(a):
                        "path": "kept neighbour lists (rebuilt when the device-side check says so)" if use_lists else "scanning kernels (3 cell-list builds and 3 scans per step)"},
             "clocks": clk, "gpu_launches": int(launches), "neighbour_lists": list_stats, "state_checksum": checksum,
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernels": per_kernel}
+    if world > 1:
+        line["ranks"] = rank_table
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -547,17 +547,19 @@ class FastSlabRunner(SlabRunner):
         e = self.e
         self.nl = None
         self.fast = None
-        with e.section("host:migrate"):
-            if self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None and \
-                    self.stats["builds"] % self.REBALANCE_EVERY == 1:
-                st = self._rebalance_rows(st)
-            else:
-                st = self._migrate(st) if self.world > 1 else st
+        recut = self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None and \
+            self.stats["builds"] % self.REBALANCE_EVERY == 1
         with e.section("host:geometry"):
-            self.geom = self._global_geom(st["pos"], st["h"])      # refreshed at every rebuild (cells follow the gas)
+            # bounding box, mean and max h, and how many particles left their slab: two all-reduces, one read
+            lo, hi, hmean, ntot, hm, moved = self._global_stats(st)
+            self.geom = E.choose_grid(lo, hi, hmean, ntot)          # refreshed at every rebuild (cells follow the gas)
             cover_h, skin = self.margins.choose()
             self.margins.built()
-            hm = self._hmax(st["h"])
+        with e.section("host:migrate"):
+            if recut:
+                st = self._rebalance_rows(st)
+            elif moved:
+                st = self._migrate(st)
         width = 2.0 * hm * (cover_h + skin) * (1.0 + 1e-6 + self.margin) + 4.0 * self.geom[1]
         with e.section("host:halo_plan"):
             hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width) if self.world > 1 \
@@ -590,12 +592,21 @@ class FastSlabRunner(SlabRunner):
                              ghost_h_stale=False)
         self.stats["builds"] += 1
         self.stale = False
-        # agree on the build's verdict (pool / unlistable) over all ranks
-        if self.world > 1:
-            bf = torch.tensor([self.nl.build_flags, 0, 0, 0], dtype=torch.int32, device=self.dev)
-            self._agree(bf)
-            self.nl.build_flags = int(bf[0].item())
+        # (a build that could not list its input leaves SPHB_NL_POOL / _UNLISTABLE in the lists' flag word: the step
+        # runs anyway, and the all-reduced flags at its end send every rank down the same road)
         self._note_rows()
+
+    def _global_stats(self, st):
+        pos, h = st["pos"], st["h"]
+        own = HaloExchanger(self.cuts, self.rank, self.world).owner_of(pos[:, 0].contiguous()) if self.world > 1 else None
+        left = (own != self.rank).sum().to(F64) if own is not None else torch.zeros((), dtype=F64, device=self.dev)
+        vmax = torch.cat([-pos.min(dim=0).values, pos.max(dim=0).values, h.max().reshape(1)])
+        vsum = torch.stack([h.sum(), torch.tensor(float(h.numel()), dtype=F64, device=self.dev), left])
+        if self.world > 1:
+            dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(vsum, op=dist.ReduceOp.SUM)
+        v = torch.cat([vmax, vsum]).tolist()
+        return [-v[0], -v[1], -v[2]], v[3:6], v[7] / v[8], int(v[8]), v[6], int(v[9])
 
     def _agree(self, flags4):
         """OR of the SPHB_NL_* flags and MAX of the two maxima over all ranks, in one all-reduce (bits as a MAX per bit;
@@ -687,9 +698,6 @@ class FastSlabRunner(SlabRunner):
     def _try(self, dt):
         """one step on the current lists -> (ok, P1, V1, U1, status)"""
         nl, f = self.nl, self.fast
-        if nl.build_flags & self._BAD:
-            self.last_flags, self.fresh_failed = nl.build_flags, False
-            return False, None, None, None, None
         stt = E.Status(E.S_COUNT, self.dev)
         P1, V1, U1 = self._slots_step(dt, stt)
         self._agree(nl.flags)
