@@ -379,7 +379,7 @@ class SlabRunner:
         hx = HaloExchanger(self.cuts, self.rank, self.world).plan_migration(st["pos"][:, 0].contiguous())
         if hx.moved == 0:
             return st
-        names = ["pos", "h", "vel", "u", "wfac"]
+        names = [f for f in ("pos", "h", "vel", "u", "wfac", "rows") if f in st]
         recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in names])
         out = dict(gid=torch.cat([st["gid"].index_select(0, hx.stay), recv[0].to(torch.int64)]))
         for f, g in zip(names, recv[1:]):
@@ -540,15 +540,17 @@ class FastSlabRunner(SlabRunner):
         with self.e.section("host:to_owned"):
             P = self._rows(f["P"], own)
             return dict(gid=self._rows(f["gid_S"], own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
-                        vel=self._rows(f["V"], own), u=self._rows(f["U"], own), wfac=self._rows(f["wfac_S"], own))
+                        vel=self._rows(f["V"], own), u=self._rows(f["U"], own), wfac=self._rows(f["wfac_S"], own),
+                        rows=self._rows(f["rows_S"], own))
 
     def _rebuild(self, st):
         """st: owned-order dict.  Migrate, plan the halo for the lists' whole life, sort, scan."""
         e = self.e
         self.nl = None
         self.fast = None
-        recut = self.balance and self.world > 1 and self.geom is not None and self._rows_weight is not None and \
-            self.stats["builds"] % self.REBALANCE_EVERY == 1
+        recut = self.balance and self.world > 1 and self.geom is not None and "rows" in st and \
+            (self._force_recut or self.stats["builds"] % self.REBALANCE_EVERY == 1)
+        self._force_recut = False
         with e.section("host:geometry"):
             # bounding box, mean and max h, and how many particles left their slab: two all-reduces, one read
             lo, hi, hmean, ntot, hm, moved = self._global_stats(st)
@@ -620,14 +622,14 @@ class FastSlabRunner(SlabRunner):
         flags4[0:1] = (v[:8] << self._bitpos).sum().to(torch.int32)
         flags4[1:3] = v[8:10]
 
-    _rows_weight = None
+    _force_recut = False
 
     def _rebalance_rows(self, st, nbins=16384):
         """work-balanced cut planes from what the drains actually walk: the list rows of each particle's warp (measured
         on the previous lists, travelling with the particle as `wfac`), one all-reduced weighted x-histogram"""
         x = st["pos"][:, 0].contiguous()
-        wgt = st["wfac"]
-        ext = torch.stack([x.min(), -x.max()])
+        wgt = (st["rows"] + 8.0) * st["wfac"]     # rows walked by the drains (+ the elementwise kernels), times the
+        ext = torch.stack([x.min(), -x.max()])    # measured cost factor of the rank the particle was calibrated on
         dist.all_reduce(ext, op=dist.ReduceOp.MIN)
         xlo, xhi = float(ext[0].item()), float(-ext[1].item())
         span = max(xhi - xlo, 1e-300)
@@ -645,12 +647,9 @@ class FastSlabRunner(SlabRunner):
         return self._migrate(st)
 
     def _note_rows(self):
-        """per-particle work weight for the next re-balance: rows of the particle's warp (+ a constant for the
-        elementwise kernels)"""
+        """per-particle work for the next re-cut: the rows of the particle's warp"""
         f, nl = self.fast, self.nl
-        rows = nl.warp_rows.to(F64).repeat_interleave(32)[:nl.n]
-        f["wfac_S"] = rows + 8.0
-        self._rows_weight = True
+        f["rows_S"] = nl.warp_rows.to(F64).repeat_interleave(32)[:nl.n].contiguous()
 
     # ---- one step in slot order ------------------------------------------------------------------------------------
     def _slots_step(self, dt, stt):
@@ -761,23 +760,37 @@ class FastSlabRunner(SlabRunner):
         return self._step(st, dt)
 
     def calibrate(self, st, dt, rounds=2):
-        """the list rows ARE the measured work: one throw-away build + step is enough to balance the cuts"""
+        """setup-time load balancing.  Each round builds the lists, runs ONE throw-away step with CUDA events around every
+        kernel, and folds this rank's time per modelled unit of work (rows walked) into the cost factors of its
+        particles -- a sparse particle on a grid sized for the dense majority costs several times more to SCAN than its
+        rows say --, then re-cuts the slabs.  Returns the state it was given (not advanced), redistributed."""
         if not self.balance or self.world == 1:
             return st
-        tok = self.step(st, dt)
-        self.statuses.pop()
-        out = dict(tok.resolve())           # the state BEFORE the throw-away step is `st`; keep it, take the weights
-        back = dict(st)
-        # weights by global id: the throw-away step did not migrate anybody (a rebuild migrates before it plans)
-        order = torch.argsort(out["gid"])
-        pos_in = torch.searchsorted(out["gid"][order], back["gid"])
-        back["wfac"] = out["wfac"][order][pos_in]
-        self.fast = None
-        self.nl = None
+        if isinstance(st, _LazyOwned):
+            st = dict(st.resolve())
+        for _ in range(rounds):
+            self.fast, self.nl = None, None
+            self._rebuild(st)
+            pre = self._to_owned()                     # the same physical state, in this build's owned order, with rows
+            self.e.prof_start()
+            self._try(dt)                              # result discarded
+            prof = self.e.prof_stop()
+            ms = sum(t for nm, (c, t) in prof.items() if not nm.startswith("host:"))
+            work = float(((pre["rows"] + 8.0) * pre["wfac"]).sum().item())
+            v = torch.tensor([ms, work], dtype=F64, device=self.dev)
+            allv = [torch.empty_like(v) for _ in range(self.world)]
+            dist.all_gather(allv, v)
+            tt, ww = sum(float(a[0]) for a in allv), sum(float(a[1]) for a in allv)
+            fac = (ms / max(work, 1e-300)) / (tt / max(ww, 1e-300))
+            pre["wfac"] = pre["wfac"] * min(max(fac, 0.5), 2.0)
+            st = pre
+            self._force_recut = True
+        self.fast, self.nl = None, None
         self.stale = True
-        self._rows_weight = True
         self.margins = E.ListMargins(self.margins.cover_h, self.margins.skin, self.margins.adaptive)
-        return back
+        self.stats = dict(steps=0, builds=0, redos=0, safe_steps=0, exchanges=0)
+        self._force_recut = True
+        return st
 
 
 class _LazyOwned(dict):
