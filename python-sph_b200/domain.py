@@ -512,6 +512,7 @@ class FastSlabRunner(SlabRunner):
     def __init__(self, eng: E.Engine, consts, world, rank, margin=0.0, balance=True, calib_steps=0, cover_h=None, skin=None,
                  adaptive=True):
         super().__init__(eng, consts, world, rank, margin=margin, balance=balance, calib_steps=calib_steps)
+        self._margins0 = (cover_h, skin, adaptive)
         self.margins = E.ListMargins(cover_h, skin, adaptive)
         self.nl = None
         self.fast = None          # slot-order state between rebuilds: dict(P, V, U, gid_S, wfac_S, ...)
@@ -770,9 +771,9 @@ class FastSlabRunner(SlabRunner):
             st = dict(st.resolve())
         for _ in range(rounds):
             self.fast, self.nl = None, None
+            self.e.prof_start()                        # the build counts: it is where sparse particles cost most
             self._rebuild(st)
             pre = self._to_owned()                     # the same physical state, in this build's owned order, with rows
-            self.e.prof_start()
             self._try(dt)                              # result discarded
             prof = self.e.prof_stop()
             ms = sum(t for nm, (c, t) in prof.items() if not nm.startswith("host:"))
@@ -787,7 +788,7 @@ class FastSlabRunner(SlabRunner):
             self._force_recut = True
         self.fast, self.nl = None, None
         self.stale = True
-        self.margins = E.ListMargins(self.margins.cover_h, self.margins.skin, self.margins.adaptive)
+        self.margins = E.ListMargins(*self._margins0)     # the real run starts like a single-GPU run does
         self.stats = dict(steps=0, builds=0, redos=0, safe_steps=0, exchanges=0)
         self._force_recut = True
         return st
