@@ -7,6 +7,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/sphb200.h"
 
 #define SPHB_FULL 0xffffffffu
@@ -31,6 +33,14 @@ extern long long g_sphb_launches;
     } while (0)
 
 static inline cudaStream_t sphb_stream(void *s) { return (cudaStream_t)s; }
+
+// one NVTX range per C-ABI entry point: shows up in Nsight Systems / ncu --nvtx timelines,
+// costs two empty calls when no tool is attached
+struct SphbNvtx {
+    explicit SphbNvtx(const char *name) { nvtxRangePushA(name); }
+    ~SphbNvtx() { nvtxRangePop(); }
+};
+#define SPHB_RANGE() SphbNvtx sphb_nvtx_range_(__func__)
 
 // x edge of a cell: cell / xdiv (IEEE division, the same on host and device)
 __host__ __device__ __forceinline__ double sphb_cellx(const sphb_grid &g)

@@ -283,6 +283,7 @@ extern "C" int sphb_pair_terms(const double *posh, const double *recB, const dou
                                const double *bgrav, double *grav_out, double *corr_out, sphb_status *status,
                                void *stream)
 {
+    SPHB_RANGE();
     if (n_pairs < 0 || !k || !status || (n_pairs > 0 && (!posh || !recB || !recC || !pairs))) return SPHB_E_ARG;
     if (n_pairs == 0) return SPHB_OK;
     k_pair_terms<<<(unsigned)((n_pairs + 127) / 128), 128, 0, sphb_stream(stream)>>>(
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(GRAV_TILE)
 extern "C" int sphb_gravity_direct(const double *posh, int64_t n, const sphb_consts *k, int32_t accumulate, double *acc,
                                    void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || !k || (n > 0 && (!posh || !acc))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_gravity_direct<<<(unsigned)((n + GRAV_TILE - 1) / GRAV_TILE), GRAV_TILE, 0, sphb_stream(stream)>>>(posh, n, *k,
@@ -395,6 +397,7 @@ __global__ void k_grav_eval(const double *__restrict__ dist, const double *__res
 extern "C" int sphb_grav_eval(const double *dist, const double *h, int64_t n, double *phi, double *force, double *dphidh,
                               void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || (n > 0 && (!dist || !h))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_grav_eval<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(dist, h, n, phi, force, dphidh);
@@ -534,6 +537,7 @@ extern "C" int64_t sphb_bounds_workspace_bytes(int64_t n)
 extern "C" int sphb_bounds(const double *posh, int64_t n, double *out8, void *workspace, int64_t workspace_bytes,
                            void *stream)
 {
+    SPHB_RANGE();
     if (n <= 0 || !posh || !out8 || !workspace || workspace_bytes < sphb_bounds_workspace_bytes(n)) return SPHB_E_ARG;
     int nb = (int)((n + RED_THREADS - 1) / RED_THREADS);
     if (nb > BOUNDS_BLOCKS) nb = BOUNDS_BLOCKS;
@@ -558,6 +562,7 @@ __global__ void k_hmax(const double *__restrict__ posh, long long n, int *__rest
 
 extern "C" int sphb_hmax(const double *posh, int64_t n, float *hmax_out, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || !hmax_out || (n > 0 && !posh)) return SPHB_E_ARG;
     SPHB_CUDA(cudaMemsetAsync(hmax_out, 0, sizeof(float), sphb_stream(stream)));
     if (n == 0) return SPHB_OK;
@@ -576,6 +581,7 @@ __global__ void k_check_neg_h(const double *__restrict__ h, long long n, sphb_st
 
 extern "C" int sphb_check_neg_h(const double *h, int64_t n, sphb_status *status, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || !status || (n > 0 && !h)) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_check_neg_h<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(h, n, status);
@@ -603,6 +609,7 @@ __global__ void k_m4_eval(const double *__restrict__ dist, const double *__restr
 extern "C" int sphb_m4_eval(const double *dist, const double *h, int64_t n, double *W, double *dW, double *dWdh,
                             void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || (n > 0 && (!dist || !h))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_m4_eval<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(dist, h, n, W, dW, dWdh);
@@ -621,6 +628,7 @@ __global__ void k_distance(const double *__restrict__ rj, const double *__restri
 
 extern "C" int sphb_distance(const double *rj, const double *ri, int64_t n, double *out, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || (n > 0 && (!rj || !ri || !out))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_distance<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(rj, ri, n, out);
@@ -677,6 +685,7 @@ extern "C" int sphb_eos(const double *posh, const double *vel, const double *u, 
                         double *rho, double *P, double *recB, double *recC, double *bgrav, sphb_status *status,
                         void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || !k || !status) return SPHB_E_ARG;
     if (n > 0 && (!posh || (!u && !P_in))) return SPHB_E_ARG;
     if ((recB != nullptr) != (recC != nullptr)) return SPHB_E_ARG;
@@ -694,6 +703,7 @@ extern "C" int sphb_eos(const double *posh, const double *vel, const double *u, 
 extern "C" int sphb_nlist_eos(const double *posh, const double *vel, const double *u, const double *omega, int64_t n,
                               const sphb_consts *k, double *recB, double *recD, sphb_status *status, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || !k || !status) return SPHB_E_ARG;
     if (n > 0 && (!posh || !vel || !u || !omega || !recB || !recD)) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
@@ -707,6 +717,7 @@ extern "C" int sphb_force(const sphb_cells *cells, const sphb_consts *k, const u
                           const double *recC, const double *bgrav, const float *hmax_global, double *acc, double *dudt,
                           sphb_status *status, const sphb_lists *lists, void *stream)
 {
+    SPHB_RANGE();
     if (!cells || !k || !recB || !recC || !hmax_global || !acc || !dudt || !status) return SPHB_E_ARG;
     if (lists && (!lists->store || !lists->broken)) return SPHB_E_ARG;
     if (cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh || !cells->frec)
@@ -730,6 +741,7 @@ extern "C" int sphb_predict(const double *posh0, const double *vel0, const doubl
                             const double *dudt0, double dt, int64_t n, double *posh_mid, double *vel_mid, double *u_mid,
                             sphb_status *status, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || !status || (n > 0 && (!posh0 || !vel0 || !u0 || !acc0 || !dudt0 || !posh_mid || !vel_mid || !u_mid)))
         return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
@@ -743,6 +755,7 @@ extern "C" int sphb_correct(const double *posh0, const double *vel0, const doubl
                             const double *dudt_mid, double dt, int64_t n, double *posh1, double *vel1, double *u1,
                             sphb_status *status, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || !status || (n > 0 && (!posh0 || !vel0 || !u0 || !acc_mid || !dudt_mid || !posh1 || !vel1 || !u1)))
         return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;

@@ -468,6 +468,7 @@ extern "C" int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k,
                                   double *omega, double *xi_out, int32_t *ngb_count, const sphb_lists *lists,
                                   void *stream)
 {
+    SPHB_RANGE();
     if (!sphb_cells_ok(cells) || !k || !sphb_lists_ok(lists)) return SPHB_E_ARG;
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
@@ -495,6 +496,7 @@ extern "C" int sphb_bisect_h(const sphb_cells *cells, const sphb_consts *k, cons
                              double *h_out, double *omega_out, int32_t *code, int32_t *oob, int32_t indexed_by_slot,
                              sphb_status *status, void *stream)
 {
+    SPHB_RANGE();
     if (!sphb_cells_ok(cells) || !k || !list || !h_out || !status) return SPHB_E_ARG;
     if (n_list == 0 || cells->n == 0) return SPHB_OK;
     long long blocks = n_list > 0 ? n_list : 296;
@@ -509,6 +511,7 @@ extern "C" int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, cons
                              const double *h_guess, double *h_out, double *omega_out, int32_t *iters, int32_t *code,
                              uint32_t *fail_list, sphb_status *status, const sphb_lists *lists, void *stream)
 {
+    SPHB_RANGE();
     if (!sphb_cells_ok(cells) || !k || !h_guess || !h_out || !fail_list || !status || !sphb_lists_ok(lists))
         return SPHB_E_ARG;
     if (cells->n == 0) return SPHB_OK;
@@ -532,6 +535,7 @@ extern "C" int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, cons
 extern "C" int sphb_neighbours(const sphb_cells *cells, const uint32_t *query, int64_t n_query, int32_t symmetric,
                                const float *hmax_global, uint32_t *out, int64_t cap, int32_t *count, void *stream)
 {
+    SPHB_RANGE();
     if (!sphb_cells_ok(cells) || !query || !out || !count || cap < 0 || n_query < 0) return SPHB_E_ARG;
     if (symmetric && !hmax_global) return SPHB_E_ARG;
     if (n_query == 0) return SPHB_OK;

@@ -302,6 +302,7 @@ static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) 
 
 extern "C" int sphb_pack_posh(const double *pos, const double *h, int64_t n, double *posh, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || (n > 0 && (!pos || !h || !posh))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_pack_posh<<<nblk(n, 256), 256, 0, sphb_stream(stream)>>>(pos, h, n, posh);
@@ -314,6 +315,7 @@ extern "C" int sphb_grid_build(const double *posh_in, const int64_t *tie_key, in
                                uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id, double *posh_sorted,
                                float *frec_sorted, void *workspace, int64_t workspace_bytes, void *stream)
 {
+    SPHB_RANGE();
     const int64_t ncell = sphb_grid_ncell(g);
     if (ncell <= 0 || n < 0 || !(g->cell > 0.0) || !cell_start || !cell_hmax || !workspace) return SPHB_E_ARG;
     if (n > 0 && (!posh_in || !perm || !cell_id || !posh_sorted || !frec_sorted)) return SPHB_E_ARG;
@@ -358,6 +360,7 @@ extern "C" int sphb_grid_set_h(const double *h_sorted, int64_t n, const sphb_gri
                                const uint32_t *cell_start, float *cell_hmax, double *posh_sorted, float *frec_sorted,
                                void *stream)
 {
+    SPHB_RANGE();
     const int64_t ncell = sphb_grid_ncell(g);
     if (ncell <= 0 || n < 0 || !cell_start || !cell_hmax) return SPHB_E_ARG;
     if (n > 0 && (!h_sorted || !posh_sorted || !frec_sorted)) return SPHB_E_ARG;
@@ -370,6 +373,7 @@ extern "C" int sphb_grid_set_h(const double *h_sorted, int64_t n, const sphb_gri
 extern "C" int sphb_gather_f64(const double *src, const uint32_t *perm, int64_t n, int32_t ncomp, double *dst,
                                void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || ncomp <= 0 || (n > 0 && (!src || !perm || !dst))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_gather<double><<<nblk(n * ncomp, 256), 256, 0, sphb_stream(stream)>>>(src, perm, n, ncomp, dst);
@@ -380,6 +384,7 @@ extern "C" int sphb_gather_f64(const double *src, const uint32_t *perm, int64_t 
 extern "C" int sphb_scatter_f64(const double *src, const uint32_t *perm, int64_t n, int32_t ncomp, double *dst,
                                 void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || ncomp <= 0 || (n > 0 && (!src || !perm || !dst))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_scatter<double><<<nblk(n * ncomp, 256), 256, 0, sphb_stream(stream)>>>(src, perm, n, ncomp, dst);
@@ -389,6 +394,7 @@ extern "C" int sphb_scatter_f64(const double *src, const uint32_t *perm, int64_t
 
 extern "C" int sphb_gather_u32(const uint32_t *src, const uint32_t *perm, int64_t n, uint32_t *dst, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || (n > 0 && (!src || !perm || !dst))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_gather<uint32_t><<<nblk(n, 256), 256, 0, sphb_stream(stream)>>>(src, perm, n, 1, dst);

@@ -600,6 +600,7 @@ __global__ void k_nl_rows(NlRowSet rs, int K, const long long *__restrict__ idx,
 extern "C" int sphb_rows_pack(double *s0, int32_t w0, double *s1, int32_t w1, double *s2, int32_t w2, double *s3,
                               int32_t w3, const int64_t *idx, int64_t n_idx, double *buf, int32_t unpack, void *stream)
 {
+    SPHB_RANGE();
     NlRowSet rs{{s0, s1, s2, s3}, {w0, w1, w2, w3}};
     int K = 0;
     for (int q = 0; q < 4; ++q) {
@@ -642,6 +643,7 @@ extern "C" int64_t sphb_nlist_pool_rows(int64_t n)
 extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float *hmax_global,
                                 const sphb_nlist *nl, const sphb_consts *k, double *omega, void *stream)
 {
+    SPHB_RANGE();
     if (omega && !k) return SPHB_E_ARG;
     if (!cells || cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh ||
         !cells->frec || !hmax_global || !nl_ok(nl) || nl->n != cells->n || nl->posh_build != cells->posh)
@@ -665,6 +667,7 @@ extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, 
 
 extern "C" int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, void *stream)
 {
+    SPHB_RANGE();
     if (!nl_ok(nl) || !posh_now) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
     long long nb = (nl->n + NL_CHECK_THREADS - 1) / NL_CHECK_THREADS;
@@ -679,6 +682,7 @@ extern "C" int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts 
                                         const double *posh, const double *rho_in, double *rho_sum, double *dwdh_sum,
                                         double *omega, int32_t *ngb_count, void *stream)
 {
+    SPHB_RANGE();
     if (!nl_ok(nl) || !k || !posh) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
     k_nl_density_omega<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, rho_in, rho_sum,
@@ -691,6 +695,7 @@ extern "C" int sphb_nlist_newton_h(const sphb_nlist *nl, const sphb_consts *k, c
                                    const double *h_guess, double *h_out, double *omega_out, double *posh_out, int32_t *iters,
                                    sphb_status *status, void *stream)
 {
+    SPHB_RANGE();
     if (!nl_ok(nl) || !k || !posh || !h_out || !status || posh_out == posh) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
     if (omega_out)
@@ -707,6 +712,7 @@ extern "C" int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, cons
                                 const double *recB, const double *recC, const double *recD, double *acc, double *dudt,
                                 sphb_status *status, void *stream)
 {
+    SPHB_RANGE();
     if (!nl_ok(nl) || !k || !posh || !recB || (!recC == !recD) || !acc || !dudt || !status) return SPHB_E_ARG;
     if (k->G != 0.0) return SPHB_E_ARG;   // the softened-gravity terms ride in the scanning kernels only
     if (nl->n == 0) return SPHB_OK;
@@ -723,6 +729,7 @@ extern "C" int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, cons
 extern "C" int sphb_gather_state(const double *pos, const double *h, const double *vel, const double *u,
                                  const uint32_t *perm, int64_t n, double *posh_s, double *vel_s, double *u_s, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || (n > 0 && !perm)) return SPHB_E_ARG;
     if (n > 0 && ((posh_s && (!pos || !h)) || (vel_s && !vel) || (u_s && !u))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
@@ -735,6 +742,7 @@ extern "C" int sphb_gather_state(const double *pos, const double *h, const doubl
 extern "C" int sphb_scatter_state(const double *posh_s, const double *vel_s, const double *u_s, const uint32_t *perm,
                                   int64_t n, double *pos, double *h, double *vel, double *u, void *stream)
 {
+    SPHB_RANGE();
     if (n < 0 || (n > 0 && !perm)) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
     k_nl_scatter_state<<<(unsigned)((n + 255) / 256), 256, 0, sphb_stream(stream)>>>(posh_s, vel_s, u_s, perm, (long long)n, pos,

@@ -115,6 +115,21 @@ def distance(rj, ri):
     return d[0] if io.torch_out else _scalar(d[0])
 
 
+def direction_i_j(rj, ri):
+    """pyfluid.py:50-54: unit vector FROM i TO j; zeros for identical positions"""
+    io = _IO(rj, ri)
+    a, b = io.dev64(rj, (3,)), io.dev64(ri, (3,))
+    if torch.equal(a, b):
+        return io.out(torch.zeros(3, dtype=torch.float64, device=a.device))
+    d = _eng().distance(a.reshape(1, 3), b.reshape(1, 3))
+    return io.out((a - b) / d[0])
+
+
+def dellM4(rj, ri, smoothlength):
+    """pyfluid.py:81-82: grad_j W = M4_d1(|r_j - r_i|, h) * direction_i_j"""
+    return M4_d1(distance(rj, ri), smoothlength) * direction_i_j(rj, ri)
+
+
 def M4(dist, smoothlength):
     """pyfluid.py:56-62 (scalar or array; elementwise)"""
     return _m4(dist, smoothlength, 0)

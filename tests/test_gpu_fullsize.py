@@ -1,6 +1,8 @@
 """Parity at BASELINE.json's full sizes (configs C2, C3, C4): size-independent properties of the whole arrays
 (momentum / energy conservation of the pair sums, idempotence of the h solve, neighbour counts) plus sampled-particle
 parity against the CPU oracle's per-particle functions (each O(N), so a handful of particles).  Tolerance 1e-10."""
+import os
+
 import numpy as np
 import pytest
 
@@ -35,6 +37,7 @@ def _check(sph, oracle_mod, w, js, n_expect=None, vel_noise_seed=5):
     sph.PARTICLE_MASS = w["m"]
     try:
         o = oracle_mod.Oracle(G=0.0, PARTICLE_MASS=w["m"])
+        o.set_num_threads(os.cpu_count() or 1)    # the sampled particles are spread over the host threads
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
         pos = w["pos"]
         rng = np.random.default_rng(vel_noise_seed)
@@ -68,6 +71,20 @@ def _check(sph, oracle_mod, w, js, n_expect=None, vel_noise_seed=5):
         if n_expect is not None:
             jn, hn, nn = n_expect
             assert len(o.neighbours(pos, jn, h[jn])) == nn and h[jn] == pytest.approx(hn, rel=1e-6)
+        # the neighbour COUNT the hot kernels see (q < 2 decided with their own r = d2 rsqrt(d2), q = r / h) equals the
+        # size of the reference-arithmetic neighbour set, for the scanning kernel and for the list drain
+        import engine as E
+        eng = sph._eng()
+        c = sph._consts()
+        dg = eng.build(eng.pack_posh(to(pos), h_t), *eng.grid_for(eng.pack_posh(to(pos), h_t)))
+        _, _, _, ng_scan = eng.density_omega(dg, c, want_rho=False, want_ngb=True)
+        nl = eng.nl_build(dg, 1.03, 0.03)
+        _, _, _, ng_list = eng.nl_density_omega(nl, c, dg.posh, want_omega=False, want_ngb=True)
+        assert nl.read_flags() == 0 and torch.equal(ng_scan, ng_list)
+        ng = eng.scatter(ng_scan.double(), dg.perm, 1).cpu().numpy()
+        for j in js[:24]:
+            assert int(ng[j]) == len(o.neighbours(pos, int(j), h[j])), j
+        del nl, dg
         return it
     finally:
         sph.PARTICLE_MASS = 1
@@ -95,4 +112,6 @@ def test_C4_sod_16M(sph, oracle_mod):
     import workloads
     w = workloads.sod_tube(384)
     assert len(w["pos"]) == 15925248
-    _check(sph, oracle_mod, w, js=[7, 14155776 - 3, 14155776 + 5])   # left bulk edge, both sides of the interface
+    # left bulk edge, both sides of the interface, and a seeded sample of 61 more
+    js = [7, 14155776 - 3, 14155776 + 5] + np.random.default_rng(9).choice(15925248, size=61, replace=False).tolist()
+    _check(sph, oracle_mod, w, js=js)

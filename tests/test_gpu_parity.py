@@ -53,6 +53,18 @@ def uniform_cloud(n, seed, density=3.75, vscale=1.0):
     return rng.random((n, 3)) * L, (rng.random((n, 3)) - 0.5) * vscale, 1 + rng.random(n), L
 
 
+def test_direction_and_dellM4_golden(sph):
+    """direction_i_j (pyfluid.py:50-54) and dellM4 (:81-82) against outputs of the reference (make_golden_r2.py)"""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyfluid_golden_r2.npz"))
+    for k in range(len(g["r2_h"])):
+        d = sph.direction_i_j(g["r2_rj"][k], g["r2_ri"][k])
+        w = sph.dellM4(g["r2_rj"][k], g["r2_ri"][k], float(g["r2_h"][k]))
+        assert isinstance(d, np.ndarray) and d.shape == (3,)
+        assert np.array_equal(d, g["r2_direction"][k])              # three IEEE divisions: the same bits
+        assert vrel(w[None], g["r2_dellM4"][k][None]) < RTOL or not g["r2_dellM4"][k].any()
+    assert not g["r2_direction"][5].any() and not sph.direction_i_j(g["r2_rj"][5], g["r2_ri"][5]).any()
+
+
 # ---- kernel function KATs ---------------------------------------------------------------------------
 def test_m4_kats(sph, golden):
     d, h = golden["kat_dist"], golden["kat_h"]
