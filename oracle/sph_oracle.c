@@ -65,6 +65,13 @@ enum {
 static int g_wide = 0;
 void oracle_set_wide(int on) { g_wide = on; }
 
+/* Per-particle masses (the authors' own NOTE at pyfluid.py:3-4).  The reference has ONE scalar
+ * PARTICLE_MASS; with a mass array set, every "PARTICLE_MASS" of a sum over i becomes m_i (pyfluid.py:95,216,327,340,474)
+ * and the one in var_density / zetaprime becomes the target's m_j (:115,238).  NULL (the default) is the reference. */
+static const double *g_mass = NULL;
+void oracle_set_masses(const double *m) { g_mass = m; }
+#define MASS_OF(c, i) (g_mass ? g_mass[i] : (c)->particle_mass)
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP
@@ -161,9 +168,9 @@ static inline void dellM4(const double *rj, const double *ri, double h, double *
 }
 
 /* pyfluid.py:237-238 var_density() */
-static inline double var_density(const oracle_consts *c, double h)
+static inline double var_density_m(const oracle_consts *c, double m, double h)
 {
-    return c->particle_mass * pow(c->coupling_const / h, 3.0);
+    return m * pow(c->coupling_const / h, 3.0);
 }
 
 /* pyfluid.py:218-224 density(): index-order sum including i == j */
@@ -172,7 +179,7 @@ static double density_j(const oracle_consts *c, const double *pos, int64_t n, in
     double rho = 0.0;
 #pragma omp parallel for reduction(+ : rho) schedule(static) if (g_wide)
     for (int64_t i = 0; i < n; ++i)
-        rho += c->particle_mass * oracle_M4(oracle_distance(pos + 3 * j, pos + 3 * i), h);
+        rho += MASS_OF(c, i) * oracle_M4(oracle_distance(pos + 3 * j, pos + 3 * i), h);
     return rho;
 }
 
@@ -182,19 +189,18 @@ static double omega_j(const oracle_consts *c, const double *pos, int64_t n, int6
     double sum = 0.0;
 #pragma omp parallel for reduction(+ : sum) schedule(static) if (g_wide)
     for (int64_t i = 0; i < n; ++i)
-        sum += c->particle_mass * oracle_M4_dh(oracle_distance(pos + 3 * j, pos + 3 * i), h);
+        sum += MASS_OF(c, i) * oracle_M4_dh(oracle_distance(pos + 3 * j, pos + 3 * i), h);
     return 1.0 + h / (3.0 * rho) * sum;
 }
 
 /* pyfluid.py:108-117 zeta_j(), zetaprime() */
-static inline double zeta_j(const oracle_consts *c, double h, double rho)
+static inline double zeta_j(const oracle_consts *c, double mj, double h, double rho)
 {
-    return var_density(c, h) - rho;
+    return var_density_m(c, mj, h) - rho;
 }
 
-static inline double zetaprime(const oracle_consts *c, double rho, double omega, double h)
+static inline double zetaprime(const oracle_consts *c, double mj, double rho, double omega, double h)
 {
-    double mj = c->particle_mass;
     return (-3.0 * rho / h * (omega - 1.0) - 3.0 * mj * pow(c->coupling_const / h, 3.0) / h);
 }
 
@@ -203,8 +209,8 @@ static double newton_iteration(const oracle_consts *c, const double *pos, int64_
 {
     double rho = density_j(c, pos, n, j, h_old);
     double om = omega_j(c, pos, n, j, rho, h_old);
-    double zeta = zeta_j(c, h_old, rho);
-    double zetap = zetaprime(c, rho, om, h_old);
+    double zeta = zeta_j(c, MASS_OF(c, j), h_old, rho);
+    double zetap = zetaprime(c, MASS_OF(c, j), rho, om, h_old);
     return h_old - zeta / zetap; /* newton_new_h :199-201 */
 }
 
@@ -215,11 +221,11 @@ static int bisection_h(const oracle_consts *c, const double *pos, int64_t n, int
     double h_a = c->bisect_a, h_b = c->bisect_b;
     int i = 0;
     while (i < c->bisect_limit) {
-        double zeta_a = zeta_j(c, h_a, density_j(c, pos, n, j, h_a));
-        double zeta_b = zeta_j(c, h_b, density_j(c, pos, n, j, h_b));
+        double zeta_a = zeta_j(c, MASS_OF(c, j), h_a, density_j(c, pos, n, j, h_a));
+        double zeta_b = zeta_j(c, MASS_OF(c, j), h_b, density_j(c, pos, n, j, h_b));
         if (zeta_a * zeta_b > 0.0) (*oob)++;
         double root = (h_a + h_b) / 2.0;
-        double zeta_root = zeta_j(c, root, density_j(c, pos, n, j, root));
+        double zeta_root = zeta_j(c, MASS_OF(c, j), root, density_j(c, pos, n, j, root));
         if (fabs(zeta_root) < c->bisect_tol) {
             *h_out = root;
             return 1;
@@ -370,9 +376,9 @@ static double energy_rate_j(const oracle_consts *c, int64_t j, const double *pos
         double gj[3], gi[3], mean[3];
         dellM4(pos + 3 * j, pos + 3 * i, h[j], gj);
         dellM4(pos + 3 * j, pos + 3 * i, h[i], gi);
-        density_change += c->particle_mass * dot3(vji, gj);
+        density_change += MASS_OF(c, i) * dot3(vji, gj);
         for (int k = 0; k < 3; ++k) mean[k] = 0.5 * (gj[k] + gi[k]);
-        viscosity_sum += (c->particle_mass * Pi_ji(c, j, i, pos, vel, P, rho, h, &stl) * dot3(vji, mean));
+        viscosity_sum += (MASS_OF(c, i) * Pi_ji(c, j, i, pos, vel, P, rho, h, &stl) * dot3(vji, mean));
     }
     *status |= stl;
     viscosity_sum *= 0.5;
@@ -426,9 +432,9 @@ static void acceleration_j(const oracle_consts *c, int64_t j, const double *pos,
 {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     int32_t stl = 0;
-    const double m = c->particle_mass;
 #pragma omp parallel for reduction(+ : a0, a1, a2) reduction(| : stl) schedule(static) if (g_wide)
     for (int64_t i = 0; i < n; ++i) {
+        const double m = MASS_OF(c, i);
         double term[3] = { 0.0, 0.0, 0.0 };
         const double *rj = pos + 3 * j, *ri = pos + 3 * i;
         int same = same_pos(rj, ri);
@@ -517,7 +523,7 @@ static int32_t stage(const oracle_consts *c, const double *pos, const double *ve
                      int64_t n, double *rho, double *omega, double *xi, double *P, double *dudt, double *acc)
 {
     int32_t status = 0;
-    for (int64_t i = 0; i < n; ++i) rho[i] = var_density(c, h[i]);        /* var_density_arr :240 */
+    for (int64_t i = 0; i < n; ++i) rho[i] = var_density_m(c, MASS_OF(c, i), h[i]);        /* var_density_arr :240 */
 #pragma omp parallel for schedule(dynamic, 8)
     for (int64_t j = 0; j < n; ++j) omega[j] = omega_j(c, pos, n, j, rho[j], h[j]); /* omega_arr :99 */
     if (c->G != 0.0) {
@@ -609,7 +615,7 @@ void oracle_step_work_sample(const oracle_consts *c, const double *pos, const do
     double *rho = (double *)malloc(sizeof(double) * N * 4);
     double *P = rho + N, *omega = P + N, *xi = omega + N;
     for (size_t i = 0; i < N; ++i) {
-        rho[i] = var_density(c, h[i]);
+        rho[i] = var_density_m(c, MASS_OF(c, i), h[i]);
         P[i] = (c->gamma - 1.0) * e[i] * rho[i];
         omega[i] = 1.0; /* frozen stand-in for the neighbours' omega; the cost does not depend on it */
         xi[i] = 0.0;
