@@ -39,10 +39,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sod", choices=["sod", "lattice", "planar"])
+    ap.add_argument("--workload", default="sod", choices=["sod", "lattice", "planar", "plummer"])
     ap.add_argument("--nx", type=int, default=384, help="sod: left-half lattice points along x (384 -> 15.9 M)")
     ap.add_argument("--side", type=int, default=100, help="lattice: cube side")
-    ap.add_argument("--n", type=int, default=262144, help="planar: particle count")
+    ap.add_argument("--n", type=int, default=None, help="planar (default 262144) / plummer (default 67108864): particle count")
     ap.add_argument("--path", default="lists", choices=["lists", "scan"],
                     help="lists: neighbour lists kept across kernels and steps (default); scan: the scanning kernels only")
     ap.add_argument("--warm-state-steps", type=int, default=0, help="untimed steps at setup so that the timed steps see a developed flow")
@@ -59,7 +59,9 @@ def make_workload(a):
         return workloads.sod_tube(a.nx)
     if a.workload == "lattice":
         return workloads.lattice_cube(a.side, vel_noise=0.01)
-    return workloads.planar_uniform(a.n, vel_noise=0.01)
+    if a.workload == "plummer":
+        return workloads.plummer(a.n or 67_108_864, seed=0)
+    return workloads.planar_uniform(a.n or 262144, vel_noise=0.01)
 
 
 class ClockSampler:
@@ -152,7 +154,7 @@ def run_reference(a):
     o = oracle.Oracle(G=0.0, PARTICLE_MASS=w["m"])
     o.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: take the box's cores at every N
     o.set_wide(True)
-    h = w["h_guess"] * (1.3012 / 1.2) if a.workload == "sod" else w["h_guess"]
+    h = w["h_guess"] * {"sod": 1.3012 / 1.2, "plummer": 1.0 / 0.8}.get(a.workload, 1.0)   # about the solved h
     rng = np.random.default_rng(7)
     cand = rng.choice(n, size=min(n, 65536), replace=False)
     t0 = time.perf_counter()
@@ -518,7 +520,7 @@ def run_ours(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": w["name"], "n_particles": n_total, "dt": dt, "warm_state_steps": a.warm_state_steps,
-                       "l2": "inputs_larger_than_L2 (state ~1 GB vs 126 MB L2)",
+                       "l2": f"inputs_larger_than_L2 (state {n_total * 64 / 1e9:.2f} GB vs 126 MB L2)",
                        "parallelism": f"slab{world}" if world > 1 else "single",
                        "path": "kept neighbour lists (rebuilt when the device-side check says so)" if use_lists else "scanning kernels (3 cell-list builds and 3 scans per step)"},
             "clocks": clk, "gpu_launches": int(launches), "neighbour_lists": list_stats, "state_checksum": checksum,

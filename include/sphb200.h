@@ -80,9 +80,24 @@ typedef struct sphb_status {
     int32_t reserved[3];
 } sphb_status;
 
+/* Nested cell grids for distributions whose h spans decades (BASELINE config 5, the Plummer sphere): one uniform grid
+ * would put 10^3..10^5 particles of the dense core into a cell sized for the mean h.  Particles are binned by the
+ * OCTAVE of their h at build time -- level l holds 2^(exp0+l) <= h < 2^(exp0+l+1), clamped to [0, nlevels-1]; h <= 0 or
+ * non-finite (unbounded support, pyfluid.py:57-60) goes to the last level -- and every level has its own grid: its own
+ * cell edge (~ one support radius of ITS particles), its own bounding box.  Cells are numbered level-major (global cell id
+ * = cell_base + local id), so the sorted order, cell_start, cell_hmax and cell_id stay single arrays and a search just
+ * walks the levels one after the other: candidates are still visited in ascending sorted slot.  A level's grid must
+ * contain all of its particles (no clamped outliers): searches skip a level whose box they do not touch. */
+#define SPHB_MAX_LEVELS 16
+typedef struct sphb_level {
+    sphb_grid grid;     /* absolute origin; xdiv is ignored (1) */
+    uint32_t cell_base; /* first global cell id of this level */
+    uint32_t ncell;     /* nx*ny*nz */
+} sphb_level;
+
 /* sorted-order particle views built by sphb_grid_build and consumed by every gather kernel */
 typedef struct sphb_cells {
-    sphb_grid grid;
+    sphb_grid grid;             /* the one grid, or (nlevels > 1) only the origin of the fp32 frame of `frec` */
     int64_t n;                  /* particles in the grid (targets + ghosts) */
     const uint32_t *cell_start; /* [ncell+1] first sorted slot of each cell */
     const float *cell_hmax;     /* [ncell]   max h in the cell, rounded up to float */
@@ -91,6 +106,10 @@ typedef struct sphb_cells {
     const float *frec;          /* [n][4]    x-ox, y-oy, z-oz, (2h+delta)^2 upper bound (fp32 prefilter record) */
     float delta;                /* absolute error bound of the fp32 positions */
     float pad_;
+    int32_t nlevels;            /* 0 or 1: one grid (`grid`); 2..SPHB_MAX_LEVELS: nested grids */
+    int32_t exp0;               /* octave of level 0 */
+    const sphb_level *levels;   /* DEVICE [nlevels] */
+    const float *level_hmax;    /* DEVICE [nlevels] max h per level, rounded up (kept current by build / set_h) */
 } sphb_cells;
 
 const char *sphb_last_cuda_error(void);
@@ -112,9 +131,21 @@ int sphb_pack_posh(const double *pos, const double *h, int64_t n, double *posh, 
 int sphb_grid_build(const double *posh_in, const int64_t *tie_key, int64_t n, const sphb_grid *g, float delta, uint32_t *perm,
                     uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id, double *posh_sorted,
                     float *frec_sorted, void *workspace, int64_t workspace_bytes, void *stream);
+/* The same for nested grids (cells->nlevels > 1): cells->grid gives the fp32 frame, cells->levels / exp0 the level table
+ * (device), cells->level_hmax is WRITTEN (device [nlevels]); the output arrays are the ones `cells` points to plus
+ * perm.  ncell = the sum of the levels' cell counts. */
+int64_t sphb_levels_workspace_bytes(int64_t n, int64_t ncell);
+int sphb_grid_build_levels(const double *posh_in, const int64_t *tie_key, int64_t n, const sphb_cells *cells, int64_t ncell,
+                           uint32_t *perm, void *workspace, int64_t workspace_bytes, void *stream);
+/* per-octave statistics of a particle set, to choose the levels from: for the 16 octaves [2^(exp_top-15+b), 2^(exp_top-14+b))
+ * (b = 0: everything below as well; b = 15: everything above, and h <= 0 / non-finite), out[b] = {count, sum h,
+ * min x, y, z, max x, y, z} (bounds rounded outward to float; empty octaves: count 0).  out: DEVICE [16][8] doubles. */
+int sphb_level_stats(const double *posh, int64_t n, int32_t exp_top, double *out, void *stream);
 /* refresh h in posh/frec/cell_hmax of an existing grid (positions unchanged) */
 int sphb_grid_set_h(const double *h_sorted, int64_t n, const sphb_grid *g, float delta, const uint32_t *cell_start,
                     float *cell_hmax, double *posh_sorted, float *frec_sorted, void *stream);
+/* nested grids: also refreshes cells->level_hmax */
+int sphb_grid_set_h_levels(const double *h_sorted, const sphb_cells *cells, int64_t ncell, void *stream);
 /* dst[s*ncomp + k] = src[perm[s]*ncomp + k]  (apply a build's permutation to any fp64 array) */
 int sphb_gather_f64(const double *src, const uint32_t *perm, int64_t n, int32_t ncomp, double *dst, void *stream);
 /* dst[perm[s]*ncomp + k] = src[s*ncomp + k]  (undo it) */

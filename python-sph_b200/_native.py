@@ -45,10 +45,19 @@ class Status(C.Structure):
 STATUS_INTS = C.sizeof(Status) // 4
 
 
+class Level(C.Structure):
+    """sphb_level: one of the nested grids (cells numbered from cell_base)"""
+    _fields_ = [("grid", Grid), ("cell_base", C.c_uint32), ("ncell", C.c_uint32)]
+
+
+MAX_LEVELS = 16
+
+
 class Cells(C.Structure):
     _fields_ = [("grid", Grid), ("n", C.c_int64), ("cell_start", C.c_void_p), ("cell_hmax", C.c_void_p),
                 ("cell_id", C.c_void_p), ("posh", C.c_void_p), ("frec", C.c_void_p), ("delta", C.c_float),
-                ("pad_", C.c_float)]
+                ("pad_", C.c_float), ("nlevels", C.c_int32), ("exp0", C.c_int32), ("levels", C.c_void_p),
+                ("level_hmax", C.c_void_p)]
 
 
 class Lists(C.Structure):
@@ -81,6 +90,10 @@ SIGNATURES = {
     "sphb_pack_posh": (C.c_int, [P, P, I64, P, P]),
     "sphb_grid_build": (C.c_int, [P, P, I64, C.POINTER(Grid), C.c_float, P, P, P, P, P, P, P, I64, P]),
     "sphb_grid_set_h": (C.c_int, [P, I64, C.POINTER(Grid), C.c_float, P, P, P, P, P]),
+    "sphb_levels_workspace_bytes": (I64, [I64, I64]),
+    "sphb_grid_build_levels": (C.c_int, [P, P, I64, C.POINTER(Cells), I64, P, P, I64, P]),
+    "sphb_level_stats": (C.c_int, [P, I64, I32, P, P]),
+    "sphb_grid_set_h_levels": (C.c_int, [P, C.POINTER(Cells), I64, P]),
     "sphb_gather_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_scatter_f64": (C.c_int, [P, P, I64, I32, P, P]),
     "sphb_gather_u32": (C.c_int, [P, P, I64, P, P]),

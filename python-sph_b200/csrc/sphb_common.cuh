@@ -49,6 +49,45 @@ __host__ __device__ __forceinline__ double sphb_cellx(const sphb_grid &g)
 }
 
 // ---------------------------------------------------------------------------------------------
+// nested cell grids (sphb_cells.nlevels > 1, include/sphb200.h): level of a particle = octave of its h
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sphb_level_of(double h, int exp0, int nlev)
+{
+    if (!(h > 0.0) || !(h < CUDART_INF)) return nlev - 1;               // unbounded support: last level
+    const int e = ((__double2hiint(h) >> 20) & 0x7ff) - 1023;           // floor(log2 h) for normal h
+    return min(max(e - exp0, 0), nlev - 1);
+}
+
+__device__ __forceinline__ sphb_level sphb_load_level(const sphb_level *lev, int b)
+{
+    sphb_level L;
+    const double *d = reinterpret_cast<const double *>(lev + b);
+    L.grid.ox = __ldg(d);
+    L.grid.oy = __ldg(d + 1);
+    L.grid.oz = __ldg(d + 2);
+    L.grid.cell = __ldg(d + 3);
+    const int2 q = __ldg(reinterpret_cast<const int2 *>(d + 4));   // the 56-byte entries are 8-byte aligned only
+    const int2 q2 = __ldg(reinterpret_cast<const int2 *>(d + 5));
+    L.grid.nx = q.x;
+    L.grid.ny = q.y;
+    L.grid.nz = q2.x;
+    L.grid.xdiv = 1;
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(d + 6));
+    L.cell_base = r.x;
+    L.ncell = r.y;
+    return L;
+}
+
+// level of a global cell id (levels are numbered by ascending cell_base)
+__device__ __forceinline__ int sphb_level_of_cell(const sphb_level *lev, int nlev, uint32_t cell)
+{
+    int b = 0;
+    for (int q = 1; q < nlev; ++q)
+        if (cell >= __ldg(&lev[q].cell_base)) b = q;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
 // exact reference geometry (membership tests, pyfluid.py:43-47): d.dot(d) is
 // fma(dz,dz,fma(dy,dy,dx*dx)) on the reference's numpy (tests/golden/make_golden.py self-test)
 // ---------------------------------------------------------------------------------------------

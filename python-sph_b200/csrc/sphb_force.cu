@@ -143,7 +143,7 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
 #endif
 }
 
-template <bool GRAV>
+template <bool GRAV, bool MULTI>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     k_force(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ recB,
             const double *__restrict__ recC, const double *__restrict__ bgrav, const float *__restrict__ hmax_global,
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
     if (parked >= 0) {
         flush(tgt ? parked : 0);
     } else {
-        sphb_warp_scan<true, SPHB_FORCE_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush);
+        sphb_warp_scan<true, SPHB_FORCE_FLUSH_ROWS, MULTI>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush);
         flush(L.count());
     }
     if (tgt) {
@@ -720,19 +720,23 @@ extern "C" int sphb_force(const sphb_cells *cells, const sphb_consts *k, const u
     SPHB_RANGE();
     if (!cells || !k || !recB || !recC || !hmax_global || !acc || !dudt || !status) return SPHB_E_ARG;
     if (lists && (!lists->store || !lists->broken)) return SPHB_E_ARG;
-    if (cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh || !cells->frec)
+    if (cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh || !cells->frec ||
+        (cells->nlevels > 1 && (cells->nlevels > SPHB_MAX_LEVELS || !cells->levels || !cells->level_hmax)))
         return SPHB_E_ARG;
     if (k->G != 0.0 && !bgrav) return SPHB_E_ARG;   // with gravity on, the grad-h correction factors are required
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
     const SphbWarpSaved *saved = lists ? reinterpret_cast<const SphbWarpSaved *>(lists->store) : nullptr;
     const int32_t *broken = lists ? lists->broken : nullptr;
-    if (bgrav)
-        k_force<true><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, bgrav,
-                                                                                  hmax_global, acc, dudt, status, saved, broken);
-    else
-        k_force<false><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, bgrav,
-                                                                                   hmax_global, acc, dudt, status, saved, broken);
+#define SPHB_K4(GR_, MU_)                                                                                          \
+    k_force<GR_, MU_><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, recB, recC, bgrav, \
+                                                                                  hmax_global, acc, dudt, status, saved, broken)
+    if (cells->nlevels > 1) {
+        if (bgrav) SPHB_K4(true, true); else SPHB_K4(false, true);
+    } else {
+        if (bgrav) SPHB_K4(true, false); else SPHB_K4(false, false);
+    }
+#undef SPHB_K4
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -71,7 +71,7 @@ __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWar
 // K2
 // ------------------------------------------------------------------------------------------------
 // PRODUCE: scan with the symmetric support and park the lists for sphb_force (sphb_lists, include/sphb200.h)
-template <bool XI, bool PRODUCE>
+template <bool XI, bool PRODUCE, bool MULTI>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_density_omega(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_target,
                     const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
@@ -113,11 +113,11 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     if (PRODUCE) {
         const float cov = (float)lists.cover * 1.000001f;
         const float RH = sphb_radius_of_h((double)lists.hmax_global[0] * (double)cov, g.delta);
-        const int nseg = sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+        const int nseg = sphb_warp_scan<true, 0, MULTI>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
         sphb_lists_save(ws, lane, L.count(), nseg, !flushed,
                         reinterpret_cast<SphbWarpSaved *>(lists.store) + ((long long)blockIdx.x * SPHB_WARPS + warp));
     } else {
-        sphb_warp_scan<false, SPHB_OWN_FLUSH_ROWS>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
+        sphb_warp_scan<false, SPHB_OWN_FLUSH_ROWS, MULTI>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
     }
     sphb_own_flush<XI>(c.posh, ws, lane, L.count(), a);
     if (tgt) {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
 #define SPHB_NEWTON_MARGIN 4e-3
 #endif
 
-template <bool FUSED, bool PRODUCE>
+template <bool FUSED, bool PRODUCE, bool MULTI>
 __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     k_newton_h(sphb_cells c, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ h_guess,
                double *__restrict__ h_out, double *__restrict__ omega_out, int32_t *__restrict__ iters,
@@ -217,12 +217,12 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
                 // symmetric support, every h taken at its cover: complete for sphb_force at any h below the cover
                 const float cov = (float)lists.cover * 1.000001f;
                 const float RH = sphb_radius_of_h((double)lists.hmax_global[0] * (double)cov, g.delta);
-                const int nseg = sphb_warp_scan<true>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+                const int nseg = sphb_warp_scan<true, 0, MULTI>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
                 sphb_lists_save(ws, lane, L.count(), nseg, !flushed,
                                 reinterpret_cast<SphbWarpSaved *>(lists.store) + ((long long)blockIdx.x * SPHB_WARPS + warp));
                 first_scan = false;
             } else {
-                sphb_warp_scan<false>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
+                sphb_warp_scan<false, 0, MULTI>(g, ws, lane, pend, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
             }
             cnt = L.count();   // 0 for lanes that were not scanned for
             have_lists = !flushed;
@@ -285,15 +285,21 @@ __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, 
                                      double fxj, double fyj, double fzj, double h, double *red /*[2*SPHB_WARPS]*/,
                                      double *sumG_out = nullptr)
 {
-    const SphbScanCtx g = sphb_make_ctx(c);
-    const double R = (h > 0.0) ? (2.0 * h * 1.000001 + (double)g.delta) * 1.00001 : (double)CUDART_INF_F;
-    const int cxl = sphb_cell_lo(fxj - R, g.inv_cellx, g.nx), cxh = sphb_cell_hi(fxj + R, g.inv_cellx, g.nx);
-    const int cyl = sphb_cell_lo(fyj - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fyj + R, g.inv_cell, g.ny);
-    const int czl = sphb_cell_lo(fzj - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fzj + R, g.inv_cell, g.nz);
-    const bool fullx = (cxl == 0 && cxh == g.nx - 1);
-    const bool fully = fullx && (cyl == 0 && cyh == g.ny - 1);
+    const SphbScanCtx gc = sphb_make_ctx(c);
+    const double R = (h > 0.0) ? (2.0 * h * 1.000001 + (double)gc.delta) * 1.00001 : (double)CUDART_INF_F;
     const double hinv = 1.0 / h;
     double sum = 0.0, sumg = 0.0;
+  for (int lb = 0; lb < gc.nlev; ++lb) {   // nested grids: level by level, ascending slots
+    const SphbLevelCtx g = sphb_level_ctx(gc, lb);
+    const double fxl = fxj - g.sx, fyl = fyj - g.sy, fzl = fzj - g.sz;
+    if (g.bounded && (sphb_axis_miss(fxl, fxl, R, g.nx, g.cellx) || sphb_axis_miss(fyl, fyl, R, g.ny, g.cell) ||
+                      sphb_axis_miss(fzl, fzl, R, g.nz, g.cell)))
+        continue;
+    const int cxl = sphb_cell_lo(fxl - R, g.inv_cellx, g.nx), cxh = sphb_cell_hi(fxl + R, g.inv_cellx, g.nx);
+    const int cyl = sphb_cell_lo(fyl - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fyl + R, g.inv_cell, g.ny);
+    const int czl = sphb_cell_lo(fzl - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fzl + R, g.inv_cell, g.nz);
+    const bool fullx = (cxl == 0 && cxh == g.nx - 1);
+    const bool fully = fullx && (cyl == 0 && cyh == g.ny - 1);
     // spans: merge rows when the x range (and the y range) cover the whole axis
     const int nzs = fully ? 1 : (czh - czl + 1);
     const int nys = fullx ? 1 : (cyh - cyl + 1);
@@ -325,6 +331,7 @@ __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, 
             }
         }
     }
+  }
     sum = sphb_warp_sum(sum);
     sumg = sphb_warp_sum(sumg);
     __syncthreads();
@@ -412,18 +419,27 @@ __global__ void __launch_bounds__(SPHB_THREADS)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long qi = (long long)blockIdx.x * SPHB_WARPS + warp;
     if (qi >= n_query) return;
-    const SphbScanCtx g = sphb_make_ctx(c);
+    const SphbScanCtx gc = sphb_make_ctx(c);
     const uint32_t j = query[qi];
     double xj, yj, zj, hj;
     sphb_load_posh(c.posh, j, xj, yj, zj, hj);
-    const float4 fj = __ldg(g.frec + j);
-    double hr = hj;
-    if (symmetric && hmax_global && !((double)hmax_global[0] <= hr)) hr = (double)hmax_global[0];
-    const double R = (hr > 0.0) ? (2.0 * hr * 1.000001 + (double)g.delta) * 1.00001 : (double)CUDART_INF_F;
-    const int cxl = sphb_cell_lo(fj.x - R, g.inv_cellx, g.nx), cxh = sphb_cell_hi(fj.x + R, g.inv_cellx, g.nx);
-    const int cyl = sphb_cell_lo(fj.y - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fj.y + R, g.inv_cell, g.ny);
-    const int czl = sphb_cell_lo(fj.z - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fj.z + R, g.inv_cell, g.nz);
+    const float4 fj = __ldg(gc.frec + j);
     long long total = 0;
+  for (int lb = 0; lb < gc.nlev; ++lb) {   // nested grids: level by level, ascending slots
+    const SphbLevelCtx g = sphb_level_ctx(gc, lb);
+    double hr = hj;
+    if (symmetric) {
+        const double hm = (gc.nlev > 1) ? (double)__ldg(gc.level_hmax + lb) : (hmax_global ? (double)hmax_global[0] : hj);
+        if (!(hm <= hr)) hr = hm;
+    }
+    const double R = (hr > 0.0) ? (2.0 * hr * 1.000001 + (double)gc.delta) * 1.00001 : (double)CUDART_INF_F;
+    const double fxl = (double)fj.x - g.sx, fyl = (double)fj.y - g.sy, fzl = (double)fj.z - g.sz;
+    if (g.bounded && (sphb_axis_miss(fxl, fxl, R, g.nx, g.cellx) || sphb_axis_miss(fyl, fyl, R, g.ny, g.cell) ||
+                      sphb_axis_miss(fzl, fzl, R, g.nz, g.cell)))
+        continue;
+    const int cxl = sphb_cell_lo(fxl - R, g.inv_cellx, g.nx), cxh = sphb_cell_hi(fxl + R, g.inv_cellx, g.nx);
+    const int cyl = sphb_cell_lo(fyl - R, g.inv_cell, g.ny), cyh = sphb_cell_hi(fyl + R, g.inv_cell, g.ny);
+    const int czl = sphb_cell_lo(fzl - R, g.inv_cell, g.nz), czh = sphb_cell_hi(fzl + R, g.inv_cell, g.nz);
     for (int rz = czl; rz <= czh; ++rz)
         for (int ry = cyl; ry <= cyh; ++ry) {
             const size_t rowbase = ((size_t)rz * g.ny + ry) * g.nx;
@@ -446,6 +462,7 @@ __global__ void __launch_bounds__(SPHB_THREADS)
                 total += __popc(m);
             }
         }
+  }
     if (lane == 0) count[qi] = (int32_t)total;
 }
 
@@ -455,7 +472,8 @@ __global__ void __launch_bounds__(SPHB_THREADS)
 static inline int sphb_cells_ok(const sphb_cells *c)
 {
     return c && c->n >= 0 && c->cell_start && c->cell_hmax && c->cell_id && c->posh && c->frec && c->grid.nx > 0 &&
-           c->grid.ny > 0 && c->grid.nz > 0 && c->grid.cell > 0.0;
+           c->grid.ny > 0 && c->grid.nz > 0 && c->grid.cell > 0.0 &&
+           (c->nlevels <= 1 || (c->nlevels <= SPHB_MAX_LEVELS && c->levels && c->level_hmax));
 }
 
 static bool sphb_lists_ok(const sphb_lists *l)
@@ -473,15 +491,21 @@ extern "C" int sphb_density_omega(const sphb_cells *cells, const sphb_consts *k,
     if (cells->n == 0) return SPHB_OK;
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
     const sphb_lists ls = lists ? *lists : sphb_lists{nullptr, nullptr, nullptr, 1.0};
-#define SPHB_K2(XI_, PR_)                                                                         \
-    k_density_omega<XI_, PR_><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(        \
+    const bool multi = cells->nlevels > 1;
+#define SPHB_K2M(XI_, PR_, MU_)                                                                   \
+    k_density_omega<XI_, PR_, MU_><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(   \
         *cells, *k, target, h_target, rho_in, rho_sum, dwdh_sum, omega, xi_out, ngb_count, ls)
+#define SPHB_K2(XI_, PR_)                                                                         \
+    do {                                                                                          \
+        if (multi) SPHB_K2M(XI_, PR_, true); else SPHB_K2M(XI_, PR_, false);                      \
+    } while (0)
     if (xi_out) {
         if (lists) SPHB_K2(true, true); else SPHB_K2(true, false);
     } else {
         if (lists) SPHB_K2(false, true); else SPHB_K2(false, false);
     }
 #undef SPHB_K2
+#undef SPHB_K2M
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
@@ -518,15 +542,21 @@ extern "C" int sphb_newton_h(const sphb_cells *cells, const sphb_consts *k, cons
     const long long blocks = (cells->n + SPHB_THREADS - 1) / SPHB_THREADS;
     SPHB_CUDA(cudaMemsetAsync(&status->nfail, 0, sizeof(int32_t), sphb_stream(stream)));
     const sphb_lists ls = lists ? *lists : sphb_lists{nullptr, nullptr, nullptr, 1.0};
+    const bool multi = cells->nlevels > 1;
+#define SPHB_K3M(FU_, PR_, MU_)                                                                             \
+    k_newton_h<FU_, PR_, MU_><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out, \
+                                                                                          omega_out, iters, code, fail_list, status, ls)
 #define SPHB_K3(FU_, PR_)                                                                                   \
-    k_newton_h<FU_, PR_><<<(unsigned)blocks, SPHB_THREADS, 0, sphb_stream(stream)>>>(*cells, *k, target, h_guess, h_out, \
-                                                                                     omega_out, iters, code, fail_list, status, ls)
+    do {                                                                                                    \
+        if (multi) SPHB_K3M(FU_, PR_, true); else SPHB_K3M(FU_, PR_, false);                                \
+    } while (0)
     if (omega_out) {
         if (lists) SPHB_K3(true, true); else SPHB_K3(true, false);
     } else {
         if (lists) SPHB_K3(false, true); else SPHB_K3(false, false);
     }
 #undef SPHB_K3
+#undef SPHB_K3M
     SPHB_LAUNCHED();
     // the fallback reads its list length from status->nfail on the device: no host round trip
     return sphb_bisect_h(cells, k, fail_list, -1, h_out, omega_out, code, nullptr, 1, status, stream);

@@ -57,11 +57,10 @@ static inline int64_t scan_blocks(int64_t ncell) { return (ncell + SCAN_TILE - 1
 static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
 
 // workspace layout: counts[ncell] | cursor[ncell] | block_sums[nblk+1] | perm_tmp[n] | cell_tmp[n]
+extern "C" int64_t sphb_levels_workspace_bytes(int64_t n, int64_t ncell);
 extern "C" int64_t sphb_grid_workspace_bytes(int64_t n, const sphb_grid *g)
 {
-    const int64_t ncell = sphb_grid_ncell(g);
-    if (ncell < 0 || n < 0) return -1;
-    return align256(4 * ncell) * 2 + align256(4 * (scan_blocks(ncell) + 1)) + align256(4 * n) * 2;
+    return sphb_levels_workspace_bytes(n, sphb_grid_ncell(g));
 }
 
 __device__ __forceinline__ uint32_t sphb_cell_of(const sphb_grid &g, double x, double y, double z)
@@ -76,6 +75,41 @@ __device__ __forceinline__ uint32_t sphb_cell_of(const sphb_grid &g, double x, d
     return (uint32_t)(((long long)cz * g.ny + (long long)cy) * g.nx + (long long)cx);
 }
 
+// what the build kernels need to place a particle: one grid (nlev <= 1), or the device table of nested grids
+struct SphbSpec {
+    sphb_grid g0;            // the one grid / the origin of the fp32 frame
+    int nlev, exp0;
+    const sphb_level *lev;   // device [nlev]
+    float *level_hmax;       // device [nlev] (written)
+};
+
+static inline SphbSpec sphb_spec_single(const sphb_grid &g)
+{
+    SphbSpec s;
+    s.g0 = g;
+    s.nlev = 1;
+    s.exp0 = 0;
+    s.lev = nullptr;
+    s.level_hmax = nullptr;
+    return s;
+}
+
+// global cell id of a particle
+__device__ __forceinline__ uint32_t sphb_cell_of_spec(const SphbSpec &sp, double x, double y, double z, double h)
+{
+    if (sp.nlev <= 1) return sphb_cell_of(sp.g0, x, y, z);
+    const sphb_level L = sphb_load_level(sp.lev, sphb_level_of(h, sp.exp0, sp.nlev));
+    return L.cell_base + sphb_cell_of(L.grid, x, y, z);
+}
+
+// raise level_hmax[b] to hm (non-negative floats order like their bit patterns; look before the atomic)
+__device__ __forceinline__ void sphb_raise_level_hmax(float *level_hmax, int b, float hm)
+{
+    int *p = reinterpret_cast<int *>(level_hmax) + b;
+    const int v = __float_as_int(hm);
+    if (v > __ldcg(p)) atomicMax(p, v);
+}
+
 __global__ void k_pack_posh(const double *__restrict__ pos, const double *__restrict__ h, long long n,
                             double *__restrict__ posh)
 {
@@ -87,14 +121,14 @@ __global__ void k_pack_posh(const double *__restrict__ pos, const double *__rest
     reinterpret_cast<double2 *>(posh)[2 * i + 1] = b;
 }
 
-__global__ void k_cell_count(const double *__restrict__ posh, long long n, sphb_grid g, uint32_t *__restrict__ cell_tmp,
+__global__ void k_cell_count(const double *__restrict__ posh, long long n, SphbSpec sp, uint32_t *__restrict__ cell_tmp,
                              uint32_t *__restrict__ counts)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double2 a = reinterpret_cast<const double2 *>(posh)[2 * i];
     const double2 b = reinterpret_cast<const double2 *>(posh)[2 * i + 1];
-    const uint32_t c = sphb_cell_of(g, a.x, a.y, b.x);
+    const uint32_t c = sphb_cell_of_spec(sp, a.x, a.y, b.x, b.y);
     cell_tmp[i] = c;
     atomicAdd(counts + c, 1u);
 }
@@ -211,7 +245,7 @@ __device__ __forceinline__ void sphb_emit_records(const double *__restrict__ pos
 }
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-    k_cell_finish(const double *__restrict__ posh_in, const long long *__restrict__ tie_key, sphb_grid g, long long ncell,
+    k_cell_finish(const double *__restrict__ posh_in, const long long *__restrict__ tie_key, SphbSpec sp, long long ncell,
                   float delta,
                   const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ perm_tmp,
                   uint32_t *__restrict__ perm, uint32_t *__restrict__ cell_id, float *__restrict__ cell_hmax,
@@ -227,6 +261,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32)
         if (lane == 0) cell_hmax[cell] = 0.f;
         return;
     }
+    const sphb_grid &g = sp.g0;   // only its origin is used below (the fp32 frame)
     if (cnt <= 32) {
         const uint32_t v = lane < cnt ? perm_tmp[s + lane] : 0xffffffffu;
         const long long key = (lane < cnt) ? (tie_key ? tie_key[v] : (long long)v) : 0x7fffffffffffffffll;
@@ -252,11 +287,14 @@ __global__ void __launch_bounds__(FIN_WARPS * 32)
             sphb_emit_records(posh_in, perm_tmp[s + a], s + a, g, delta, (uint32_t)cell, perm, cell_id, posh, frec, hm);
     }
     hm = sphb_warp_max(hm);
-    if (lane == 0) cell_hmax[cell] = hm;
+    if (lane == 0) {
+        cell_hmax[cell] = hm;
+        if (sp.nlev > 1) sphb_raise_level_hmax(sp.level_hmax, sphb_level_of_cell(sp.lev, sp.nlev, (uint32_t)cell), hm);
+    }
 }
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-    k_set_h(const double *__restrict__ h_sorted, sphb_grid g, long long ncell, float delta,
+    k_set_h(const double *__restrict__ h_sorted, SphbSpec sp, long long ncell, float delta,
             const uint32_t *__restrict__ cell_start, float *__restrict__ cell_hmax, double *__restrict__ posh,
             float *__restrict__ frec)
 {
@@ -273,7 +311,10 @@ __global__ void __launch_bounds__(FIN_WARPS * 32)
         else hm = CUDART_INF_F;
     }
     hm = sphb_warp_max(hm);
-    if (lane == 0) cell_hmax[cell] = hm;
+    if (lane == 0) {
+        cell_hmax[cell] = hm;
+        if (sp.nlev > 1 && e > s) sphb_raise_level_hmax(sp.level_hmax, sphb_level_of_cell(sp.lev, sp.nlev, (uint32_t)cell), hm);
+    }
 }
 
 template <typename T>
@@ -310,18 +351,15 @@ extern "C" int sphb_pack_posh(const double *pos, const double *h, int64_t n, dou
     return SPHB_OK;
 }
 
-extern "C" int sphb_grid_build(const double *posh_in, const int64_t *tie_key, int64_t n, const sphb_grid *g, float delta,
-                               uint32_t *perm,
-                               uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id, double *posh_sorted,
-                               float *frec_sorted, void *workspace, int64_t workspace_bytes, void *stream)
+// the build pipeline for one grid or for nested grids (`sp`): counting sort by global cell id
+static int sphb_build_impl(const double *posh_in, const int64_t *tie_key, int64_t n, const SphbSpec &sp, int64_t ncell,
+                           float delta, uint32_t *perm, uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id,
+                           double *posh_sorted, float *frec_sorted, void *workspace, int64_t workspace_bytes, cudaStream_t st)
 {
-    SPHB_RANGE();
-    const int64_t ncell = sphb_grid_ncell(g);
-    if (ncell <= 0 || n < 0 || !(g->cell > 0.0) || !cell_start || !cell_hmax || !workspace) return SPHB_E_ARG;
+    if (ncell <= 0 || n < 0 || !cell_start || !cell_hmax || !workspace) return SPHB_E_ARG;
     if (n > 0 && (!posh_in || !perm || !cell_id || !posh_sorted || !frec_sorted)) return SPHB_E_ARG;
     if (n >= (int64_t)0xfffffff0ll || ncell >= (int64_t)0xfffffff0ll) return SPHB_E_ARG;
-    if (workspace_bytes < sphb_grid_workspace_bytes(n, g)) return SPHB_E_ARG;
-    cudaStream_t st = sphb_stream(stream);
+    if (workspace_bytes < sphb_levels_workspace_bytes(n, ncell)) return SPHB_E_ARG;
     const int64_t nb = scan_blocks(ncell);
     char *w = (char *)workspace;
     uint32_t *counts = (uint32_t *)w;
@@ -335,8 +373,9 @@ extern "C" int sphb_grid_build(const double *posh_in, const int64_t *tie_key, in
     uint32_t *cell_tmp = (uint32_t *)w;
 
     SPHB_CUDA(cudaMemsetAsync(counts, 0, (size_t)align256(4 * ncell) * 2, st));   // counts + cursor
+    if (sp.nlev > 1) SPHB_CUDA(cudaMemsetAsync(sp.level_hmax, 0, sizeof(float) * sp.nlev, st));
     if (n > 0) {
-        k_cell_count<<<nblk(n, 256), 256, 0, st>>>(posh_in, n, *g, cell_tmp, counts);
+        k_cell_count<<<nblk(n, 256), 256, 0, st>>>(posh_in, n, sp, cell_tmp, counts);
         SPHB_LAUNCHED();
     }
     k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(counts, ncell, block_sums);
@@ -349,10 +388,162 @@ extern "C" int sphb_grid_build(const double *posh_in, const int64_t *tie_key, in
         k_cell_scatter<<<nblk(n, 256), 256, 0, st>>>(cell_tmp, n, cell_start, cursor, perm_tmp);
         SPHB_LAUNCHED();
     }
-    k_cell_finish<<<nblk(ncell, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(posh_in, (const long long *)tie_key, *g, ncell, delta,
-                                                                     cell_start, perm_tmp,
-                                                                     perm, cell_id, cell_hmax, posh_sorted, frec_sorted);
+    k_cell_finish<<<nblk(ncell, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(posh_in, (const long long *)tie_key, sp, ncell, delta,
+                                                                     cell_start, perm_tmp, perm, cell_id, cell_hmax,
+                                                                     posh_sorted, frec_sorted);
     SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int64_t sphb_levels_workspace_bytes(int64_t n, int64_t ncell)
+{
+    if (ncell < 0 || n < 0) return -1;
+    return align256(4 * ncell) * 2 + align256(4 * (scan_blocks(ncell) + 1)) + align256(4 * n) * 2;
+}
+
+extern "C" int sphb_grid_build(const double *posh_in, const int64_t *tie_key, int64_t n, const sphb_grid *g, float delta,
+                               uint32_t *perm,
+                               uint32_t *cell_start, float *cell_hmax, uint32_t *cell_id, double *posh_sorted,
+                               float *frec_sorted, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    SPHB_RANGE();
+    const int64_t ncell = sphb_grid_ncell(g);
+    if (ncell <= 0 || !(g->cell > 0.0)) return SPHB_E_ARG;
+    return sphb_build_impl(posh_in, tie_key, n, sphb_spec_single(*g), ncell, delta, perm, cell_start, cell_hmax, cell_id,
+                           posh_sorted, frec_sorted, workspace, workspace_bytes, sphb_stream(stream));
+}
+
+static inline bool sphb_spec_of_cells(const sphb_cells *c, SphbSpec &sp)
+{
+    if (!c || c->nlevels < 2 || c->nlevels > SPHB_MAX_LEVELS || !c->levels || !c->level_hmax) return false;
+    sp.g0 = c->grid;
+    sp.nlev = c->nlevels;
+    sp.exp0 = c->exp0;
+    sp.lev = c->levels;
+    sp.level_hmax = const_cast<float *>(c->level_hmax);
+    return true;
+}
+
+extern "C" int sphb_grid_build_levels(const double *posh_in, const int64_t *tie_key, int64_t n, const sphb_cells *cells,
+                                      int64_t ncell, uint32_t *perm, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    SPHB_RANGE();
+    SphbSpec sp;
+    if (!sphb_spec_of_cells(cells, sp) || cells->n != n) return SPHB_E_ARG;
+    return sphb_build_impl(posh_in, tie_key, n, sp, ncell, cells->delta, perm, const_cast<uint32_t *>(cells->cell_start),
+                           const_cast<float *>(cells->cell_hmax), const_cast<uint32_t *>(cells->cell_id),
+                           const_cast<double *>(cells->posh), const_cast<float *>(cells->frec), workspace, workspace_bytes,
+                           sphb_stream(stream));
+}
+
+// per-octave statistics (sphb_level_stats): lanes of a warp mostly share an octave, so each octave present in the warp
+// is reduced by shuffles and lands in shared memory with one atomic per quantity; one set of global atomics per block
+#define LS_BINS 16
+#define LS_THREADS 256
+#define LS_BLOCKS 1184
+__device__ __forceinline__ int sphb_f2ord_down(double v) { return sphb_f2ord(__double2float_rd(v)); }
+__device__ __forceinline__ int sphb_f2ord_up(double v) { return sphb_f2ord(__double2float_ru(v)); }
+
+__global__ void __launch_bounds__(LS_THREADS)
+    k_level_stats(const double *__restrict__ posh, long long n, int exp_top, unsigned long long *__restrict__ cnt,
+                  double *__restrict__ sumh, int *__restrict__ lo, int *__restrict__ hi)
+{
+    __shared__ unsigned int s_cnt[LS_BINS];
+    __shared__ double s_sum[LS_BINS];
+    __shared__ int s_lo[LS_BINS][3], s_hi[LS_BINS][3];
+    for (int q = threadIdx.x; q < LS_BINS; q += blockDim.x) {
+        s_cnt[q] = 0;
+        s_sum[q] = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            s_lo[q][c] = 0x7fffffff;
+            s_hi[q][c] = (int)0x80000000;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+        const long long i = i0 + threadIdx.x;
+        int bin = -1;
+        double x = 0.0, y = 0.0, z = 0.0, h = 0.0;
+        if (i < n) {
+            sphb_ld4(posh, (size_t)i, x, y, z, h);
+            bin = sphb_level_of(h, exp_top - (LS_BINS - 1), LS_BINS);
+        }
+        unsigned rem = __ballot_sync(SPHB_FULL, bin >= 0);
+        while (rem) {
+            const int b = __shfl_sync(SPHB_FULL, bin, __ffs(rem) - 1);
+            const bool in = bin == b;
+            const unsigned m = __ballot_sync(SPHB_FULL, in);
+            rem &= ~m;
+            const double sh = sphb_warp_sum(in && h > 0.0 && h < CUDART_INF ? h : 0.0);
+            const int lx = __reduce_min_sync(SPHB_FULL, in ? sphb_f2ord_down(x) : 0x7fffffff);
+            const int ly = __reduce_min_sync(SPHB_FULL, in ? sphb_f2ord_down(y) : 0x7fffffff);
+            const int lz = __reduce_min_sync(SPHB_FULL, in ? sphb_f2ord_down(z) : 0x7fffffff);
+            const int hx = __reduce_max_sync(SPHB_FULL, in ? sphb_f2ord_up(x) : (int)0x80000000);
+            const int hy = __reduce_max_sync(SPHB_FULL, in ? sphb_f2ord_up(y) : (int)0x80000000);
+            const int hz = __reduce_max_sync(SPHB_FULL, in ? sphb_f2ord_up(z) : (int)0x80000000);
+            if (lane == 0) {
+                atomicAdd(&s_cnt[b], (unsigned)__popc(m));
+                atomicAdd(&s_sum[b], sh);
+                atomicMin(&s_lo[b][0], lx);
+                atomicMin(&s_lo[b][1], ly);
+                atomicMin(&s_lo[b][2], lz);
+                atomicMax(&s_hi[b][0], hx);
+                atomicMax(&s_hi[b][1], hy);
+                atomicMax(&s_hi[b][2], hz);
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < LS_BINS; q += blockDim.x) {
+        if (s_cnt[q] == 0) continue;
+        atomicAdd(cnt + q, (unsigned long long)s_cnt[q]);
+        atomicAdd(sumh + q, s_sum[q]);
+        for (int c = 0; c < 3; ++c) {
+            atomicMin(lo + 3 * q + c, s_lo[q][c]);
+            atomicMax(hi + 3 * q + c, s_hi[q][c]);
+        }
+    }
+}
+
+__global__ void k_level_stats_out(const unsigned long long *__restrict__ cnt, const double *__restrict__ sumh,
+                                  const int *__restrict__ lo, const int *__restrict__ hi, double *__restrict__ out)
+{
+    const int q = threadIdx.x;
+    if (q >= LS_BINS) return;
+    out[8 * q] = (double)cnt[q];
+    out[8 * q + 1] = sumh[q];
+    for (int c = 0; c < 3; ++c) {
+        out[8 * q + 2 + c] = cnt[q] ? (double)sphb_ord2f(lo[3 * q + c]) : 0.0;
+        out[8 * q + 5 + c] = cnt[q] ? (double)sphb_ord2f(hi[3 * q + c]) : 0.0;
+    }
+}
+
+// `out` doubles as scratch: [0..16) counts (u64), [16..32) sums, [32..80) lo (int), [80..128) hi (int) while reducing
+extern "C" int sphb_level_stats(const double *posh, int64_t n, int32_t exp_top, double *out, void *stream)
+{
+    SPHB_RANGE();
+    if (n < 0 || !out || (n > 0 && !posh)) return SPHB_E_ARG;
+    cudaStream_t st = sphb_stream(stream);
+    // scratch behind the 128 output doubles would need a second buffer: use a static device allocation per call instead
+    unsigned long long *cnt = nullptr;
+    SPHB_CUDA(cudaMallocAsync((void **)&cnt, 16 * 8 + 16 * 8 + 48 * 4 + 48 * 4, st));
+    double *sumh = reinterpret_cast<double *>(cnt + LS_BINS);
+    int *lo = reinterpret_cast<int *>(sumh + LS_BINS);
+    int *hi = lo + 3 * LS_BINS;
+    SPHB_CUDA(cudaMemsetAsync(cnt, 0, 16 * 8 + 16 * 8, st));
+    SPHB_CUDA(cudaMemsetAsync(lo, 0x7f, 48 * 4, st));   // 0x7f7f7f7f: above every finite float's key
+    SPHB_CUDA(cudaMemsetAsync(hi, 0x80, 48 * 4, st));   // 0x80808080: below
+    if (n > 0) {
+        long long nb = (n + LS_THREADS - 1) / LS_THREADS;
+        if (nb > LS_BLOCKS) nb = LS_BLOCKS;
+        k_level_stats<<<(unsigned)nb, LS_THREADS, 0, st>>>(posh, (long long)n, exp_top, cnt, sumh, lo, hi);
+        SPHB_LAUNCHED();
+    }
+    k_level_stats_out<<<1, 32, 0, st>>>(cnt, sumh, lo, hi, out);
+    SPHB_LAUNCHED();
+    SPHB_CUDA(cudaFreeAsync(cnt, st));
     return SPHB_OK;
 }
 
@@ -364,8 +555,24 @@ extern "C" int sphb_grid_set_h(const double *h_sorted, int64_t n, const sphb_gri
     const int64_t ncell = sphb_grid_ncell(g);
     if (ncell <= 0 || n < 0 || !cell_start || !cell_hmax) return SPHB_E_ARG;
     if (n > 0 && (!h_sorted || !posh_sorted || !frec_sorted)) return SPHB_E_ARG;
-    k_set_h<<<nblk(ncell, FIN_WARPS), FIN_WARPS * 32, 0, sphb_stream(stream)>>>(h_sorted, *g, ncell, delta, cell_start,
-                                                                                cell_hmax, posh_sorted, frec_sorted);
+    k_set_h<<<nblk(ncell, FIN_WARPS), FIN_WARPS * 32, 0, sphb_stream(stream)>>>(h_sorted, sphb_spec_single(*g), ncell, delta,
+                                                                                cell_start, cell_hmax, posh_sorted, frec_sorted);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_grid_set_h_levels(const double *h_sorted, const sphb_cells *cells, int64_t ncell, void *stream)
+{
+    SPHB_RANGE();
+    SphbSpec sp;
+    if (!sphb_spec_of_cells(cells, sp) || ncell <= 0 || !cells->cell_start || !cells->cell_hmax) return SPHB_E_ARG;
+    if (cells->n > 0 && (!h_sorted || !cells->posh || !cells->frec)) return SPHB_E_ARG;
+    cudaStream_t st = sphb_stream(stream);
+    SPHB_CUDA(cudaMemsetAsync(sp.level_hmax, 0, sizeof(float) * sp.nlev, st));
+    k_set_h<<<nblk(ncell, FIN_WARPS), FIN_WARPS * 32, 0, st>>>(h_sorted, sp, ncell, cells->delta, cells->cell_start,
+                                                               const_cast<float *>(cells->cell_hmax),
+                                                               const_cast<double *>(cells->posh),
+                                                               const_cast<float *>(cells->frec));
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void nl_flush_own(const double *__restrict__ posh, co
 // OMEGA: also return Omega(pos, h) of the build-time records (pyfluid.py:91-105 with the algebraic density, :503):
 // every chunk is drained once more from the staging area while it is stored -- the first gather pass of the step that
 // follows a rebuild comes for the price of its arithmetic, without reading a single row back.
-template <bool OMEGA>
+template <bool OMEGA, bool MULTI>
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     k_nl_build(sphb_cells c, const uint8_t *__restrict__ target, const float *__restrict__ hmax_global, sphb_nlist nl,
                sphb_consts kc, double *__restrict__ omega)
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     for (int pass = 0; pass < 2; ++pass) {
         SphbList L;
         L.init(ws, lane);
-        sphb_warp_scan<true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+        sphb_warp_scan<true, 0, MULTI>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
         emit(L.count(), true);
         if (mode != 1 || over) break;
         alloc(total);
@@ -646,7 +646,8 @@ extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, 
     SPHB_RANGE();
     if (omega && !k) return SPHB_E_ARG;
     if (!cells || cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh ||
-        !cells->frec || !hmax_global || !nl_ok(nl) || nl->n != cells->n || nl->posh_build != cells->posh)
+        !cells->frec || !hmax_global || !nl_ok(nl) || nl->n != cells->n || nl->posh_build != cells->posh ||
+        (cells->nlevels > 1 && (cells->nlevels > SPHB_MAX_LEVELS || !cells->levels || !cells->level_hmax)))
         return SPHB_E_ARG;
     cudaStream_t st = sphb_stream(stream);
     SPHB_CUDA(cudaMemsetAsync(nl->cursor, 0, sizeof(unsigned long long), st));
@@ -654,13 +655,17 @@ extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, 
     if (nl->maxima) SPHB_CUDA(cudaMemsetAsync(nl->maxima, 0, 2 * sizeof(int32_t), st));
     if (cells->n == 0) return SPHB_OK;
     const int smem = (int)(NL_WARPS * sizeof(NlWarpShared));   // > 48 KB of dynamic shared memory needs the opt-in
-    if (omega) {
-        SPHB_CUDA(cudaFuncSetAttribute(k_nl_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_nl_build<true><<<nl_blocks(cells->n), NL_THREADS, smem, st>>>(*cells, target, hmax_global, *nl, *k, omega);
+#define SPHB_NLB(OM_, MU_, KC_, OMP_)                                                                               \
+    do {                                                                                                             \
+        SPHB_CUDA(cudaFuncSetAttribute(k_nl_build<OM_, MU_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+        k_nl_build<OM_, MU_><<<nl_blocks(cells->n), NL_THREADS, smem, st>>>(*cells, target, hmax_global, *nl, KC_, OMP_); \
+    } while (0)
+    if (cells->nlevels > 1) {
+        if (omega) SPHB_NLB(true, true, *k, omega); else SPHB_NLB(false, true, sphb_consts{}, nullptr);
     } else {
-        SPHB_CUDA(cudaFuncSetAttribute(k_nl_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_nl_build<false><<<nl_blocks(cells->n), NL_THREADS, smem, st>>>(*cells, target, hmax_global, *nl, sphb_consts{}, nullptr);
+        if (omega) SPHB_NLB(true, false, *k, omega); else SPHB_NLB(false, false, sphb_consts{}, nullptr);
     }
+#undef SPHB_NLB
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -123,6 +123,11 @@ struct SphbScanCtx {
     double cell, inv_cell;     // y,z edge
     double cellx, inv_cellx;   // x edge = cell / xdiv
     float delta;
+    // nested grids (nlev > 1): the fields above are replaced level by level from this table
+    int nlev;
+    const sphb_level *levels;
+    const float *level_hmax;
+    double ox, oy, oz;         // origin of the fp32 frame
 };
 
 __device__ __forceinline__ SphbScanCtx sphb_make_ctx(const sphb_cells &c)
@@ -139,7 +144,62 @@ __device__ __forceinline__ SphbScanCtx sphb_make_ctx(const sphb_cells &c)
     s.cellx = sphb_cellx(c.grid);
     s.inv_cellx = 1.0 / s.cellx;
     s.delta = c.delta;
+    s.nlev = c.nlevels > 1 ? c.nlevels : 1;
+    s.levels = c.levels;
+    s.level_hmax = c.level_hmax;
+    s.ox = c.grid.ox;
+    s.oy = c.grid.oy;
+    s.oz = c.grid.oz;
     return s;
+}
+
+// one level of the search: the grid to walk, where it sits in the fp32 frame, and how far its particles reach
+struct SphbLevelCtx {
+    const uint32_t *cell_start;
+    const float *cell_hmax;
+    int nx, ny, nz;
+    double cell, inv_cell, cellx, inv_cellx;
+    double sx, sy, sz;   // level origin minus frame origin: frame coordinate - s = coordinate in the level's grid
+    bool bounded;        // the grid contains all of its particles: a search that does not touch its box skips it
+};
+
+template <bool MULTI = true>
+__device__ __forceinline__ SphbLevelCtx sphb_level_ctx(const SphbScanCtx &g, int b)
+{
+    SphbLevelCtx l;
+    if (MULTI && g.nlev > 1) {
+        const sphb_level L = sphb_load_level(g.levels, b);
+        l.cell_start = g.cell_start + L.cell_base;
+        l.cell_hmax = g.cell_hmax + L.cell_base;
+        l.nx = L.grid.nx;
+        l.ny = L.grid.ny;
+        l.nz = L.grid.nz;
+        l.cell = l.cellx = L.grid.cell;
+        l.inv_cell = l.inv_cellx = 1.0 / L.grid.cell;
+        l.sx = L.grid.ox - g.ox;
+        l.sy = L.grid.oy - g.oy;
+        l.sz = L.grid.oz - g.oz;
+        l.bounded = true;
+    } else {
+        l.cell_start = g.cell_start;
+        l.cell_hmax = g.cell_hmax;
+        l.nx = g.nx;
+        l.ny = g.ny;
+        l.nz = g.nz;
+        l.cell = g.cell;
+        l.inv_cell = g.inv_cell;
+        l.cellx = g.cellx;
+        l.inv_cellx = g.inv_cellx;
+        l.sx = l.sy = l.sz = 0.0;
+        l.bounded = false;   // outliers are clamped into border cells: those are unbounded
+    }
+    return l;
+}
+
+// does [lo - R, hi + R] miss the axis range [0, n cell] of a bounded level?
+__device__ __forceinline__ bool sphb_axis_miss(double lo, double hi, double R, int n, double cell)
+{
+    return (hi + R < -1e-6 * cell) || (lo - R > ((double)n + 1e-6) * cell);
 }
 
 // lowest / highest cell index that can hold a coordinate >= v / <= v (clamped like the build clamps)
@@ -158,11 +218,11 @@ __device__ __forceinline__ int sphb_cell_hi(double v, double inv_cell, int n)
 
 // distance from the interval [lo, hi] to cell c of an axis with n cells (border cells are unbounded:
 // the build clamps outliers into them)
-__device__ __forceinline__ double sphb_axis_gap(double lo, double hi, int c, int n, double cell)
+__device__ __forceinline__ double sphb_axis_gap(double lo, double hi, int c, int n, double cell, bool bounded = false)
 {
     double g = 0.0;
-    if (c > 0) g = fmax(g, (double)c * cell - hi);
-    if (c < n - 1) g = fmax(g, lo - (double)(c + 1) * cell);
+    if (c > 0 || bounded) g = fmax(g, (double)c * cell - hi);
+    if (c < n - 1 || bounded) g = fmax(g, lo - (double)(c + 1) * cell);
     return g;
 }
 
@@ -214,7 +274,8 @@ __device__ __forceinline__ uint32_t sphb_list_get(const WS &ws, int lane, int k)
 //   symscale : SYM only, >= 1: the candidates' supports are taken as symscale times what the grid stores (lists
 //              that have to stay complete while every h may still grow by that factor)
 // Returns the number of live segments (what sphb_lists_save needs).
-template <bool SYM, int FLUSH_ROWS = 0, class WS, class Flush>
+//   MULTI    : the cell list may be a set of nested grids (sphb_cells.nlevels > 1); false compiles the level loop away
+template <bool SYM, int FLUSH_ROWS = 0, bool MULTI = false, class WS, class Flush>
 __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int lane, bool tgt, float fx,
                                               float fy, float fz, float Rj, float thr, uint32_t cid, float RH,
                                               SphbList &L, Flush &&flush, float symscale = 1.f)
@@ -222,14 +283,31 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
     int nseg = 0;   // live entries of ws.segbase (warp-uniform)
     unsigned remaining = __ballot_sync(SPHB_FULL, tgt);
     // group key: number of breaks at or before the lane
-    const uint32_t row = cid / (uint32_t)g.nx, cx = cid - row * (uint32_t)g.nx;
     uint32_t gkey;
     {
-        const float rmax = fmaxf(sphb_warp_max(tgt ? Rj : 0.f), SYM ? RH : 0.f);
-        const float gapf = ceilf(2.f * rmax * (float)g.inv_cellx);               // +inf, NaN -> no x breaks
+        // the lane's own level, and its cell within it
+        uint32_t local = cid, own_nx = (uint32_t)g.nx;
+        float own_inv_cellx = (float)g.inv_cellx, own_RH = SYM ? RH : 0.f;
+        int lev = 0;
+        if (MULTI && g.nlev > 1) {
+            lev = (cid != 0xffffffffu) ? sphb_level_of_cell(g.levels, g.nlev, cid) : g.nlev;
+            if (cid != 0xffffffffu) {
+                const sphb_level Lo = sphb_load_level(g.levels, lev);
+                local = cid - Lo.cell_base;
+                own_nx = (uint32_t)Lo.grid.nx;
+                own_inv_cellx = (float)(1.0 / Lo.grid.cell);
+                // lanes are merged by their OWN radii only: a merged box is walked through every level, and on a finer
+                // level the cells between two far-apart lanes of a sparse coarse level can hold the whole dense core
+                own_RH = 0.f;
+            }
+        }
+        const uint32_t row = local / own_nx, cx = local - row * own_nx;
+        const float rmax = fmaxf(sphb_warp_max(tgt ? Rj : 0.f), own_RH);
+        const float gapf = ceilf(2.f * rmax * own_inv_cellx);                    // +inf, NaN -> no x breaks
         const uint32_t gap = (gapf < 1e9f) ? (uint32_t)fmaxf(gapf, 1.f) : 0xffffffffu;
         const uint32_t prow = __shfl_up_sync(SPHB_FULL, row, 1), pcx = __shfl_up_sync(SPHB_FULL, cx, 1);
-        const bool brk = (lane == 0) || (row != prow) || (cx > pcx && cx - pcx > gap);
+        const int plev = __shfl_up_sync(SPHB_FULL, lev, 1);
+        const bool brk = (lane == 0) || (row != prow) || (lev != plev) || (cx > pcx && cx - pcx > gap);
         gkey = (uint32_t)__popc(__ballot_sync(SPHB_FULL, brk) & (0xffffffffu >> (31 - lane)));
     }
     while (remaining) {
@@ -244,27 +322,42 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
         const float xmin_f = sphb_warp_min(ing ? fx : inf), xmax_f = sphb_warp_max(ing ? fx : -inf);
         const float ymin_f = sphb_warp_min(ing ? fy : inf), ymax_f = sphb_warp_max(ing ? fy : -inf);
         const float zmin_f = sphb_warp_min(ing ? fz : inf), zmax_f = sphb_warp_max(ing ? fz : -inf);
-        const double xmin = xmin_f, xmax = xmax_f, ymin = ymin_f, ymax = ymax_f, zmin = zmin_f, zmax = zmax_f;
+        const double xmin0 = xmin_f, xmax0 = xmax_f, ymin0 = ymin_f, ymax0 = ymax_f, zmin0 = zmin_f, zmax0 = zmax_f;
         const double Rg = sphb_warp_max(ing ? Rj : 0.f);
-        const double Rw = SYM ? fmax(Rg, (double)RH) : Rg;
 
         // group-local frame: centre of the box; err bounds the fp32 rounding of the re-centred test
         const float ox = 0.5f * (xmin_f + xmax_f), oy = 0.5f * (ymin_f + ymax_f), oz = 0.5f * (zmin_f + zmax_f);
         const float tx = fx - ox, ty = fy - oy, tz = fz - oz;
         const float tt = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
         const float hdx = xmax_f - xmin_f, hdy = ymax_f - ymin_f, hdz = zmax_f - zmin_f;
-        const float dmax = 0.5f * (hdx + hdy + hdz) + (float)Rw + 1.8f * (float)g.cell;   // >= |c'| of anything in range
-        const float err = 4e-6f * dmax * dmax;
         const float m2x = -2.f * tx, m2y = -2.f * ty, m2z = -2.f * tz;
 #if SPHB_FILTER_X2
         const unsigned long long m2x2 = sphb_pack2(m2x, m2x), m2y2 = sphb_pack2(m2y, m2y), m2z2 = sphb_pack2(m2z, m2z);
 #endif
+
+      // nested grids: the levels one after the other (ascending cell_base = ascending sorted slot)
+      const int nlev = MULTI ? g.nlev : 1;
+      for (int lb = 0; lb < nlev; ++lb) {
+        const SphbLevelCtx G = sphb_level_ctx<MULTI>(g, lb);
+        double Rw = Rg;
+        if (SYM) {
+            const float RHb = (MULTI && g.nlev > 1) ? sphb_radius_of_h((double)__ldg(g.level_hmax + lb) * (double)symscale, g.delta) : RH;
+            Rw = fmax(Rg, (double)RHb);
+        }
+        // the group's box in the level's own coordinates
+        const double xmin = xmin0 - G.sx, xmax = xmax0 - G.sx, ymin = ymin0 - G.sy, ymax = ymax0 - G.sy;
+        const double zmin = zmin0 - G.sz, zmax = zmax0 - G.sz;
+        if (MULTI && G.bounded && (sphb_axis_miss(xmin, xmax, Rw, G.nx, G.cellx) || sphb_axis_miss(ymin, ymax, Rw, G.ny, G.cell) ||
+                          sphb_axis_miss(zmin, zmax, Rw, G.nz, G.cell)))
+            continue;
+        const float dmax = 0.5f * (hdx + hdy + hdz) + (float)Rw + 1.8f * (float)G.cell;   // >= |c'| of anything in range
+        const float err = 4e-6f * dmax * dmax;
         // pass  <=>  |c'|^2 - 2 c'.t' <= thr - |t'|^2 + err ; lanes outside the group never pass
         const float thrp = ing ? (thr - tt + err) : -inf;
         const float offp = ing ? (err - tt) : -inf;   // SYM: candidate threshold + offp
 
-        const int cyl = sphb_cell_lo(ymin - Rw, g.inv_cell, g.ny), cyh = sphb_cell_hi(ymax + Rw, g.inv_cell, g.ny);
-        const int czl = sphb_cell_lo(zmin - Rw, g.inv_cell, g.nz), czh = sphb_cell_hi(zmax + Rw, g.inv_cell, g.nz);
+        const int cyl = sphb_cell_lo(ymin - Rw, G.inv_cell, G.ny), cyh = sphb_cell_hi(ymax + Rw, G.inv_cell, G.ny);
+        const int czl = sphb_cell_lo(zmin - Rw, G.inv_cell, G.nz), czh = sphb_cell_hi(zmax + Rw, G.inv_cell, G.nz);
         const int nry = cyh - cyl + 1;
         const long long nrows = (long long)nry * (long long)(czh - czl + 1);
 
@@ -274,25 +367,25 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
             const long long rr = rb + lane;
             if (rr < nrows) {
                 const int ry = cyl + (int)(rr % nry), rz = czl + (int)(rr / nry);
-                const double gy = sphb_axis_gap(ymin, ymax, ry, g.ny, g.cell);
-                const double gz = sphb_axis_gap(zmin, zmax, rz, g.nz, g.cell);
+                const double gy = sphb_axis_gap(ymin, ymax, ry, G.ny, G.cell, G.bounded);
+                const double gz = sphb_axis_gap(zmin, zmax, rz, G.nz, G.cell, G.bounded);
                 const double g2 = gy * gy + gz * gz;
                 int lo = 0x7fffffff, hi = -1;
                 if (g2 < Rg * Rg) {
                     const double hx = sqrt(Rg * Rg - g2);   // +inf stays +inf
-                    lo = sphb_cell_lo(xmin - hx, g.inv_cellx, g.nx);
-                    hi = sphb_cell_hi(xmax + hx, g.inv_cellx, g.nx);
+                    lo = sphb_cell_lo(xmin - hx, G.inv_cellx, G.nx);
+                    hi = sphb_cell_hi(xmax + hx, G.inv_cellx, G.nx);
                 }
-                const size_t rowbase = ((size_t)rz * g.ny + ry) * (size_t)g.nx;
+                const size_t rowbase = ((size_t)rz * G.ny + ry) * (size_t)G.nx;
                 if (SYM && g2 < Rw * Rw) {
                     const double hxw = sqrt(Rw * Rw - g2);
-                    const int wl = sphb_cell_lo(xmin - hxw, g.inv_cellx, g.nx);
-                    const int wh = sphb_cell_hi(xmax + hxw, g.inv_cellx, g.nx);
+                    const int wl = sphb_cell_lo(xmin - hxw, G.inv_cellx, G.nx);
+                    const int wh = sphb_cell_hi(xmax + hxw, G.inv_cellx, G.nx);
                     // extend the tight range outwards to the farthest cell whose h_max reaches the group
                     for (int cx = wl; cx < lo && cx <= wh; ++cx) {
-                        const double hm = (double)g.cell_hmax[rowbase + cx] * (double)symscale;
+                        const double hm = (double)G.cell_hmax[rowbase + cx] * (double)symscale;
                         const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
-                        const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cellx);
+                        const double gx = sphb_axis_gap(xmin, xmax, cx, G.nx, G.cellx, G.bounded);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             lo = cx;
                             if (hi < lo) hi = lo;
@@ -300,9 +393,9 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                         }
                     }
                     for (int cx = wh; cx > hi && cx >= wl; --cx) {
-                        const double hm = (double)g.cell_hmax[rowbase + cx] * (double)symscale;
+                        const double hm = (double)G.cell_hmax[rowbase + cx] * (double)symscale;
                         const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
-                        const double gx = sphb_axis_gap(xmin, xmax, cx, g.nx, g.cellx);
+                        const double gx = sphb_axis_gap(xmin, xmax, cx, G.nx, G.cellx, G.bounded);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             hi = cx;
                             if (lo > hi) lo = hi;
@@ -311,8 +404,8 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                     }
                 }
                 if (hi >= lo) {
-                    s = g.cell_start[rowbase + lo];
-                    e = g.cell_start[rowbase + hi + 1];
+                    s = G.cell_start[rowbase + lo];
+                    e = G.cell_start[rowbase + hi + 1];
                 }
             }
             const int nb = (int)((nrows - rb) < 32 ? (nrows - rb) : 32);
@@ -447,6 +540,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                 }
             }
         }
+      }   // levels
     }
     return nseg;
 }

@@ -102,6 +102,36 @@ class Status:
         return self.t.cpu().numpy()
 
 
+class Levels:
+    """Nested cell grids (include/sphb200.h sphb_level): particles binned by the octave of h, one grid per octave,
+    cells numbered level-major.  frame: a Grid whose origin is the origin of the fp32 prefilter frame."""
+
+    def __init__(self, frame, exp0, grids):
+        self.frame = frame
+        self.exp0 = int(exp0)
+        self.grids = list(grids)
+        self.bases = []
+        tot = 0
+        for g in self.grids:
+            self.bases.append(tot)
+            tot += g.ncell
+        self.ncell = tot
+
+    @property
+    def nlevels(self):
+        return len(self.grids)
+
+    def table(self):
+        """the device table as bytes (sphb_level[nlevels])"""
+        arr = (N.Level * self.nlevels)()
+        for b, g in enumerate(self.grids):
+            arr[b].grid = g
+            arr[b].grid.xdiv = 1
+            arr[b].cell_base = self.bases[b]
+            arr[b].ncell = g.ncell
+        return bytes(arr)
+
+
 class DeviceGrid:
     """One cell list over one snapshot of positions (K1 output)."""
 
@@ -109,6 +139,11 @@ class DeviceGrid:
         self.n = int(n)
         self.grid = grid
         self.delta = float(delta)
+        self.levels = grid if isinstance(grid, Levels) else None
+        if self.levels is not None:
+            tb = self.levels.table()
+            self.level_table = torch.frombuffer(bytearray(tb), dtype=torch.uint8).to(device)
+            self.level_hmax = torch.zeros(self.levels.nlevels, dtype=torch.float32, device=device)
         nc = grid.ncell
         self.perm = torch.empty(self.n, dtype=torch.int32, device=device)
         self.cell_start = torch.empty(nc + 1, dtype=torch.int32, device=device)
@@ -121,7 +156,14 @@ class DeviceGrid:
     def cells(self):
         if self._cells is None:
             c = N.Cells()
-            c.grid = self.grid
+            if self.levels is not None:
+                c.grid = self.levels.frame
+                c.nlevels = self.levels.nlevels
+                c.exp0 = self.levels.exp0
+                c.levels = self.level_table.data_ptr()
+                c.level_hmax = self.level_hmax.data_ptr()
+            else:
+                c.grid = self.grid
             c.n = self.n
             c.cell_start = self.cell_start.data_ptr()
             c.cell_hmax = self.cell_hmax.data_ptr()
@@ -181,6 +223,35 @@ def choose_grid(lo, hi, h_mean, n, pad_cells=1.0, cell=None, xdiv=None):
     L = max(dims[0] / xdiv, dims[1], dims[2]) * cell
     delta = 2.0 * 4.0 * 2.0 ** -23 * L
     return g, delta
+
+
+# nested grids (one per octave of h) when the largest h exceeds this multiple of the mean h; 0 = never
+LEVEL_SPREAD = float(os.environ.get("SPHB_LEVEL_SPREAD", "6.0"))
+
+
+def choose_levels(stats, exp_top, lo, hi, hmax):
+    """Nested grids from sphb_level_stats' per-octave rows [count, sum h, lo xyz, hi xyz] (16 octaves ending at exp_top)
+    and the global bounding box.  -> (Levels, delta), or None when fewer than two octaves are occupied."""
+    occ = [b for b in range(16) if stats[b][0] > 0]
+    if not occ or 16 - occ[0] < 2:
+        return None
+    b0 = occ[0]
+    exp0 = exp_top - 15 + b0
+    pad = 2.0 * hmax if math.isfinite(hmax) and hmax > 0 else 0.0
+    ext = max(max(hi[k] - lo[k], 0.0) for k in range(3)) + 2.0 * pad
+    ext = max(ext, 1e-300)
+    frame = N.Grid(lo[0] - pad, lo[1] - pad, lo[2] - pad, ext, 1, 1, 1, 1)
+    delta = 2.0 * 4.0 * 2.0 ** -23 * ext
+    grids = []
+    for b in range(b0, 16):
+        cnt, sh = stats[b][0], stats[b][1]
+        if cnt <= 0:
+            grids.append(N.Grid(frame.ox, frame.oy, frame.oz, ext, 1, 1, 1, 1))
+            continue
+        hm = sh / cnt if sh > 0 else 2.0 ** (exp0 + (b - b0))
+        g, _ = choose_grid(list(stats[b][2:5]), list(stats[b][5:8]), hm, int(cnt), xdiv=1)
+        grids.append(g)
+    return Levels(frame, exp0, grids), delta
 
 
 class _Section:
@@ -255,28 +326,49 @@ class Engine:
         return b[0:3], b[3:6], b[6], b[7] / n
 
     def grid_for(self, posh, cell=None):
+        """-> (grid, delta): one Grid, or nested Levels when h spans decades (LEVEL_SPREAD)"""
         lo, hi, hmax, hmean = self.bounds(posh)
         if not all(math.isfinite(v) for v in lo + hi):
             raise ValueError("non-finite particle positions")
+        if (cell is None and LEVEL_SPREAD > 0 and math.isfinite(hmax) and math.isfinite(hmean) and hmean > 0
+                and hmax > LEVEL_SPREAD * hmean):
+            lv = self.levels_for(posh, lo, hi, hmax)
+            if lv is not None:
+                return lv
         return choose_grid(lo, hi, hmean if math.isfinite(hmean) and hmean > 0 else hmax, posh.shape[0], cell=cell)
+
+    def levels_for(self, posh, lo, hi, hmax):
+        """per-octave statistics of h (one small kernel, one 1 KB D2H read) -> (Levels, delta) or None"""
+        exp_top = math.frexp(hmax)[1] - 1            # floor(log2 hmax)
+        out = torch.empty((16, 8), dtype=F64, device=self.device)
+        self._run("level_stats", self.lib.sphb_level_stats, _ptr(posh), posh.shape[0], exp_top, _ptr(out), _stream())
+        return choose_levels(out.cpu().tolist(), exp_top, lo, hi, hmax)
 
     def build(self, posh_in, grid, delta, tie_key=None, out=None) -> DeviceGrid:
         """out: a DeviceGrid of the same n and cell count to rebuild in place (the Stepper's per-stage pool)"""
         n = posh_in.shape[0]
-        if out is not None and out.n == n and out.grid.ncell == grid.ncell:
+        nested = isinstance(grid, Levels)
+        if out is not None and out.n == n and out.grid.ncell == grid.ncell and not nested and out.levels is None:
             dg = out
             dg.grid, dg.delta, dg._cells = grid, float(delta), None
         else:
             dg = DeviceGrid(n, grid, delta, self.device)
-        need = int(self.lib.sphb_grid_workspace_bytes(n, C.byref(grid)))
+        need = int(self.lib.sphb_levels_workspace_bytes(n, grid.ncell))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if nested:
+            self._run("grid_build", self.lib.sphb_grid_build_levels, _ptr(posh_in), _ptr(tie_key), n, dg.cells(), grid.ncell,
+                      _ptr(dg.perm), _ptr(self._ws), self._ws.numel(), _stream())
+            return dg
         self._run("grid_build", self.lib.sphb_grid_build, _ptr(posh_in), _ptr(tie_key), n, C.byref(grid), C.c_float(delta), _ptr(dg.perm), _ptr(dg.cell_start),
                                          _ptr(dg.cell_hmax), _ptr(dg.cell_id), _ptr(dg.posh), _ptr(dg.frec),
                                          _ptr(self._ws), self._ws.numel(), _stream())
         return dg
 
     def set_h(self, dg: DeviceGrid, h_sorted):
+        if dg.levels is not None:
+            self._run("grid_set_h", self.lib.sphb_grid_set_h_levels, _ptr(h_sorted), dg.cells(), dg.grid.ncell, _stream())
+            return
         self._run("grid_set_h", self.lib.sphb_grid_set_h, _ptr(h_sorted), dg.n, C.byref(dg.grid), C.c_float(dg.delta), _ptr(dg.cell_start),
                                          _ptr(dg.cell_hmax), _ptr(dg.posh), _ptr(dg.frec), _stream())
 
@@ -611,6 +703,11 @@ class Stepper:
         posh0 = e.pack_posh(pos0, h0)
         grid, delta = self.geom if self.geom is not None else e.grid_for(posh0)
 
+        def geom_of(posh):
+            """one grid serves the three snapshots of a step (outliers are clamped into its border cells); nested grids
+            must contain their particles, so they are drawn again for every snapshot"""
+            return e.grid_for(posh) if (self.geom is None and isinstance(grid, Levels)) else (grid, delta)
+
         # State stays in CALLER order between stages; every cell list is built from caller-order positions, so
         # ties inside a cell are always broken by the caller index and every sum has one fixed order (the
         # multi-GPU runner does the same with global ids: k-rank results equal 1-rank results bit for bit).
@@ -652,7 +749,7 @@ class Stepper:
         # ---- predictor: pyfluid.py:511-515 ---------------------------------------------------------
         posh_m, vel_m, u_m = e.predict(posh0, vel0, u0, acc0, dudt0, dt, st.ptr(S_PRED))
         # ---- h_mid = newton(pos_mid, h0), stage mid: pyfluid.py:516-522 -------------------------------
-        g1 = pool[1] = e.build(posh_m, grid, delta, out=pool[1])
+        g1 = pool[1] = e.build(posh_m, *geom_of(posh_m), out=pool[1])
         # the mid-step Newton kernel scans with the symmetric support and a cover of PARK_COVER on every h: its lists
         # serve the force kernel at h_mid as long as no h grew by more than that (else the force kernel scans itself)
         l1 = e.park_lists(g1, cover=PARK_COVER) if (park and not grav) else None
@@ -666,7 +763,7 @@ class Stepper:
             hooks.after_corrector(posh_1, vel1, u1)   # pos1, vel1, u1 are final: their copy-out can start now
         # ---- h1 = newton(pos1, h_mid): pyfluid.py:530 ------------------------------------------------------
         posh_1 = e.pack_posh(posh_1[:, :3].contiguous(), h_mid)
-        g2 = pool[2] = e.build(posh_1, grid, delta, out=pool[2])
+        g2 = pool[2] = e.build(posh_1, *geom_of(posh_1), out=pool[2])
         r = solve_h(g2, S_NEWTON_1, want_omega=want_omega1)
         h1 = e.scatter(r[0] if want_omega1 else r, g2.perm, 1)
         pos1 = posh_1[:, :3].contiguous()

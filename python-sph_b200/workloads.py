@@ -63,4 +63,28 @@ def uniform_random(n, seed=0, density=3.75, vscale=1.0):
                 h_guess=np.full(n, 0.8), m=1.0, dt=1e-3, name=f"uniform random cloud, N={n}")
 
 
-WORKLOADS = {"sod": sod_tube, "lattice": lattice_cube, "planar": planar_uniform}
+def plummer(n=67_108_864, seed=0, u=1.0, guess=0.8, eta=1.3):
+    """C5: Plummer sphere: scale a = 1, r = a / sqrt(U^(-2/3) - 1) with U ~ U(0, 0.999] (r < 38.7 a),
+    isotropic directions, equal masses m = 1/N, v = 0, u = const, G = 0 for the metric.  h guess = `guess` x the h of the
+    analytic local density, eta (m/rho)^(1/3) with rho = 3/(4 pi) (1 + r^2)^(-5/2) / 0.999: from 5e-3 in the core to > 2
+    at the edge for 64 M particles -- nearly three decades, more once the sparse rim is solved."""
+    rng = np.random.default_rng(seed)
+    U = 0.999 * (1.0 - rng.random(n))                      # (0, 0.999]
+    r = 1.0 / np.sqrt(U ** (-2.0 / 3.0) - 1.0)
+    cz = 2.0 * rng.random(n) - 1.0
+    ph = 2.0 * np.pi * rng.random(n)
+    sz = np.sqrt(np.maximum(0.0, 1.0 - cz * cz))
+    pos = np.empty((n, 3))
+    pos[:, 0] = r * sz * np.cos(ph)
+    pos[:, 1] = r * sz * np.sin(ph)
+    pos[:, 2] = r * cz
+    m = 1.0 / n
+    rho = 3.0 / (4.0 * np.pi) * (1.0 + r * r) ** -2.5 / 0.999
+    hg = guess * eta * (m / rho) ** (1.0 / 3.0)
+    cs = np.sqrt(5.0 / 3.0 * (2.0 / 3.0) * u)
+    dt = 0.05 * float(hg.min() / guess) / cs               # a twentieth of the sound crossing time of the smallest h
+    return dict(pos=pos, vel=np.zeros((n, 3)), u=np.full(n, float(u)), h_guess=hg, m=m, dt=dt,
+                name=f"C5 Plummer sphere, N={n}")
+
+
+WORKLOADS = {"plummer": plummer, "sod": sod_tube, "lattice": lattice_cube, "planar": planar_uniform}

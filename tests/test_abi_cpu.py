@@ -33,7 +33,8 @@ def test_struct_sizes_match_header(native):
     assert C.sizeof(native.Consts) == 8 * 3 + 4 * 2 + 8 * 8
     assert C.sizeof(native.Grid) == 8 * 4 + 4 * 4
     assert C.sizeof(native.Status) == 32
-    assert C.sizeof(native.Cells) == 48 + 8 + 5 * 8 + 8
+    assert C.sizeof(native.Cells) == 48 + 8 + 5 * 8 + 8 + 2 * 4 + 2 * 8   # + nlevels, exp0, levels, level_hmax
+    assert C.sizeof(native.Level) == 48 + 2 * 4
     assert C.sizeof(native.Lists) == 3 * 8 + 8
     assert C.sizeof(native.NList) == native.load().sphb_sizeof_nlist()
 
@@ -92,3 +93,43 @@ def test_gridref_stable_sort():
     for c in range(54):
         seg = perm[start[c]:start[c + 1]]
         assert (np.diff(seg) > 0).all()
+
+
+def test_choose_levels_and_level_table():
+    """nested grids: levels from per-octave statistics (what sphb_level_stats returns), numbered level-major; the
+    device table has the layout of sphb_level (56 bytes); the numpy restatement bins by the same octaves"""
+    import ctypes
+    import numpy as np
+    import _native
+    import engine
+    import gridref
+    assert ctypes.sizeof(_native.Level) == 56 and ctypes.sizeof(_native.Cells) == 128
+    import workloads
+    n = 40000
+    w = workloads.plummer(n, seed=1)
+    pos, h = w["pos"], w["h_guess"] / 0.8                 # ~7 octaves of h, small h in the core only
+    hmax = float(h.max())
+    exp_top = int(np.floor(np.log2(hmax)))
+    bins = gridref.level_of(h, exp_top - 15, 16)
+    stats = []
+    for b in range(16):
+        m = bins == b
+        if m.any():
+            stats.append([float(m.sum()), float(h[m].sum())] + pos[m].min(axis=0).tolist() + pos[m].max(axis=0).tolist())
+        else:
+            stats.append([0.0] * 8)
+    lv, delta = engine.choose_levels(stats, exp_top, pos.min(axis=0).tolist(), pos.max(axis=0).tolist(), hmax)
+    occupied = [b for b in range(16) if stats[b][0] > 0]
+    assert lv.nlevels == 16 - occupied[0] and lv.exp0 == exp_top - 15 + occupied[0] and delta > 0
+    assert lv.bases[0] == 0 and lv.ncell == sum(g.ncell for g in lv.grids) and len(lv.table()) == 56 * lv.nlevels
+    lev = gridref.level_of(h, lv.exp0, lv.nlevels)
+    for b, g in enumerate(lv.grids):
+        p = pos[lev == b]
+        if len(p):   # every level's grid contains its particles, with about one support radius per cell
+            c = (p - np.array([g.ox, g.oy, g.oz])) / g.cell
+            assert (c >= 0).all() and (c < np.array([g.nx, g.ny, g.nz])).all()
+            assert 0.5 < g.cell / (2 * h[lev == b].mean()) < 2.0, (b, len(p), g.cell, h[lev == b].mean())
+    ids, perm, start = gridref.build_levels(pos, h, lv.exp0, [((g.ox, g.oy, g.oz), g.cell, (g.nx, g.ny, g.nz)) for g in lv.grids])
+    assert start[-1] == n and (np.diff(ids[perm]) >= 0).all() and (np.diff(lev[perm]) >= 0).all()
+    # one occupied octave: no nesting
+    assert engine.choose_levels([[0.0] * 8] * 15 + [[10.0, 5.0, 0, 0, 0, 1, 1, 1]], 0, [0, 0, 0], [1, 1, 1], 0.6) is None
