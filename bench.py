@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="planar (default 262144) / plummer (default 67108864): particle count")
     ap.add_argument("--path", default="lists", choices=["lists", "scan"],
                     help="lists: neighbour lists kept across kernels and steps (default); scan: the scanning kernels only")
+    ap.add_argument("--decomp", default=None, choices=["slab", "range"],
+                    help="multi-GPU decomposition: slabs along x (default; sod, lattice, planar) or ranges of sorted slots of one "
+                         "global cell list (default for plummer)")
     ap.add_argument("--warm-state-steps", type=int, default=0, help="untimed steps at setup so that the timed steps see a developed flow")
     ap.add_argument("--dt-scale", type=float, default=1.0, help="multiply the workload's dt (sod: 0.05 a; 6 is a CFL-sized step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,7 +233,8 @@ def run_ours(a):
 
     if world > 1:
         import domain
-        runner = domain.make_runner(eng, consts, world, rank, lists=use_lists)
+        decomp = a.decomp or ("range" if a.workload == "plummer" else "slab")
+        runner = domain.make_runner(eng, consts, world, rank, lists=use_lists, decomp=decomp)
         state = runner.scatter_initial(w)
     else:
         runner = None
@@ -521,7 +525,7 @@ def run_ours(a):
             "data": "synthetic",
             "config": {"workload": w["name"], "n_particles": n_total, "dt": dt, "warm_state_steps": a.warm_state_steps,
                        "l2": f"inputs_larger_than_L2 (state {n_total * 64 / 1e9:.2f} GB vs 126 MB L2)",
-                       "parallelism": f"slab{world}" if world > 1 else "single",
+                       "parallelism": f"{decomp}{world}" if world > 1 else "single",
                        "path": "kept neighbour lists (rebuilt when the device-side check says so)" if use_lists else "scanning kernels (3 cell-list builds and 3 scans per step)"},
             "clocks": clk, "gpu_launches": int(launches), "neighbour_lists": list_stats, "state_checksum": checksum,
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "kernels": per_kernel}

@@ -445,8 +445,7 @@ __device__ __forceinline__ int sphb_f2ord_down(double v) { return sphb_f2ord(__d
 __device__ __forceinline__ int sphb_f2ord_up(double v) { return sphb_f2ord(__double2float_ru(v)); }
 
 __global__ void __launch_bounds__(LS_THREADS)
-    k_level_stats(const double *__restrict__ posh, long long n, int exp_top, unsigned long long *__restrict__ cnt,
-                  double *__restrict__ sumh, int *__restrict__ lo, int *__restrict__ hi)
+    k_level_stats(const double *__restrict__ posh, long long n, int exp_top, double *__restrict__ out)
 {
     __shared__ unsigned int s_cnt[LS_BINS];
     __shared__ double s_sum[LS_BINS];
@@ -498,52 +497,56 @@ __global__ void __launch_bounds__(LS_THREADS)
     __syncthreads();
     for (int q = threadIdx.x; q < LS_BINS; q += blockDim.x) {
         if (s_cnt[q] == 0) continue;
-        atomicAdd(cnt + q, (unsigned long long)s_cnt[q]);
-        atomicAdd(sumh + q, s_sum[q]);
+        atomicAdd(reinterpret_cast<unsigned long long *>(out) + 8 * q, (unsigned long long)s_cnt[q]);
+        atomicAdd(out + 8 * q + 1, s_sum[q]);
         for (int c = 0; c < 3; ++c) {
-            atomicMin(lo + 3 * q + c, s_lo[q][c]);
-            atomicMax(hi + 3 * q + c, s_hi[q][c]);
+            atomicMin(reinterpret_cast<int *>(out + 8 * q + 2 + c), s_lo[q][c]);
+            atomicMax(reinterpret_cast<int *>(out + 8 * q + 5 + c), s_hi[q][c]);
         }
     }
 }
 
-__global__ void k_level_stats_out(const unsigned long long *__restrict__ cnt, const double *__restrict__ sumh,
-                                  const int *__restrict__ lo, const int *__restrict__ hi, double *__restrict__ out)
+__global__ void k_level_stats_out(double *__restrict__ out)
 {
     const int q = threadIdx.x;
     if (q >= LS_BINS) return;
-    out[8 * q] = (double)cnt[q];
-    out[8 * q + 1] = sumh[q];
-    for (int c = 0; c < 3; ++c) {
-        out[8 * q + 2 + c] = cnt[q] ? (double)sphb_ord2f(lo[3 * q + c]) : 0.0;
-        out[8 * q + 5 + c] = cnt[q] ? (double)sphb_ord2f(hi[3 * q + c]) : 0.0;
+    const unsigned long long cnt = reinterpret_cast<unsigned long long *>(out)[8 * q];
+    out[8 * q] = (double)cnt;
+    for (int c = 2; c < 8; ++c) {
+        const int key = reinterpret_cast<int *>(out + 8 * q + c)[0];
+        out[8 * q + c] = cnt ? (double)sphb_ord2f(key) : 0.0;
     }
 }
 
-// `out` doubles as scratch: [0..16) counts (u64), [16..32) sums, [32..80) lo (int), [80..128) hi (int) while reducing
+// the 16 x 8 output doubles double as the reduction scratch: row b = {count (u64), sum h, then the six bounds as
+// ordered-int keys in the low words}; k_level_stats_out converts the row in place
+__global__ void k_level_stats_init(double *out)
+{
+    const int q = threadIdx.x;
+    if (q >= LS_BINS) return;
+    reinterpret_cast<unsigned long long *>(out)[8 * q] = 0ull;
+    out[8 * q + 1] = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        reinterpret_cast<int *>(out + 8 * q + 2 + c)[0] = 0x7fffffff;
+        reinterpret_cast<int *>(out + 8 * q + 5 + c)[0] = (int)0x80000000;
+    }
+}
+
 extern "C" int sphb_level_stats(const double *posh, int64_t n, int32_t exp_top, double *out, void *stream)
 {
     SPHB_RANGE();
     if (n < 0 || !out || (n > 0 && !posh)) return SPHB_E_ARG;
     cudaStream_t st = sphb_stream(stream);
-    // scratch behind the 128 output doubles would need a second buffer: use a static device allocation per call instead
-    unsigned long long *cnt = nullptr;
-    SPHB_CUDA(cudaMallocAsync((void **)&cnt, 16 * 8 + 16 * 8 + 48 * 4 + 48 * 4, st));
-    double *sumh = reinterpret_cast<double *>(cnt + LS_BINS);
-    int *lo = reinterpret_cast<int *>(sumh + LS_BINS);
-    int *hi = lo + 3 * LS_BINS;
-    SPHB_CUDA(cudaMemsetAsync(cnt, 0, 16 * 8 + 16 * 8, st));
-    SPHB_CUDA(cudaMemsetAsync(lo, 0x7f, 48 * 4, st));   // 0x7f7f7f7f: above every finite float's key
-    SPHB_CUDA(cudaMemsetAsync(hi, 0x80, 48 * 4, st));   // 0x80808080: below
+    k_level_stats_init<<<1, 32, 0, st>>>(out);
+    SPHB_LAUNCHED();
     if (n > 0) {
         long long nb = (n + LS_THREADS - 1) / LS_THREADS;
         if (nb > LS_BLOCKS) nb = LS_BLOCKS;
-        k_level_stats<<<(unsigned)nb, LS_THREADS, 0, st>>>(posh, (long long)n, exp_top, cnt, sumh, lo, hi);
+        k_level_stats<<<(unsigned)nb, LS_THREADS, 0, st>>>(posh, (long long)n, exp_top, out);
         SPHB_LAUNCHED();
     }
-    k_level_stats_out<<<1, 32, 0, st>>>(cnt, sumh, lo, hi, out);
+    k_level_stats_out<<<1, 32, 0, st>>>(out);
     SPHB_LAUNCHED();
-    SPHB_CUDA(cudaFreeAsync(cnt, st));
     return SPHB_OK;
 }
 

@@ -66,6 +66,7 @@ template <int LIST>
 struct SphbWarpSharedT {
     static constexpr int kList = LIST;
     float4 tile[32];      // x', y', z', |c'|^2 of the staged candidates (NaN-padded)
+    float wthr[32];       // nested grids, SYM: the staged candidates' own squared thresholds
     uint32_t segbase[SPHB_NSEG]; // first sorted slot of each live segment
     uint16_t list[LIST * 32];
 };
@@ -307,7 +308,16 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
         const uint32_t gap = (gapf < 1e9f) ? (uint32_t)fmaxf(gapf, 1.f) : 0xffffffffu;
         const uint32_t prow = __shfl_up_sync(SPHB_FULL, row, 1), pcx = __shfl_up_sync(SPHB_FULL, cx, 1);
         const int plev = __shfl_up_sync(SPHB_FULL, lev, 1);
-        const bool brk = (lane == 0) || (row != prow) || (lev != plev) || (cx > pcx && cx - pcx > gap);
+        bool brk = (lane == 0) || (row != prow) || (lev != plev) || (cx > pcx && cx - pcx > gap);
+        if (MULTI && g.nlev > 1) {
+            // Nested grids: a sparse coarse level puts every lane of a warp into another row of cells, and 32 one-lane
+            // groups would each walk their (large) sphere through the fine levels, row by row.  Lanes follow each other
+            // in one group while they stay within one search diameter of their predecessor in every coordinate.
+            const float px = __shfl_up_sync(SPHB_FULL, fx, 1), py = __shfl_up_sync(SPHB_FULL, fy, 1);
+            const float pz = __shfl_up_sync(SPHB_FULL, fz, 1);
+            const float far = 2.f * rmax;   // +inf: never
+            brk = (lane == 0) || (lev != plev) || !(fabsf(fx - px) <= far && fabsf(fy - py) <= far && fabsf(fz - pz) <= far);
+        }
         gkey = (uint32_t)__popc(__ballot_sync(SPHB_FULL, brk) & (0xffffffffu >> (31 - lane)));
     }
     while (remaining) {
@@ -464,6 +474,9 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                         if (SYM) {
                             const float ttile = __int_as_float(__reduce_max_sync(SPHB_FULL, __float_as_int(wthr)));
                             th = fmaxf(thrp, __fmul_ru(ttile, symscale * symscale) + offp);
+                            // within one level h spans an octave: under the tile's largest threshold alone a lane would
+                            // list up to 8x the volume it needs; survivors are tested again with their own threshold
+                            if (MULTI) ws.wthr[lane] = __fmul_ru(wthr, symscale * symscale);
                         }
                         __syncwarp();
                         const int nt = (int)((t1 - t) < 32u ? (t1 - t) : 32u);
@@ -530,7 +543,9 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                                 sv[c] = fmaf(f[c].x, m2x, fmaf(f[c].y, m2y, fmaf(f[c].z, m2z, f[c].w)));
 #pragma unroll
                             for (int c = 0; c < SPHB_SUB; ++c)
-                                if (sv[c] <= th) L.push(code + c);
+                                if (sv[c] <= th) {
+                                    if (!(SYM && MULTI) || sv[c] <= fmaxf(thrp, ws.wthr[c0 + c] + offp)) L.push(code + c);
+                                }
 #endif
                             code += SPHB_SUB;
                         }

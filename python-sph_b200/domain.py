@@ -828,8 +828,13 @@ class _LazyOwned(dict):
 
 
 
-def make_runner(eng, consts, world, rank, lists=True, **kw):
-    """the slab runner bench.py and the tests use: kept neighbour lists when `lists` (and G = 0), else the scanning one"""
+def make_runner(eng, consts, world, rank, lists=True, decomp="slab", **kw):
+    """the runner bench.py and the tests use.  decomp "slab": cut planes along x, kept neighbour lists when `lists` (and
+    G = 0), else the scanning kernels; "range": ranges of sorted slots on one global cell list (ranges.RangeRunner),
+    for distributions whose h spans decades"""
+    if decomp == "range":
+        import ranges
+        return ranges.RangeRunner(eng, consts, world, rank, **kw)
     if lists and consts.G == 0.0:
         return FastSlabRunner(eng, consts, world, rank, **kw)
     return SlabRunner(eng, consts, world, rank, **kw)

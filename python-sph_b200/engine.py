@@ -67,6 +67,19 @@ class KeptLists:
         self.build_flags = 0
         self.moved = self.grown = 0.0
 
+    @classmethod
+    def view(cls, src, n, warp_off, warp_rows, posh_build):
+        """the lists of `src` seen through renamed slots (sphb_nlist_remap): same pool, cursor and flag words, other
+        warp tables and build-time records"""
+        nl = cls.__new__(cls)
+        nl.n, nl.dg, nl.cover_h, nl.skin = int(n), src.dg, src.cover_h, src.skin
+        nl.pool_rows, nl.warp_off, nl.warp_rows, nl.pool, nl.cursor, nl.flags = src.pool_rows, warp_off, warp_rows, src.pool, src.cursor, src.flags
+        nl.posh_build = posh_build
+        nl.c = N.NList(nl.n, warp_off.data_ptr(), warp_rows.data_ptr(), nl.pool.data_ptr(), nl.pool_rows, nl.cursor.data_ptr(),
+                       nl.flags.data_ptr(), posh_build.data_ptr(), nl.cover_h, nl.skin, nl.flags.data_ptr() + 4)
+        nl.build_flags, nl.moved, nl.grown, nl.omega0 = src.build_flags, 0.0, 0.0, None
+        return nl
+
     def ref(self):
         return C.byref(self.c)
 
@@ -481,6 +494,15 @@ class Engine:
             pool_rows = need
             del nl
         return nl
+
+    def nl_mark(self, nl, rows_used, n_slots):
+        """-> uint8 (n_slots): which sorted slots the lists name"""
+        mark = torch.zeros(n_slots, dtype=torch.uint8, device=self.device)
+        self._run("nl_mark", self.lib.sphb_nlist_mark, nl.ref(), int(rows_used), _ptr(mark), _stream())
+        return mark
+
+    def nl_remap(self, nl, rows_used, slot_map):
+        self._run("nl_remap", self.lib.sphb_nlist_remap, nl.ref(), int(rows_used), _ptr(slot_map), _stream())
 
     def nl_check(self, nl, posh):
         self._run("nl_check", self.lib.sphb_nlist_check, nl.ref(), _ptr(posh), _stream())

@@ -26,17 +26,23 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
     nsteps = int(os.environ.get("CHECK_STEPS", "2"))
     lists = os.environ.get("CHECK_PATH", "lists") == "lists"
-    w = workloads.sod_tube(int(sys.argv[2])) if len(sys.argv) > 2 else workloads.uniform_random(n, seed=3, vscale=0.5)
+    decomp = os.environ.get("CHECK_DECOMP", "slab")
+    if len(sys.argv) > 2 and sys.argv[2] == "plummer":
+        w = workloads.plummer(n, seed=3)
+    else:
+        w = workloads.sod_tube(int(sys.argv[2])) if len(sys.argv) > 2 else workloads.uniform_random(n, seed=3, vscale=0.5)
     k = dict(PARTICLE_MASS=w["m"], COUPLING_CONST=1.3, SMOOTHLENGTH_VARIATION_TOLERANCE=1e-3, NEWTON_ITERATION_LIMIT=20,
              BISECTION_ITERATION_LIMIT=100, ALPHA_SPH=1.0, BETA_SPH=2.0, EPSILON=0.01, BISECTION_TOLERANCE=1e-10,
              INITIAL_BISECTION_SMOOTHLENGTH_A=1e3, INITIAL_BISECTION_SMOOTHLENGTH_B=1e-3, G=0.0, ADIABATIC_INDEX=5 / 3)
     consts = E.make_consts(k)
     dt = w["dt"]
-    runner = domain.make_runner(eng, consts, world, rank, lists=lists)
+    runner = domain.make_runner(eng, consts, world, rank, lists=lists, decomp=decomp)
     st = runner.scatter_initial(w)
-    geom0 = runner._global_geom(st["pos"], st["h"])
+    geom0 = runner._global_geom(st["pos"], st["h"]) if decomp == "slab" else None
     st = runner.cold_solve(st)
     geom1 = runner.geom
+    if geom0 is None:
+        geom0 = geom1          # range decomposition: the cold solve's own (global) cell list
     if os.environ.get("CHECK_CALIBRATE"):
         st = runner.calibrate(st, dt)          # re-cuts the slabs by measured time: must not change a bit of the physics
     for _ in range(nsteps):
@@ -68,7 +74,7 @@ def main():
             res[name] = {"max_abs_diff": float((a - b).abs().max().item()), "bit_identical": bool(torch.equal(a, b)),
                          "scale": float(b.abs().max().item())}
         stats = res.pop("_lists", None)
-        print(json.dumps({"world": world, "n": int(pos.shape[0]), "steps": nsteps, "path": "lists" if lists else "scan",
+        print(json.dumps({"world": world, "n": int(pos.shape[0]), "steps": nsteps, "path": "lists" if lists else "scan", "decomp": decomp,
                           "list_stats": stats, "compare": res}))
         ok = all(v["max_abs_diff"] <= 1e-12 * max(v["scale"], 1e-300) for v in res.values())
         if not ok:

@@ -12,10 +12,10 @@ import torch
 import engine as E
 import workloads
 
-nx = int(sys.argv[1]) if len(sys.argv) > 1 else 192
+a1 = sys.argv[1] if len(sys.argv) > 1 else "192"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 dts = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
-w = workloads.sod_tube(nx)
+w = workloads.plummer(int(a1.split(":")[1])) if a1.startswith("plummer:") else workloads.sod_tube(int(a1))   # or plummer:N
 eng = E.Engine()
 k = dict(PARTICLE_MASS=w["m"], COUPLING_CONST=1.3, SMOOTHLENGTH_VARIATION_TOLERANCE=1e-3, NEWTON_ITERATION_LIMIT=20,
          BISECTION_ITERATION_LIMIT=100, ALPHA_SPH=1.0, BETA_SPH=2.0, EPSILON=0.01, BISECTION_TOLERANCE=1e-10,
@@ -44,4 +44,7 @@ for s in range(steps):
     print(f"step {s:3d} built {fs.stats['builds'] - b0} age {fs.age} cover_h {nl.cover_h:.4f} skin {nl.skin:.4f} moved {nl.moved:.5f} "
           f"grown {nl.grown:.5f} | >half-skin {(d > 0.5 * nl.skin).sum().item()} >half-grow {(g > 0.5 * (nl.cover_h - 1)).sum().item()} "
           f"rows/warp {nl.warp_rows.double().mean().item():.1f} redos {fs.stats['redos']}")
+    if a1.startswith("plummer:") and s < 3:
+        k = int(torch.argmax(g))
+        print("      largest growth at slot", k, "r", float(P[k, :3].norm()), "h_build", float(nl.dg.posh[k, 3]), "h_now", float(P[k, 3]))
 E.raise_for_status(fs.last_status.read(), printer=lambda *_: None)

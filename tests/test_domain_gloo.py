@@ -134,3 +134,58 @@ def test_equal_count_cuts():
     assert len(c) == 5 and c[0] == -np.inf and c[-1] == np.inf
     counts = [int(((x >= c[r]) & (x < c[r + 1])).sum()) for r in range(4)]
     assert counts == [250] * 4
+
+
+def _worker_ranges(rank, world, port, q):
+    """ranges.py: weighted slot cuts, the ghost request exchange, refresh in the compact local numbering"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ranges
+        n = 5000
+        rng = np.random.default_rng(2)
+        wgt = torch.from_numpy(1.0 + 9.0 * (np.arange(n) < 1500) + rng.random(n))       # the first slots are heavy
+        cuts = ranges.weighted_cuts(torch.cumsum(wgt, 0), world)
+        s0, s1 = cuts[rank], cuts[rank + 1]
+        ok = cuts[0] == 0 and cuts[-1] == n and all(c % 32 == 0 for c in cuts[:-1])
+        part = [float(wgt[cuts[r]:cuts[r + 1]].sum()) for r in range(world)]
+        ok = ok and max(part) < 1.05 * min(part)
+        # a ghost set: random slots of the other ranges, ascending, some low ones repeated like the padding dummies
+        others = np.setdiff1d(np.arange(n), np.arange(s0, s1))
+        g = np.sort(np.random.default_rng(10 + rank).choice(others, size=400, replace=False))
+        n_low = int((g < s0).sum())
+        pad = (-n_low) % 32
+        ghosts = torch.from_numpy(np.concatenate([np.repeat(g[:1], pad) if n_low else np.empty(0, np.int64), g]).astype(np.int64))
+        if not n_low:
+            pad = 0
+        req, send_counts, recv_counts = ranges.ghost_plan(ghosts, cuts, rank, world)
+        ok = ok and bool(((req >= s0) & (req < s1)).all()) and sum(recv_counts) == ghosts.numel()
+        o0, n_own = pad + n_low, s1 - s0
+        n_loc = o0 + n_own + (len(g) - n_low)
+        ghost_local = torch.cat([torch.arange(0, o0), torch.arange(o0 + n_own, n_loc)])
+        sx = ranges.slot_exchanger(ranges._Plan(world, send_counts, recv_counts), req - s0 + o0, ghost_local)
+        glob = torch.cat([ghosts[:o0], torch.arange(s0, s1), ghosts[o0:]])             # global slot of every local record
+        own_l = torch.zeros(n_loc, dtype=torch.bool)
+        own_l[o0:o0 + n_own] = True
+        f = lambda s, c: (s.to(torch.float64) + 1.0) * (c + 1)
+        a = torch.where(own_l, f(glob, 0), torch.full((n_loc,), -1.0, dtype=torch.float64))
+        b = torch.stack([torch.where(own_l, f(glob, c), torch.full((n_loc,), -1.0, dtype=torch.float64)) for c in (1, 2)], 1)
+        sx.refresh([a, b])
+        ok = ok and bool((a == f(glob, 0)).all()) and bool((b[:, 0] == f(glob, 1)).all()) and bool((b[:, 1] == f(glob, 2)).all())
+        q.put((rank, bool(ok), int(ghosts.numel())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_range_decomposition_plumbing_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ranges, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(ng > 0 for _, _, ng in res)

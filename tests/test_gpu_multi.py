@@ -32,3 +32,20 @@ def test_ranks_bit_identical_to_one(args, path, steps):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     cmp_ = json.loads(line)["compare"]
     assert all(v["bit_identical"] for v in cmp_.values()), cmp_
+
+
+@pytest.mark.parametrize("args", [["30000"], ["40000", "plummer"]])
+def test_range_decomposition_bit_identical_to_one(args):
+    """ranges of sorted slots on one global cell list (ranges.RangeRunner; nested grids for the Plummer sphere) == the
+    single-GPU FastStepper, bit for bit"""
+    k = _ranks()
+    if k == 0:
+        pytest.skip("needs at least 2 GPUs")
+    env = dict(os.environ, CHECK_PATH="lists", CHECK_STEPS="5", CHECK_DECOMP="range")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(k), "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "scripts", "check_multi.py")] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    cmp_ = json.loads(line)["compare"]
+    assert all(v["bit_identical"] for v in cmp_.values()), cmp_
