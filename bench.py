@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--workload", default="sod", choices=["sod", "lattice", "planar", "plummer"])
     ap.add_argument("--nx", type=int, default=384, help="sod: left-half lattice points along x (384 -> 15.9 M)")
     ap.add_argument("--side", type=int, default=100, help="lattice: cube side")
-    ap.add_argument("--n", type=int, default=None, help="planar (default 262144) / plummer (default 67108864): particle count")
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=None, help="planar (default 262144) / plummer (default 67108864): particle count")
     ap.add_argument("--path", default="lists", choices=["lists", "scan"],
                     help="lists: neighbour lists kept across kernels and steps (default); scan: the scanning kernels only")
     ap.add_argument("--decomp", default=None, choices=["slab", "range"],

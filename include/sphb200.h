@@ -212,10 +212,10 @@ int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, const float
                      const sphb_consts *k, double *omega, void *stream);
 int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, void *stream);
 /* Decomposition by ranges of sorted slots (every rank sorts the same global cell list and lists only its own range of
- * targets): mark[s] = 1 for every slot the first rows_used rows of the pool name -- the rank's exact ghost set --, and
- * rename the slots in place, entry v -> map[v] (map increasing on the named slots: rows stay in ascending order). */
-int sphb_nlist_mark(const sphb_nlist *nl, int64_t rows_used, uint8_t *mark, void *stream);
-int sphb_nlist_remap(const sphb_nlist *nl, int64_t rows_used, const int32_t *map, void *stream);
+ * targets): mark[s] = 1 for every slot the lists name -- the rank's exact ghost set --, and rename the slots in place,
+ * entry v -> map[v] (map increasing on the named slots: rows stay in ascending order). */
+int sphb_nlist_mark(const sphb_nlist *nl, uint8_t *mark, void *stream);
+int sphb_nlist_remap(const sphb_nlist *nl, const int32_t *map, void *stream);
 /* sphb_density_omega on kept lists (h_j = posh[j][3]) */
 int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts *k, const uint8_t *target, const double *posh,
                              const double *rho_in, double *rho_sum, double *dwdh_sum, double *omega, int32_t *ngb_count,

@@ -102,8 +102,8 @@ SIGNATURES = {
     "sphb_sizeof_nlist": (I64, []),
     "sphb_nlist_build": (C.c_int, [C.POINTER(Cells), P, P, C.POINTER(NList), C.POINTER(Consts), P, P]),
     "sphb_nlist_check": (C.c_int, [C.POINTER(NList), P, P]),
-    "sphb_nlist_mark": (C.c_int, [C.POINTER(NList), I64, P, P]),
-    "sphb_nlist_remap": (C.c_int, [C.POINTER(NList), I64, P, P]),
+    "sphb_nlist_mark": (C.c_int, [C.POINTER(NList), P, P]),
+    "sphb_nlist_remap": (C.c_int, [C.POINTER(NList), P, P]),
     "sphb_nlist_density_omega": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P]),
     "sphb_nlist_newton_h": (C.c_int, [C.POINTER(NList), C.POINTER(Consts), P, P, P, P, P, P, P, P, P]),
     "sphb_nlist_eos": (C.c_int, [P, P, P, P, I64, C.POINTER(Consts), P, P, P, P]),

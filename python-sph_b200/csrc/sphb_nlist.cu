@@ -670,42 +670,53 @@ extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, 
     return SPHB_OK;
 }
 
-// which sorted slots do the first `rows_used` rows of the pool name?  (mark[s] = 1)  A rank that lists only its own range
-// of targets learns its exact ghost set from this: the decomposition then needs no geometric halo width at all.
-__global__ void k_nl_mark(const uint32_t *__restrict__ pool, long long n_entries, uint8_t *__restrict__ mark)
+// which sorted slots do the lists name?  (mark[s] = 1)  A rank that lists only its own range of targets learns its exact
+// ghost set from this: the decomposition then needs no geometric halo width at all.  Walks every warp's own rows (a
+// heavy warp's reserve holds rows it never wrote).
+__global__ void k_nl_mark(sphb_nlist nl, uint8_t *__restrict__ mark)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (long long)gridDim.x * blockDim.x) {
-        const uint32_t v = __ldg(pool + i);
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w * 32 >= nl.n) return;
+    const uint32_t rows = nl.warp_rows[w];
+    const uint32_t *p = nl.pool + (size_t)nl.warp_off[w] * 32 + lane;
+    for (uint32_t r = 0; r < rows; ++r) {
+        const uint32_t v = __ldg(p + (size_t)r * 32);
         if (v != SPHB_NL_NONE) mark[v] = 1;   // idempotent: racing writers store the same byte
     }
 }
 
 // rename the slots in place (pool entry v -> map[v]); map must be increasing on the named slots so that rows stay in
 // ascending order, i.e. every sum keeps its order
-__global__ void k_nl_remap(uint32_t *__restrict__ pool, long long n_entries, const int32_t *__restrict__ map)
+__global__ void k_nl_remap(sphb_nlist nl, const int32_t *__restrict__ map)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (long long)gridDim.x * blockDim.x) {
-        const uint32_t v = pool[i];
-        if (v != SPHB_NL_NONE) pool[i] = (uint32_t)__ldg(map + v);
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w * 32 >= nl.n) return;
+    const uint32_t rows = nl.warp_rows[w];
+    uint32_t *p = nl.pool + (size_t)nl.warp_off[w] * 32 + lane;
+    for (uint32_t r = 0; r < rows; ++r) {
+        const uint32_t v = p[(size_t)r * 32];
+        if (v != SPHB_NL_NONE) p[(size_t)r * 32] = (uint32_t)__ldg(map + v);
     }
 }
 
-extern "C" int sphb_nlist_mark(const sphb_nlist *nl, int64_t rows_used, uint8_t *mark, void *stream)
+extern "C" int sphb_nlist_mark(const sphb_nlist *nl, uint8_t *mark, void *stream)
 {
     SPHB_RANGE();
-    if (!nl_ok(nl) || rows_used < 0 || rows_used > nl->pool_rows || !mark) return SPHB_E_ARG;
-    if (rows_used == 0) return SPHB_OK;
-    k_nl_mark<<<1184 * 2, 256, 0, sphb_stream(stream)>>>(nl->pool, (long long)rows_used * 32, mark);
+    if (!nl_ok(nl) || !mark) return SPHB_E_ARG;
+    if (nl->n == 0) return SPHB_OK;
+    k_nl_mark<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, mark);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
 
-extern "C" int sphb_nlist_remap(const sphb_nlist *nl, int64_t rows_used, const int32_t *map, void *stream)
+extern "C" int sphb_nlist_remap(const sphb_nlist *nl, const int32_t *map, void *stream)
 {
     SPHB_RANGE();
-    if (!nl_ok(nl) || rows_used < 0 || rows_used > nl->pool_rows || !map) return SPHB_E_ARG;
-    if (rows_used == 0) return SPHB_OK;
-    k_nl_remap<<<1184 * 2, 256, 0, sphb_stream(stream)>>>(nl->pool, (long long)rows_used * 32, map);
+    if (!nl_ok(nl) || !map) return SPHB_E_ARG;
+    if (nl->n == 0) return SPHB_OK;
+    k_nl_remap<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, map);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -495,14 +495,14 @@ class Engine:
             del nl
         return nl
 
-    def nl_mark(self, nl, rows_used, n_slots):
+    def nl_mark(self, nl, n_slots):
         """-> uint8 (n_slots): which sorted slots the lists name"""
         mark = torch.zeros(n_slots, dtype=torch.uint8, device=self.device)
-        self._run("nl_mark", self.lib.sphb_nlist_mark, nl.ref(), int(rows_used), _ptr(mark), _stream())
+        self._run("nl_mark", self.lib.sphb_nlist_mark, nl.ref(), _ptr(mark), _stream())
         return mark
 
-    def nl_remap(self, nl, rows_used, slot_map):
-        self._run("nl_remap", self.lib.sphb_nlist_remap, nl.ref(), int(rows_used), _ptr(slot_map), _stream())
+    def nl_remap(self, nl, slot_map):
+        self._run("nl_remap", self.lib.sphb_nlist_remap, nl.ref(), _ptr(slot_map), _stream())
 
     def nl_check(self, nl, posh):
         self._run("nl_check", self.lib.sphb_nlist_check, nl.ref(), _ptr(posh), _stream())

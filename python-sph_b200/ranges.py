@@ -214,9 +214,8 @@ class RangeRunner(domain.FastSlabRunner):
         pool_rows = self.pool_rows_hint if getattr(self, "pool_rows_hint", None) else ((n_own + 31) // 32) * 176 + 65536
         nl_g = e.nl_build(dg, cover_h, skin, target=mask if self.world > 1 else None, consts=self.consts, pool_rows=pool_rows)
         self.pool_rows_hint = max(nl_g.pool_rows, ((n_own + 31) // 32) * 176 + 65536)
-        used = nl_g.rows_used() if not (nl_g.build_flags & E.N.NL_POOL) else 0
         with e.section("host:local_numbering"):
-            mark = e.nl_mark(nl_g, used, n)
+            mark = e.nl_mark(nl_g, n)
             mark[s0:s1] = 1
             loc = torch.nonzero(mark).flatten()                      # ascending global slots: ghosts below, own, ghosts above
             n_low = int((loc < s0).sum().item())
@@ -226,7 +225,7 @@ class RangeRunner(domain.FastSlabRunner):
                 loc = torch.cat([loc[:1].expand(pad), loc])           # dummy records: never named, never targets
             slot_map = torch.full((n,), -1, dtype=torch.int32, device=self.dev)
             slot_map[loc[pad:]] = torch.arange(pad, n_loc, dtype=torch.int32, device=self.dev)
-            e.nl_remap(nl_g, used, slot_map)
+            e.nl_remap(nl_g, slot_map)
             o0 = pad + n_low                                           # local index of the first own slot
             nw = (n_loc + 31) // 32
             w_off = torch.zeros(nw, dtype=torch.int32, device=self.dev)
