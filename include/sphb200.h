@@ -200,8 +200,16 @@ typedef struct sphb_nlist {
     const double *posh_build;  /* [n][4] the sorted records the lists were built from (must stay alive and unchanged) */
     double cover_h;            /* >= 1 */
     double skin;               /* >= 0, in units of each record's h at build time */
-    int32_t *maxima;           /* optional device [2], zeroed by the build: float bit patterns of the largest
-                                  |x_now - x_build| / h_build and h_now / h_build - 1 any check has seen since */
+    int32_t *maxima;           /* optional device [2], zeroed by the build: float bit patterns of the largest FRACTIONS of
+                                  their allowances any record has used up in any check since: |x_now - x_build| / (s_i h_build)
+                                  and (h_now / h_build - 1) / (c_i - 1) */
+    const float *margins;      /* optional device [n][2] = {c_i, s_i}: PER-PARTICLE cover (>= 1) and skin (>= 0) in place of
+                                  cover_h / skin (which must then be their maxima).  A pair is listed iff
+                                  |r_j - r_i| <= 2 max(c_j h_j, c_i h_i) + s_j h_j + s_i h_i: a fast particle pays for its own
+                                  allowance, its partners keep tight lists; all records are listed for the whole life of the
+                                  lists as long as every one of them stays within its own bounds */
+    const float *level_dmax;   /* with margins: device [max(nlevels, 1)] upper bounds of s_i h_i over the records of each
+                                  level of the cell list (one entry for a single grid): bounds the cells searched */
 } sphb_nlist;
 int64_t sphb_nlist_pool_rows(int64_t n);
 int64_t sphb_sizeof_nlist(void); /* sizeof(sphb_nlist), for bindings to check their own layout against */

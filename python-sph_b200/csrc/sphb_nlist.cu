@@ -99,13 +99,19 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
         f = __ldg(g.frec + j);
         cid = c.cell_id[j];
     }
-    // complete for any later state with h <= cover_h h_build and |dx| <= skin h_build on both sides of a pair:
-    // |r_build| <= |r_now| + |dx_j| + |dx_i| < 2 max(h_now) + skin (h_j + h_i) <= 2 max(h_build) (cover_h + skin)
-    const double kappa = nl.cover_h + nl.skin;
-    const double hs = h * kappa;
-    const float Rj = sphb_radius_of_h(hs, g.delta), thr = sphb_thr_of_h(hs, g.delta);
-    const float cov = (float)kappa * 1.000001f;
-    const float RH = sphb_radius_of_h((double)hmax_global[0] * (double)cov, g.delta);
+    // complete for any later state with h_i <= c_i h_build and |dx_i| <= s_i h_build for every record (c, s per particle,
+    // or the uniform cover_h, skin): |r_build| <= |r_now| + |dx_j| + |dx_i| < 2 max(c_j h_j, c_i h_i) + s_j h_j + s_i h_i
+    SphbPpm pm;
+    pm.margins = reinterpret_cast<const float2 *>(nl.margins);
+    pm.cu = __double2float_ru(nl.cover_h);
+    pm.su = __double2float_ru(nl.skin);
+    pm.Aj = pm.Dj = 0.f;
+    if (valid) sphb_ppm_of(pm, (uint32_t)j, f.w, pm.Aj, pm.Dj);
+    pm.level_dmax = nl.level_dmax;
+    pm.hmax_u = hmax_global[0];
+    const float cov = pm.cu * 1.000001f;                                          // >= every c_i
+    const float Rj = __fadd_ru(pm.Aj, pm.Dj);
+    const float thr = 0.f, RH = 0.f;                                              // (formed level by level inside the scan)
 
     // mode 0: the lists are expected to fit the staging area: one exact allocation at the end, one store.
     // A warp that has to flush before the end of its scan (heavy: a sparse target next to a dense region) takes a
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     for (int pass = 0; pass < 2; ++pass) {
         SphbList L;
         L.init(ws, lane);
-        sphb_warp_scan<true, 0, MULTI>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov);
+        sphb_warp_scan<true, 0, MULTI, true>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, RH, L, flush, cov, pm);
         emit(L.count(), true);
         if (mode != 1 || over) break;
         alloc(total);
@@ -187,8 +193,8 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
 #define NL_CHECK_THREADS 256
 #define NL_CHECK_BLOCKS 1184
 __global__ void __launch_bounds__(NL_CHECK_THREADS)
-    k_nl_check(const double *__restrict__ posh_build, const double *__restrict__ posh_now, long long n, double skin,
-               double cover_h, int32_t *__restrict__ flags, int32_t *__restrict__ maxima)
+    k_nl_check(const double *__restrict__ posh_build, const double *__restrict__ posh_now, long long n, double skin_u,
+               double cover_u, const float *__restrict__ margins, int32_t *__restrict__ flags, int32_t *__restrict__ maxima)
 {
     __shared__ int sh[3][NL_CHECK_THREADS / 32];
     int fl = 0;
@@ -197,13 +203,23 @@ __global__ void __launch_bounds__(NL_CHECK_THREADS)
         double x0, y0, z0, h0, x1, y1, z1, h1;
         sphb_load_posh(posh_build, (size_t)i, x0, y0, z0, h0);
         sphb_load_posh(posh_now, (size_t)i, x1, y1, z1, h1);
+        double skin = skin_u, cover_h = cover_u;
+        if (margins) {
+            const float2 m = __ldg(reinterpret_cast<const float2 *>(margins) + i);
+            cover_h = (double)m.x;
+            skin = (double)m.y;
+        }
         const double dx = x1 - x0, dy = y1 - y0, dz = z1 - z0;
         const double d2 = dx * dx + dy * dy + dz * dz, lim = skin * h0;
         if (!(d2 <= lim * lim) || !(h1 <= cover_h * h0)) fl |= SPHB_NL_BROKEN;
         if (!(d2 <= 0.25 * (lim * lim)) || !(h1 <= (1.0 + 0.5 * (cover_h - 1.0)) * h0)) fl |= SPHB_NL_AGING;
         if (h0 > 0.0) {   // non-negative floats order like their bit patterns; a NaN (> +inf as an integer) sticks
-            dr = __int_as_float(max(__float_as_int(dr), __float_as_int(__double2float_ru(sqrt(d2) / h0))));
-            gr = __int_as_float(max(__float_as_int(gr), __float_as_int(fmaxf(__double2float_ru(h1 / h0 - 1.0), 0.f))));
+            // the fractions of the two allowances this record has used up
+            const double fd = (lim > 0.0) ? sqrt(d2) / lim : ((d2 > 0.0) ? (double)CUDART_INF_F : 0.0);
+            const double gw = cover_h - 1.0, gg = h1 / h0 - 1.0;
+            const double fg = (gg > 0.0) ? ((gw > 0.0) ? gg / gw : (double)CUDART_INF_F) : ((gg == gg) ? 0.0 : gg);
+            dr = __int_as_float(max(__float_as_int(dr), __float_as_int(__double2float_ru(fd))));
+            gr = __int_as_float(max(__float_as_int(gr), __float_as_int(__double2float_ru(fg))));
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -337,7 +353,8 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
         hb = nl.posh_build[4 * j + 3];
     }
     const double h_in = h_cur;
-    const double h_cover = hb * nl.cover_h, h_old = hb * (1.0 + 0.5 * (nl.cover_h - 1.0));
+    const double cj = (nl.margins && valid) ? (double)__ldg(nl.margins + 2 * j) : nl.cover_h;   // this record's own cover
+    const double h_cover = hb * cj, h_old = hb * (1.0 + 0.5 * (cj - 1.0));
     const int nrows = (int)nl.warp_rows[w];
     const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
     const uint32_t self = valid ? (uint32_t)j : 0u;
@@ -397,7 +414,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
     }
     if (nl.maxima) {
         float gr = 0.f;
-        if (tgt && hb > 0.0 && h_res > hb) gr = __double2float_ru(h_res / hb - 1.0);
+        if (tgt && hb > 0.0 && h_res > hb) gr = (cj > 1.0) ? __double2float_ru((h_res / hb - 1.0) / (cj - 1.0)) : CUDART_INF_F;
         const int mg = __reduce_max_sync(SPHB_FULL, __float_as_int(gr));
         // most warps do not raise the maximum: look before the atomic (half a million of them on one address serialise)
         if (lane == 0 && mg > 0 && mg > __ldcg(nl.maxima + 1)) atomicMax(nl.maxima + 1, mg);
@@ -625,7 +642,7 @@ static inline bool nl_ok(const sphb_nlist *nl)
 {
     return nl && nl->n >= 0 && nl->warp_off && nl->warp_rows && nl->pool && nl->pool_rows > 0 &&
            nl->pool_rows < (int64_t)0xffffffffll && nl->cursor && nl->flags && nl->posh_build && nl->cover_h >= 1.0 &&
-           nl->skin >= 0.0 && nl->cover_h + nl->skin < 4.0;
+           nl->skin >= 0.0 && nl->cover_h + nl->skin < 4.0 && (!nl->margins || nl->level_dmax);
 }
 
 static inline unsigned nl_blocks(int64_t n) { return (unsigned)((n + NL_THREADS - 1) / NL_THREADS); }
@@ -729,7 +746,7 @@ extern "C" int sphb_nlist_check(const sphb_nlist *nl, const double *posh_now, vo
     long long nb = (nl->n + NL_CHECK_THREADS - 1) / NL_CHECK_THREADS;
     if (nb > NL_CHECK_BLOCKS) nb = NL_CHECK_BLOCKS;
     k_nl_check<<<(unsigned)nb, NL_CHECK_THREADS, 0, sphb_stream(stream)>>>(nl->posh_build, posh_now, (long long)nl->n, nl->skin,
-                                                                          nl->cover_h, nl->flags, nl->maxima);
+                                                                          nl->cover_h, nl->margins, nl->flags, nl->maxima);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

@@ -66,7 +66,8 @@ template <int LIST>
 struct SphbWarpSharedT {
     static constexpr int kList = LIST;
     float4 tile[32];      // x', y', z', |c'|^2 of the staged candidates (NaN-padded)
-    float wthr[32];       // nested grids, SYM: the staged candidates' own squared thresholds
+    float wthr[32];       // nested grids, SYM: the staged candidates' own squared thresholds (PPM: their radii A)
+    float wd[32];         // PPM: the staged candidates' displacement allowances D
     uint32_t segbase[SPHB_NSEG]; // first sorted slot of each live segment
     uint16_t list[LIST * 32];
 };
@@ -255,6 +256,36 @@ __device__ __forceinline__ uint32_t sphb_list_get(const WS &ws, int lane, int k)
     return ws.segbase[code >> SPHB_SEG_BITS] + (code & (SPHB_SEG_LEN - 1u));
 }
 
+// Per-particle list margins (the list builder only; PPM = true).  Particle i may move by D_i = s_i h_i and grow to
+// c_i h_i while the lists are in use; a pair belongs on the lists iff
+//       |r_j - r_i|  <=  max(A_j, A_i) + D_j + D_i,        A = 2 c h (+ the fp32 position error)
+// which covers every later true pair: r_build <= r_now + |dx_j| + |dx_i| < 2 max(c_j h_j, c_i h_i) + D_j + D_i.  The sum
+// form lets a fast particle pay for itself: its partners keep their tight margins.  margins: [n][2] = {c_i, s_i}, or
+// NULL for the uniform {cu, su}.  Aj, Dj: the calling lane's own.  dpad = (largest D of the level searched) + (largest
+// D of the group of targets): how far beyond its own support a
+// candidate may sit and still reach a target (bounds the cells searched) -- taken level by level on nested grids, so
+// that the allowance of a large-h record of the rim does not widen the searches of the dense core.
+struct SphbPpm {
+    const float2 *margins;
+    float cu, su;              // uniform margins, or (margins != NULL) upper bounds of every c_i, s_i
+    float Aj, Dj;
+    const float *level_dmax;   // [levels] largest D_i of each level's records (one entry for a single grid); NULL: su h_max
+    float hmax_u;              // single grid: h_max of all records
+};
+
+__device__ __forceinline__ void sphb_ppm_of(const SphbPpm &pm, uint32_t i, float w, float &A, float &D)
+{
+    float c = pm.cu, sk = pm.su;
+    if (pm.margins) {
+        const float2 m = __ldg(pm.margins + i);
+        c = m.x;
+        sk = m.y;
+    }
+    const float rw = __fsqrt_ru(w);                 // >= 2 h + delta (frec.w is that, squared, rounded up); +inf: unbounded h
+    A = __fmul_ru(rw, c);
+    D = (sk > 0.f) ? __fmul_ru(sk, 0.5f * rw) : 0.f;
+}
+
 // One full scan for the calling warp.  Every lane must call it (inactive lanes pass tgt = false).
 //   fx,fy,fz : the lane's own fp32 record position;  Rj: its search radius (float, rounded up, may be +inf)
 //   thr      : its squared threshold (float, rounded up, may be +inf)
@@ -276,10 +307,11 @@ __device__ __forceinline__ uint32_t sphb_list_get(const WS &ws, int lane, int k)
 //              that have to stay complete while every h may still grow by that factor)
 // Returns the number of live segments (what sphb_lists_save needs).
 //   MULTI    : the cell list may be a set of nested grids (sphb_cells.nlevels > 1); false compiles the level loop away
-template <bool SYM, int FLUSH_ROWS = 0, bool MULTI = false, class WS, class Flush>
+//   PPM      : per-particle margins (see SphbPpm): Rj = Aj + Dj + max D, thr is unused, symscale = max c, RH includes dpad
+template <bool SYM, int FLUSH_ROWS = 0, bool MULTI = false, bool PPM = false, class WS, class Flush>
 __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int lane, bool tgt, float fx,
                                               float fy, float fz, float Rj, float thr, uint32_t cid, float RH,
-                                              SphbList &L, Flush &&flush, float symscale = 1.f)
+                                              SphbList &L, Flush &&flush, float symscale = 1.f, SphbPpm pm = SphbPpm())
 {
     int nseg = 0;   // live entries of ws.segbase (warp-uniform)
     unsigned remaining = __ballot_sync(SPHB_FULL, tgt);
@@ -333,7 +365,8 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
         const float ymin_f = sphb_warp_min(ing ? fy : inf), ymax_f = sphb_warp_max(ing ? fy : -inf);
         const float zmin_f = sphb_warp_min(ing ? fz : inf), zmax_f = sphb_warp_max(ing ? fz : -inf);
         const double xmin0 = xmin_f, xmax0 = xmax_f, ymin0 = ymin_f, ymax0 = ymax_f, zmin0 = zmin_f, zmax0 = zmax_f;
-        const double Rg = sphb_warp_max(ing ? Rj : 0.f);
+        const double Rg0 = sphb_warp_max(ing ? Rj : 0.f);        // PPM: Rj = Aj + Dj
+        const float Dg = PPM ? sphb_warp_max(ing ? pm.Dj : 0.f) : 0.f;
 
         // group-local frame: centre of the box; err bounds the fp32 rounding of the re-centred test
         const float ox = 0.5f * (xmin_f + xmax_f), oy = 0.5f * (ymin_f + ymax_f), oz = 0.5f * (zmin_f + zmax_f);
@@ -349,9 +382,19 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
       const int nlev = MULTI ? g.nlev : 1;
       for (int lb = 0; lb < nlev; ++lb) {
         const SphbLevelCtx G = sphb_level_ctx<MULTI>(g, lb);
+        double Rg = Rg0;
+        float dpad = 0.f;
+        const float hmax_b = (MULTI && g.nlev > 1) ? __ldg(g.level_hmax + lb) : (PPM ? pm.hmax_u : 0.f);
+        if (PPM) {
+            const float dl = pm.level_dmax ? __ldg(pm.level_dmax + lb)
+                                           : ((pm.su > 0.f) ? __fmul_ru(pm.su, 0.5f * sphb_radius_of_h((double)hmax_b, g.delta)) : 0.f);
+            Rg = Rg0 + (double)dl;
+            dpad = __fadd_ru(dl, Dg);
+        }
         double Rw = Rg;
         if (SYM) {
-            const float RHb = (MULTI && g.nlev > 1) ? sphb_radius_of_h((double)__ldg(g.level_hmax + lb) * (double)symscale, g.delta) : RH;
+            const float RHb = (PPM || (MULTI && g.nlev > 1))
+                                  ? __fadd_ru(sphb_radius_of_h((double)hmax_b * (double)symscale, g.delta), dpad) : RH;
             Rw = fmax(Rg, (double)RHb);
         }
         // the group's box in the level's own coordinates
@@ -394,7 +437,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                     // extend the tight range outwards to the farthest cell whose h_max reaches the group
                     for (int cx = wl; cx < lo && cx <= wh; ++cx) {
                         const double hm = (double)G.cell_hmax[rowbase + cx] * (double)symscale;
-                        const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
+                        const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001 + (double)dpad;
                         const double gx = sphb_axis_gap(xmin, xmax, cx, G.nx, G.cellx, G.bounded);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             lo = cx;
@@ -404,7 +447,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                     }
                     for (int cx = wh; cx > hi && cx >= wl; --cx) {
                         const double hm = (double)G.cell_hmax[rowbase + cx] * (double)symscale;
-                        const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001;
+                        const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001 + (double)dpad;
                         const double gx = sphb_axis_gap(xmin, xmax, cx, G.nx, G.cellx, G.bounded);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             hi = cx;
@@ -445,7 +488,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                     for (uint32_t t = t0; t < t1; t += 32) {
                         const uint32_t ci = t + lane;
                         float4 rec = make_float4(CUDART_NAN_F, 0.f, 0.f, 0.f);
-                        float wthr = 0.f;
+                        float wthr = 0.f, ac = 0.f, dc = 0.f;
                         if (ci < t1) {
                             const float4 f = __ldg(g.frec + ci);
                             rec.x = f.x - ox;
@@ -453,6 +496,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                             rec.z = f.z - oz;
                             rec.w = fmaf(rec.z, rec.z, fmaf(rec.y, rec.y, rec.x * rec.x));
                             wthr = f.w;
+                            if (PPM) sphb_ppm_of(pm, ci, f.w, ac, dc);
                         }
 #if SPHB_FILTER_X2
                         {
@@ -471,7 +515,16 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                         // warp reduction per 32 candidates instead of a load + max per candidate; thresholds are
                         // non-negative floats, so their bit patterns order like integers)
                         float th = thrp;
-                        if (SYM) {
+                        if (PPM) {
+                            // the tile's largest radius and allowance bound every candidate's criterion; survivors are
+                            // tested again with their own
+                            const float at = __int_as_float(__reduce_max_sync(SPHB_FULL, __float_as_int(ac)));
+                            const float dt_ = __int_as_float(__reduce_max_sync(SPHB_FULL, __float_as_int(dc)));
+                            const float R = __fadd_ru(__fadd_ru(fmaxf(pm.Aj, at), pm.Dj), dt_);
+                            th = __fmul_ru(R, R) + offp;      // non-group lanes: offp = -inf (inf - inf = NaN never passes)
+                            ws.wthr[lane] = ac;
+                            ws.wd[lane] = dc;
+                        } else if (SYM) {
                             const float ttile = __int_as_float(__reduce_max_sync(SPHB_FULL, __float_as_int(wthr)));
                             th = fmaxf(thrp, __fmul_ru(ttile, symscale * symscale) + offp);
                             // within one level h spans an octave: under the tile's largest threshold alone a lane would
@@ -544,7 +597,12 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
 #pragma unroll
                             for (int c = 0; c < SPHB_SUB; ++c)
                                 if (sv[c] <= th) {
-                                    if (!(SYM && MULTI) || sv[c] <= fmaxf(thrp, ws.wthr[c0 + c] + offp)) L.push(code + c);
+                                    if (PPM) {
+                                        const float Rc = __fadd_ru(__fadd_ru(fmaxf(pm.Aj, ws.wthr[c0 + c]), pm.Dj), ws.wd[c0 + c]);
+                                        if (sv[c] <= __fmul_ru(Rc, Rc) + offp) L.push(code + c);
+                                    } else if (!(SYM && MULTI) || sv[c] <= fmaxf(thrp, ws.wthr[c0 + c] + offp)) {
+                                        L.push(code + c);
+                                    }
                                 }
 #endif
                             code += SPHB_SUB;

@@ -379,7 +379,7 @@ class SlabRunner:
         hx = HaloExchanger(self.cuts, self.rank, self.world).plan_migration(st["pos"][:, 0].contiguous())
         if hx.moved == 0:
             return st
-        names = [f for f in ("pos", "h", "vel", "u", "wfac", "rows") if f in st]
+        names = [f for f in ("pos", "h", "vel", "u", "wfac", "rows", "rd", "rg") if f in st]
         recv = hx.exchange([st["gid"].to(F64)] + [st[f] for f in names])
         out = dict(gid=torch.cat([st["gid"].index_select(0, hx.stay), recv[0].to(torch.int64)]))
         for f, g in zip(names, recv[1:]):
@@ -540,9 +540,18 @@ class FastSlabRunner(SlabRunner):
         own = f["own_sorted"]
         with self.e.section("host:to_owned"):
             P = self._rows(f["P"], own)
-            return dict(gid=self._rows(f["gid_S"], own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
-                        vel=self._rows(f["V"], own), u=self._rows(f["U"], own), wfac=self._rows(f["wfac_S"], own),
-                        rows=self._rows(f["rows_S"], own))
+            out = dict(gid=self._rows(f["gid_S"], own), pos=P[:, :3].contiguous(), h=P[:, 3].contiguous(),
+                       vel=self._rows(f["V"], own), u=self._rows(f["U"], own), wfac=self._rows(f["wfac_S"], own),
+                       rows=self._rows(f["rows_S"], own))
+            # every record's own motion per step, measured against the lists' build-time records: what the next lists'
+            # per-particle margins are sized with (it migrates with the particle)
+            if self.margins.per_particle and self.nl is not None:
+                if self.margins.age >= 1:
+                    rd, rg = E.slot_rates(self.nl.posh_build, f["P"], self.margins.age)
+                    out["rd"], out["rg"] = self._rows(rd, own), self._rows(rg, own)
+                elif f.get("rd_S") is not None:
+                    out["rd"], out["rg"] = self._rows(f["rd_S"], own), self._rows(f["rg_S"], own)
+            return out
 
     def _rebuild(self, st):
         """st: owned-order dict.  Migrate, plan the halo for the lists' whole life, sort, scan."""
@@ -556,7 +565,14 @@ class FastSlabRunner(SlabRunner):
             # bounding box, mean and max h, and how many particles left their slab: two all-reduces, one read
             lo, hi, hmean, ntot, hm, moved = self._global_stats(st)
             self.geom = E.choose_grid(lo, hi, hmean, ntot)          # refreshed at every rebuild (cells follow the gas)
-            cover_h, skin = self.margins.choose()
+            pp = self.margins.per_particle and "rd" in st
+            if pp:
+                # the life of the new lists and the bounds of their margins, agreed over all ranks
+                self.margins.plan(st["rd"], st["rg"], self.stats["steps"], reduce=self._plan_reduce)
+                cover_h, skin = self.margins.cover_h, self.margins.skin
+            else:
+                cover_h, skin = self.margins.choose()
+                self.margins.life = 1 if self.margins.per_particle else 10 ** 9
             self.margins.built()
         with e.section("host:migrate"):
             if recut:
@@ -569,17 +585,25 @@ class FastSlabRunner(SlabRunner):
                 else None
         n_own = st["gid"].numel()
         with e.section("host:halo_exchange"):
+            rd_L = rg_L = None
             if hx is not None:
-                g = hx.exchange([st["gid"].to(F64), st["pos"], st["h"], st["vel"], st["u"]])
+                g = hx.exchange([st["gid"].to(F64), st["pos"], st["h"], st["vel"], st["u"]] + ([st["rd"], st["rg"]] if pp else []))
                 gid_all = torch.cat([st["gid"], g[0].to(torch.int64)])
                 pos_L, h_L = torch.cat([st["pos"], g[1]]), torch.cat([st["h"], g[2]])
                 vel_L, u_L = torch.cat([st["vel"], g[3]]), torch.cat([st["u"], g[4]])
+                if pp:
+                    rd_L, rg_L = torch.cat([st["rd"], g[5]]), torch.cat([st["rg"], g[6]])
             else:
                 gid_all, pos_L, h_L, vel_L, u_L = st["gid"], st["pos"], st["h"], st["vel"], st["u"]
+                if pp:
+                    rd_L, rg_L = st["rd"], st["rg"]
         dg = e.build(e.pack_posh(pos_L, h_L), *self.geom, tie_key=gid_all)
         perm = dg.perm.long()                                   # slot -> local index
         target = (perm < n_own).to(torch.uint8)
-        self.nl = e.nl_build(dg, cover_h, skin, target=target if self.world > 1 else None, consts=self.consts)
+        rd_S = e.gather(rd_L, dg.perm, 1) if pp else None
+        rg_S = e.gather(rg_L, dg.perm, 1) if pp else None
+        self.nl = e.nl_build(dg, cover_h, skin, target=target if self.world > 1 else None, consts=self.consts,
+                             margins=self.margins.margins_for(rd_S, rg_S) if pp else None)
         with e.section("host:slot_state"):
             slot_of_loc = torch.empty_like(perm)
             slot_of_loc[perm] = torch.arange(perm.numel(), device=perm.device)
@@ -592,12 +616,29 @@ class FastSlabRunner(SlabRunner):
                              target=target if self.world > 1 else None,
                              own_sorted=torch.nonzero(target).flatten() if self.world > 1 else slot_of_loc,
                              n_own=n_own, sx=SlotExchanger(hx, slot_of_loc, n_own, engine=e) if hx is not None else None, fresh=True,
-                             ghost_h_stale=False)
+                             ghost_h_stale=False, rd_S=rd_S, rg_S=rg_S)
         self.stats["builds"] += 1
         self.stale = False
         # (a build that could not list its input leaves SPHB_NL_POOL / _UNLISTABLE in the lists' flag word: the step
         # runs anyway, and the all-reduced flags at its end send every rank down the same road)
         self._note_rows()
+
+    def _plan_reduce(self, sums, maxes):
+        if self.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(maxes, op=dist.ReduceOp.MAX)
+
+    def _note(self, nl, flags):
+        """after a successful step: should the lists be rebuilt before the next one?"""
+        if nl.margins is not None or self.margins.per_particle:
+            return self.margins.note_used(nl.used_d, nl.used_g)
+        return self.margins.note(nl.moved, nl.grown, flags & E.N.NL_AGING)
+
+    def _failed(self):
+        """a step ended with broken lists -> False: give up on lists for a while"""
+        if self.nl.margins is not None:
+            return self.margins.failed_pp()
+        return self.margins.failed(self.fresh_failed, self.nl.moved, self.nl.grown)
 
     def _global_stats(self, st):
         pos, h = st["pos"], st["h"]
@@ -704,7 +745,7 @@ class FastSlabRunner(SlabRunner):
         flags = self.last_flags = nl.read_flags()
         ok = (flags & self._BAD) == 0
         self.fresh_failed = f["fresh"] and not ok
-        if ok and self.margins.note(nl.moved, nl.grown, flags & E.N.NL_AGING):
+        if ok and self._note(nl, flags):
             self.stale = True
         return ok, P1, V1, U1, stt
 
@@ -737,7 +778,7 @@ class FastSlabRunner(SlabRunner):
             self.stats["redos"] += 1
             if self.last_flags & (E.N.NL_UNLISTABLE | E.N.NL_POOL):
                 break
-            if not self.margins.failed(self.fresh_failed, self.nl.moved, self.nl.grown):
+            if not self._failed():
                 break
         # the lists cannot serve this step: scanning path for a while
         st = self._to_owned()

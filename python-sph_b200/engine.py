@@ -47,8 +47,12 @@ class KeptLists:
     """sphb_nlist: neighbour lists that outlive kernels and steps, with the buffers they point to.
     Built from ONE cell list (dg); the drain kernels then only need the current sorted records."""
 
-    def __init__(self, engine, dg, cover_h, skin, pool_rows=None):
+    def __init__(self, engine, dg, cover_h, skin, pool_rows=None, margins=None, level_dmax=None):
+        """margins (n,2) float32 = per-particle {cover, skin} in slot order (cover_h / skin are then their upper bounds),
+        level_dmax: float32 upper bounds of skin_i h_i per level of the cell list"""
         lib, dev = engine.lib, engine.device
+        self.margins, self.level_dmax = margins, level_dmax
+        self.posh_build = dg.posh
         n = dg.n
         nw = max(1, (n + 31) // 32)
         self.n = n
@@ -63,21 +67,27 @@ class KeptLists:
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # [0] SPHB_NL_* flags, [1..2] the maxima
         self.c = N.NList(n, self.warp_off.data_ptr(), self.warp_rows.data_ptr(), self.pool.data_ptr(), rows,
                          self.cursor.data_ptr(), self.flags.data_ptr(), dg.posh.data_ptr(), self.cover_h, self.skin,
-                         self.flags.data_ptr() + 4)
+                         self.flags.data_ptr() + 4, margins.data_ptr() if margins is not None else None,
+                         level_dmax.data_ptr() if level_dmax is not None else None)
         self.build_flags = 0
         self.moved = self.grown = 0.0
+        self.used_d = self.used_g = 0.0
 
     @classmethod
-    def view(cls, src, n, warp_off, warp_rows, posh_build):
+    def view(cls, src, n, warp_off, warp_rows, posh_build, margins=None):
         """the lists of `src` seen through renamed slots (sphb_nlist_remap): same pool, cursor and flag words, other
-        warp tables and build-time records"""
+        warp tables, build-time records and per-particle margins"""
         nl = cls.__new__(cls)
+        nl.margins, nl.level_dmax = margins, src.level_dmax
+        nl.posh_build = posh_build
         nl.n, nl.dg, nl.cover_h, nl.skin = int(n), src.dg, src.cover_h, src.skin
         nl.pool_rows, nl.warp_off, nl.warp_rows, nl.pool, nl.cursor, nl.flags = src.pool_rows, warp_off, warp_rows, src.pool, src.cursor, src.flags
-        nl.posh_build = posh_build
         nl.c = N.NList(nl.n, warp_off.data_ptr(), warp_rows.data_ptr(), nl.pool.data_ptr(), nl.pool_rows, nl.cursor.data_ptr(),
-                       nl.flags.data_ptr(), posh_build.data_ptr(), nl.cover_h, nl.skin, nl.flags.data_ptr() + 4)
+                       nl.flags.data_ptr(), posh_build.data_ptr(), nl.cover_h, nl.skin, nl.flags.data_ptr() + 4,
+                       margins.data_ptr() if margins is not None else None,
+                       src.level_dmax.data_ptr() if (margins is not None and src.level_dmax is not None) else None)
         nl.build_flags, nl.moved, nl.grown, nl.omega0 = src.build_flags, 0.0, 0.0, None
+        nl.used_d = nl.used_g = 0.0
         return nl
 
     def ref(self):
@@ -88,7 +98,11 @@ class KeptLists:
         displacement / h_build and h growth the checks have seen since the build"""
         v = self.flags.cpu()
         mx = v[1:3].view(torch.float32)
-        self.moved, self.grown = float(mx[0]), float(mx[1])
+        # the device reports the largest FRACTIONS of their allowances the records have used; with uniform margins
+        # .moved / .grown are those in absolute terms (displacement / h_build, h growth)
+        self.used_d, self.used_g = float(mx[0]), float(mx[1])
+        self.moved = self.used_d * self.skin if self.used_d > 0.0 else 0.0
+        self.grown = self.used_g * (self.cover_h - 1.0) if self.used_g > 0.0 else 0.0
         return int(v[0])
 
     def rows_used(self):
@@ -470,8 +484,22 @@ class Engine:
         return out, cnt
 
     # -- kept neighbour lists (sphb_nlist) -------------------------------------------------------
+    def level_dmax(self, dg, margins):
+        """float32 upper bounds of skin_i h_i (as the builder forms it) over the records of each level of the cell list"""
+        h = dg.posh[:, 3]
+        d = margins[:, 1].double() * (h * 1.00002 + dg.delta)
+        d = torch.where((h > 0) & torch.isfinite(h), d, torch.full_like(d, float("inf")))
+        if dg.levels is None:
+            m = d.max().reshape(1) if d.numel() else torch.zeros(1, dtype=F64, device=self.device)
+        else:
+            idx = torch.tensor(dg.levels.bases + [dg.levels.ncell], dtype=torch.int64, device=self.device)
+            edges = dg.cell_start.long().index_select(0, idx).tolist()
+            zero = torch.zeros((), dtype=F64, device=self.device)
+            m = torch.stack([d[a:b].max() if b > a else zero for a, b in zip(edges[:-1], edges[1:])])
+        return torch.nextafter(m.float(), torch.full_like(m, float("inf")).float())
+
     def nl_build(self, dg, cover_h, skin, target=None, hmax=None, pool_rows=None, max_bytes=96 * 2 ** 30,
-                 consts=None) -> KeptLists:
+                 consts=None, margins=None) -> KeptLists:
         """scan the cell list once and keep every warp's candidate rows.  Reads the build's flags (one 4-byte D2H
         after the kernel): a pool that turned out too small is enlarged to what the build asked for and the build is
         repeated.  The returned lists may still carry SPHB_NL_UNLISTABLE / SPHB_NL_POOL (nl.build_flags): the caller then
@@ -479,8 +507,9 @@ class Engine:
         consts: also form Omega of the build-time records while the lists are in the staging area -> nl.omega0"""
         hm = hmax if hmax is not None else self.hmax(dg.posh)
         om = torch.empty(dg.n, dtype=F64, device=self.device) if consts is not None else None
+        ldm = self.level_dmax(dg, margins) if margins is not None else None
         for _ in range(3):
-            nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows)
+            nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows, margins=margins, level_dmax=ldm)
             nl._hmax = hm
             nl.omega0 = om
             self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(),
@@ -812,7 +841,7 @@ class ListMargins:
     MAX_SKIN = 0.25
     MAX_GROW = 0.25
     SAFETY = float(os.environ.get("SPHB_NL_SAFETY", "1.25"))                  # margin on the extrapolated motion
-    BUILD_OVER_DRAIN = float(os.environ.get("SPHB_NL_BUILD_COST", "0.28"))    # one rebuild / one step's drains
+    BUILD_OVER_DRAIN = float(os.environ.get("SPHB_NL_BUILD_COST", "0.4"))    # one rebuild / one step's drains
 
     def __init__(self, cover_h=None, skin=None, adaptive=True):
         self.cover_h = NL_COVER_H if cover_h is None else float(cover_h)
@@ -823,6 +852,86 @@ class ListMargins:
         self.age = 0                       # steps run on the current lists
         self._moved = self._grown = 0.0
         self.widened = 0
+        self.per_particle = adaptive and self.PER_PARTICLE
+        self.pp_safety = self.PP_SAFETY
+        self.life = 1                      # planned life of the current lists (per-particle margins)
+
+    # ---- per-particle margins -----------------------------------------------------------------------------------------
+    # The largest motion belongs to a few per cent of the particles (free surfaces, the contact of the Sod tube, a close
+    # pair in the Plummer core).  Uniform margins sized for them make every list long, or every life short; with
+    # sphb_nlist.margins each record gets the cover and skin ITS OWN measured motion asks for over the planned life.
+    PER_PARTICLE = os.environ.get("SPHB_NL_PP", "1") != "0"
+    PP_SAFETY = float(os.environ.get("SPHB_NL_PP_SAFETY", "2.0"))
+    PP_FLOOR = 0.003      # every record may move / grow by at least this much (fractions of h)
+    PP_MAX = 0.45         # no record is given more; a life that would need more is not planned
+    LIVES = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32)
+    PP_BINS = 128
+
+    def plan(self, rd, rg, steps_seen, reduce=None):
+        """rd, rg: per-record per-step displacement / h and relative h growth, measured over the `self.age` steps the
+        last lists lived (device tensors, any order).  Chooses the life L (steps) of the next lists by the modelled cost
+        -- mean list volume (1 + cover + skin)^3 + BUILD_OVER_DRAIN / L --, and returns margins (n,2) float32 =
+        {cover_i, skin_i} in the order of rd / rg, plus their upper bounds.  A start-up flow accelerates: rates measured
+        over steps [T - age, T] are scaled by (T + L/2) / (T - age/2) (constant acceleration from rest), at most 6x.
+        reduce(counts, maxes): all-reduce over ranks (sum of int64 / max) so that every rank plans the same life."""
+        f = self.pp_safety
+        dev = rd.device
+        age = max(self.age, 1)
+        T = max(float(steps_seen), float(age))
+        Ls = torch.tensor(self.LIVES, dtype=F64, device=dev)
+        ramp = ((T + 0.5 * Ls) / max(T - 0.5 * age, 0.5)).clamp(max=6.0)
+        # a 2-D histogram of the two rates (three bins per octave, 2^-36 .. 2^6): integer counts do not depend on the
+        # order of the records or on how they are spread over ranks, so every run of the same physics plans the same life
+        nb = self.PP_BINS
+        bd = ((torch.log2(rd) + 36.0) * 3.0).floor().clamp_(0, nb - 1).long()
+        bg = ((torch.log2(rg) + 36.0) * 3.0).floor().clamp_(0, nb - 1).long()
+        sums = torch.bincount(bd * nb + bg, minlength=nb * nb)
+        maxes = torch.stack([rd.max(), rg.max()]) if rd.numel() else torch.zeros(2, dtype=F64, device=dev)
+        if reduce is not None:
+            reduce(sums, maxes)
+        rep = torch.exp2((torch.arange(nb, dtype=F64, device=dev) + 1.0) / 3.0 - 36.0)      # upper edge of each bin
+        k = (f * ramp * Ls)[:, None]
+        s_b = (k * rep[None, :] + self.PP_FLOOR).clamp(max=self.PP_MAX)                     # (lives, bins)
+        vol = (1.0 + s_b[:, :, None] + s_b[:, None, :]) ** 3                                # (lives, bins_d, bins_g)
+        cnt = sums.to(F64).reshape(1, nb, nb)
+        mean_vol = ((vol * cnt).sum(dim=(1, 2)) / cnt.sum().clamp(min=1.0)).tolist()
+        maxes, kk = maxes.tolist(), (f * ramp * Ls).tolist()
+        best = None
+        for i, L in enumerate(self.LIVES):
+            need = kk[i] * max(maxes[0], maxes[1]) + self.PP_FLOOR
+            if best is not None and need > self.PP_MAX:
+                break
+            cost = mean_vol[i] + self.BUILD_OVER_DRAIN / L
+            if best is None or cost < best[0]:
+                best = (cost, i)
+        i = best[1]
+        self.life = self.LIVES[i]
+        self.pp_k = kk[i]
+        self.cover_h = 1.0 + min(self.PP_MAX, kk[i] * maxes[1] + self.PP_FLOOR) * 1.000001 + 1e-7
+        self.skin = min(self.PP_MAX, kk[i] * maxes[0] + self.PP_FLOOR) * 1.000001 + 1e-7
+        return self.margins_for(rd, rg)
+
+    def margins_for(self, rd, rg):
+        """{cover_i, skin_i} (n,2) float32 for the planned life: a pure function of each record's own rates, so a ghost
+        copy gets the very margins its owner gives the record"""
+        skin = (self.pp_k * rd + self.PP_FLOOR).clamp(max=self.PP_MAX)
+        cover = 1.0 + (self.pp_k * rg + self.PP_FLOOR).clamp(max=self.PP_MAX)
+        m = torch.stack([cover, skin], dim=1).float()
+        return torch.nan_to_num(m, nan=1.0 + self.PP_MAX, posinf=1.0 + self.PP_MAX).contiguous()
+
+    def note_used(self, used_d, used_g):
+        """after a successful step on per-particle margins: used_* = the largest fraction of its allowance any record has
+        used up.  -> True when the lists should be rebuilt before the next step (planned life over, or the next step --
+        at the pace so far, with a quarter in hand -- would break them)"""
+        self.age += 1
+        u = max(used_d, used_g)
+        return self.age >= self.life or u * (self.age + 1.0) / self.age * 1.25 > 1.0
+
+    def failed_pp(self):
+        """lists with per-particle margins broke before their planned life: plan with more in hand.  -> False: give up"""
+        self.pp_safety *= 1.5
+        self.widened += 1
+        return self.pp_safety <= 12.0
 
     def choose(self):
         """-> cover_h, skin of the next build"""
@@ -882,6 +991,16 @@ class ListMargins:
         return True
 
 
+def slot_rates(posh_build, posh_now, age):
+    """per-record motion per step since the lists were built: displacement / h_build and relative h growth (non-finite:
+    a large number, i.e. the widest margins)"""
+    hb = posh_build[:, 3]
+    rd = (posh_now[:, :3] - posh_build[:, :3]).norm(dim=1) / hb / age
+    rg = (posh_now[:, 3] / hb - 1.0).clamp(min=0.0) / age
+    big = 10.0
+    return torch.nan_to_num(rd, nan=big, posinf=big).clamp_(max=big), torch.nan_to_num(rg, nan=big, posinf=big).clamp_(max=big)
+
+
 class FastStepper:
     """var_smoothlength_leapfrog (pyfluid.py:498-532, G = 0) on neighbour lists that are kept across kernels and steps.
 
@@ -920,9 +1039,18 @@ class FastStepper:
         self._consts = None       # the constants of the current call (the build forms Omega with them)
 
     # ---- builds ------------------------------------------------------------------------------------
-    def _rebuild_from(self, posh_in, vel_in, u_in, ids_in):
+    def _rates(self):
+        """per-record motion per step over the life of the current lists, in their slot order: (displacement / h_build,
+        relative h growth), or None when nothing has been measured"""
+        nl, age = self.nl, self.margins.age
+        if nl is None or age < 1 or not self.margins.per_particle or self.P is None or self.P.shape[0] != nl.n:
+            return None
+        return slot_rates(nl.posh_build, self.P, age)
+
+    def _rebuild_from(self, posh_in, vel_in, u_in, ids_in, rates=None):
         """sort records (any order; ids_in = caller index of each input row, None = identity) into a fresh cell list,
-        scan it once, and take the state along in the new slot order"""
+        scan it once, and take the state along in the new slot order.  rates: _rates() of the lists being replaced, in
+        the order of posh_in -- the new lists then get per-particle margins"""
         e = self.e
         if self.geom is not None:
             grid, delta = self.geom
@@ -940,10 +1068,16 @@ class FastStepper:
             self.ids = e.gather(ids_in.view(F64), dg.perm, 1).view(torch.int64)   # a bit-pattern copy
             self.perm = self.ids.to(torch.int32)
         self.P = dg.posh                     # never written in place: every kernel below returns fresh arrays
-        cover_h, skin = self.margins.choose()
+        pp = None
+        if rates is not None:
+            pp = self.margins.plan(e.gather(rates[0], dg.perm, 1), e.gather(rates[1], dg.perm, 1), self.stats["steps"])
+            cover_h, skin = self.margins.cover_h, self.margins.skin
+        else:
+            cover_h, skin = self.margins.choose()
+            self.margins.life = 1 if self.margins.per_particle else 10 ** 9
         self.margins.built()
         # Omega(pos0, h0) of the step that follows comes out of the build itself (the lists are in the staging area)
-        self.nl = e.nl_build(dg, cover_h, skin, pool_rows=self.pool_rows, consts=self._consts)
+        self.nl = e.nl_build(dg, cover_h, skin, pool_rows=self.pool_rows, consts=self._consts, margins=pp)
         self.pool_rows = max(self.nl.pool_rows, self.pool_rows or 0)
         self.stats["builds"] += 1
         self.stale = False
@@ -965,7 +1099,10 @@ class FastStepper:
         """a step failed on its lists (flags = SPHB_NL_*): what to change before the rebuild.  -> False: give up"""
         if flags & (N.NL_UNLISTABLE | N.NL_POOL):
             return False      # Engine.nl_build already enlarged the pool as far as it may
-        ok = self.margins.failed(self.fresh_failed, self.nl.moved, self.nl.grown)
+        if self.nl.margins is not None:
+            ok = self.margins.failed_pp()
+        else:
+            ok = self.margins.failed(self.fresh_failed, self.nl.moved, self.nl.grown)
         self.stats["widened"] = self.margins.widened
         return ok
 
@@ -1008,8 +1145,14 @@ class FastStepper:
         ok = (fl & self._BAD) == 0
         self.fresh_failed = self.fresh and not ok
         self.fresh = False
-        if ok and self.margins.note(self.nl.moved, self.nl.grown, fl & N.NL_AGING):
-            self.stale = True
+        if ok:
+            if self.nl.margins is not None or self.margins.per_particle:
+                # (uniform first lists of a per-particle run: one step, to measure every record's motion)
+                stale = self.margins.note_used(self.nl.used_d, self.nl.used_g)
+            else:
+                stale = self.margins.note(self.nl.moved, self.nl.grown, fl & N.NL_AGING)
+            if stale:
+                self.stale = True
         return ok, P1, V1, U1, st
 
     # ---- resident-state API ---------------------------------------------------------------------------
@@ -1048,7 +1191,7 @@ class FastStepper:
             return self._safe_advance(dt, consts, defer_status, printer)
         for attempt in range(self.MAX_ATTEMPTS):
             if self.stale or attempt > 0:
-                self._rebuild_from(self.P, self.V, self.U, self.ids)
+                self._rebuild_from(self.P, self.V, self.U, self.ids, rates=self._rates())
             ok, P1, V1, U1, st = self._try(dt, consts)
             if ok:
                 self.P, self.V, self.U = P1, V1, U1
@@ -1082,10 +1225,12 @@ class FastStepper:
             self.last_status = self.safe.last_status
             return r
         fh = _FastHooks(self, hooks, vel0, u0) if hooks is not None else None
-        reuse = self.nl is not None and not self.stale and self.nl.n == n
-        if reuse:
+        have_old = self.nl is not None and self.nl.n == n and self.perm is not None
+        reuse = have_old and not self.stale
+        if have_old:
             # the new input in the old slot order; does it pass the lists' own validity check?
             self.P, _, _ = e.gather_state(self.perm, pos=pos0, h=h0)
+        if reuse:
             e.nl_check(self.nl, self.P)
             if self.nl.read_flags() & (self._BAD | (0 if self.margins.adaptive else N.NL_AGING)):
                 reuse = False
@@ -1096,7 +1241,14 @@ class FastStepper:
             if not reuse:
                 if fh is not None:
                     fh.wait_inputs()
-                self._rebuild_from(e.pack_posh(pos0, h0), vel0, u0, None)
+                rates = self._rates() if have_old else None
+                if rates is not None:
+                    # the lists being replaced measured every record's motion: the new ones get per-particle margins
+                    _, V_old, U_old = e.gather_state(self.perm, vel=vel0, u=u0)
+                    self._rebuild_from(self.P, V_old, U_old, self.ids, rates=rates)
+                else:
+                    self._rebuild_from(e.pack_posh(pos0, h0), vel0, u0, None)
+                have_old = False
                 if fh is not None:
                     fh.have_state()
             ok, P1, V1, U1, st = self._try(dt, consts, fh)

@@ -22,7 +22,7 @@ import domain
 import engine as E
 
 F64 = torch.float64
-COLS = ("gid", "pos", "h", "vel", "u", "rows", "wfac")   # what travels at a rebuild: 1 + 3 + 1 + 3 + 1 + 1 + 1 doubles
+COLS = ("gid", "pos", "h", "vel", "u", "rows", "wfac", "rd", "rg")   # what travels at a rebuild: 13 doubles per particle
 
 
 def _geom_to_plain(g):
@@ -202,7 +202,16 @@ class RangeRunner(domain.FastSlabRunner):
         full, dg = self._sorted_world(st)
         n = dg.n
         perm = dg.perm.long()
-        cover_h, skin = self.margins.choose()
+        pp = self.margins.per_particle and "rd" in full
+        if pp:
+            # every rank holds every record's rates: the same plan everywhere, no reduction needed
+            m_all = self.margins.plan(full["rd"], full["rg"], self.stats["steps"])
+            cover_h, skin = self.margins.cover_h, self.margins.skin
+            m_S = m_all.index_select(0, perm)
+        else:
+            cover_h, skin = self.margins.choose()
+            self.margins.life = 1 if self.margins.per_particle else 10 ** 9
+            m_S = None
         self.margins.built()
         with e.section("host:cuts"):
             w_S = (full["rows"] + 8.0) * full["wfac"]
@@ -212,7 +221,8 @@ class RangeRunner(domain.FastSlabRunner):
         mask[s0:s1] = 1
         # lists of the own targets only, in global slot names
         pool_rows = self.pool_rows_hint if getattr(self, "pool_rows_hint", None) else ((n_own + 31) // 32) * 176 + 65536
-        nl_g = e.nl_build(dg, cover_h, skin, target=mask if self.world > 1 else None, consts=self.consts, pool_rows=pool_rows)
+        nl_g = e.nl_build(dg, cover_h, skin, target=mask if self.world > 1 else None, consts=self.consts, pool_rows=pool_rows,
+                          margins=m_S)
         self.pool_rows_hint = max(nl_g.pool_rows, ((n_own + 31) // 32) * 176 + 65536)
         with e.section("host:local_numbering"):
             mark = e.nl_mark(nl_g, n)
@@ -234,7 +244,7 @@ class RangeRunner(domain.FastSlabRunner):
             w_off[o0 // 32:o0 // 32 + nwo] = nl_g.warp_off[s0 // 32:s0 // 32 + nwo]
             w_rows[o0 // 32:o0 // 32 + nwo] = nl_g.warp_rows[s0 // 32:s0 // 32 + nwo]
             P = dg.posh.index_select(0, loc)
-            self.nl = E.KeptLists.view(nl_g, n_loc, w_off, w_rows, P)
+            self.nl = E.KeptLists.view(nl_g, n_loc, w_off, w_rows, P, margins=m_S.index_select(0, loc) if m_S is not None else None)
             if nl_g.omega0 is not None:
                 om = torch.ones(n_loc, dtype=F64, device=self.dev)
                 om[o0:o0 + n_own] = nl_g.omega0[s0:s1]
@@ -254,7 +264,8 @@ class RangeRunner(domain.FastSlabRunner):
         self.fast = dict(P=P, V=V, U=U, gid_S=full["gid"].index_select(0, src), wfac_S=full["wfac"].index_select(0, src),
                          target=target if self.world > 1 else None,
                          own_sorted=torch.arange(o0, o0 + n_own, device=self.dev), n_own=n_own, sx=sx, fresh=True,
-                         ghost_h_stale=False, range=(s0, s1), n_ghost=n_loc - pad - n_own)
+                         ghost_h_stale=False, range=(s0, s1), n_ghost=n_loc - pad - n_own,
+                         rd_S=full["rd"].index_select(0, src) if pp else None, rg_S=full["rg"].index_select(0, src) if pp else None)
         self.stats["builds"] += 1
         self.stale = False
         self._note_rows()
@@ -295,7 +306,7 @@ class RangeRunner(domain.FastSlabRunner):
             self.stats["redos"] += 1
             if self.last_flags & (E.N.NL_UNLISTABLE | E.N.NL_POOL):
                 break
-            if not self.margins.failed(self.fresh_failed, self.nl.moved, self.nl.grown):
+            if not self._failed():
                 break
         st = self._to_owned()
         self.nl = None

@@ -41,9 +41,11 @@ for s in range(steps):
     P = fs.P
     d = (P[:, :3] - nl.dg.posh[:, :3]).norm(dim=1) / nl.dg.posh[:, 3]
     g = P[:, 3] / nl.dg.posh[:, 3] - 1
-    print(f"step {s:3d} built {fs.stats['builds'] - b0} age {fs.age} cover_h {nl.cover_h:.4f} skin {nl.skin:.4f} moved {nl.moved:.5f} "
-          f"grown {nl.grown:.5f} | >half-skin {(d > 0.5 * nl.skin).sum().item()} >half-grow {(g > 0.5 * (nl.cover_h - 1)).sum().item()} "
-          f"rows/warp {nl.warp_rows.double().mean().item():.1f} redos {fs.stats['redos']}")
+    mm = nl.margins
+    ms = f"mean cover {mm[:, 0].double().mean().item():.4f} skin {mm[:, 1].double().mean().item():.4f}" if mm is not None else "uniform"
+    print(f"step {s:3d} built {fs.stats['builds'] - b0} age {fs.age}/{fs.margins.life} max cover_h {nl.cover_h:.4f} skin {nl.skin:.4f} {ms} "
+          f"used {nl.used_d:.3f} {nl.used_g:.3f} | max moved {d.max().item():.5f} grown {g.max().item():.5f} "
+          f"rows/warp {nl.warp_rows.double().mean().item():.1f} redos {fs.stats['redos']} safety {fs.margins.pp_safety}")
     if a1.startswith("plummer:") and s < 3:
         k = int(torch.argmax(g))
         print("      largest growth at slot", k, "r", float(P[k, :3].norm()), "h_build", float(nl.dg.posh[k, 3]), "h_now", float(P[k, 3]))

@@ -133,3 +133,46 @@ def test_choose_levels_and_level_table():
     assert start[-1] == n and (np.diff(ids[perm]) >= 0).all() and (np.diff(lev[perm]) >= 0).all()
     # one occupied octave: no nesting
     assert engine.choose_levels([[0.0] * 8] * 15 + [[10.0, 5.0, 0, 0, 0, 1, 1, 1]], 0, [0, 0, 0], [1, 1, 1], 0.6) is None
+
+
+def test_per_particle_margin_plan_is_order_independent():
+    """ListMargins.plan: every record gets margins from its OWN measured motion; the planned life comes from integer
+    histogram counts, so it does not depend on the order of the records (slot order, rank decomposition)"""
+    import torch
+    import engine
+    torch.manual_seed(0)
+    n = 50000
+    rd = torch.rand(n, dtype=torch.float64) ** 8 * 0.04        # a few fast records, a quiet majority
+    rg = torch.rand(n, dtype=torch.float64) ** 8 * 0.02
+    rd[7] = 0.0
+    a, b = engine.ListMargins(), engine.ListMargins()
+    a.age = b.age = 2
+    ma = a.plan(rd, rg, 20)
+    perm = torch.randperm(n)
+    mb = b.plan(rd[perm], rg[perm], 20)
+    assert a.life == b.life >= 1 and torch.equal(mb, ma[perm])
+    assert ma.dtype == torch.float32 and ma.shape == (n, 2)
+    assert float(ma[:, 0].max()) <= a.cover_h and float(ma[:, 1].max()) <= a.skin          # the uniform bounds cover all
+    assert float(ma[:, 1].mean()) < 0.25 * float(ma[:, 1].max())                            # the majority keeps tight lists
+    assert float(ma[7, 1]) == pytest.approx(a.PP_FLOOR)
+    # two "ranks": the same plan from all-reduced counts
+    c = engine.ListMargins()
+    c.age = 2
+    half = n // 2
+    other = {}
+
+    def reduce(counts, maxes):
+        cd = engine.ListMargins()
+        cd.age = 2
+        def grab(c2, m2):
+            other["c"], other["m"] = c2.clone(), m2.clone()
+        cd.plan(rd[half:], rg[half:], 20, reduce=grab)
+        counts += other["c"]
+        torch.maximum(maxes, other["m"], out=maxes)
+    mc = c.plan(rd[:half], rg[:half], 20, reduce=reduce)
+    assert c.life == a.life and torch.equal(mc, ma[:half])
+    # a faster flow plans a shorter life
+    d = engine.ListMargins()
+    d.age = 2
+    d.plan(rd * 8, rg * 8, 20)
+    assert d.life <= a.life

@@ -68,7 +68,7 @@ def _to(a):
 
 
 @pytest.mark.parametrize("case", ["cloud", "two_density"])
-@pytest.mark.parametrize("cover_h,skin", [(1.0, 0.0), (1.03, 0.03)])
+@pytest.mark.parametrize("cover_h,skin", [(1.0, 0.0), (1.03, 0.03), (1.25, 0.25)])
 def test_drains_equal_scanning_kernels_bit_for_bit(sph, case, cover_h, skin):
     import torch
     import engine as E
@@ -90,7 +90,7 @@ def test_drains_equal_scanning_kernels_bit_for_bit(sph, case, cover_h, skin):
         fl = nl.read_flags()
         assert fl == 0, fl
         rows = nl.warp_rows.cpu().numpy()
-        if case == "two_density":
+        if case == "two_density" and cover_h >= 1.2:
             assert rows.max() > 192, "the interface warps were meant to overflow the builder's staging area"
         # exact symmetric neighbour sets are subsets of the rows
         q = torch.arange(0, dg.n, 97, dtype=torch.int32, device="cuda")
