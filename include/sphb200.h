@@ -210,6 +210,9 @@ typedef struct sphb_nlist {
                                   lists as long as every one of them stays within its own bounds */
     const float *level_dmax;   /* with margins: device [max(nlevels, 1)] upper bounds of s_i h_i over the records of each
                                   level of the cell list (one entry for a single grid): bounds the cells searched */
+    const float *cell_dmax;    /* optional device [ncell] upper bounds of s_i h_i over the records of each cell (0 for an empty
+                                  cell): cells beyond the targets' own reach are then searched only where their records'
+                                  allowances bridge the gap -- a fast record does not widen the search of a quiet region */
 } sphb_nlist;
 int64_t sphb_nlist_pool_rows(int64_t n);
 int64_t sphb_sizeof_nlist(void); /* sizeof(sphb_nlist), for bindings to check their own layout against */

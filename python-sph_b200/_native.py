@@ -70,7 +70,7 @@ class NList(C.Structure):
     _fields_ = [("n", C.c_int64), ("warp_off", C.c_void_p), ("warp_rows", C.c_void_p), ("pool", C.c_void_p),
                 ("pool_rows", C.c_int64), ("cursor", C.c_void_p), ("flags", C.c_void_p), ("posh_build", C.c_void_p),
                 ("cover_h", C.c_double), ("skin", C.c_double), ("maxima", C.c_void_p), ("margins", C.c_void_p),
-                ("level_dmax", C.c_void_p)]
+                ("level_dmax", C.c_void_p), ("cell_dmax", C.c_void_p)]
 
 
 NL_NONE = 0xFFFFFFFF

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
     pm.Aj = pm.Dj = 0.f;
     if (valid) sphb_ppm_of(pm, (uint32_t)j, f.w, pm.Aj, pm.Dj);
     pm.level_dmax = nl.level_dmax;
+    pm.cell_dmax = nl.cell_dmax;
     pm.hmax_u = hmax_global[0];
     const float cov = pm.cu * 1.000001f;                                          // >= every c_i
     const float Rj = __fadd_ru(pm.Aj, pm.Dj);

@@ -270,6 +270,7 @@ struct SphbPpm {
     float cu, su;              // uniform margins, or (margins != NULL) upper bounds of every c_i, s_i
     float Aj, Dj;
     const float *level_dmax;   // [levels] largest D_i of each level's records (one entry for a single grid); NULL: su h_max
+    const float *cell_dmax;    // [ncell] largest D_i of each cell's records, or NULL (then the level's bound is used)
     float hmax_u;              // single grid: h_max of all records
 };
 
@@ -367,6 +368,7 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
         const double xmin0 = xmin_f, xmax0 = xmax_f, ymin0 = ymin_f, ymax0 = ymax_f, zmin0 = zmin_f, zmax0 = zmax_f;
         const double Rg0 = sphb_warp_max(ing ? Rj : 0.f);        // PPM: Rj = Aj + Dj
         const float Dg = PPM ? sphb_warp_max(ing ? pm.Dj : 0.f) : 0.f;
+        const double Ag = PPM ? (double)sphb_warp_max(ing ? pm.Aj : 0.f) : 0.0;
 
         // group-local frame: centre of the box; err bounds the fp32 rounding of the re-centred test
         const float ox = 0.5f * (xmin_f + xmax_f), oy = 0.5f * (ymin_f + ymax_f), oz = 0.5f * (zmin_f + zmax_f);
@@ -385,17 +387,26 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
         double Rg = Rg0;
         float dpad = 0.f;
         const float hmax_b = (MULTI && g.nlev > 1) ? __ldg(g.level_hmax + lb) : (PPM ? pm.hmax_u : 0.f);
+        const float *cdm = nullptr;   // the level's slice of cell_dmax
+        double Rwide = 0.0;
         if (PPM) {
             const float dl = pm.level_dmax ? __ldg(pm.level_dmax + lb)
                                            : ((pm.su > 0.f) ? __fmul_ru(pm.su, 0.5f * sphb_radius_of_h((double)hmax_b, g.delta)) : 0.f);
-            Rg = Rg0 + (double)dl;
             dpad = __fadd_ru(dl, Dg);
+            if (pm.cell_dmax) {
+                // cells within the targets' own reach are always walked; farther ones only if THEIR records' allowances
+                // (or supports) bridge the gap -- the search of a quiet region is not widened by a fast record elsewhere
+                cdm = pm.cell_dmax + (G.cell_hmax - g.cell_hmax);
+                Rwide = Ag + (double)Dg + (double)dl;   // the farthest any cell's records can matter
+            } else {
+                Rg = Rg0 + (double)dl;
+            }
         }
         double Rw = Rg;
         if (SYM) {
             const float RHb = (PPM || (MULTI && g.nlev > 1))
                                   ? __fadd_ru(sphb_radius_of_h((double)hmax_b * (double)symscale, g.delta), dpad) : RH;
-            Rw = fmax(Rg, (double)RHb);
+            Rw = fmax(fmax(Rg, Rwide), (double)RHb);
         }
         // the group's box in the level's own coordinates
         const double xmin = xmin0 - G.sx, xmax = xmax0 - G.sx, ymin = ymin0 - G.sy, ymax = ymax0 - G.sy;
@@ -437,7 +448,8 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                     // extend the tight range outwards to the farthest cell whose h_max reaches the group
                     for (int cx = wl; cx < lo && cx <= wh; ++cx) {
                         const double hm = (double)G.cell_hmax[rowbase + cx] * (double)symscale;
-                        const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001 + (double)dpad;
+                        const double Rc = (PPM && cdm) ? fmax(Ag, (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001) + (double)Dg + (double)cdm[rowbase + cx] * 1.000001
+                                                       : (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001 + (double)dpad;
                         const double gx = sphb_axis_gap(xmin, xmax, cx, G.nx, G.cellx, G.bounded);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             lo = cx;
@@ -447,7 +459,8 @@ __device__ __forceinline__ int sphb_warp_scan(const SphbScanCtx &g, WS &ws, int 
                     }
                     for (int cx = wh; cx > hi && cx >= wl; --cx) {
                         const double hm = (double)G.cell_hmax[rowbase + cx] * (double)symscale;
-                        const double Rc = (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001 + (double)dpad;
+                        const double Rc = (PPM && cdm) ? fmax(Ag, (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001) + (double)Dg + (double)cdm[rowbase + cx] * 1.000001
+                                                       : (2.0 * hm * 1.000001 + (double)g.delta) * 1.00001 + (double)dpad;
                         const double gx = sphb_axis_gap(xmin, xmax, cx, G.nx, G.cellx, G.bounded);
                         if (hm > 0.0 && g2 + gx * gx < Rc * Rc) {
                             hi = cx;

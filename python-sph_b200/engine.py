@@ -47,11 +47,11 @@ class KeptLists:
     """sphb_nlist: neighbour lists that outlive kernels and steps, with the buffers they point to.
     Built from ONE cell list (dg); the drain kernels then only need the current sorted records."""
 
-    def __init__(self, engine, dg, cover_h, skin, pool_rows=None, margins=None, level_dmax=None):
+    def __init__(self, engine, dg, cover_h, skin, pool_rows=None, margins=None, level_dmax=None, cell_dmax=None):
         """margins (n,2) float32 = per-particle {cover, skin} in slot order (cover_h / skin are then their upper bounds),
         level_dmax: float32 upper bounds of skin_i h_i per level of the cell list"""
         lib, dev = engine.lib, engine.device
-        self.margins, self.level_dmax = margins, level_dmax
+        self.margins, self.level_dmax, self.cell_dmax = margins, level_dmax, cell_dmax
         self.posh_build = dg.posh
         n = dg.n
         nw = max(1, (n + 31) // 32)
@@ -68,7 +68,8 @@ class KeptLists:
         self.c = N.NList(n, self.warp_off.data_ptr(), self.warp_rows.data_ptr(), self.pool.data_ptr(), rows,
                          self.cursor.data_ptr(), self.flags.data_ptr(), dg.posh.data_ptr(), self.cover_h, self.skin,
                          self.flags.data_ptr() + 4, margins.data_ptr() if margins is not None else None,
-                         level_dmax.data_ptr() if level_dmax is not None else None)
+                         level_dmax.data_ptr() if level_dmax is not None else None,
+                         cell_dmax.data_ptr() if cell_dmax is not None else None)
         self.build_flags = 0
         self.moved = self.grown = 0.0
         self.used_d = self.used_g = 0.0
@@ -78,14 +79,14 @@ class KeptLists:
         """the lists of `src` seen through renamed slots (sphb_nlist_remap): same pool, cursor and flag words, other
         warp tables, build-time records and per-particle margins"""
         nl = cls.__new__(cls)
-        nl.margins, nl.level_dmax = margins, src.level_dmax
+        nl.margins, nl.level_dmax, nl.cell_dmax = margins, src.level_dmax, None   # (the builder alone reads cell_dmax)
         nl.posh_build = posh_build
         nl.n, nl.dg, nl.cover_h, nl.skin = int(n), src.dg, src.cover_h, src.skin
         nl.pool_rows, nl.warp_off, nl.warp_rows, nl.pool, nl.cursor, nl.flags = src.pool_rows, warp_off, warp_rows, src.pool, src.cursor, src.flags
         nl.c = N.NList(nl.n, warp_off.data_ptr(), warp_rows.data_ptr(), nl.pool.data_ptr(), nl.pool_rows, nl.cursor.data_ptr(),
                        nl.flags.data_ptr(), posh_build.data_ptr(), nl.cover_h, nl.skin, nl.flags.data_ptr() + 4,
                        margins.data_ptr() if margins is not None else None,
-                       src.level_dmax.data_ptr() if (margins is not None and src.level_dmax is not None) else None)
+                       src.level_dmax.data_ptr() if (margins is not None and src.level_dmax is not None) else None, None)
         nl.build_flags, nl.moved, nl.grown, nl.omega0 = src.build_flags, 0.0, 0.0, None
         nl.used_d = nl.used_g = 0.0
         return nl
@@ -485,10 +486,15 @@ class Engine:
 
     # -- kept neighbour lists (sphb_nlist) -------------------------------------------------------
     def level_dmax(self, dg, margins):
-        """float32 upper bounds of skin_i h_i (as the builder forms it) over the records of each level of the cell list"""
+        """float32 upper bounds of skin_i h_i (as the builder forms it) over the records of each level of the cell list,
+        and over the records of each cell"""
         h = dg.posh[:, 3]
         d = margins[:, 1].double() * (h * 1.00002 + dg.delta)
         d = torch.where((h > 0) & torch.isfinite(h), d, torch.full_like(d, float("inf")))
+        up = lambda t: torch.nextafter(t.float(), torch.full_like(t, float("inf")).float())
+        cell = torch.zeros(dg.grid.ncell, dtype=torch.float32, device=self.device)
+        cell.scatter_reduce_(0, dg.cell_id.long(), up(d), reduce="amax", include_self=True)
+        self._cell_dmax = cell
         if dg.levels is None:
             m = d.max().reshape(1) if d.numel() else torch.zeros(1, dtype=F64, device=self.device)
         else:
@@ -508,8 +514,10 @@ class Engine:
         hm = hmax if hmax is not None else self.hmax(dg.posh)
         om = torch.empty(dg.n, dtype=F64, device=self.device) if consts is not None else None
         ldm = self.level_dmax(dg, margins) if margins is not None else None
+        cdm = self._cell_dmax if margins is not None else None
+        self._cell_dmax = None
         for _ in range(3):
-            nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows, margins=margins, level_dmax=ldm)
+            nl = KeptLists(self, dg, cover_h, skin, pool_rows=pool_rows, margins=margins, level_dmax=ldm, cell_dmax=cdm)
             nl._hmax = hm
             nl.omega0 = om
             self._run("nl_build", self.lib.sphb_nlist_build, dg.cells(), _ptr(target), _ptr(hm), nl.ref(),
