@@ -57,6 +57,11 @@ typedef struct sphb_consts {
     double bisect_b;       /* INITIAL_BISECTION_SMOOTHLENGTH_B  :26 */
     double G;              /* G (gravity is outside this path; must be 0 for sphb_force) :35 */
     double gamma;          /* ADIABATIC_INDEX                   :41 */
+    const double *mass;    /* optional DEVICE array of PER-PARTICLE masses (the reference authors' own
+                              NOTE at pyfluid.py:3-4), indexed like the particle arrays of the call (sorted slots for the
+                              gather kernels); NULL: every particle has particle_mass, which is the reference.  With it
+                              every "PARTICLE_MASS" inside a sum over i becomes m_i (:95,216,327,340,474) and the one of
+                              var_density / zetaprime becomes the target's m_j (:115,238) */
 } sphb_consts;
 
 /* Cell grid: edge `cell` in y and z, edge cell/xdiv in x (x is the fastest axis: finer x cells make the row

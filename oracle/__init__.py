@@ -130,7 +130,9 @@ class Oracle:
     def var_density_arr(self, h):
         """pyfluid.py:240 (same pow() the C side uses)"""
         h = _f64(h)
-        return np.array([self.k["PARTICLE_MASS"] * (self.k["COUPLING_CONST"] / float(x)) ** 3 for x in h])
+        m = getattr(self, "_masses", None)
+        return np.array([(self.k["PARTICLE_MASS"] if m is None else float(m[i])) * (self.k["COUPLING_CONST"] / float(x)) ** 3
+                         for i, x in enumerate(h)])
 
     def omega_j(self, j, pos, rho_j, h_j):
         """pyfluid.py:91 for each j in the list."""
@@ -291,6 +293,18 @@ class Oracle:
     def set_wide(self, on):
         """bench.py only: split each per-particle O(N) loop over the OpenMP threads"""
         self.L.oracle_set_wide(C.c_int(1 if on else 0))
+
+    def set_masses(self, m):
+        """per-particle masses (the reference has one scalar PARTICLE_MASS, pyfluid.py:3-5): every
+        PARTICLE_MASS inside a sum over i becomes m[i], the one of var_density / zetaprime the target's m[j].
+        None: back to the reference's scalar.  The array is process-wide state of the oracle library, like its
+        thread count; keep `m` alive until it is unset."""
+        if m is None:
+            self._masses = None
+            self.L.oracle_set_masses(None)
+            return
+        self._masses = np.ascontiguousarray(m, dtype=np.float64)
+        self.L.oracle_set_masses(self._masses.ctypes.data_as(C.c_void_p))
 
     def num_threads(self):
         return int(self.L.oracle_num_threads())

@@ -24,7 +24,7 @@ class Consts(C.Structure):
         ("newton_limit", C.c_int32), ("bisect_limit", C.c_int32),
         ("alpha", C.c_double), ("beta", C.c_double), ("epsilon", C.c_double),
         ("bisect_tol", C.c_double), ("bisect_a", C.c_double), ("bisect_b", C.c_double),
-        ("G", C.c_double), ("gamma", C.c_double),
+        ("G", C.c_double), ("gamma", C.c_double), ("mass", C.c_void_p),
     ]
 
 

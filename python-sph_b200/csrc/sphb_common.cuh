@@ -188,11 +188,21 @@ __device__ __forceinline__ double sphb_m4_fp(double q)
 }
 
 // pyfluid.py:237-238 var_density(): m (eta/h)^3
-__device__ __forceinline__ double sphb_var_density(const sphb_consts &k, double h)
+__device__ __forceinline__ double sphb_var_density_m(const sphb_consts &k, double m, double h)
 {
     double t = k.coupling_const / h;
-    return k.particle_mass * (t * t * t);
+    return m * (t * t * t);
 }
+__device__ __forceinline__ double sphb_var_density(const sphb_consts &k, double h)
+{
+    return sphb_var_density_m(k, k.particle_mass, h);
+}
+
+// per-particle masses (sphb_consts.mass): the mass of particle i; the weight a pair term carries inside a sum (m_i, or
+// exactly 1 when the uniform mass is applied once after the sum, as the kernels always did); and that final factor
+__device__ __forceinline__ double sphb_mass_of(const sphb_consts &k, size_t i) { return k.mass ? __ldg(k.mass + i) : k.particle_mass; }
+__device__ __forceinline__ double sphb_mass_w(const sphb_consts &k, size_t i) { return k.mass ? __ldg(k.mass + i) : 1.0; }
+__device__ __forceinline__ double sphb_mass_after(const sphb_consts &k) { return k.mass ? 1.0 : k.particle_mass; }
 
 // ---------------------------------------------------------------------------------------------
 // warp reductions (all 32 lanes participate)

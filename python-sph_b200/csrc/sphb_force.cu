@@ -29,7 +29,7 @@ __global__ void k_eos(const double *__restrict__ posh, const double *__restrict_
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double h = posh[4 * i + 3];
-    const double rho = rho_in ? rho_in[i] : sphb_var_density(k, h);
+    const double rho = rho_in ? rho_in[i] : sphb_var_density_m(k, sphb_mass_of(k, (size_t)i), h);
     // (ADIABATIC_INDEX - 1) * energy * density
     const double P = P_in ? P_in[i] : __dmul_rn(__dmul_rn(k.gamma - 1.0, u[i]), rho);
     if (P < 0.0) atomicOr(&status->flags, SPHB_ST_NEG_P);
@@ -87,7 +87,7 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
             id = sphb_list_get(ws, lane, n_ + 3);
             sphb_load4(posh, id, D[0], D[1], D[2], D[3]);
         }
-        sphb_force_pair2<GRAV>(recB, recC, bgrav, ia, ib, A, B, n_ + 1 < cnt, k, a);
+        sphb_force_pair2<GRAV, false, false, false, true>(recB, recC, bgrav, ia, ib, A, B, n_ + 1 < cnt, k, a);
         n_ += 2;
         if (n_ >= cnt) break;
         A[0] = A[1] = A[2] = B[0] = B[1] = B[2] = 0.0;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
             ib = sphb_list_get(ws, lane, n_ + 3);
             sphb_load4(posh, ib, B[0], B[1], B[2], B[3]);
         }
-        sphb_force_pair2<GRAV>(recB, recC, bgrav, ic, id, C, D, n_ + 1 < cnt, k, a);
+        sphb_force_pair2<GRAV, false, false, false, true>(recB, recC, bgrav, ic, id, C, D, n_ + 1 < cnt, k, a);
         n_ += 2;
     }
 #elif SPHB_FORCE_ILP == 2
@@ -115,7 +115,7 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
             ib = sphb_list_get(ws, lane, n_ + 1);
             sphb_load4(posh, ib, B[0], B[1], B[2], B[3]);
         }
-        sphb_force_pair2<GRAV>(recB, recC, bgrav, ia, ib, A, B, n_ + 1 < cnt, k, a);
+        sphb_force_pair2<GRAV, false, false, false, true>(recB, recC, bgrav, ia, ib, A, B, n_ + 1 < cnt, k, a);
     }
 #else
     double ax, ay, az, ah, bx, by, bz, bh;
@@ -130,14 +130,14 @@ __device__ __forceinline__ void sphb_force_flush(const double *posh, const doubl
             ib = sphb_list_get(ws, lane, n_ + 1);
             sphb_load4(posh, ib, bx, by, bz, bh);
         }
-        sphb_force_pair<GRAV>(recB, recC, bgrav, ia, ax, ay, az, ah, k, a);
+        sphb_force_pair<GRAV>(recB, recC, bgrav, ia, ax, ay, az, ah, k, a, sphb_mass_w(k, ia));
         ++n_;
         if (n_ >= cnt) break;
         if (n_ + 1 < cnt) {
             ia = sphb_list_get(ws, lane, n_ + 1);
             sphb_load4(posh, ia, ax, ay, az, ah);
         }
-        sphb_force_pair<GRAV>(recB, recC, bgrav, ib, bx, by, bz, bh, k, a);
+        sphb_force_pair<GRAV>(recB, recC, bgrav, ib, bx, by, bz, bh, k, a, sphb_mass_w(k, ib));
         ++n_;
     }
 #endif
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_FORCE)
         flush(L.count());
     }
     if (tgt) {
-        const double m = k.particle_mass;
+        const double m = sphb_mass_after(k);
         acc[3 * j] = m * a.ax;
         acc[3 * j + 1] = m * a.ay;
         acc[3 * j + 2] = m * a.az;
@@ -250,7 +250,7 @@ __global__ void k_pair_terms(const double *__restrict__ posh, const double *__re
             const double d[3] = {dx / dist, dy / dist, dz / dist};                            // direction_i_j
             for (int c = 0; c < 3; ++c) {
                 const double gJ = wj * d[c], gI = wi * d[c];
-                a[c] = -k.particle_mass * ((Aj * gJ + Ai * gI) + pi * 0.5 * (gJ + gI));
+                a[c] = -sphb_mass_of(k, i) * ((Aj * gJ + Ai * gI) + pi * 0.5 * (gJ + gI));
             }
         }
         acc_out[3 * p] = a[0];
@@ -263,7 +263,7 @@ __global__ void k_pair_terms(const double *__restrict__ posh, const double *__re
         if (!same) {
             const double f = sphb_grav_force(dist, hj) + sphb_grav_force(dist, hi);
             const double d[3] = {dx / dist, dy / dist, dz / dist};
-            for (int c = 0; c < 3; ++c) gq[c] = -k.G / 2.0 * k.particle_mass * (f * d[c]);
+            for (int c = 0; c < 3; ++c) gq[c] = -k.G / 2.0 * sphb_mass_of(k, i) * (f * d[c]);
         }
         for (int c = 0; c < 3; ++c) grav_out[3 * p + c] = gq[c];
     }
@@ -272,7 +272,7 @@ __global__ void k_pair_terms(const double *__restrict__ posh, const double *__re
         if (!same && bgrav) {
             const double wj = sphb_m4_fp(dist / hj) * gj, wi = sphb_m4_fp(dist / hi) * gi;
             const double d[3] = {dx / dist, dy / dist, dz / dist};
-            for (int c = 0; c < 3; ++c) cq[c] = -k.particle_mass * (bgrav[j] * (wj * d[c]) + bgrav[i] * (wi * d[c]));
+            for (int c = 0; c < 3; ++c) cq[c] = -sphb_mass_of(k, i) * (bgrav[j] * (wj * d[c]) + bgrav[i] * (wi * d[c]));
         }
         for (int c = 0; c < 3; ++c) corr_out[3 * p + c] = cq[c];
     }
@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(GRAV_TILE)
     k_gravity_direct(const double *__restrict__ posh, long long n, sphb_consts k, int accumulate, double *__restrict__ acc)
 {
     __shared__ double4 tile[GRAV_TILE];
+    __shared__ double tmass[GRAV_TILE];   // the candidates' weights: m_i with per-particle masses, else exactly 1
     const long long j = (long long)blockIdx.x * GRAV_TILE + threadIdx.x;
     double xj = 0.0, yj = 0.0, zj = 0.0, hj = 1.0;
     if (j < n) sphb_load4(posh, (size_t)j, xj, yj, zj, hj);
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(GRAV_TILE)
         if (i < n) sphb_load4(posh, (size_t)i, c.x, c.y, c.z, c.w);
         __syncthreads();
         tile[threadIdx.x] = c;
+        tmass[threadIdx.x] = (i < n) ? sphb_mass_w(k, (size_t)i) : 0.0;
         __syncthreads();
         const int nt = (int)((n - t0) < GRAV_TILE ? (n - t0) : GRAV_TILE);
         for (int q = 0; q < nt; ++q) {
@@ -352,14 +354,14 @@ __global__ void __launch_bounds__(GRAV_TILE)
             if (dx == 0.0 && dy == 0.0 && dz == 0.0) continue;   // np.array_equal(rj, ri) -> 0, pyfluid.py:422
             const double d = __dsqrt_rn(sphb_d2(dx, dy, dz));
             const double f = sphb_grav_force(d, hj) + sphb_grav_force(d, p.w);
-            const double s = f / d;
+            const double s = tmass[q] * (f / d);
             ax = fma(s, dx, ax);
             ay = fma(s, dy, ay);
             az = fma(s, dz, az);
         }
     }
     if (j < n) {
-        const double w = -k.G / 2.0 * k.particle_mass;
+        const double w = -k.G / 2.0 * sphb_mass_after(k);
         if (accumulate) {
             acc[3 * j] += w * ax;
             acc[3 * j + 1] += w * ay;

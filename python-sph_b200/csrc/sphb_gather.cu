@@ -23,45 +23,45 @@
 //  2: no look-ahead, fewer registers; 0: one entry at a time with one record of look-ahead)
 template <bool XI = false>
 __device__ __forceinline__ void sphb_own_flush(const double *posh, const SphbWarpShared &ws, int lane, int cnt,
-                                               SphbOwnAcc &a)
+                                               SphbOwnAcc &a, const double *mass = nullptr)
 {
 #if SPHB_OWN_ILP == 1
     double A[4], B[4], C[4], D[4];
     A[0] = A[1] = A[2] = B[0] = B[1] = B[2] = 0.0;
-    if (cnt > 0) sphb_load_posh(posh, sphb_list_get(ws, lane, 0), A[0], A[1], A[2], A[3]);
-    if (cnt > 1) sphb_load_posh(posh, sphb_list_get(ws, lane, 1), B[0], B[1], B[2], B[3]);
+    if (cnt > 0) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, 0), A[0], A[1], A[2], A[3]);
+    if (cnt > 1) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, 1), B[0], B[1], B[2], B[3]);
     int k = 0;
     while (k < cnt) {
         C[0] = C[1] = C[2] = D[0] = D[1] = D[2] = 0.0;
-        if (k + 2 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 2), C[0], C[1], C[2], C[3]);
-        if (k + 3 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 3), D[0], D[1], D[2], D[3]);
-        sphb_own_pair2<XI>(A, B, k + 1 < cnt, a);
+        if (k + 2 < cnt) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k + 2), C[0], C[1], C[2], C[3]);
+        if (k + 3 < cnt) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k + 3), D[0], D[1], D[2], D[3]);
+        sphb_own_pair2<XI, true>(A, B, k + 1 < cnt, a);
         k += 2;
         if (k >= cnt) break;
-        if (k + 2 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 2), A[0], A[1], A[2], A[3]);
-        if (k + 3 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 3), B[0], B[1], B[2], B[3]);
-        sphb_own_pair2<XI>(C, D, k + 1 < cnt, a);
+        if (k + 2 < cnt) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k + 2), A[0], A[1], A[2], A[3]);
+        if (k + 3 < cnt) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k + 3), B[0], B[1], B[2], B[3]);
+        sphb_own_pair2<XI, true>(C, D, k + 1 < cnt, a);
         k += 2;
     }
 #elif SPHB_OWN_ILP == 2
     for (int k = 0; k < cnt; k += 2) {
         double A[4], B[4];
         B[0] = B[1] = B[2] = 0.0;
-        sphb_load_posh(posh, sphb_list_get(ws, lane, k), A[0], A[1], A[2], A[3]);
-        if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), B[0], B[1], B[2], B[3]);
-        sphb_own_pair2<XI>(A, B, k + 1 < cnt, a);
+        sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k), A[0], A[1], A[2], A[3]);
+        if (k + 1 < cnt) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k + 1), B[0], B[1], B[2], B[3]);
+        sphb_own_pair2<XI, true>(A, B, k + 1 < cnt, a);
     }
 #else
     double ax, ay, az, ah, bx, by, bz, bh;
-    if (cnt > 0) sphb_load_posh(posh, sphb_list_get(ws, lane, 0), ax, ay, az, ah);
+    if (cnt > 0) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, 0), ax, ay, az, ah);
     int k = 0;
     while (k < cnt) {
-        if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), bx, by, bz, bh);
-        sphb_own_pair<XI>(ax, ay, az, a);
+        if (k + 1 < cnt) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k + 1), bx, by, bz, bh);
+        sphb_own_pair<XI>(ax, ay, az, a, ah);
         ++k;
         if (k >= cnt) break;
-        if (k + 1 < cnt) sphb_load_posh(posh, sphb_list_get(ws, lane, k + 1), ax, ay, az, ah);
-        sphb_own_pair<XI>(bx, by, bz, a);
+        if (k + 1 < cnt) sphb_load_posw(posh, mass, sphb_list_get(ws, lane, k + 1), ax, ay, az, ah);
+        sphb_own_pair<XI>(bx, by, bz, a, bh);
         ++k;
     }
 #endif
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     bool flushed = false;   // warp-uniform
     auto flush = [&](int n_) {
         flushed = true;
-        sphb_own_flush<XI>(c.posh, ws, lane, n_, a);
+        sphb_own_flush<XI>(c.posh, ws, lane, n_, a, k.mass);
     };
     if (PRODUCE) {
         const float cov = (float)lists.cover * 1.000001f;
@@ -119,18 +119,18 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
     } else {
         sphb_warp_scan<false, SPHB_OWN_FLUSH_ROWS, MULTI>(g, ws, lane, tgt, f.x, f.y, f.z, Rj, thr, cid, 0.f, L, flush);
     }
-    sphb_own_flush<XI>(c.posh, ws, lane, L.count(), a);
+    sphb_own_flush<XI>(c.posh, ws, lane, L.count(), a, k.mass);
     if (tgt) {
-        const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
+        const double pref = sphb_mass_after(k) / (SPHB_PI * (h * h * h));
         const double rs = pref * a.sumF;
         const double ds = -(pref / h) * a.sumG;
         if (rho_sum) rho_sum[j] = rs;
         if (dwdh_sum) dwdh_sum[j] = ds;
-        const double rho = rho_in ? rho_in[j] : sphb_var_density(k, h);
+        const double rho = rho_in ? rho_in[j] : sphb_var_density_m(k, sphb_mass_of(k, (size_t)j), h);
         if (omega) omega[j] = 1.0 + h / (3.0 * rho) * ds;   // pyfluid.py:97
         if (XI) {
             // xi_j = -h/(3 rho) sum_i m dphi/dh = -h/(3 rho) * (-(m/h^2) sum pX), pyfluid.py:401-410
-            const double sx = k.particle_mass * (-(1.0 / (h * h)) * a.sumX);
+            const double sx = sphb_mass_after(k) * (-(1.0 / (h * h)) * a.sumX);
             xi_out[j] = -h / (3.0 * rho) * sx;
         }
         if (ngb_count) ngb_count[j] = a.nn;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
             bool flushed = false;   // warp-uniform: did a list overflow during this scan?
             auto flush = [&](int n_) {
                 flushed = true;
-                sphb_own_flush(c.posh, ws, lane, n_, a);
+                sphb_own_flush(c.posh, ws, lane, n_, a, k.mass);
             };
             if (PRODUCE && first_scan) {
                 // symmetric support, every h taken at its cover: complete for sphb_force at any h below the cover
@@ -228,13 +228,13 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
             have_lists = !flushed;
             h_cover = pend ? hs : 0.0;
         }
-        sphb_own_flush(c.posh, ws, lane, pend ? cnt : 0, a);
+        sphb_own_flush(c.posh, ws, lane, pend ? cnt : 0, a, k.mass);
         if (want == 1) {
             // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
-            const double pref = k.particle_mass / (SPHB_PI * (h_cur * h_cur * h_cur));
+            const double pref = sphb_mass_after(k) / (SPHB_PI * (h_cur * h_cur * h_cur));
             const double rho = pref * a.sumF;
             const double sdh = -(pref / h_cur) * a.sumG;
-            const double vd = sphb_var_density(k, h_cur);
+            const double vd = sphb_var_density_m(k, sphb_mass_of(k, (size_t)j), h_cur);
             const double zeta = vd - rho;
             const double zetap = -sdh - 3.0 * vd / h_cur;
             const double h_new = h_cur - zeta / zetap;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(SPHB_THREADS, SPHB_MINB_OWN)
             }
             h_cur = h_new;
         } else if (want == 2) {
-            omega_out[j] = sphb_omega_from_sumG(k, h_cur, a.sumG);
+            omega_out[j] = sphb_omega_from_sumG(k, h_cur, a.sumG, sphb_mass_of(k, (size_t)j), sphb_mass_after(k));
             want = 0;
         }
         __syncwarp();
@@ -326,8 +326,9 @@ __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, 
                 const double q = sqrt(d2) * hinv;
                 double f, fp;
                 sphb_m4(q, f, fp);
-                sum += f;
-                sumg += fma(q, fp, 3.0 * f);
+                const double w = sphb_mass_w(k, i);
+                sum += w * f;
+                sumg += w * fma(q, fp, 3.0 * f);
             }
         }
     }
@@ -346,7 +347,7 @@ __device__ double sphb_block_density(const sphb_cells &c, const sphb_consts &k, 
         totg += red[SPHB_WARPS + w];
     }
     if (sumG_out) *sumG_out = totg;
-    return k.particle_mass / (SPHB_PI * (h * h * h)) * tot;
+    return sphb_mass_after(k) / (SPHB_PI * (h * h * h)) * tot;
 }
 
 // bisection_h, pyfluid.py:123-153 (density at h_a / h_b is re-used instead of recomputed: same value)
@@ -363,15 +364,16 @@ __global__ void __launch_bounds__(SPHB_THREADS)
         sphb_load_posh(c.posh, j, xj, yj, zj, hj);
         const float4 f = __ldg(reinterpret_cast<const float4 *>(c.frec) + j);
         double h_a = k.bisect_a, h_b = k.bisect_b;
-        double zeta_a = sphb_var_density(k, h_a) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, h_a, red);
-        double zeta_b = sphb_var_density(k, h_b) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, h_b, red);
+        const double mj = sphb_mass_of(k, (size_t)j);
+        double zeta_a = sphb_var_density_m(k, mj, h_a) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, h_a, red);
+        double zeta_b = sphb_var_density_m(k, mj, h_b) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, h_b, red);
         int i = 0, oob = 0, res = 2;
         double root = CUDART_NAN;
         while (i < k.bisect_limit) {
             if (zeta_a * zeta_b > 0.0) ++oob;   // "ERROR: Root out of bisection bounds."
             const double cand = (h_a + h_b) / 2.0;
             const double zeta_root =
-                sphb_var_density(k, cand) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, cand, red);
+                sphb_var_density_m(k, mj, cand) - sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, cand, red);
             if (fabs(zeta_root) < k.bisect_tol) {
                 root = cand;
                 res = 1;
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(SPHB_THREADS)
         if (omega_out && res == 1) {   // Omega at the bisection root (algebraic density, like the step)
             double sg = 0.0;
             sphb_block_density(c, k, xj, yj, zj, f.x, f.y, f.z, root, red, &sg);
-            om = sphb_omega_from_sumG(k, root, sg);
+            om = sphb_omega_from_sumG(k, root, sg, mj, sphb_mass_after(k));
         }
         if (threadIdx.x == 0) {
             const long long o = indexed_by_slot ? (long long)j : e;

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_BUILD)
         nl.warp_off[w] = row0;
         nl.warp_rows[w] = over ? 0u : used;
     }
-    if (OMEGA && tgt) omega[j] = over ? CUDART_NAN : sphb_omega_from_sumG(kc, h, oa.sumG);
+    if (OMEGA && tgt) omega[j] = over ? CUDART_NAN : sphb_omega_from_sumG(kc, h, oa.sumG, kc.particle_mass, kc.particle_mass);
 }
 
 // did any record leave what the lists were built to cover?  (half of a bound used up: SPHB_NL_AGING)
@@ -259,6 +259,17 @@ __device__ __forceinline__ void nl_fetch(const double *__restrict__ posh, uint32
     if (!real) p[0] = 1e150;
 }
 
+// the same for the own-support sums with per-particle masses: m_i rides in the record's fourth component (h_i is not
+// used by those sums)
+__device__ __forceinline__ void nl_fetch_m(const double *__restrict__ posh, const double *__restrict__ mass, uint32_t s,
+                                           uint32_t self, double (&p)[4])
+{
+    const bool real = s != SPHB_NL_NONE;
+    sphb_load_posh(posh, (size_t)(real ? s : self), p[0], p[1], p[2], p[3]);
+    p[3] = real ? __ldg(mass + s) : 0.0;
+    if (!real) p[0] = 1e150;
+}
+
 __device__ __forceinline__ uint32_t nl_row(const uint32_t *__restrict__ p, int k, int nrows)
 {
     return (k < nrows) ? __ldg(p + (size_t)k * 32) : SPHB_NL_NONE;
@@ -266,33 +277,38 @@ __device__ __forceinline__ uint32_t nl_row(const uint32_t *__restrict__ p, int k
 
 // sumF, sumG (, nn) over the lane's rows: two entries side by side (two independent FP64 chains), the records of the
 // next two rows and the indices of the two after them in flight
+template <bool MASS = false>
 __device__ __forceinline__ void nl_own_drain(const double *__restrict__ posh, const uint32_t *__restrict__ rows, int nrows,
-                                             int lane, uint32_t self, SphbOwnAcc &a)
+                                             int lane, uint32_t self, SphbOwnAcc &a, const double *__restrict__ mass = nullptr)
 {
     const uint32_t *p = rows + lane;
     uint32_t i0 = nl_row(p, 0, nrows), i1 = nl_row(p, 1, nrows), i2 = nl_row(p, 2, nrows), i3 = nl_row(p, 3, nrows);
     double A[4], B[4], C[4], D[4];
-    nl_fetch(posh, i0, self, A);
-    nl_fetch(posh, i1, self, B);
+    auto fetch = [&](uint32_t s, double (&r)[4]) {
+        if (MASS) nl_fetch_m(posh, mass, s, self, r); else nl_fetch(posh, s, self, r);
+    };
+    fetch(i0, A);
+    fetch(i1, B);
     int k = 0;
     while (k < nrows) {
-        nl_fetch(posh, i2, self, C);
-        nl_fetch(posh, i3, self, D);
+        fetch(i2, C);
+        fetch(i3, D);
         i0 = nl_row(p, k + 4, nrows);
         i1 = nl_row(p, k + 5, nrows);
-        sphb_own_pair2<false>(A, B, true, a);
+        sphb_own_pair2<false, MASS>(A, B, true, a);
         k += 2;
         if (k >= nrows) break;
-        nl_fetch(posh, i0, self, A);
-        nl_fetch(posh, i1, self, B);
+        fetch(i0, A);
+        fetch(i1, B);
         i2 = nl_row(p, k + 4, nrows);
         i3 = nl_row(p, k + 5, nrows);
-        sphb_own_pair2<false>(C, D, true, a);
+        sphb_own_pair2<false, MASS>(C, D, true, a);
         k += 2;
     }
 }
 
 // K2 on kept lists: density / density_arr (pyfluid.py:218-232), omega_j / omega_arr (:91-105)
+template <bool MASS>
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
     k_nl_density_omega(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
                        const double *__restrict__ rho_in, double *__restrict__ rho_sum, double *__restrict__ dwdh_sum,
@@ -314,14 +330,14 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
     a.nn = 0;
     const int nrows = (int)nl.warp_rows[w];
     const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
-    nl_own_drain(posh, rows, nrows, lane, valid ? (uint32_t)j : 0u, a);
+    nl_own_drain<MASS>(posh, rows, nrows, lane, valid ? (uint32_t)j : 0u, a, k.mass);
     if (tgt) {
-        const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
+        const double pref = (MASS ? 1.0 : k.particle_mass) / (SPHB_PI * (h * h * h));
         const double rs = pref * a.sumF;
         const double ds = -(pref / h) * a.sumG;
         if (rho_sum) rho_sum[j] = rs;
         if (dwdh_sum) dwdh_sum[j] = ds;
-        const double rho = rho_in ? rho_in[j] : sphb_var_density(k, h);
+        const double rho = rho_in ? rho_in[j] : sphb_var_density_m(k, MASS ? __ldg(k.mass + j) : k.particle_mass, h);
         if (omega) omega[j] = 1.0 + h / (3.0 * rho) * ds;   // pyfluid.py:97
         if (ngb_count) ngb_count[j] = a.nn;
     }
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
 // pass over the rows.  What the lists cannot serve -- an iterate outside (0, cover_h h_build], or no convergence
 // within the limit (the reference then bisects over all particles, :178-179) -- sets SPHB_NL_BROKEN: the caller
 // redoes the step with the scanning kernels, which replay the reference to the letter.
-template <bool FUSED>
+template <bool FUSED, bool MASS>
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
     k_nl_newton_h(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
                   const double *__restrict__ h_guess, double *__restrict__ h_out, double *__restrict__ omega_out, double *__restrict__ posh_out,
@@ -359,6 +375,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
     const int nrows = (int)nl.warp_rows[w];
     const uint32_t *rows = nl.pool + (size_t)nl.warp_off[w] * 32;
     const uint32_t self = valid ? (uint32_t)j : 0u;
+    const double mj = (MASS && valid) ? __ldg(k.mass + j) : k.particle_mass;   // (uniform: a constant-bank operand)
     // what the lane needs next: 1 = the sums of a Newton iterate at h_cur, 2 = sum m dW/dh at the converged h_cur
     // (FUSED: Omega at the solved h, pyfluid.py:518), 0 = nothing
     int want = tgt ? 1 : 0, it = 0, fl = 0;
@@ -368,13 +385,13 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
         a.hinv = 1.0 / h_cur;
         a.sumF = a.sumG = a.sumX = 0.0;
         a.nn = 0;
-        nl_own_drain(posh, rows, nrows, lane, self, a);
+        nl_own_drain<MASS>(posh, rows, nrows, lane, self, a, k.mass);
         if (want == 1) {
             // newton_smoothlength_iteration, pyfluid.py:155-163 (zetaprime with the rho-free identity)
-            const double pref = k.particle_mass / (SPHB_PI * (h_cur * h_cur * h_cur));
+            const double pref = (MASS ? 1.0 : k.particle_mass) / (SPHB_PI * (h_cur * h_cur * h_cur));
             const double rho = pref * a.sumF;
             const double sdh = -(pref / h_cur) * a.sumG;
-            const double vd = sphb_var_density(k, h_cur);
+            const double vd = sphb_var_density_m(k, mj, h_cur);
             const double zeta = vd - rho;
             const double zetap = -sdh - 3.0 * vd / h_cur;
             const double h_new = h_cur - zeta / zetap;
@@ -393,7 +410,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
             }
             h_cur = h_new;
         } else if (want == 2) {
-            omega_out[j] = sphb_omega_from_sumG(k, h_cur, a.sumG);
+            omega_out[j] = sphb_omega_from_sumG(k, h_cur, a.sumG, mj, MASS ? 1.0 : k.particle_mass);
             want = 0;
         }
         __syncwarp();
@@ -425,7 +442,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_OWN)
 // K4 on kept lists: energy_rate / _arr (pyfluid.py:316-361), Pi (:261-285), fluid_accel_viscosity_comp (:459-474),
 // acceleration / _arr (:477-493) with G = 0.  posh carries the CURRENT h; recB / recC are sphb_eos's records, or
 // (DENSE) recB and sphb_nlist_eos's dense {rho, cs}.
-template <bool DENSE>
+template <bool DENSE, bool MASS>
 __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
     k_nl_force(sphb_nlist nl, sphb_consts k, const uint8_t *__restrict__ target, const double *__restrict__ posh,
                const double *__restrict__ recB, const double *__restrict__ recC, double *__restrict__ acc,
@@ -479,7 +496,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
             nl_fetch(recB, i2, self, VC);
             nl_fetch(recB, i3, self, VD);
             uint32_t n0 = nl_row(p, kk + 4, nrows), n1 = nl_row(p, kk + 5, nrows);
-            sphb_force_pair2<false, DENSE, true>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a,
+            sphb_force_pair2<false, DENSE, true, MASS>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a,
                                                  i0 != SPHB_NL_NONE, VA, VB);
             kk += 2;
             if (kk >= nrows) break;
@@ -491,7 +508,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
             nl_fetch(recB, i1, self, VB);
             n0 = nl_row(p, kk + 4, nrows);
             n1 = nl_row(p, kk + 5, nrows);
-            sphb_force_pair2<false, DENSE, true>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a,
+            sphb_force_pair2<false, DENSE, true, MASS>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a,
                                                  i2 != SPHB_NL_NONE, VC, VD);
             i2 = n0;
             i3 = n1;
@@ -509,7 +526,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
             nl_fetch(posh, i2, self, C);
             nl_fetch(posh, i3, self, D);
             uint32_t n0 = nl_row(p, kk + 4, nrows), n1 = nl_row(p, kk + 5, nrows);
-            sphb_force_pair2<false, DENSE>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a, i0 != SPHB_NL_NONE);
+            sphb_force_pair2<false, DENSE, false, MASS>(recB, recC, nullptr, i0, i1, A, B, i1 != SPHB_NL_NONE, k, a, i0 != SPHB_NL_NONE);
             kk += 2;
             if (kk >= nrows) break;
             i0 = n0;
@@ -518,7 +535,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
             nl_fetch(posh, i1, self, B);
             n0 = nl_row(p, kk + 4, nrows);
             n1 = nl_row(p, kk + 5, nrows);
-            sphb_force_pair2<false, DENSE>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a, i2 != SPHB_NL_NONE);
+            sphb_force_pair2<false, DENSE, false, MASS>(recB, recC, nullptr, i2, i3, C, D, i3 != SPHB_NL_NONE, k, a, i2 != SPHB_NL_NONE);
             i2 = n0;
             i3 = n1;
             kk += 2;
@@ -526,7 +543,7 @@ __global__ void __launch_bounds__(NL_THREADS, SPHB_MINB_NL_FORCE)
     }
 #endif
     if (tgt) {
-        const double m = k.particle_mass;
+        const double m = MASS ? 1.0 : k.particle_mass;
         acc[3 * j] = m * a.ax;
         acc[3 * j + 1] = m * a.ay;
         acc[3 * j + 2] = m * a.az;
@@ -662,7 +679,7 @@ extern "C" int sphb_nlist_build(const sphb_cells *cells, const uint8_t *target, 
                                 const sphb_nlist *nl, const sphb_consts *k, double *omega, void *stream)
 {
     SPHB_RANGE();
-    if (omega && !k) return SPHB_E_ARG;
+    if (omega && (!k || k->mass)) return SPHB_E_ARG;   // per-particle masses: Omega comes from sphb_nlist_density_omega
     if (!cells || cells->n < 0 || !cells->cell_start || !cells->cell_hmax || !cells->cell_id || !cells->posh ||
         !cells->frec || !hmax_global || !nl_ok(nl) || nl->n != cells->n || nl->posh_build != cells->posh ||
         (cells->nlevels > 1 && (cells->nlevels > SPHB_MAX_LEVELS || !cells->levels || !cells->level_hmax)))
@@ -759,8 +776,12 @@ extern "C" int sphb_nlist_density_omega(const sphb_nlist *nl, const sphb_consts 
     SPHB_RANGE();
     if (!nl_ok(nl) || !k || !posh) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
-    k_nl_density_omega<<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, rho_in, rho_sum,
-                                                                                 dwdh_sum, omega, ngb_count);
+    if (k->mass)
+        k_nl_density_omega<true><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, rho_in, rho_sum,
+                                                                                           dwdh_sum, omega, ngb_count);
+    else
+        k_nl_density_omega<false><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, rho_in, rho_sum,
+                                                                                            dwdh_sum, omega, ngb_count);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
@@ -772,12 +793,15 @@ extern "C" int sphb_nlist_newton_h(const sphb_nlist *nl, const sphb_consts *k, c
     SPHB_RANGE();
     if (!nl_ok(nl) || !k || !posh || !h_out || !status || posh_out == posh) return SPHB_E_ARG;
     if (nl->n == 0) return SPHB_OK;
-    if (omega_out)
-        k_nl_newton_h<true><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, h_guess, h_out,
-                                                                                      omega_out, posh_out, iters, status);
-    else
-        k_nl_newton_h<false><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, h_guess, h_out,
-                                                                                       omega_out, posh_out, iters, status);
+#define SPHB_NLN(FU_, MA_)                                                                                            \
+    k_nl_newton_h<FU_, MA_><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, h_guess, h_out, \
+                                                                                      omega_out, posh_out, iters, status)
+    if (k->mass) {
+        if (omega_out) SPHB_NLN(true, true); else SPHB_NLN(false, true);
+    } else {
+        if (omega_out) SPHB_NLN(true, false); else SPHB_NLN(false, false);
+    }
+#undef SPHB_NLN
     SPHB_LAUNCHED();
     return SPHB_OK;
 }
@@ -790,12 +814,15 @@ extern "C" int sphb_nlist_force(const sphb_nlist *nl, const sphb_consts *k, cons
     if (!nl_ok(nl) || !k || !posh || !recB || (!recC == !recD) || !acc || !dudt || !status) return SPHB_E_ARG;
     if (k->G != 0.0) return SPHB_E_ARG;   // the softened-gravity terms ride in the scanning kernels only
     if (nl->n == 0) return SPHB_OK;
-    if (recD)
-        k_nl_force<true><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recD, acc,
-                                                                                   dudt, status);
-    else
-        k_nl_force<false><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, recC, acc,
-                                                                                    dudt, status);
+#define SPHB_NLF(DE_, MA_, RC_)                                                                                       \
+    k_nl_force<DE_, MA_><<<nl_blocks(nl->n), NL_THREADS, 0, sphb_stream(stream)>>>(*nl, *k, target, posh, recB, RC_, acc, \
+                                                                                   dudt, status)
+    if (k->mass) {
+        if (recD) SPHB_NLF(true, true, recD); else SPHB_NLF(false, true, recC);
+    } else {
+        if (recD) SPHB_NLF(true, false, recD); else SPHB_NLF(false, false, recC);
+    }
+#undef SPHB_NLF
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

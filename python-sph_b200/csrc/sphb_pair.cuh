@@ -9,6 +9,15 @@ __device__ __forceinline__ void sphb_load_posh(const double *posh, size_t i, dou
     sphb_ld4(posh, i, x, y, z, h);
 }
 
+// the record of an own-support pair with its weight in the fourth component (those sums never use h_i): m_i with
+// per-particle masses, else exactly 1
+__device__ __forceinline__ void sphb_load_posw(const double *posh, const double *mass, size_t i, double &x, double &y, double &z,
+                                               double &w)
+{
+    sphb_ld4(posh, i, x, y, z, w);
+    w = mass ? __ldg(mass + i) : 1.0;
+}
+
 // One evaluation of sumF = sum f(q), sumG = sum (q f'(q) + 3 f(q)) over the lane's list.
 // rho_sum = m sumF/(pi h^3) (pyfluid.py:218-224), sum m dW/dh = -m sumG/(pi h^4) (pyfluid.py:85-87,91-97).
 struct SphbOwnAcc {
@@ -27,8 +36,10 @@ __device__ __forceinline__ double sphb_grav_pX(double x)
     return (x < 1.0) ? in : ((x >= 1.0 && x < 2.0) ? mid : 0.0);
 }
 
+// w: the weight of the pair inside the sums (m_i with per-particle masses; 1 -- a multiplication the compiler drops, or an
+// exact one -- when the uniform mass is applied after the sum)
 template <bool XI = false>
-__device__ __forceinline__ void sphb_own_pair(double x, double y, double z, SphbOwnAcc &a)
+__device__ __forceinline__ void sphb_own_pair(double x, double y, double z, SphbOwnAcc &a, double w = 1.0)
 {
     const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
     const double d2 = sphb_d2(dx, dy, dz);
@@ -36,16 +47,16 @@ __device__ __forceinline__ void sphb_own_pair(double x, double y, double z, Sphb
     const double q = r * a.hinv;
     double f, fp;
     sphb_m4c(q, f, fp);
-    a.sumF += f;
-    a.sumG += fma(q, fp, 3.0 * f);
+    a.sumF += w * f;
+    a.sumG += w * fma(q, fp, 3.0 * f);
     a.nn += (q < 2.0) ? 1 : 0;
-    if (XI) a.sumX += sphb_grav_pX(q);
+    if (XI) a.sumX += w * sphb_grav_pX(q);
 }
 
 // the pair's terms without touching the accumulators: two of these are independent instruction streams
 template <bool XI = false>
 __device__ __forceinline__ void sphb_own_terms(double x, double y, double z, const SphbOwnAcc &a, double &f, double &g,
-                                               int &in, double &px)
+                                               int &in, double &px, double w = 1.0)
 {
     const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
     const double d2 = sphb_d2(dx, dy, dz);
@@ -53,19 +64,21 @@ __device__ __forceinline__ void sphb_own_terms(double x, double y, double z, con
     const double q = r * a.hinv;
     double fp;
     sphb_m4c(q, f, fp);
-    g = fma(q, fp, 3.0 * f);
+    g = w * fma(q, fp, 3.0 * f);
+    f = w * f;
     in = (q < 2.0) ? 1 : 0;
-    px = XI ? sphb_grav_pX(q) : 0.0;
+    px = XI ? w * sphb_grav_pX(q) : 0.0;
 }
 
 // entries k and k+1 evaluated side by side (the second only counted when it exists), accumulated in list order
-template <bool XI = false>
+// W: the records' fourth component is the pair's weight (the loader put m_i there: own-support sums never use h_i)
+template <bool XI = false, bool W = false>
 __device__ __forceinline__ void sphb_own_pair2(const double (&p)[4], const double (&q)[4], bool second, SphbOwnAcc &a)
 {
     double f0, g0, x0, f1, g1, x1;
     int n0, n1;
-    sphb_own_terms<XI>(p[0], p[1], p[2], a, f0, g0, n0, x0);
-    sphb_own_terms<XI>(q[0], q[1], q[2], a, f1, g1, n1, x1);
+    sphb_own_terms<XI>(p[0], p[1], p[2], a, f0, g0, n0, x0, W ? p[3] : 1.0);
+    sphb_own_terms<XI>(q[0], q[1], q[2], a, f1, g1, n1, x1, W ? q[3] : 1.0);
     a.sumF += f0;
     a.sumG += g0;
     a.nn += n0;
@@ -80,11 +93,13 @@ __device__ __forceinline__ void sphb_own_pair2(const double (&p)[4], const doubl
 
 
 // Omega from the grad-h sum at h with the algebraic density (pyfluid.py:91-97 as the step uses it, :503/:518)
-__device__ __forceinline__ double sphb_omega_from_sumG(const sphb_consts &k, double h, double sumG)
+// mj: the target's own mass (sphb_mass_of)
+// mafter: the factor still to be applied to the sum (sphb_mass_after)
+__device__ __forceinline__ double sphb_omega_from_sumG(const sphb_consts &k, double h, double sumG, double mj, double mafter)
 {
-    const double pref = k.particle_mass / (SPHB_PI * (h * h * h));
-    const double ds = -(pref / h) * sumG;                       // sum_i m dW/dh
-    return 1.0 + h / (3.0 * sphb_var_density(k, h)) * ds;       // pyfluid.py:97 with rho = m (eta/h)^3
+    const double pref = mafter / (SPHB_PI * (h * h * h));
+    const double ds = -(pref / h) * sumG;                           // sum_i m_i dW/dh
+    return 1.0 + h / (3.0 * sphb_var_density_m(k, mj, h)) * ds;     // pyfluid.py:97 with rho = m_j (eta/h)^3
 }
 
 
@@ -154,10 +169,12 @@ extern "C" int sphb_debug_force_get(uint32_t *list_host, double *val_host)
 // GRAV: the compact grad-h correction of the softened gravity (smoothed_gravity_correction_comp, pyfluid.py:434-437)
 // has the same shape as the pressure term, -m (B_j gradW(h_j) + B_i gradW(h_i)) with B = (G/2) xi/Omega, and rides
 // in the acceleration coefficient only (du/dt keeps the pure A_j).
+// wi: the pair's weight inside the sums (m_i with per-particle masses, else 1: the uniform mass is applied per target);
+// every term of the sums is linear in (s_j, s_i), so the weight enters there and nowhere else
 template <bool GRAV>
 __device__ __forceinline__ void sphb_force_pair(const double *recB, const double *recC, const double *bgrav, uint32_t i,
                                                 double x, double y, double z, double hi, const sphb_consts &k,
-                                                SphbForceAcc &a)
+                                                SphbForceAcc &a, double wi = 1.0)
 {
     const double dx = a.xj - x, dy = a.yj - y, dz = a.zj - z;
     const double d2 = sphb_d2(dx, dy, dz);
@@ -173,8 +190,8 @@ __device__ __forceinline__ void sphb_force_pair(const double *recB, const double
     if (!(qj < 2.0) && !(qi < 2.0)) return;   // prefilter false positive
     double vxi, vyi, vzi, Ai;
     sphb_load4(recB, i, vxi, vyi, vzi, Ai);
-    const double sj = sphb_m4c_fp(qj) * a.gj * rinv;
-    const double si = sphb_m4c_fp(qi) * gi * rinv;
+    const double sj = wi * (sphb_m4c_fp(qj) * a.gj * rinv);
+    const double si = wi * (sphb_m4c_fp(qi) * gi * rinv);
     const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
     const double vdr = sphb_dot3(dx, dy, dz, dvx, dvy, dvz);
     a.dens = fma(sj, vdr, a.dens);
@@ -215,7 +232,8 @@ struct SphbPairTerms {
 // dependent load latency less per pair, a few wasted loads for the candidates that fail the test; same bits
 template <bool PRE = false>
 __device__ __forceinline__ void sphb_force_geom(const double *recB, uint32_t i, const double (&p)[4], bool present,
-                                                const SphbForceAcc &a, SphbPairTerms &t, const double *vb = nullptr)
+                                                const SphbForceAcc &a, SphbPairTerms &t, const double *vb = nullptr,
+                                                double wi = 1.0)
 {
     t.dx = a.xj - p[0];
     t.dy = a.yj - p[1];
@@ -239,8 +257,8 @@ __device__ __forceinline__ void sphb_force_geom(const double *recB, uint32_t i, 
     } else if (t.ok) {
         sphb_load4(recB, i, vxi, vyi, vzi, t.Ai);
     }
-    t.sj = sphb_m4c_fp(qj) * a.gj * rinv;
-    t.si = sphb_m4c_fp(qi) * gi * rinv;
+    t.sj = wi * (sphb_m4c_fp(qj) * a.gj * rinv);
+    t.si = wi * (sphb_m4c_fp(qi) * gi * rinv);
     const double dvx = a.vxj - vxi, dvy = a.vyj - vyi, dvz = a.vzj - vzi;
     t.vdr = sphb_dot3(t.dx, t.dy, t.dz, dvx, dvy, dvz);
 }
@@ -275,15 +293,19 @@ __device__ __forceinline__ void sphb_force_accumulate(const double *bgrav, uint3
 
 // DENSE: recC is a dense [n][2] array of (rho, cs) instead of the 32-byte record (a gathered 16-byte entry shares its
 // cache line with seven neighbours instead of three)
-template <bool GRAV, bool DENSE = false, bool PRE = false>
+// MASS: per-particle masses (k.mass != NULL): one more 8-byte gather per pair
+// RTM: decide at run time (k.mass), for the scanning kernels: one predictable branch and two exact multiplications by 1
+template <bool GRAV, bool DENSE = false, bool PRE = false, bool MASS = false, bool RTM = false>
 __device__ __forceinline__ void sphb_force_pair2(const double *recB, const double *recC, const double *bgrav, uint32_t i0,
                                                  uint32_t i1, const double (&p0)[4], const double (&p1)[4], bool second,
                                                  const sphb_consts &k, SphbForceAcc &a, bool first = true,
                                                  const double *vb0 = nullptr, const double *vb1 = nullptr)
 {
     SphbPairTerms t0, t1;
-    sphb_force_geom<PRE>(recB, i0, p0, first, a, t0, vb0);
-    sphb_force_geom<PRE>(recB, i1, p1, second, a, t1, vb1);
+    const bool wm = MASS || (RTM && k.mass != nullptr);
+    const double w0 = (wm && first) ? __ldg(k.mass + i0) : 1.0, w1 = (wm && second) ? __ldg(k.mass + i1) : 1.0;
+    sphb_force_geom<PRE>(recB, i0, p0, first, a, t0, vb0, w0);
+    sphb_force_geom<PRE>(recB, i1, p1, second, a, t1, vb1, w1);
     const bool v0 = t0.ok && t0.vdr < 0.0, v1 = t1.ok && t1.vdr < 0.0;
     double ph0 = 0.0, ph1 = 0.0;
     if (v0 || v1) {

@@ -213,6 +213,17 @@ def make_consts(k) -> N.Consts:
         float(k["G"]), float(k["ADIABATIC_INDEX"]))
 
 
+def with_mass(consts, mass_t):
+    """a copy of `consts` whose sphb_consts.mass points at mass_t (a device fp64 tensor indexed like the particle arrays
+    of the calls it is used for), or `consts` itself when mass_t is None.  The copy keeps the tensor alive."""
+    if mass_t is None:
+        return consts
+    c = N.Consts.from_buffer_copy(consts)
+    c.mass = mass_t.data_ptr()
+    c._mass_t = mass_t
+    return c
+
+
 # cell edge (y,z) = CELL_FACTOR * 2 * mean(h): one cell ~ one support radius of a typical particle; x edge = that / XDIV
 CELL_FACTOR = float(__import__('os').environ.get('SPHB_CELL_FACTOR', '0.9'))
 XDIV = int(__import__('os').environ.get('SPHB_XDIV', '1'))
@@ -753,7 +764,7 @@ class Stepper:
         self._pool = [None, None, None]   # the three cell lists of a step, rebuilt in place while n and the grid size hold
 
     def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, omega0=None, want_omega1=False,
-             hooks=None):
+             hooks=None, mass=None):
         """omega0 (caller order, optional): Omega(pos0, h0) if the caller already has it -- the time loop does, because
         the previous step's last Newton kernel returns it (want_omega1=True appends omega1 to the result).  Without
         it the step computes Omega0 itself, exactly like a stand-alone var_smoothlength_leapfrog call."""
@@ -771,12 +782,15 @@ class Stepper:
         # ties inside a cell are always broken by the caller index and every sum has one fixed order (the
         # multi-GPU runner does the same with global ids: k-rank results equal 1-rank results bit for bit).
         grav = consts.G != 0.0
+        consts0 = consts
+        of = lambda dg: with_mass(consts0, e.gather(mass, dg.perm, 1)) if mass is not None else consts0   # masses in grid order
 
         park = os.environ.get("SPHB_NO_PARK") is None
 
         def stage(dg, vel_c, u_c, sidx, om=None, lists=None):
             """the six calls at pyfluid.py:502-507 / :517-522 -> acc, dudt in caller order
             (om: Omega already produced by the Newton kernel for this snapshot; lists: its parked neighbour lists)"""
+            consts = of(dg)
             if not grav and om is None:
                 lists = e.park_lists(dg) if park else None   # the Omega pass scans once for itself and for the force
                 _, _, om, _ = e.density_omega(dg, consts, want_rho=False, want_omega=True, lists=lists)
@@ -797,7 +811,7 @@ class Stepper:
 
         def solve_h(dg, sidx, want_omega=False, lists=None):
             """newton_smoothlength_arr(pos, guess = the h carried in the snapshot), grid order"""
-            r = e.newton(dg, consts, dg.posh[:, 3].contiguous(), st.ptr(sidx), want_omega=want_omega, lists=lists)
+            r = e.newton(dg, of(dg), dg.posh[:, 3].contiguous(), st.ptr(sidx), want_omega=want_omega, lists=lists)
             e.check_neg_h(r[0] if want_omega else r, st.ptr(sidx))
             return r
 
@@ -1045,6 +1059,7 @@ class FastStepper:
         self.caller_state = None  # resident state in caller order while on hold
         self.stats = dict(steps=0, builds=0, redos=0, safe_steps=0, reuse_rejected=0)
         self._consts = None       # the constants of the current call (the build forms Omega with them)
+        self.M = None             # per-particle masses in slot order (None: the uniform consts.particle_mass)
 
     # ---- builds ------------------------------------------------------------------------------------
     def _rates(self):
@@ -1055,7 +1070,7 @@ class FastStepper:
             return None
         return slot_rates(nl.posh_build, self.P, age)
 
-    def _rebuild_from(self, posh_in, vel_in, u_in, ids_in, rates=None):
+    def _rebuild_from(self, posh_in, vel_in, u_in, ids_in, rates=None, mass_in=None):
         """sort records (any order; ids_in = caller index of each input row, None = identity) into a fresh cell list,
         scan it once, and take the state along in the new slot order.  rates: _rates() of the lists being replaced, in
         the order of posh_in -- the new lists then get per-particle margins"""
@@ -1069,6 +1084,7 @@ class FastStepper:
         dg = e.build(posh_in, grid, delta, tie_key=ids_in)
         self.V = e.gather(vel_in, dg.perm, 3) if vel_in is not None else None
         self.U = e.gather(u_in, dg.perm, 1) if u_in is not None else None
+        self.M = e.gather(mass_in, dg.perm, 1) if mass_in is not None else None   # per-particle masses, slot order
         if ids_in is None:
             self.perm = dg.perm
             self.ids = dg.perm.long()
@@ -1085,7 +1101,8 @@ class FastStepper:
             self.margins.life = 1 if self.margins.per_particle else 10 ** 9
         self.margins.built()
         # Omega(pos0, h0) of the step that follows comes out of the build itself (the lists are in the staging area)
-        self.nl = e.nl_build(dg, cover_h, skin, pool_rows=self.pool_rows, consts=self._consts, margins=pp)
+        self.nl = e.nl_build(dg, cover_h, skin, pool_rows=self.pool_rows, consts=self._consts if self.M is None else None,
+                             margins=pp)
         self.pool_rows = max(self.nl.pool_rows, self.pool_rows or 0)
         self.stats["builds"] += 1
         self.stale = False
@@ -1118,6 +1135,7 @@ class FastStepper:
     def _slots_step(self, P0, V0, U0, dt, consts, st, hooks=None):
         """pyfluid.py:502-530 on the kept lists -> P1 (x, y, z, h1), V1, U1 in slot order; inputs untouched"""
         e, nl = self.e, self.nl
+        consts = with_mass(consts, self.M)
         if self.fresh and nl.omega0 is not None and P0 is nl.dg.posh:
             om0 = nl.omega0                                                             # :503, formed by the build
         else:
@@ -1166,13 +1184,15 @@ class FastStepper:
     # ---- resident-state API ---------------------------------------------------------------------------
     SAFE_HOLD = 8
 
-    def load(self, pos, vel, u, h, consts=None):
-        """take a caller-order state (device tensors); it stays resident, in slot order, until state() is asked for"""
+    def load(self, pos, vel, u, h, consts=None, mass=None):
+        """take a caller-order state (device tensors); it stays resident, in slot order, until state() is asked for.
+        mass (n,): per-particle masses (SURVEY.md 8(f) #4); None: the uniform consts.particle_mass"""
         self.caller_state = None
         self.hold = 0
         if consts is not None:
             self._consts = consts
-        self._rebuild_from(self.e.pack_posh(pos, h), vel, u, None)
+        self.mass_caller = mass
+        self._rebuild_from(self.e.pack_posh(pos, h), vel, u, None, mass_in=mass)
 
     def state(self):
         """-> pos, vel, u, h in caller order"""
@@ -1184,11 +1204,12 @@ class FastStepper:
     def _safe_advance(self, dt, consts, defer_status, printer):
         self.stats["safe_steps"] += 1
         pos, vel, u, h = self.caller_state
-        self.caller_state = self.safe.step(pos, vel, u, h, dt, consts, defer_status=defer_status, printer=printer)
+        mass = getattr(self, "mass_caller", None)
+        self.caller_state = self.safe.step(pos, vel, u, h, dt, consts, defer_status=defer_status, printer=printer, mass=mass)
         self.last_status = self.safe.last_status
         self.hold -= 1
         if self.hold <= 0:
-            self.load(*self.caller_state)
+            self.load(*self.caller_state, mass=mass)
 
     def advance(self, dt, consts, defer_status=True, printer=print):
         if consts.G != 0.0:
@@ -1199,7 +1220,7 @@ class FastStepper:
             return self._safe_advance(dt, consts, defer_status, printer)
         for attempt in range(self.MAX_ATTEMPTS):
             if self.stale or attempt > 0:
-                self._rebuild_from(self.P, self.V, self.U, self.ids, rates=self._rates())
+                self._rebuild_from(self.P, self.V, self.U, self.ids, rates=self._rates(), mass_in=self.M)
             ok, P1, V1, U1, st = self._try(dt, consts)
             if ok:
                 self.P, self.V, self.U = P1, V1, U1
@@ -1217,11 +1238,12 @@ class FastStepper:
         self._safe_advance(dt, consts, defer_status, printer)
 
     # ---- pure-function API (same contract as Stepper.step) -----------------------------------------------
-    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, hooks=None):
+    def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, hooks=None, mass=None):
         if consts.G != 0.0:
-            r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks)
+            r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks, mass=mass)
             self.last_status = self.safe.last_status
             return r
+        self.mass_caller = mass
         e = self.e
         n = pos0.shape[0]
         self._consts = consts
@@ -1229,7 +1251,7 @@ class FastStepper:
         if self.hold > 0:
             self.hold -= 1
             self.stats["safe_steps"] += 1
-            r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks)
+            r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks, mass=mass)
             self.last_status = self.safe.last_status
             return r
         fh = _FastHooks(self, hooks, vel0, u0) if hooks is not None else None
@@ -1245,6 +1267,8 @@ class FastStepper:
                 self.stats["reuse_rejected"] += 1
             elif fh is None:
                 _, self.V, self.U = e.gather_state(self.perm, vel=vel0, u=u0)
+            if reuse:
+                self.M = e.gather(mass, self.perm, 1) if mass is not None else None
         for attempt in range(self.MAX_ATTEMPTS):
             if not reuse:
                 if fh is not None:
@@ -1253,9 +1277,10 @@ class FastStepper:
                 if rates is not None:
                     # the lists being replaced measured every record's motion: the new ones get per-particle margins
                     _, V_old, U_old = e.gather_state(self.perm, vel=vel0, u=u0)
-                    self._rebuild_from(self.P, V_old, U_old, self.ids, rates=rates)
+                    M_old = e.gather(mass, self.perm, 1) if mass is not None else None
+                    self._rebuild_from(self.P, V_old, U_old, self.ids, rates=rates, mass_in=M_old)
                 else:
-                    self._rebuild_from(e.pack_posh(pos0, h0), vel0, u0, None)
+                    self._rebuild_from(e.pack_posh(pos0, h0), vel0, u0, None, mass_in=mass)
                 have_old = False
                 if fh is not None:
                     fh.have_state()
@@ -1279,7 +1304,7 @@ class FastStepper:
         self.nl = None
         self.stale = True
         self.hold = self.SAFE_HOLD
-        r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks)
+        r = self.safe.step(pos0, vel0, u0, h0, dt, consts, defer_status=defer_status, printer=printer, hooks=hooks, mass=mass)
         self.last_status = self.safe.last_status
         return r
 

@@ -53,11 +53,33 @@ def _eng() -> _E.Engine:
     return _engine
 
 
-def _consts(hydro_only=False):
+def _mass_array():
+    """PARTICLE_MASS as a device tensor when the caller made it an ARRAY (extension, SURVEY.md 8(f) #4: the reference's
+    own NOTE at pyfluid.py:3-4 asks for per-particle masses); None for the reference's scalar"""
+    m = PARTICLE_MASS
+    if isinstance(m, torch.Tensor):
+        return m.to(device=_eng().device, dtype=torch.float64).reshape(-1).contiguous() if m.dim() > 0 else None
+    if isinstance(m, np.ndarray) and m.ndim > 0:
+        return torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64).reshape(-1)).to(_eng().device)
+    return None
+
+
+def _consts(hydro_only=False, dg=None, order=True):
+    """the module constants at call time.  With an array PARTICLE_MASS the masses ride along: in the grid order of `dg`
+    (what the gather kernels index by), or in caller order when dg is None"""
     k = {name: globals()[name] for name in _CONST_NAMES}
     if hydro_only:
         k["G"] = 0.0
-    return _E.make_consts(k)
+    m = _mass_array()
+    if m is None:
+        return _E.make_consts(k)
+    k["PARTICLE_MASS"] = float("nan")     # never used as a uniform mass by accident
+    c = _E.make_consts(k)
+    if dg is not None:
+        if m.shape[0] != dg.n:
+            raise ValueError("PARTICLE_MASS has %d entries for %d particles" % (m.shape[0], dg.n))
+        m = _eng().gather(m, dg.perm, 1)
+    return _E.with_mass(c, m)
 
 
 class _IO:
@@ -168,7 +190,7 @@ def omega_j(j, position_arr, density_j, smoothlength_j):
     dg = _grid_and_order(e, pos, h)
     s = _slot_of(dg, j)
     rho = torch.full((n,), float(density_j), dtype=torch.float64, device=e.device)
-    _, _, om, _ = e.density_omega(dg, _consts(), target=_one_hot(dg, s), rho_in=rho, want_rho=False, want_omega=True)
+    _, _, om, _ = e.density_omega(dg, _consts(dg=dg), target=_one_hot(dg, s), rho_in=rho, want_rho=False, want_omega=True)
     return _scalar(om[s])
 
 
@@ -179,7 +201,7 @@ def omega_arr(position_arr, density_arr, smoothlength_arr):
     pos = io.dev64(position_arr, (-1, 3))
     dg = _grid_and_order(e, pos, io.dev64(smoothlength_arr, (-1,)))
     rho_s = e.gather(io.dev64(density_arr, (-1,)), dg.perm, 1)
-    _, _, om, _ = e.density_omega(dg, _consts(), rho_in=rho_s, want_rho=False, want_omega=True)
+    _, _, om, _ = e.density_omega(dg, _consts(dg=dg), rho_in=rho_s, want_rho=False, want_omega=True)
     return io.out(e.scatter(om, dg.perm, 1))
 
 
@@ -219,7 +241,7 @@ def bisection_h(j, position_arr):
     dg = e.build(posh, grid, delta)
     st = _E.Status(1, e.device)
     slot = torch.tensor([_slot_of(dg, j)], dtype=torch.int32, device=e.device)
-    hb, code, oob = e.bisect(dg, _consts(), slot, st.ptr(0))
+    hb, code, oob = e.bisect(dg, _consts(dg=dg), slot, st.ptr(0))
     _report(st)
     return None if int(code[0].item()) == 2 else _scalar(hb[0])
 
@@ -243,7 +265,7 @@ def newton_smoothlength_while(j, position_arr, initial_smoothlength_j, _details=
     dg = _grid_and_order(e, pos, hg)
     s = _slot_of(dg, j)
     st = _E.Status(1, e.device)
-    h, it, code = e.newton(dg, _consts(), hg, st.ptr(0), target=_one_hot(dg, s), details=True)
+    h, it, code = e.newton(dg, _consts(dg=dg), hg, st.ptr(0), target=_one_hot(dg, s), details=True)
     _report(st)
     c = int(code[s].item())
     hv = None if c == 2 else _scalar(h[s])
@@ -258,7 +280,7 @@ def newton_smoothlength_arr(position_arr, old_smoothlength_arr, _details=False):
     hg = io.dev64(old_smoothlength_arr, (-1,))
     dg = _grid_and_order(e, pos, hg)
     st = _E.Status(1, e.device)
-    h, it, code = e.newton(dg, _consts(), dg.posh[:, 3].contiguous(), st.ptr(0), details=True)
+    h, it, code = e.newton(dg, _consts(dg=dg), dg.posh[:, 3].contiguous(), st.ptr(0), details=True)
     e.check_neg_h(h, st.ptr(0))
     _report(st)
     out = io.out(e.scatter(h, dg.perm, 1))
@@ -285,7 +307,7 @@ def density(j, position_arr, smoothlength_j):
     h = torch.full((n,), float(smoothlength_j), dtype=torch.float64, device=e.device)
     dg = _grid_and_order(e, pos, h)
     s = _slot_of(dg, j)
-    rho, _, _, _ = e.density_omega(dg, _consts(), target=_one_hot(dg, s))
+    rho, _, _, _ = e.density_omega(dg, _consts(dg=dg), target=_one_hot(dg, s))
     return _scalar(rho[s])
 
 
@@ -294,7 +316,7 @@ def density_arr(position_arr, smoothlength_arr):
     io = _IO(position_arr, smoothlength_arr)
     e = _eng()
     dg = _grid_and_order(e, io.dev64(position_arr, (-1, 3)), io.dev64(smoothlength_arr, (-1,)))
-    rho, _, _, _ = e.density_omega(dg, _consts())
+    rho, _, _, _ = e.density_omega(dg, _consts(dg=dg))
     return io.out(e.scatter(rho, dg.perm, 1))
 
 
@@ -371,7 +393,7 @@ def xi(j, position_arr, density_j, smoothlength_j):
     dg = _grid_and_order(e, pos, h)
     s = _slot_of(dg, j)
     rho = torch.full((n,), float(density_j), dtype=torch.float64, device=e.device)
-    r = e.density_omega(dg, _consts(), target=_one_hot(dg, s), rho_in=rho, want_rho=False, want_xi=True)
+    r = e.density_omega(dg, _consts(dg=dg), target=_one_hot(dg, s), rho_in=rho, want_rho=False, want_xi=True)
     return _scalar(r[4][s])
 
 
@@ -381,7 +403,7 @@ def xi_arr(density_arr, smoothlength_arr, position_arr):
     e = _eng()
     dg = _grid_and_order(e, io.dev64(position_arr, (-1, 3)), io.dev64(smoothlength_arr, (-1,)))
     rho_s = e.gather(io.dev64(density_arr, (-1,)), dg.perm, 1)
-    r = e.density_omega(dg, _consts(), rho_in=rho_s, want_rho=False, want_xi=True)
+    r = e.density_omega(dg, _consts(dg=dg), rho_in=rho_s, want_rho=False, want_xi=True)
     return io.out(e.scatter(r[4], dg.perm, 1))
 
 
@@ -390,9 +412,9 @@ def _force_arrays(io, position_arr, velocity_arr, pressure_arr_, density_arr_, s
     """xi_arr_ != None: include the gravity terms of acceleration() (pyfluid.py:481-483) when G != 0"""
     e = _eng()
     grav = xi_arr_ is not None and G != 0
-    k = _consts(hydro_only=not grav)
     pos = io.dev64(position_arr, (-1, 3))
     dg = _grid_and_order(e, pos, io.dev64(smoothlength_arr, (-1,)))
+    k = _consts(hydro_only=not grav, dg=dg)
     g = lambda a, nc: e.gather(io.dev64(a, (-1, nc) if nc > 1 else (-1,)), dg.perm, nc)
     st = _E.Status(1, e.device)
     r = e.eos(dg.posh, g(velocity_arr, 3), None, g(omega_arr_, 1), k, st.ptr(0), rho_in=g(density_arr_, 1),
@@ -576,8 +598,10 @@ def var_smoothlength_leapfrog(pos0, vel0, energy0, h0, dt, out=None):
         # pinned host tensors in -> pinned host tensors out, transfers overlapped with the kernels
         return tuple(_E.step_pinned(_stepper, pos0.reshape(-1, 3), vel0.reshape(-1, 3), energy0.reshape(-1), h0.reshape(-1),
                                     float(dt), _consts(), out=list(out) if out is not None else None))
+    mass = _mass_array()
+    c = _consts() if mass is None else _E.make_consts(dict({n_: globals()[n_] for n_ in _CONST_NAMES}, PARTICLE_MASS=float("nan")))
     p, v, u, h = _stepper.step(io.dev64(pos0, (-1, 3)), io.dev64(vel0, (-1, 3)), io.dev64(energy0, (-1,)),
-                               io.dev64(h0, (-1,)), float(dt), _consts())
+                               io.dev64(h0, (-1,)), float(dt), c, mass=mass)
     return io.out(p), io.out(v), io.out(u), io.out(h)
 
 
@@ -690,20 +714,22 @@ def var_smoothlength_sim(time_arr, positions0, velocities0, energies0, smoothlen
         put, finish = writer.put, writer.finish
     put(0, (pos, vel, u, h))
     stepper = _get_stepper()
-    consts = _consts()
+    mass = _mass_array()
+    _c = lambda: _consts() if mass is None else _E.make_consts(dict({n_: globals()[n_] for n_ in _CONST_NAMES}, PARTICLE_MASS=float("nan")))
+    consts = _c()
     if isinstance(stepper, _E.FastStepper) and consts.G == 0.0:
         # the state stays resident in the neighbour lists' slot order; it is brought back to caller order only
         # for the snapshots that are kept
-        stepper.load(pos, vel, u, h)
+        stepper.load(pos, vel, u, h, mass=mass)
         for t in range(Nt - 1):
             print("time step:", t, "of", Nt)
-            stepper.advance(dt, _consts(), defer_status=False)
+            stepper.advance(dt, _c(), defer_status=False)
             if (t + 1) % stride == 0:
                 put((t + 1) // stride, stepper.state())
     else:
         for t in range(Nt - 1):
             print("time step:", t, "of", Nt)
-            pos, vel, u, h = stepper.step(pos, vel, u, h, dt, _consts())
+            pos, vel, u, h = stepper.step(pos, vel, u, h, dt, _c(), mass=mass)
             if (t + 1) % stride == 0:
                 put((t + 1) // stride, (pos, vel, u, h))
     finish()

@@ -30,7 +30,7 @@ def test_header_symbols_exported(native):
 
 def test_struct_sizes_match_header(native):
     # sizes implied by include/sphb200.h (LP64)
-    assert C.sizeof(native.Consts) == 8 * 3 + 4 * 2 + 8 * 8
+    assert C.sizeof(native.Consts) == 8 * 3 + 4 * 2 + 8 * 8 + 8   # + the per-particle mass pointer
     assert C.sizeof(native.Grid) == 8 * 4 + 4 * 4
     assert C.sizeof(native.Status) == 32
     assert C.sizeof(native.Cells) == 48 + 8 + 5 * 8 + 8 + 2 * 4 + 2 * 8   # + nlevels, exp0, levels, level_hmax

@@ -193,3 +193,29 @@ def test_oracle_bit_exact_report(golden, oracle_mod, capsys):
     with capsys.disabled():
         print("\n[oracle bit-exact fractions vs reference]", exact)
     assert exact["h"] > 0.9
+
+
+def test_mass_array_reduces_to_the_golden_vectors_when_uniform(oracle_mod, golden):
+    """per-particle masses in the oracle: with every m_i = PARTICLE_MASS it reproduces the
+    reference's outputs like the scalar does (the reference itself cannot take an array), and the array is really used"""
+    g = golden
+    o = oracle_mod.Oracle(G=0.0)
+    pos, vel, e, h = g["B_pos"], g["B_vel"], g["B_e"], g["B_h"]
+    n = len(h)
+    try:
+        o.set_masses(np.ones(n))
+        assert np.max(np.abs(o.newton_smoothlength_arr(pos, np.full(n, 0.8)) - h) / h) < 1e-14
+        rho = o.var_density_arr(h)
+        om = o.omega_arr(pos, rho, h)
+        assert np.max(np.abs(om - g["B_omega"]) / np.abs(g["B_omega"])) < 1e-13
+        o.set_masses(np.full(n, 2.0))
+        rho2 = o.var_density_arr(h)
+        assert np.allclose(rho2, 2.0 * rho, rtol=1e-15)
+    finally:
+        o.set_masses(None)
+    d1 = o.density_arr(pos, h)
+    o.set_masses(np.full(n, 2.0))
+    try:
+        assert np.allclose(o.density_arr(pos, h), 2.0 * d1, rtol=1e-15)
+    finally:
+        o.set_masses(None)
