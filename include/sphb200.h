@@ -55,7 +55,7 @@ typedef struct sphb_consts {
     double bisect_tol;     /* BISECTION_TOLERANCE               :24 */
     double bisect_a;       /* INITIAL_BISECTION_SMOOTHLENGTH_A  :25 */
     double bisect_b;       /* INITIAL_BISECTION_SMOOTHLENGTH_B  :26 */
-    double G;              /* G (gravity is outside this path; must be 0 for sphb_force) :35 */
+    double G;              /* G (0: hydro only; else sphb_force needs bgrav and sphb_gravity_direct adds the pair sum) :35 */
     double gamma;          /* ADIABATIC_INDEX                   :41 */
     const double *mass;    /* optional DEVICE array of PER-PARTICLE masses (the reference authors' own
                               NOTE at pyfluid.py:3-4), indexed like the particle arrays of the call (sorted slots for the
@@ -321,6 +321,10 @@ int sphb_force(const sphb_cells *cells, const sphb_consts *k, const uint8_t *tar
  * order; acc in the same order. */
 int sphb_gravity_direct(const double *posh, int64_t n, const sphb_consts *k, int32_t accumulate, double *acc,
                         void *stream);
+/* The same sum for a SUBSET of targets against all sources: what each rank of a decomposed run evaluates for its own
+ * particles once the sources (x, y, z, h of every rank) have been all-gathered.  k->mass, if set, indexes the sources. */
+int sphb_gravity_direct_targets(const double *posh_targets, int64_t n_targets, const double *posh_sources, int64_t n_sources,
+                                const sphb_consts *k, int32_t accumulate, double *acc, void *stream);
 /* grav_potential, grav_force, grav_potential_smoothlength_derivative elementwise (pyfluid.py:365-399) */
 int sphb_grav_eval(const double *dist, const double *h, int64_t n, double *phi, double *force, double *dphidh,
                    void *stream);

@@ -119,6 +119,7 @@ SIGNATURES = {
     "sphb_eos": (C.c_int, [P, P, P, P, P, P, P, I64, C.POINTER(Consts), P, P, P, P, P, P, P]),
     "sphb_force": (C.c_int, [C.POINTER(Cells), C.POINTER(Consts), P, P, P, P, P, P, P, P, C.POINTER(Lists), P]),
     "sphb_gravity_direct": (C.c_int, [P, I64, C.POINTER(Consts), I32, P, P]),
+    "sphb_gravity_direct_targets": (C.c_int, [P, I64, P, I64, C.POINTER(Consts), I32, P, P]),
     "sphb_grav_eval": (C.c_int, [P, P, I64, P, P, P, P]),
     "sphb_pair_terms": (C.c_int, [P, P, P, P, I64, C.POINTER(Consts), P, P, P, P, P, P, P]),
     "sphb_predict": (C.c_int, [P, P, P, P, P, C.c_double, I64, P, P, P, P, P]),

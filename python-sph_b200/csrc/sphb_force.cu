@@ -331,13 +331,15 @@ __device__ __forceinline__ double sphb_grav_dphidh(double dist, double h)
 #define GRAV_TILE 128
 // acc[j] (+)= sum_i -G/2 m (grav_force(d, h_j) + grav_force(d, h_i)) (r_j - r_i)/d   for r_i != r_j
 __global__ void __launch_bounds__(GRAV_TILE)
-    k_gravity_direct(const double *__restrict__ posh, long long n, sphb_consts k, int accumulate, double *__restrict__ acc)
+    k_gravity_direct(const double *__restrict__ posh_t, long long n_t, const double *__restrict__ posh, long long n,
+                     sphb_consts k, int accumulate, double *__restrict__ acc)
 {
+    // targets posh_t[0..n_t), sources posh[0..n) (k.mass, if any, indexes the sources)
     __shared__ double4 tile[GRAV_TILE];
     __shared__ double tmass[GRAV_TILE];   // the candidates' weights: m_i with per-particle masses, else exactly 1
     const long long j = (long long)blockIdx.x * GRAV_TILE + threadIdx.x;
     double xj = 0.0, yj = 0.0, zj = 0.0, hj = 1.0;
-    if (j < n) sphb_load4(posh, (size_t)j, xj, yj, zj, hj);
+    if (j < n_t) sphb_load4(posh_t, (size_t)j, xj, yj, zj, hj);
     double ax = 0.0, ay = 0.0, az = 0.0;
     for (long long t0 = 0; t0 < n; t0 += GRAV_TILE) {
         const long long i = t0 + threadIdx.x;
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(GRAV_TILE)
             az = fma(s, dz, az);
         }
     }
-    if (j < n) {
+    if (j < n_t) {
         const double w = -k.G / 2.0 * sphb_mass_after(k);
         if (accumulate) {
             acc[3 * j] += w * ax;
@@ -380,8 +382,22 @@ extern "C" int sphb_gravity_direct(const double *posh, int64_t n, const sphb_con
     SPHB_RANGE();
     if (n < 0 || !k || (n > 0 && (!posh || !acc))) return SPHB_E_ARG;
     if (n == 0) return SPHB_OK;
-    k_gravity_direct<<<(unsigned)((n + GRAV_TILE - 1) / GRAV_TILE), GRAV_TILE, 0, sphb_stream(stream)>>>(posh, n, *k,
+    k_gravity_direct<<<(unsigned)((n + GRAV_TILE - 1) / GRAV_TILE), GRAV_TILE, 0, sphb_stream(stream)>>>(posh, n, posh, n, *k,
                                                                                                       accumulate, acc);
+    SPHB_LAUNCHED();
+    return SPHB_OK;
+}
+
+extern "C" int sphb_gravity_direct_targets(const double *posh_targets, int64_t n_targets, const double *posh_sources,
+                                           int64_t n_sources, const sphb_consts *k, int32_t accumulate, double *acc,
+                                           void *stream)
+{
+    SPHB_RANGE();
+    if (n_targets < 0 || n_sources < 0 || !k || (n_targets > 0 && (!posh_targets || !acc)) || (n_sources > 0 && !posh_sources))
+        return SPHB_E_ARG;
+    if (n_targets == 0) return SPHB_OK;
+    k_gravity_direct<<<(unsigned)((n_targets + GRAV_TILE - 1) / GRAV_TILE), GRAV_TILE, 0, sphb_stream(stream)>>>(
+        posh_targets, n_targets, posh_sources, n_sources, *k, accumulate, acc);
     SPHB_LAUNCHED();
     return SPHB_OK;
 }

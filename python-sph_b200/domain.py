@@ -127,9 +127,8 @@ class SlabRunner:
     """var_smoothlength_leapfrog on a slab-decomposed particle set (one rank per GPU)."""
 
     def __init__(self, eng: E.Engine, consts, world, rank, margin=0.05, balance=True, calib_steps=0):
-        if consts.G != 0.0:
-            raise NotImplementedError("SlabRunner: the all-pairs gravity sum is single-GPU only; run with G = 0")
         self.e, self.consts, self.world, self.rank, self.margin = eng, consts, world, rank, margin
+        self.grav = consts.G != 0.0     # the reference's default (pyfluid.py:35): scanning kernels + all-gathered pair sum
         self.balance = balance
         self.park = os.environ.get("SPHB_NO_PARK") is None   # share neighbour lists between kernels of one snapshot
         self.calib_left = calib_steps if balance else 0   # optional: time the first steps per rank and re-balance
@@ -224,6 +223,8 @@ class SlabRunner:
         """the six calls of pyfluid.py:502-507 for the owned particles -> acc, dudt (owned order)
         lists: neighbour lists parked by the Newton kernel of this snapshot (else the Omega pass parks its own)"""
         e, dg = self.e, snap["dg"]
+        if self.grav:
+            return self._stage_gravity(snap, status_ptr)
         if om_own is None:
             lists = e.park_lists(dg) if self.park else None
             _, _, om_S, _ = e.density_omega(dg, self.consts, target=snap["target"], want_rho=False, want_omega=True,
@@ -235,6 +236,35 @@ class SlabRunner:
         _, _, rB, rC = e.eos(dg.posh, vel_S, u_S, self._to_grid(snap, om_L, 1), self.consts, status_ptr)
         acc_S, dudt_S = e.force(dg, self.consts, rB, rC, e.hmax(dg.posh), status_ptr, target=snap["target"], lists=lists)
         return self._owned_from_grid(snap, acc_S, 3), self._owned_from_grid(snap, dudt_S, 1)
+
+    def _stage_gravity(self, snap, status_ptr):
+        """the stage with the softened self-gravity of the reference's default G (pyfluid.py:481-483): xi rides in the
+        Omega pass (:401-418), its compact grad-h correction in the force kernel (:434-437), and the 1/r^2 pair sum
+        (:420-432) runs over ALL particles -- every rank's records are all-gathered (32 bytes each) and each rank sums
+        for its own targets.  O(N^2 / ranks): the N <~ 1e6 regime the exact sum is meant for."""
+        e, dg, c = self.e, snap["dg"], self.consts
+        _, _, om_S, _, xi_S = e.density_omega(dg, c, target=snap["target"], want_rho=False, want_omega=True, want_xi=True)
+        om_own, xi_own = self._owned_from_grid(snap, om_S, 1), self._owned_from_grid(snap, xi_S, 1)
+        g = snap["hx"].exchange([om_own, xi_own])
+        om_L, xi_L = torch.cat([om_own, g[0]]), torch.cat([xi_own, g[1]])
+        vel_S, u_S = self._to_grid(snap, snap["vel"], 3), self._to_grid(snap, snap["u"], 1)
+        _, _, rB, rC, bg = e.eos(dg.posh, vel_S, u_S, self._to_grid(snap, om_L, 1), c, status_ptr,
+                                 xi=self._to_grid(snap, xi_L, 1), want_bgrav=True)
+        acc_S, dudt_S = e.force(dg, c, rB, rC, e.hmax(dg.posh), status_ptr, target=snap["target"], bgrav=bg)
+        acc = self._owned_from_grid(snap, acc_S, 3)
+        n_own = snap["n_own"]
+        posh_own = e.pack_posh(snap["pos"][:n_own].contiguous(), snap["h"][:n_own].contiguous())
+        if self.world > 1:
+            n = torch.tensor([n_own], dtype=torch.int64, device=self.dev)
+            ns = [torch.empty_like(n) for _ in range(self.world)]
+            dist.all_gather(ns, n)
+            ns = [int(t.item()) for t in ns]
+            src = torch.empty((sum(ns), 4), dtype=F64, device=self.dev)
+            dist.all_gather(list(src.split(ns)), posh_own)
+        else:
+            src = posh_own
+        e.gravity_direct_targets(posh_own, src, c, acc)
+        return acc, self._owned_from_grid(snap, dudt_S, 1)
 
     def _newton(self, snap, status_ptr, want_omega=False, lists=None):
         e, dg = self.e, snap["dg"]
@@ -357,7 +387,7 @@ class SlabRunner:
         s1 = self._snapshot(mid, ["pos", "h", "vel", "u"])
         # the Newton kernel parks symmetric-support lists that stay complete while no h (own or ghost, hence the
         # all-reduce of the flag) grows by more than PARK_COVER; the mid-stage force kernel drains them
-        l1 = e.park_lists(s1["dg"], cover=E.PARK_COVER) if self.park else None
+        l1 = e.park_lists(s1["dg"], cover=E.PARK_COVER) if (self.park and not self.grav) else None
         h_mid, om_mid = self._newton(s1, stt.ptr(E.S_NEWTON_MID), want_omega=True, lists=l1)
         if l1 is not None:
             dist.all_reduce(l1.broken, op=dist.ReduceOp.MAX)
@@ -511,6 +541,8 @@ class FastSlabRunner(SlabRunner):
 
     def __init__(self, eng: E.Engine, consts, world, rank, margin=0.0, balance=True, calib_steps=0, cover_h=None, skin=None,
                  adaptive=True):
+        if consts.G != 0.0:
+            raise ValueError("kept neighbour lists run the G = 0 path; make_runner() gives the scanning SlabRunner for G != 0")
         super().__init__(eng, consts, world, rank, margin=margin, balance=balance, calib_steps=calib_steps)
         self._margins0 = (cover_h, skin, adaptive)
         self.margins = E.ListMargins(cover_h, skin, adaptive)

@@ -646,6 +646,12 @@ class Engine:
                   _ptr(out), _stream())
         return out
 
+    def gravity_direct_targets(self, posh_targets, posh_sources, consts, acc):
+        """the long-range sum for a subset of targets against all sources (decomposed runs); adds into acc"""
+        self._run("gravity_direct", self.lib.sphb_gravity_direct_targets, _ptr(posh_targets), posh_targets.shape[0],
+                  _ptr(posh_sources), posh_sources.shape[0], C.byref(consts), 1, _ptr(acc), _stream())
+        return acc
+
     def grav_eval(self, dist, h):
         n = dist.shape[0]
         phi, f, dp = (torch.empty(n, dtype=F64, device=self.device) for _ in range(3))

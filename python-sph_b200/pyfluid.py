@@ -86,7 +86,9 @@ class _IO:
     """numpy <-> device plumbing: remembers what kind the caller passed."""
 
     def __init__(self, *arrays):
-        self.torch_out = any(isinstance(a, torch.Tensor) for a in arrays)
+        ts = [a for a in arrays if isinstance(a, torch.Tensor)]
+        self.torch_out = bool(ts)
+        self.cpu_out = bool(ts) and not any(t.is_cuda for t in ts)     # CPU tensors in -> CPU tensors out
         self.dev = _eng().device
 
     def dev64(self, a, shape=None):
@@ -99,7 +101,9 @@ class _IO:
         return t.contiguous()
 
     def out(self, t):
-        return t if self.torch_out else t.cpu().numpy()
+        if self.torch_out:
+            return t.cpu() if self.cpu_out else t
+        return t.cpu().numpy()
 
 
 def _scalar(t):

@@ -33,7 +33,8 @@ def main():
         w = workloads.sod_tube(int(sys.argv[2])) if len(sys.argv) > 2 else workloads.uniform_random(n, seed=3, vscale=0.5)
     k = dict(PARTICLE_MASS=w["m"], COUPLING_CONST=1.3, SMOOTHLENGTH_VARIATION_TOLERANCE=1e-3, NEWTON_ITERATION_LIMIT=20,
              BISECTION_ITERATION_LIMIT=100, ALPHA_SPH=1.0, BETA_SPH=2.0, EPSILON=0.01, BISECTION_TOLERANCE=1e-10,
-             INITIAL_BISECTION_SMOOTHLENGTH_A=1e3, INITIAL_BISECTION_SMOOTHLENGTH_B=1e-3, G=0.0, ADIABATIC_INDEX=5 / 3)
+             INITIAL_BISECTION_SMOOTHLENGTH_A=1e3, INITIAL_BISECTION_SMOOTHLENGTH_B=1e-3, G=float(os.environ.get("CHECK_G", "0")),
+             ADIABATIC_INDEX=5 / 3)
     consts = E.make_consts(k)
     dt = w["dt"]
     runner = domain.make_runner(eng, consts, world, rank, lists=lists, decomp=decomp)

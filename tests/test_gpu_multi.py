@@ -49,3 +49,19 @@ def test_range_decomposition_bit_identical_to_one(args):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     cmp_ = json.loads(line)["compare"]
     assert all(v["bit_identical"] for v in cmp_.values()), cmp_
+
+
+def test_ranks_with_the_reference_default_gravity():
+    """the reference's default G = 39.4227 (pyfluid.py:35) on k ranks: xi and its correction through the slab kernels, the
+    pair sum over all-gathered records.  The pair sum runs in another order than on one GPU: 1e-12, not bit for bit"""
+    k = _ranks()
+    if k == 0:
+        pytest.skip("needs at least 2 GPUs")
+    env = dict(os.environ, CHECK_PATH="scan", CHECK_STEPS="2", CHECK_G="39.4227")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(k), "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "scripts", "check_multi.py"), "12000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    cmp_ = json.loads(line)["compare"]
+    assert all(v["max_abs_diff"] <= 1e-12 * max(v["scale"], 1e-300) for v in cmp_.values()), cmp_
