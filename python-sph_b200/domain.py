@@ -253,7 +253,7 @@ class SlabRunner:
         acc_S, dudt_S = e.force(dg, c, rB, rC, e.hmax(dg.posh), status_ptr, target=snap["target"], bgrav=bg)
         acc = self._owned_from_grid(snap, acc_S, 3)
         n_own = snap["n_own"]
-        posh_own = e.pack_posh(snap["pos"][:n_own].contiguous(), snap["h"][:n_own].contiguous())
+        posh_own = self._owned_from_grid(snap, dg.posh, 4)    # the grid's records: they carry the solved h at the mid stage
         if self.world > 1:
             n = torch.tensor([n_own], dtype=torch.int64, device=self.dev)
             ns = [torch.empty_like(n) for _ in range(self.world)]
