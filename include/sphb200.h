@@ -181,7 +181,8 @@ typedef struct sphb_lists {
 size_t sphb_lists_bytes(int64_t n);
 
 /* ---- neighbour lists kept across kernels AND steps (no reference counterpart: the reference sums over all N) ----------
- * sphb_nlist_build scans the cell list ONCE -- symmetric support 2 max(h_j, h_i), every h widened by cover_h + skin --
+ * sphb_nlist_build scans the cell list ONCE -- every pair with |r_j - r_i| <= 2 max(c_j h_j, c_i h_i) + s_j h_j + s_i h_i,
+ * c = cover_h and s = skin (or the per-particle `margins`): the symmetric support plus what both records may move --
  * and stores each warp's candidates (32 consecutive sorted slots = one warp) as rows of slot indices in `pool`.  The
  * sphb_nlist_* gather kernels only drain those rows: they read the CURRENT sorted records (positions and h rewritten in
  * place, slot order frozen) and decide membership pair by pair in fp64, exactly like the scanning kernels; entries

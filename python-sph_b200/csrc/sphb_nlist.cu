@@ -3,7 +3,7 @@
 // The scanning kernels (sphb_gather.cu, sphb_force.cu) find every target's candidates again in each launch; one
 // var_smoothlength_leapfrog step (pyfluid.py:498-532) launches five of them on three snapshots that differ by
 // v dt -- a small fraction of h.  Here the candidates are found ONCE (sphb_nlist_build: the same warp scan, with the
-// symmetric support 2 max(h_j, h_i) widened by cover_h + skin) and stored as rows of sorted-slot indices; the gather
+// symmetric support 2 max(c_j h_j, c_i h_i) plus the allowances s_j h_j + s_i h_i) and stored as rows of sorted-slot indices; the gather
 // kernels below (density / Omega, Newton h solve, momentum + energy) are pure drains: no cell list, no scan code, no
 // shared-memory lists, far fewer registers.  The particle state stays in the build's slot order, positions and h are
 // rewritten in place, and the lists stay complete while
