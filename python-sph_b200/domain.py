@@ -178,6 +178,9 @@ class SlabRunner:
         """migrate, then fix the halo send lists and the ghost ids until the next re-plan (the only place with
         device->host reads: send counts and h_max)"""
         st = self._migrate(st)
+        # the cells follow the gas: the fp32 pre-filter's error bound (delta) only holds while positions stay within a few
+        # box lengths of the grid origin, and a free expansion does not (host reads are fine here)
+        self.geom = self._global_geom(st["pos"], st["h"])
         hm = self._hmax(st["h"])
         width = 2.0 * hm * (1.0 + self.margin) * extra + 2.0 * self.skin * hm + 4.0 * self.geom[1]
         hx = HaloExchanger(self.cuts, self.rank, self.world).plan(st["pos"][:, 0].contiguous(), width)

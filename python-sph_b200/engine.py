@@ -766,7 +766,10 @@ class Stepper:
     def __init__(self, engine: Engine):
         self.e = engine
         self.last_status = None
-        self.geom = None   # (grid, delta) reused across steps when set by the caller
+        # (grid, delta) reused across steps when set by the caller.  A pinned geometry is the caller's to keep valid: delta
+        # bounds the fp32 pre-filter error only while |x - origin| stays within ~4 box lengths (outliers are clamped into
+        # border cells, which is exact but slow); leave it None and every step draws its cells from the bounding box
+        self.geom = None
         self._pool = [None, None, None]   # the three cell lists of a step, rebuilt in place while n and the grid size hold
 
     def step(self, pos0, vel0, u0, h0, dt, consts, defer_status=False, printer=print, omega0=None, want_omega1=False,
