@@ -51,6 +51,9 @@ def test_range_decomposition_bit_identical_to_one(args):
     assert all(v["bit_identical"] for v in cmp_.values()), cmp_
 
 
+@pytest.mark.skipif(os.environ.get("SPHB_TEST_MULTI_GRAVITY") is None,
+                    reason="SlabRunner._stage_gravity was written after the round's GPU budget was spent and has not run on "
+                           "hardware yet: set SPHB_TEST_MULTI_GRAVITY=1 to run it")
 def test_ranks_with_the_reference_default_gravity():
     """the reference's default G = 39.4227 (pyfluid.py:35) on k ranks: xi and its correction through the slab kernels, the
     pair sum over all-gathered records.  The pair sum runs in another order than on one GPU: 1e-12, not bit for bit"""
