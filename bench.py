@@ -164,7 +164,7 @@ def run_reference(a):
     o.step_work_sample(w["pos"], w["vel"], w["u"], h, cand[:1])
     t1 = time.perf_counter() - t0
     budget = 150.0 / max(1, a.steps + a.warmup)
-    nj = int(max(1, min(4096, budget / max(t1, 1e-6))))
+    nj = int(max(1, min(4096, budget / max(t1, 1e-6), (len(cand) - 1) // max(1, a.steps + a.warmup))))   # distinct particles per step
     k = 1
     for _ in range(a.warmup):
         o.step_work_sample(w["pos"], w["vel"], w["u"], h, cand[k:k + nj]); k += nj
