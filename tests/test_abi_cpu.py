@@ -176,3 +176,25 @@ def test_per_particle_margin_plan_is_order_independent():
     d.age = 2
     d.plan(rd * 8, rg * 8, 20)
     assert d.life <= a.life
+
+
+def test_range_decomposition_host_helpers():
+    """ranges.py: weighted slot cuts (aligned to warps, monotone, degenerate weights) and the geometry that rank 0 draws
+    and broadcasts survives its plain-tuple form, for one grid and for nested grids"""
+    import torch
+    import engine
+    import ranges
+    w = torch.ones(1000, dtype=torch.float64)
+    c = ranges.weighted_cuts(torch.cumsum(w, 0), 4)
+    assert c[0] == 0 and c[-1] == 1000 and c == sorted(c) and all(x % 32 == 0 for x in c[:-1])
+    assert max(b - a for a, b in zip(c[:-1], c[1:])) <= 250 + 32
+    w[:10] = 1e6                                      # all the work in the first ten slots: later ranks get empty ranges, no crash
+    c = ranges.weighted_cuts(torch.cumsum(w, 0), 4)
+    assert c[0] == 0 and c[-1] == 1000 and c == sorted(c)
+    assert ranges.weighted_cuts(torch.cumsum(torch.ones(64, dtype=torch.float64), 0), 1) == [0, 64]
+    g, delta = engine.choose_grid([0, 0, 0], [10, 5, 2], 0.5, 1000)
+    g2, d2 = ranges._geom_from_plain(ranges._geom_to_plain((g, delta)))
+    assert d2 == delta and bytes(g2) == bytes(g)
+    lv = engine.Levels(g, -7, [g, engine.choose_grid([1, 1, 1], [3, 3, 2], 0.05, 500)[0]])
+    lv2, d3 = ranges._geom_from_plain(ranges._geom_to_plain((lv, 0.125)))
+    assert d3 == 0.125 and lv2.exp0 == -7 and lv2.ncell == lv.ncell and lv2.table() == lv.table() and bytes(lv2.frame) == bytes(lv.frame)
