@@ -725,16 +725,36 @@ class Engine:
 S_STAGE0, S_PRED, S_NEWTON_MID, S_STAGE_MID, S_CORR, S_NEWTON_1, S_COUNT = range(7)
 
 
+MAX_REPEAT_PRINTS = 1000
+
+
+def max_cell_population(cell_start):
+    """largest number of particles in one cell of a cell list (cell_start: the [ncell+1] start table).  Above 8192 the
+    build keeps the atomics' order inside that cell instead of the stable (input index / global id) order, and sums
+    over such a cell are no longer reproducible bit for bit; nested grids (engine.Levels) keep cells at ~ a dozen"""
+    if cell_start.numel() < 2:
+        return 0
+    return int(torch.diff(cell_start.long()).max().item())
+
+
+CROWDED_CELL = 8192   # FIN_SORT_MAX of csrc/sphb_grid.cu
+
+
 def raise_for_status(st, printer=print):
     """Map the device status blocks of one step to the reference's prints and RuntimeErrors,
     in program order (pyfluid.py:498-532)."""
+    def emit(count, text):
+        # the reference prints one line per event; beyond MAX_REPEAT_PRINTS the rest is summarised, never dropped silently
+        n = int(count)
+        for _ in range(min(n, MAX_REPEAT_PRINTS)):
+            printer(text)
+        if n > MAX_REPEAT_PRINTS:
+            printer("[sph-b200] ... and %d more: %s" % (n - MAX_REPEAT_PRINTS, text))
+
     def soft(row):
-        for _ in range(min(int(row[1]), 1000)):
-            printer("WARNING: Failure to converge in newton_new_h.")          # pyfluid.py:178
-        for _ in range(min(int(row[2]), 1000)):
-            printer("ERROR: Root out of bisection bounds.")                    # pyfluid.py:136
-        for _ in range(min(int(row[3]), 1000)):
-            printer("ERROR: Failure to converge in Bisection_new_h.")          # pyfluid.py:153
+        emit(row[1], "WARNING: Failure to converge in newton_new_h.")          # pyfluid.py:178
+        emit(row[2], "ERROR: Root out of bisection bounds.")                    # pyfluid.py:136
+        emit(row[3], "ERROR: Failure to converge in Bisection_new_h.")          # pyfluid.py:153
 
     def hard(flags):
         if flags & N.ST_NEG_P:
@@ -1114,6 +1134,14 @@ class FastStepper:
                              margins=pp)
         self.pool_rows = max(self.nl.pool_rows, self.pool_rows or 0)
         self.stats["builds"] += 1
+        try:   # a diagnostic, never a reason to fail a step
+            if max_cell_population(dg.cell_start) > CROWDED_CELL:
+                import warnings
+                warnings.warn("a cell holds more than %d particles: the order inside it (and the last bits of sums over it) "
+                              "is not reproducible; the input is far more clustered than its cell size" % CROWDED_CELL)
+                self.stats["crowded_builds"] = self.stats.get("crowded_builds", 0) + 1
+        except Exception:
+            pass
         self.stale = False
         self.fresh = True                    # no step has run on these lists yet
 

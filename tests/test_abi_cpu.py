@@ -198,3 +198,22 @@ def test_range_decomposition_host_helpers():
     lv = engine.Levels(g, -7, [g, engine.choose_grid([1, 1, 1], [3, 3, 2], 0.05, 500)[0]])
     lv2, d3 = ranges._geom_from_plain(ranges._geom_to_plain((lv, 0.125)))
     assert d3 == 0.125 and lv2.exp0 == -7 and lv2.ncell == lv.ncell and lv2.table() == lv.table() and bytes(lv2.frame) == bytes(lv.frame)
+
+
+def test_status_prints_are_summarised_not_dropped_and_crowded_cells_are_seen():
+    import numpy as np
+    import torch
+    import engine
+    out = []
+    st = np.zeros((2, 8), dtype=np.int32)
+    st[0, 1] = 3                       # three Newton warnings
+    st[1, 2] = engine.MAX_REPEAT_PRINTS + 500
+    engine.raise_for_status(st, printer=out.append)
+    assert out[:3] == ["WARNING: Failure to converge in newton_new_h."] * 3
+    assert out.count("ERROR: Root out of bisection bounds.") == engine.MAX_REPEAT_PRINTS
+    assert out[-1].startswith("[sph-b200] ... and 500 more: ERROR: Root out of bisection bounds.")
+    st[1, 0] = 2
+    with pytest.raises(RuntimeError, match="Obtained negative pressure."):
+        engine.raise_for_status(st, printer=lambda *_: None)
+    assert engine.max_cell_population(torch.tensor([0, 3, 3, 10000, 10001], dtype=torch.int32)) == 9997
+    assert engine.max_cell_population(torch.tensor([0], dtype=torch.int32)) == 0
