@@ -213,3 +213,35 @@ def test_C5_plummer_1M_sampled(sph, oracle_mod):
     ng = eng.scatter(ng_scan.double(), dg.perm, 1).cpu().numpy()
     for j in js[:24]:
         assert int(ng[j]) == len(o.neighbours(pos, int(j), h[j])), j
+
+
+def test_plummer_kept_lists_with_per_particle_margins_vs_oracle(sph, oracle_mod):
+    """four steps of the resident FastStepper on a small Plummer sphere: from the second build on the lists carry
+    per-particle margins ON nested grids (level-wise and cell-wise allowance bounds in the builder's search); every step
+    is checked against the oracle's leapfrog, so a pair missing from a list would show as an error far above 1e-10"""
+    import torch
+    import engine as E
+    n = 3000
+    w = _plummer(n, 11)
+    sph.PARTICLE_MASS = w["m"]
+    o = oracle_mod.Oracle(G=0.0, PARTICLE_MASS=w["m"])
+    o.set_num_threads(os.cpu_count() or 1)
+    pos, vel, u = w["pos"], w["vel"] * (0.2 + 4.0 * np.random.default_rng(3).random((n, 1))), w["u"]   # slow and fast movers
+    h = sph.newton_smoothlength_arr(pos, w["h_guess"])
+    eng = sph._eng()
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    c = sph._consts()
+    fs = E.FastStepper(eng)
+    fs.load(to(pos), to(vel), to(u), to(h), consts=c)
+    dt = 2.0 * w["dt"]
+    s = (pos, vel, u, h)
+    saw_margins = False
+    for _ in range(4):
+        fs.advance(dt, c, defer_status=False)
+        s = o.var_smoothlength_leapfrog(*s, dt)
+        if fs.nl is not None:
+            saw_margins = saw_margins or (fs.nl.margins is not None and fs.nl.dg.levels is not None)
+        r = [x.cpu().numpy() for x in fs.state()]
+        assert np.abs(r[0] - s[0]).max() < RTOL * np.abs(s[0]).max()
+        assert vrel(r[1], s[1]) < 1e-9 and rel(r[2], s[2]) < RTOL and rel(r[3], s[3]) < RTOL
+    assert saw_margins or fs.stats["safe_steps"] > 0
